@@ -1,0 +1,74 @@
+/* C interface of oracle/_ref/libvamp_ref.so — TEST INFRASTRUCTURE ONLY.
+ *
+ * The library behind this header is the UNMODIFIED reference validation path, compiled from the
+ * sources where they lie under /root/reference/src/impl (see oracle/ref/Makefile), wrapped in a
+ * thin harness (ref_env.cc, ref_robot.hh).  It is the parity checker and the CPU baseline; the
+ * product (vamp_mvt_b200) never links or loads it.
+ *
+ * Robot ids: 0 panda, 1 ur5, 2 fetch, 3 baxter.
+ */
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    void *ref_env_create(void);
+    void ref_env_destroy(void *env);
+    /* fields exactly as stored by the reference's shapes (collision/shapes.hh) */
+    void ref_env_add_sphere(void *env, const float *xyzr);
+    void ref_env_add_cuboid(void *env, const float *f15);
+    void ref_env_add_capsule(void *env, const float *f8);
+    void ref_env_add_heightfield(void *env, const float *f6, size_t xd, size_t yd, const float *data);
+    void ref_env_add_capt(void *env, const float *pts, size_t n, float r_min, float r_max, float r_point);
+    void ref_env_add_mvt(
+        void *env,
+        const float *pts,
+        size_t n,
+        float r_min,
+        float r_max,
+        const float *aabb_min,
+        const float *aabb_max,
+        float r_point);
+    void ref_env_attach(void *env, const float *tf12, const float *spheres_xyzr, size_t n);
+    void ref_env_detach(void *env);
+    /* kind: 0 spheres 1 capsules 2 z_capsules 3 cuboids 4 z_cuboids.  Writes, in the container's
+       (sorted) order, the stored fields followed by min_distance; returns the object count. */
+    size_t ref_env_dump(void *env, int kind, float *out, size_t cap_floats);
+
+    int ref_robot_dim(int robot);
+    int ref_robot_n_spheres(int robot);
+    int ref_robot_resolution(int robot);
+
+    /* out[i] = validate_motion<Robot,8,1>(q_i,q_i,env)  (what vamp.<robot>.validate runs) */
+    void ref_validate_configs(int robot, void *env, const float *q, size_t n, uint8_t *out, int threads);
+    /* out[i] = validate_motion<Robot,8,Robot::resolution>(a_i,b_i,env) */
+    void
+    ref_validate_edges(int robot, void *env, const float *a, const float *b, size_t n, uint8_t *out, int threads);
+    /* out[i][s] = (x,y,z,r) of fine sphere s via Robot::sphere_fk<8> */
+    void ref_sphere_fk(int robot, const float *q, size_t n, float *out_xyzr);
+    /* Robot::eefk -> 4x4 row-major */
+    void ref_eefk(int robot, const float *q, float *out16);
+    /* fkcc_debug: env_hits = (sphere, object-id) pairs, self_hits = (sphere, sphere) pairs.
+       object ids are the insertion order of the add_* calls. Returns counts through n_env/n_self. */
+    void ref_debug(
+        int robot,
+        void *env,
+        const float *q,
+        int32_t *env_hits,
+        size_t cap_env,
+        size_t *n_env,
+        int32_t *self_hits,
+        size_t cap_self,
+        size_t *n_self);
+    /* seconds for `reps` passes of ref_validate_configs / edges with `threads` threads (best pass) */
+    double ref_time_configs(int robot, void *env, const float *q, size_t n, int threads, int reps);
+    double
+    ref_time_edges(int robot, void *env, const float *a, const float *b, size_t n, int threads, int reps);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,209 @@
+// Per-robot harness over the UNMODIFIED reference headers — TEST INFRASTRUCTURE ONLY.
+// Each function calls the reference's own entry points:
+//   validate_motion<Robot,8,res>   src/impl/vamp/planning/validate.hh:70
+//   Robot::sphere_fk<8>            src/impl/vamp/robots/<robot>.hh
+//   Robot::fkcc_debug<8>           src/impl/vamp/robots/<robot>.hh
+//   Robot::eefk                    src/impl/vamp/robots/<robot>.hh
+// exactly as the nanobind layer does (src/impl/vamp/bindings/robot_helper.hh:234-267).
+#pragma once
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <vamp/collision/environment.hh>
+#include <vamp/planning/validate.hh>
+#include <vamp/vector.hh>
+
+namespace refh
+{
+    using EnvF = vamp::collision::Environment<float>;
+    using EnvV = vamp::collision::Environment<vamp::FloatVector<vamp::FloatVectorWidth>>;
+    static constexpr std::size_t rake = vamp::FloatVectorWidth;
+
+    struct RobotVTable
+    {
+        int dim;
+        int n_spheres;
+        int resolution;
+        void (*validate_configs)(const EnvF &, const float *, std::size_t, std::uint8_t *, int);
+        void (*validate_edges)(const EnvF &, const float *, const float *, std::size_t, std::uint8_t *, int);
+        void (*sphere_fk)(const float *, std::size_t, float *);
+        void (*eefk)(const float *, float *);
+        void (*debug)(
+            const EnvF &,
+            const float *,
+            std::vector<std::pair<int, int>> &,
+            std::vector<std::pair<int, int>> &);
+    };
+
+    template <typename Fn>
+    inline void parallel_for(std::size_t n, int threads, Fn &&fn)
+    {
+        if (threads <= 1 or n < 2)
+        {
+            fn(std::size_t(0), n);
+            return;
+        }
+
+        std::vector<std::thread> pool;
+        const std::size_t chunk = (n + threads - 1) / threads;
+        for (int t = 0; t < threads; ++t)
+        {
+            const std::size_t lo = std::min(n, chunk * t);
+            const std::size_t hi = std::min(n, lo + chunk);
+            if (lo < hi)
+            {
+                pool.emplace_back([=, &fn] { fn(lo, hi); });
+            }
+        }
+
+        for (auto &th : pool)
+        {
+            th.join();
+        }
+    }
+
+    template <typename Robot>
+    struct Harness
+    {
+        using Configuration = typename Robot::Configuration;
+        using ConfigurationArray = typename Robot::ConfigurationArray;
+
+        static auto load(const float *q) -> Configuration
+        {
+            ConfigurationArray a;
+            for (std::size_t j = 0; j < Robot::dimension; ++j)
+            {
+                a[j] = q[j];
+            }
+            return Configuration(a);
+        }
+
+        static void
+        validate_configs(const EnvF &env, const float *q, std::size_t n, std::uint8_t *out, int threads)
+        {
+            parallel_for(
+                n,
+                threads,
+                [&](std::size_t lo, std::size_t hi)
+                {
+                    // one private vectorised environment per thread, as the bindings build per call
+                    // (bindings/robot_helper.hh:266) but hoisted out of the loop
+                    const EnvV ev(env);
+                    for (std::size_t i = lo; i < hi; ++i)
+                    {
+                        const auto c = load(q + i * Robot::dimension);
+                        out[i] = vamp::planning::validate_motion<Robot, rake, 1>(c, c, ev) ? 1 : 0;
+                    }
+                });
+        }
+
+        static void validate_edges(
+            const EnvF &env,
+            const float *a,
+            const float *b,
+            std::size_t n,
+            std::uint8_t *out,
+            int threads)
+        {
+            parallel_for(
+                n,
+                threads,
+                [&](std::size_t lo, std::size_t hi)
+                {
+                    const EnvV ev(env);
+                    for (std::size_t i = lo; i < hi; ++i)
+                    {
+                        const auto ca = load(a + i * Robot::dimension);
+                        const auto cb = load(b + i * Robot::dimension);
+                        out[i] =
+                            vamp::planning::validate_motion<Robot, rake, Robot::resolution>(ca, cb, ev) ? 1 :
+                                                                                                          0;
+                    }
+                });
+        }
+
+        static void sphere_fk(const float *q, std::size_t n, float *out)
+        {
+            for (std::size_t i = 0; i < n; ++i)
+            {
+                typename Robot::template ConfigurationBlock<rake> block;
+                for (std::size_t j = 0; j < Robot::dimension; ++j)
+                {
+                    block[j] = q[i * Robot::dimension + j];
+                }
+
+                typename Robot::template Spheres<rake> s;
+                Robot::template sphere_fk<rake>(block, s);
+                for (std::size_t k = 0; k < Robot::n_spheres; ++k)
+                {
+                    float *o = out + (i * Robot::n_spheres + k) * 4;
+                    o[0] = s.x[{k, 0}];
+                    o[1] = s.y[{k, 0}];
+                    o[2] = s.z[{k, 0}];
+                    o[3] = s.r[{k, 0}];
+                }
+            }
+        }
+
+        static void eefk(const float *q, float *out16)
+        {
+            std::array<float, Robot::dimension> a;
+            for (std::size_t j = 0; j < Robot::dimension; ++j)
+            {
+                a[j] = q[j];
+            }
+
+            const auto m = Robot::eefk(a).matrix();
+            for (int r = 0; r < 4; ++r)
+            {
+                for (int c = 0; c < 4; ++c)
+                {
+                    out16[r * 4 + c] = m(r, c);
+                }
+            }
+        }
+
+        static void debug(
+            const EnvF &env,
+            const float *q,
+            std::vector<std::pair<int, int>> &env_hits,
+            std::vector<std::pair<int, int>> &self_hits)
+        {
+            typename Robot::template ConfigurationBlock<rake> block;
+            for (std::size_t j = 0; j < Robot::dimension; ++j)
+            {
+                block[j] = q[j];
+            }
+
+            const auto dbg = Robot::template fkcc_debug<rake>(EnvV(env), block);
+            for (std::size_t s = 0; s < dbg.first.size(); ++s)
+            {
+                for (const auto &name : dbg.first[s])
+                {
+                    env_hits.emplace_back(static_cast<int>(s), std::atoi(name.c_str()));
+                }
+            }
+
+            for (const auto &p : dbg.second)
+            {
+                self_hits.emplace_back(static_cast<int>(p.first), static_cast<int>(p.second));
+            }
+        }
+
+        static constexpr RobotVTable vtable{
+            static_cast<int>(Robot::dimension),
+            static_cast<int>(Robot::n_spheres),
+            static_cast<int>(Robot::resolution),
+            &validate_configs,
+            &validate_edges,
+            &sphere_fk,
+            &eefk,
+            &debug};
+    };
+}  // namespace refh
