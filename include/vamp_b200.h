@@ -1,0 +1,141 @@
+/* vamp_b200.h -- C ABI of the B200-native batched configuration / motion validation engine.
+ *
+ * Drop-in boundary for the validation path of chingchennn/vamp_mvt (reference paths below are
+ * relative to /root/reference).  The reference has no FFI for this path -- the boundary there is a
+ * set of C++ templates plus a nanobind surface -- so each entry point cites the
+ * reference interface it replaces.  Plain pointers and sizes only; no exceptions cross the ABI;
+ * every call returns VMV_OK (0) or a negative error code, with a message in vmv_last_error().
+ *
+ * Ownership: the caller owns every host/device buffer it passes; the library owns the
+ * environment's device memory.  After vmv_env_commit() an environment is immutable and may be
+ * shared by concurrent calls on distinct streams.
+ *
+ * There is no CPU fallback: every compute entry point fails with VMV_ERR_CUDA when no CUDA device
+ * is usable.
+ */
+#ifndef VAMP_B200_H
+#define VAMP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    enum
+    {
+        VMV_OK = 0,
+        VMV_ERR_ARG = -1,    /* bad argument (null pointer, unknown robot, uncommitted env ...) */
+        VMV_ERR_CUDA = -2,   /* CUDA runtime error, see vmv_last_error() */
+        VMV_ERR_STATE = -3,  /* call not legal in this state (e.g. add after commit) */
+        VMV_ERR_LIMIT = -4   /* environment too large for the shared-memory staging area */
+    };
+
+    /* robots: src/impl/vamp/robots/{panda,ur5,fetch,baxter}.hh */
+    enum
+    {
+        VMV_PANDA = 0,
+        VMV_UR5 = 1,
+        VMV_FETCH = 2,
+        VMV_BAXTER = 3,
+        VMV_N_ROBOTS = 4
+    };
+
+    const char *vmv_last_error(void);
+    const char *vmv_version(void);
+
+    /* number of usable CUDA devices (0 => every compute call fails) and device selection */
+    int vmv_device_count(void);
+    int vmv_set_device(int device);
+
+    /* --- robot constants: Robot::dimension / n_spheres / resolution / s_a / s_m
+     *     (robots/panda.hh:14-18,50-66) ------------------------------------------------------- */
+    int vmv_robot_id(const char *name); /* "panda" -> VMV_PANDA, unknown -> VMV_ERR_ARG */
+    const char *vmv_robot_name(int robot);
+    int vmv_robot_dof(int robot);
+    int vmv_robot_n_spheres(int robot);
+    int vmv_robot_resolution(int robot);
+    int vmv_robot_bounds(int robot, float *lower, float *range); /* dof floats each */
+
+    /* --- environment: vamp.Environment and its adders (bindings/environment.cc:111-181) ---------
+     * Shapes are passed with exactly the fields the reference stores (collision/shapes.hh):
+     *   sphere  (4):  x y z r                                              shapes.hh:229-232
+     *   cuboid  (15): x y z | axis_1 xyz | axis_2 xyz | axis_3 xyz | half extents 1 2 3   :34-50
+     *   capsule (8):  x1 y1 z1 | xv yv zv | r | rdv = 1/|v|^2                            :135-148
+     * min_distance, the z-aligned classification (cuboid: axis_3_z == 1; capsule: xv == 0 &&
+     * yv == 0) and the ascending-min_distance sort happen inside (shapes.hh:52-67,165-189,238;
+     * environment.cc:120-147; environment.hh:46-72). */
+    typedef struct vmv_env vmv_env;
+    vmv_env *vmv_env_create(void);
+    void vmv_env_destroy(vmv_env *env);
+    int vmv_env_add_spheres(vmv_env *env, const float *xyzr, size_t n);
+    int vmv_env_add_cuboids(vmv_env *env, const float *f15, size_t n);
+    int vmv_env_add_capsules(vmv_env *env, const float *f8, size_t n);
+    /* HeightField(x,y,z, xs,ys,zs, xd,yd, data): shapes.hh:262-283; f6 = x y z xs ys zs where
+     * xs,ys,zs are the INVERSE scales as stored (factory.hh:365-386) */
+    int vmv_env_add_heightfield(vmv_env *env, const float *f6, size_t xd, size_t yd, const float *data);
+    /* CAPT(points, r_min, r_max, r_point): capt.hh:299-369 (add_capt_pointcloud, environment.cc:150-160) */
+    int vmv_env_add_capt(vmv_env *env, const float *points_xyz, size_t n, float r_min, float r_max, float r_point);
+    /* Attachment(tf) + add_spheres (attachments.hh:12-56, environment.cc:177-181).  tf12 =
+     * translation(3) followed by the 3x3 rotation in column-major order (vector/math.hh:39-51). */
+    int vmv_env_attach(vmv_env *env, const float *tf12, const float *spheres_xyzr, size_t n);
+    int vmv_env_detach(vmv_env *env);
+    /* sort + classify + pack + upload.  Adders may be called again afterwards; the next commit
+     * re-packs.  Compute calls require a committed environment. */
+    int vmv_env_commit(vmv_env *env);
+    /* introspection used by the tests: kind 0 spheres, 1 capsules, 2 z-capsules, 3 cuboids,
+     * 4 z-cuboids; writes the stored fields followed by min_distance, in sorted order; returns count */
+    long vmv_env_dump(const vmv_env *env, int kind, float *out, size_t cap_floats);
+
+    /* --- batched validation -------------------------------------------------------------------
+     * valid_bits: bit (i & 31) of word (i >> 5) is 1 iff unit i is valid; ceil(n/32) words.
+     *
+     * vmv_validate_configs*: unit i = vamp.<robot>.validate(q_i, env)
+     *   = validate_motion<Robot,8,1>(q_i, q_i, env)   (bindings/robot_helper.hh:255-267,
+     *   planning/validate.hh:70-77) = Robot::fkcc / fkcc_attach on the state (robots/panda.hh:5227).
+     * vmv_validate_edges*: unit i = validate_motion<Robot,8,resolution>(a_i, b_i, env)
+     *   (planning/validate.hh:24-77); resolution <= 0 selects Robot::resolution.
+     * q, a, b: row-major [n][dof] float32.
+     *
+     * *_dev: all pointers are device pointers on the current device; asynchronous on `stream`
+     * (a cudaStream_t, may be NULL).  The plain versions take host pointers and include the
+     * host<->device copies and a synchronisation. */
+    int vmv_validate_configs_dev(int robot, const vmv_env *env, const float *d_q, size_t n, uint32_t *d_valid_bits, void *stream);
+    int vmv_validate_edges_dev(int robot, const vmv_env *env, const float *d_a, const float *d_b, size_t n, int resolution, uint32_t *d_valid_bits, void *stream);
+    int vmv_validate_configs(int robot, const vmv_env *env, const float *q, size_t n, uint32_t *valid_bits);
+    int vmv_validate_edges(int robot, const vmv_env *env, const float *a, const float *b, size_t n, int resolution, uint32_t *valid_bits);
+
+    /* PRM-style edge sets (prm.hh:136-146): edge i joins vertices pairs[2i], pairs[2i+1] of a
+     * vertex table [n_vertices][dof]; 8 bytes per edge instead of 8*dof. */
+    int vmv_validate_edges_indexed_dev(int robot, const vmv_env *env, const float *d_vertices, size_t n_vertices, const uint32_t *d_pairs, size_t n_edges, int resolution, uint32_t *d_valid_bits, void *stream);
+
+    /* Robot::sphere_fk (robots/panda.hh:117-462; vamp.<robot>.fk, robot_helper.hh:234-247):
+     * out[i][s] = (x, y, z, r) of fine sphere s for configuration i. */
+    int vmv_sphere_fk_dev(int robot, const float *d_q, size_t n, float *d_xyzr, void *stream);
+    int vmv_sphere_fk(int robot, const float *q, size_t n, float *xyzr);
+
+    /* Robot::fkcc_debug (robots/panda.hh:468-5224; vamp.<robot>.debug): for ONE configuration,
+     * env_hits receives (fine sphere, object id) pairs -- object ids count the shapes in the
+     * order they were added -- and self_hits (sphere, sphere) pairs.  Counts are returned through
+     * n_env / n_self even when they exceed the capacities. */
+    int vmv_debug(int robot, const vmv_env *env, const float *q, int32_t *env_hits, size_t cap_env, size_t *n_env, int32_t *self_hits, size_t cap_self, size_t *n_self);
+
+    /* --- device buffers for callers that do not bring their own allocator ---------------------- */
+    void *vmv_dev_alloc(size_t bytes);
+    void vmv_dev_free(void *p);
+    void *vmv_host_alloc_pinned(size_t bytes);
+    void vmv_host_free_pinned(void *p);
+    int vmv_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+    int vmv_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+    int vmv_stream_sync(void *stream);
+
+    /* --- measurement helpers -------------------------------------------------------------------
+     * number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+    uint64_t vmv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAMP_B200_H */

@@ -459,18 +459,25 @@ class Tracer:
 
 
 def axis_rotation(tr, axis, s, c):
-    """Rodrigues rotation about a constant unit axis with symbolic sin/cos."""
+    """Rotation about a constant unit axis with symbolic sin/cos: R = c I + s [a]x + (1-c) a a^T.
+    Axis-aligned axes (every joint of the four shipped robots) get the exact sparse form."""
     ax = np.array(axis, float)
     ax = ax / np.linalg.norm(ax)
     K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
-    KK = K @ K
-    one_minus_c = tr.sub(tr.const(1.0), c)
+    aligned = np.sum(np.abs(ax) > 1e-12) == 1
+    one_minus_c = None if aligned else tr.sub(tr.const(1.0), c)
     R = [[None] * 3 for _ in range(3)]
     for i in range(3):
         for j in range(3):
-            e = tr.const(1.0 if i == j else 0.0)
-            e = tr.add(e, tr.mul(tr.const(K[i, j]), s))
-            e = tr.add(e, tr.mul(tr.const(KK[i, j]), one_minus_c))
+            if aligned:
+                if i == j:
+                    e = tr.const(1.0) if abs(ax[i]) > 0.5 else c
+                else:
+                    e = tr.mul(tr.const(K[i, j]), s)
+            else:
+                e = tr.mul(tr.const(1.0 if i == j else 0.0), c)
+                e = tr.add(e, tr.mul(tr.const(K[i, j]), s))
+                e = tr.add(e, tr.mul(tr.const(ax[i] * ax[j]), one_minus_c))
             R[i][j] = e
     return R
 
@@ -632,25 +639,75 @@ def emit_cuda(model, tr, frames):
 
 
 def emit_tables(model):
-    """Constant tables shared by every kernel of this robot (C++ header, host+device)."""
+    """Constant tables for the kernels (device) and the host side of the C ABI.
+
+    Environment tasks are listed in the order the reference sweeps links (distal link first, e.g.
+    robots/panda.hh:5629-6010): one bounding-sphere task per collision link followed by that link's
+    fine-sphere tasks.  `skip` of a bounding task is the index of the next link's bounding task
+    (taken when the bounding sphere is clear); a fine task has skip = -1."""
     name = model["name"]
-    N = name.upper()
     L = model["links"]
+
+    def f(v):
+        x = repr(float(np.float32(v)))
+        if "e" not in x and "." not in x and "inf" not in x and "nan" not in x:
+            x += ".0"
+        return x + "f"
+
+    tasks = []  # (cx, cy, cz, r, body, skip, link, sphere)
+    for li in range(len(L) - 1, -1, -1):
+        l = L[li]
+        skip = len(tasks) + 1 + len(l["spheres"])
+        tasks.append((*l["bound"], l["body"], skip, li, -1))
+        for k, sp in enumerate(l["spheres"]):
+            tasks.append((*sp, l["body"], -1, li, l["first_sphere"] + k))
+
     out = []
     out.append(f"// GENERATED by tools/robot_compiler.py from the {name} robot description -- do not edit.")
     out.append("#pragma once")
+    out.append('#include "../robot_tables.h"')
     out.append("")
     out.append("namespace vmv { namespace gen {")
     out.append("")
     out.append(f"struct {name}_model")
     out.append("{")
+    out.append(f'    static constexpr const char *kName = "{name}";')
     out.append(f"    static constexpr int kDof = {model['dof']};")
-    out.append(f"    static constexpr int kBodies = {len(model['bodies'])};")
+    out.append(f"    static constexpr int kBodies = {len(model['bodies'])};  // body 0 is world-fixed")
     out.append(f"    static constexpr int kLinks = {len(L)};")
     out.append(f"    static constexpr int kSpheres = {model['n_spheres']};")
     out.append(f"    static constexpr int kPairs = {len(model['self_pairs'])};")
+    out.append(f"    static constexpr int kTasks = {len(tasks)};")
     out.append(f"    static constexpr int kResolution = {model['resolution']};")
+    out.append(f"    static constexpr int kAttachLinks = {len(model['attach_links'])};")
+    out.append(f"    static constexpr int kEeBody = {model['end_effector']['body']};")
     out.append("};")
+    out.append("")
+    out.append(f"static const float {name}_lower[{model['dof']}] = {{" + ", ".join(f(v) for v in model["lower"]) + "};")
+    out.append(f"static const float {name}_range[{model['dof']}] = {{" + ", ".join(f(v) for v in model["range"]) + "};")
+    out.append("")
+    out.append(f"static const vmv::SphereTask {name}_tasks_host[{len(tasks)}] = {{")
+    for t in tasks:
+        out.append(f"    {{{f(t[0])}, {f(t[1])}, {f(t[2])}, {f(t[3])}, {t[4]}, {t[5]}, {t[6]}, {t[7]}}},")
+    out.append("};")
+    out.append("")
+    out.append("// collision link -> {first fine sphere, count, body, index of its bounding task}")
+    out.append(f"static const vmv::LinkInfo {name}_links_host[{len(L)}] = {{")
+    btask = {t[6]: i for i, t in enumerate(tasks) if t[7] < 0}
+    for li, l in enumerate(L):
+        out.append(f"    {{{l['first_sphere']}, {len(l['spheres'])}, {l['body']}, {btask[li]}}},  // {l['name']}")
+    out.append("};")
+    out.append("")
+    out.append(f"static const vmv::LinkPair {name}_pairs_host[{max(1, len(model['self_pairs']))}] = {{")
+    for a, b in model["self_pairs"]:
+        out.append(f"    {{{a}, {b}}},")
+    if not model["self_pairs"]:
+        out.append("    {0, 0},")
+    out.append("};")
+    out.append("")
+    out.append(f"static const int {name}_attach_links_host[{max(1, len(model['attach_links']))}] = {{" + ", ".join(str(a) for a in (model["attach_links"] or [0])) + "};")
+    ee = np.array(model["end_effector"]["T"]).reshape(-1)
+    out.append(f"static const float {name}_ee_tf_host[12] = {{" + ", ".join(f(v) for v in ee) + "};")
     out.append("")
     out.append("}}  // namespace vmv::gen")
     return "\n".join(out) + "\n"
@@ -673,6 +730,7 @@ def main():
         model["fk_ops"] = stats
         (out / "robots" / f"{name}.json").write_text(json.dumps(model, indent=1))
         (out / "csrc" / "gen" / f"{name}_fk.cuh").write_text(code)
+        (out / "csrc" / "gen" / f"{name}_tables.h").write_text(emit_tables(model))
         print(
             f"{name}: dof={model['dof']} bodies={len(model['bodies'])} links={len(model['links'])} "
             f"spheres={model['n_spheres']} pairs={len(model['self_pairs'])} fk_ops={stats}"

@@ -1,0 +1,334 @@
+// Device-side building blocks of the validation engine (sm_100a).
+//
+//  * sincos_f32         -- trigonometry with the reference's numerics (its cephes variant has up to
+//                          4e-6 absolute error, which defines the reference's FK; we reproduce the
+//                          same range reduction and polynomials so FK centres agree to ~5e-7 m)
+//  * PackedEnv          -- layout of the environment blob staged into shared memory by one TMA bulk copy
+//  * sphere_hits_env    -- one robot sphere against every container, sorted early-out
+//                          (reference collision/validity.hh:46-158)
+//  * capt_collides      -- CAPT descent + affordance scan (reference collision/capt.hh:428-512)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "robot_tables.h"
+
+namespace vmv
+{
+    // ------------------------------------------------------------------------------------------
+    // packed environment (all offsets in 4-byte words from the start of the blob; every record
+    // array is 16-byte aligned so records are read with 128-bit shared-memory loads)
+    // ------------------------------------------------------------------------------------------
+    struct EnvHeader
+    {
+        uint32_t n_spheres, n_capsules, n_zcapsules, n_cuboids;
+        uint32_t n_zcuboids, n_heightfields, n_capts, n_attach;
+        uint32_t off_spheres, off_capsules, off_zcapsules, off_cuboids;
+        uint32_t off_zcuboids, off_heightfields, off_capts, off_attach;
+    };
+
+    static constexpr int kSphereRec = 8;     // {x y z r}{min_d 0 0 0}
+    static constexpr int kCapsuleRec = 12;   // {x1 y1 z1 r}{xv yv zv rdv}{min_d 0 0 0}
+    static constexpr int kZCapsuleRec = 8;   // {x1 y1 z1 r}{zv rdv min_d 0}
+    static constexpr int kCuboidRec = 16;    // {x y z r1}{a1x a1y a1z r2}{a2x a2y a2z r3}{a3x a3y a3z min_d}
+    static constexpr int kZCuboidRec = 12;   // {x y z min_d}{a1x a1y a2x a2y}{r1 r2 r3 0}
+    static constexpr int kHeightRec = 12;    // {x y z xs}{ys zs xd yd}{xd2 yd2 ptr_lo ptr_hi}
+    static constexpr int kCaptRec = 20;      // see CaptRec
+    static constexpr int kAttachHdr = 4;     // {n 0 0 0} then n x {x y z r} (attachment-local)
+
+    struct CaptRec
+    {
+        float r_point;
+        uint32_t nlog2, n_tests, pad0;
+        float lo[3];
+        float pad1;
+        float hi[3];
+        float pad2;
+        const float *tests;       // Eytzinger split values, 2^nlog2 - 1
+        const float4 *aabbs;      // per leaf: {lo.x lo.y lo.z hi.x}{hi.y hi.z start end}  (2 float4 per leaf)
+        const float4 *points;     // affordance points {x y z 0}, padded per leaf to a multiple of 4 with +inf
+        const void *pad3;
+    };
+    static_assert(sizeof(CaptRec) == kCaptRec * 4, "CaptRec layout");
+
+    __device__ __forceinline__ bool sign_set(float v)
+    {
+        return __float_as_int(v) < 0;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // trigonometry (reference vector/avx.hh:454-548 and vector/interface.hh:451-458)
+    // ------------------------------------------------------------------------------------------
+    __device__ __forceinline__ float ref_sin(float x)
+    {
+        const uint32_t sign_in = __float_as_uint(x) & 0x80000000u;
+        x = fabsf(x);
+        // j = (rint(x * 4/pi) + 1) & ~1   (the reference rounds -- cvtps -- where cephes truncates)
+        int j = __float2int_rn(x * 1.27323954473516f);
+        j = (j + 1) & ~1;
+        const float y = __int2float_rn(j);
+        const uint32_t sign = sign_in ^ (static_cast<uint32_t>(j & 4) << 29);
+        x = fmaf(y, -0.78515625f, x);
+        x = fmaf(y, -2.4187564849853515625e-4f, x);
+        x = fmaf(y, -3.77489497744594108e-8f, x);
+        const float z = x * x;
+        const bool use_sin = (j & 2) == 0;
+        // both polynomials share the Horner shape ((k0 z + k1) z + k2) z
+        const float k0 = use_sin ? -1.9515295891E-4f : 2.443315711809948E-005f;
+        const float k1 = use_sin ? 8.3321608736E-3f : -1.388731625493765E-003f;
+        const float k2 = use_sin ? -1.6666654611E-1f : 4.166664568298827E-002f;
+        float p = fmaf(k0, z, k1);
+        p = fmaf(p, z, k2);
+        p = p * z;
+        // sin: p*x + x ; cos: p*z - z/2 + 1
+        const float a = use_sin ? x : z;
+        const float b = use_sin ? x : fmaf(z, -0.5f, 1.0f);
+        const float r = fmaf(p, a, b);
+        return __uint_as_float(__float_as_uint(r) ^ sign);
+    }
+
+    __device__ __forceinline__ void sincos_f32(float x, float &s, float &c)
+    {
+        s = ref_sin(x);
+        // cos(x) = sin(x + pi/2), wrapped by 2 pi when the sum reaches pi (interface.hh:451-458)
+        float v = x + 1.57079637050628662109375f;
+        v = (v >= 3.1415927410125732421875f) ? v - 6.283185482025146484375f : v;
+        c = ref_sin(v);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // CAPT query for one sphere (reference collision/capt.hh:428-512, one lane)
+    // ------------------------------------------------------------------------------------------
+    __device__ __forceinline__ bool capt_collides(const CaptRec &t, float x, float y, float z, float r)
+    {
+        // top-level AABB reject uses r, not r + r_point (capt.hh:431-438)
+        if (!((x + r >= t.lo[0]) & (x - r <= t.hi[0]) & (y + r >= t.lo[1]) & (y - r <= t.hi[1]) & (z + r >= t.lo[2]) &
+              (z - r <= t.hi[2])))
+        {
+            return false;
+        }
+
+        const float c[3] = {x, y, z};
+        uint32_t idx = 0;
+        int k = 0;
+        for (uint32_t i = 0; i < t.nlog2; ++i)
+        {
+            const float split = __ldg(t.tests + idx);
+            const float v = (k == 0) ? c[0] : ((k == 1) ? c[1] : c[2]);
+            idx = 2 * idx + 1 + (v >= split ? 1u : 0u);
+            k = (k == 2) ? 0 : k + 1;
+        }
+
+        const uint32_t leaf = idx - t.n_tests;
+        const float rr = r + t.r_point;
+        const float rc_sq = rr * rr;
+        const float4 b0 = __ldg(t.aabbs + 2 * leaf);
+        const float4 b1 = __ldg(t.aabbs + 2 * leaf + 1);
+        const float d0 = x - fminf(fmaxf(x, b0.x), b0.w);
+        const float d1 = y - fminf(fmaxf(y, b0.y), b1.x);
+        const float d2 = z - fminf(fmaxf(z, b0.z), b1.y);
+        if (!(d0 * d0 + d1 * d1 + d2 * d2 <= rc_sq))
+        {
+            return false;
+        }
+
+        const uint32_t start = __float_as_uint(b1.z), end = __float_as_uint(b1.w);
+        for (uint32_t i = start; i < end; ++i)
+        {
+            const float4 p = __ldg(t.points + i);
+            const float ex = p.x - x, ey = p.y - y, ez = p.z - z;
+            if (ex * ex + ey * ey + ez * ez <= rc_sq)
+            {
+                return true;
+            }
+        }
+        return false;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // one robot sphere against the whole environment
+    // ------------------------------------------------------------------------------------------
+    // E points at the blob in shared memory.  Containers are swept in the reference's order; inside
+    // a container objects are sorted by min_distance (distance of the object's nearest point from
+    // the world origin) and the sweep stops at the first object that cannot be reached:
+    // min_distance >= |p| + r.  The reference evaluates |p| with a 12-bit rsqrt and so sometimes
+    // stops one object early or late; we use a (slightly inflated) accurate bound, so the set of
+    // objects we test is a superset of every object that can actually touch the sphere.
+    __device__ __forceinline__ bool sphere_hits_env(const float *__restrict__ E, float x, float y, float z, float r)
+    {
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
+        const float ext = fmaf(__fsqrt_rn(fmaf(x, x, fmaf(y, y, z * z))), 1.0000002f, r);
+
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_spheres);
+            for (uint32_t i = 0; i < H.n_spheres; ++i)
+            {
+                const float4 a = p[2 * i];
+                const float min_d = E[H.off_spheres + kSphereRec * i + 4];
+                if (!(min_d < ext))
+                {
+                    break;
+                }
+                const float dx = a.x - x, dy = a.y - y, dz = a.z - z;
+                const float rs = a.w + r;
+                if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                {
+                    return true;
+                }
+            }
+        }
+
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_capsules);
+            for (uint32_t i = 0; i < H.n_capsules; ++i)
+            {
+                const float min_d = E[H.off_capsules + kCapsuleRec * i + 8];
+                if (!(min_d < ext))
+                {
+                    break;
+                }
+                const float4 a = p[3 * i], v = p[3 * i + 1];
+                const float dot = (x - a.x) * v.x + (y - a.y) * v.y + (z - a.z) * v.z;
+                const float cdf = fminf(fmaxf(dot * v.w, 0.F), 1.F);
+                const float dx = x - (a.x + v.x * cdf), dy = y - (a.y + v.y * cdf), dz = z - (a.z + v.z * cdf);
+                const float rs = r + a.w;
+                if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                {
+                    return true;
+                }
+            }
+        }
+
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_zcapsules);
+            for (uint32_t i = 0; i < H.n_zcapsules; ++i)
+            {
+                const float4 a = p[2 * i], v = p[2 * i + 1];
+                if (!(v.z < ext))
+                {
+                    break;
+                }
+                const float dot = (z - a.z) * v.x;
+                const float cdf = fminf(fmaxf(dot * v.y, 0.F), 1.F);
+                const float dx = x - a.x, dy = y - a.y, dz = z - (a.z + v.x * cdf);
+                const float rs = r + a.w;
+                if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                {
+                    return true;
+                }
+            }
+        }
+
+        const float rsq = r * r;
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_cuboids);
+            for (uint32_t i = 0; i < H.n_cuboids; ++i)
+            {
+                const float4 a3 = p[4 * i + 3];
+                if (!(a3.w < ext))
+                {
+                    break;
+                }
+                const float4 c = p[4 * i], a1 = p[4 * i + 1], a2 = p[4 * i + 2];
+                const float xs = x - c.x, ys = y - c.y, zs = z - c.z;
+                const float e1 = fmaxf(fabsf(a1.x * xs + a1.y * ys + a1.z * zs) - c.w, 0.F);
+                const float e2 = fmaxf(fabsf(a2.x * xs + a2.y * ys + a2.z * zs) - a1.w, 0.F);
+                const float e3 = fmaxf(fabsf(a3.x * xs + a3.y * ys + a3.z * zs) - a2.w, 0.F);
+                if (sign_set((e1 * e1 + e2 * e2 + e3 * e3) - rsq))
+                {
+                    return true;
+                }
+            }
+        }
+
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_zcuboids);
+            for (uint32_t i = 0; i < H.n_zcuboids; ++i)
+            {
+                const float4 c = p[3 * i];
+                if (!(c.w < ext))
+                {
+                    break;
+                }
+                const float4 ax = p[3 * i + 1], h = p[3 * i + 2];
+                const float xs = x - c.x, ys = y - c.y, zs = z - c.z;
+                const float e1 = fmaxf(fabsf(ax.x * xs + ax.y * ys) - h.x, 0.F);
+                const float e2 = fmaxf(fabsf(ax.z * xs + ax.w * ys) - h.y, 0.F);
+                const float e3 = fmaxf(fabsf(zs) - h.z, 0.F);
+                if (sign_set((e1 * e1 + e2 * e2 + e3 * e3) - rsq))
+                {
+                    return true;
+                }
+            }
+        }
+
+        for (uint32_t i = 0; i < H.n_heightfields; ++i)
+        {
+            // reference collision/sphere_heightfield.hh:9-30
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_heightfields + kHeightRec * i);
+            const float4 a = p[0], b = p[1], c = p[2];
+            const float xo = a.x - x, yo = a.y - y;
+            const float xi = floorf(fminf(fmaxf(fmaf(a.w, xo, c.x), 0.F), b.z));
+            const float yi = floorf(fminf(fmaxf(fmaf(b.x, yo, c.y), 0.F), b.w));
+            const int index = __float2int_rn(fmaf(yi, b.z, xi));
+            const float *data = reinterpret_cast<const float *>(
+                (static_cast<unsigned long long>(__float_as_uint(c.w)) << 32) | __float_as_uint(c.z));
+            const float zh = __ldg(data + index);
+            if (sign_set(z - r - fmaf(b.y, zh, a.z)))
+            {
+                return true;
+            }
+        }
+
+        for (uint32_t i = 0; i < H.n_capts; ++i)
+        {
+            const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * i);
+            if (capt_collides(t, x, y, z, r))
+            {
+                return true;
+            }
+        }
+
+        return false;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+    // ------------------------------------------------------------------------------------------
+    __device__ __forceinline__ uint32_t smem_u32(const void *p)
+    {
+        return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    }
+
+    __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+            "l"(src_gmem),
+            "r"(bytes),
+            "r"(smem_u32(bar))
+            : "memory");
+    }
+
+    __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "DONE:\n"
+            "}\n" ::"r"(smem_u32(bar)),
+            "r"(phase)
+            : "memory");
+    }
+}  // namespace vmv

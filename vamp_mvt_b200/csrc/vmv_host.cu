@@ -1,0 +1,1309 @@
+// Host side of the C ABI (include/vamp_b200.h): environment construction, packing and upload,
+// robot registry, kernel launches.  No torch, no CPU fallback: every compute entry point needs a
+// CUDA device.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/vamp_b200.h"
+#include "vmv_kernels.cuh"
+
+#include "gen/panda_fk.cuh"
+#include "gen/ur5_fk.cuh"
+#include "gen/fetch_fk.cuh"
+#include "gen/baxter_fk.cuh"
+#include "gen/panda_tables.h"
+#include "gen/ur5_tables.h"
+#include "gen/fetch_tables.h"
+#include "gen/baxter_tables.h"
+
+namespace
+{
+    thread_local std::string g_error;
+    std::atomic<uint64_t> g_launches{0};
+
+    int fail(int code, const std::string &msg)
+    {
+        g_error = msg;
+        return code;
+    }
+
+    int cuda_fail(cudaError_t e, const char *what)
+    {
+        return fail(VMV_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    }
+
+#define VMV_CUDA(call)                        \
+    do                                        \
+    {                                         \
+        cudaError_t e_ = (call);              \
+        if (e_ != cudaSuccess)                \
+        {                                     \
+            return cuda_fail(e_, #call);      \
+        }                                     \
+    } while (0)
+
+    // ---------------------------------------------------------------------------------------
+    // robots
+    // ---------------------------------------------------------------------------------------
+#define VMV_ROBOT(NAME)                                                               \
+    struct NAME##_robot                                                               \
+    {                                                                                 \
+        using Model = vmv::gen::NAME##_model;                                         \
+        template <typename Sink>                                                      \
+        static __device__ __forceinline__ void frames(const float (&q)[Model::kDof], Sink &s) \
+        {                                                                             \
+            vmv::gen::NAME##_frames(q, s);                                            \
+        }                                                                             \
+    };
+    VMV_ROBOT(panda)
+    VMV_ROBOT(ur5)
+    VMV_ROBOT(fetch)
+    VMV_ROBOT(baxter)
+#undef VMV_ROBOT
+
+    struct RobotHost
+    {
+        const char *name;
+        int dof, n_spheres, n_links, n_pairs, n_tasks, resolution, n_attach_links, ee_body;
+        const float *lower, *range;
+        const vmv::SphereTask *tasks;
+        const vmv::LinkInfo *links;
+        const vmv::LinkPair *pairs;
+        const int *attach_links;
+        const float *ee_tf;
+    };
+
+#define VMV_ROBOT_HOST(NAME)                                                                                  \
+    {                                                                                                         \
+        vmv::gen::NAME##_model::kName, vmv::gen::NAME##_model::kDof, vmv::gen::NAME##_model::kSpheres,        \
+            vmv::gen::NAME##_model::kLinks, vmv::gen::NAME##_model::kPairs, vmv::gen::NAME##_model::kTasks,   \
+            vmv::gen::NAME##_model::kResolution, vmv::gen::NAME##_model::kAttachLinks,                        \
+            vmv::gen::NAME##_model::kEeBody, vmv::gen::NAME##_lower, vmv::gen::NAME##_range,                  \
+            vmv::gen::NAME##_tasks_host, vmv::gen::NAME##_links_host, vmv::gen::NAME##_pairs_host,            \
+            vmv::gen::NAME##_attach_links_host, vmv::gen::NAME##_ee_tf_host                                   \
+    }
+    const RobotHost g_robots[VMV_N_ROBOTS] = {
+        VMV_ROBOT_HOST(panda), VMV_ROBOT_HOST(ur5), VMV_ROBOT_HOST(fetch), VMV_ROBOT_HOST(baxter)};
+#undef VMV_ROBOT_HOST
+
+    constexpr int kMaxDevices = 16;
+    struct RobotDevTables
+    {
+        bool ready = false;
+        vmv::RobotDev dev{};
+    };
+    RobotDevTables g_dev_tables[kMaxDevices][VMV_N_ROBOTS];
+    std::mutex g_mutex;
+
+    int robot_tables(int robot, vmv::RobotDev &out)
+    {
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        if (device >= kMaxDevices)
+        {
+            return fail(VMV_ERR_ARG, "device index too large");
+        }
+        std::lock_guard<std::mutex> lock(g_mutex);
+        RobotDevTables &t = g_dev_tables[device][robot];
+        if (!t.ready)
+        {
+            const RobotHost &r = g_robots[robot];
+            void *p = nullptr;
+            VMV_CUDA(cudaMalloc(&p, r.n_tasks * sizeof(vmv::SphereTask)));
+            VMV_CUDA(cudaMemcpy(p, r.tasks, r.n_tasks * sizeof(vmv::SphereTask), cudaMemcpyHostToDevice));
+            t.dev.tasks = static_cast<const vmv::SphereTask *>(p);
+            VMV_CUDA(cudaMalloc(&p, r.n_links * sizeof(vmv::LinkInfo)));
+            VMV_CUDA(cudaMemcpy(p, r.links, r.n_links * sizeof(vmv::LinkInfo), cudaMemcpyHostToDevice));
+            t.dev.links = static_cast<const vmv::LinkInfo *>(p);
+            const int np = std::max(1, r.n_pairs);
+            VMV_CUDA(cudaMalloc(&p, np * sizeof(vmv::LinkPair)));
+            VMV_CUDA(cudaMemcpy(p, r.pairs, np * sizeof(vmv::LinkPair), cudaMemcpyHostToDevice));
+            t.dev.pairs = static_cast<const vmv::LinkPair *>(p);
+            const int na = std::max(1, r.n_attach_links);
+            VMV_CUDA(cudaMalloc(&p, na * sizeof(int)));
+            VMV_CUDA(cudaMemcpy(p, r.attach_links, na * sizeof(int), cudaMemcpyHostToDevice));
+            t.dev.attach_links = static_cast<const int *>(p);
+            t.ready = true;
+        }
+        out = t.dev;
+        return VMV_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // environment (host restatement of collision/shapes.hh min_distance, environment.cc
+    // classification, environment.hh sort; CAPT build per collision/capt.hh:106-369)
+    // ---------------------------------------------------------------------------------------
+    inline float dot3(float ax, float ay, float az, float bx, float by, float bz)
+    {
+        return (ax * bx) + (ay * by) + (az * bz);
+    }
+
+    inline float clamp_ref(float v, float lo, float hi)
+    {
+        // collision::clamp<float>, math.hh:52-55
+        return std::max(std::min(v, hi), lo);
+    }
+
+    struct HSphere
+    {
+        float x, y, z, r, min_d;
+        int id;
+    };
+    struct HCapsule
+    {
+        float x1, y1, z1, xv, yv, zv, r, rdv, min_d;
+        int id;
+    };
+    struct HCuboid
+    {
+        float f[15];
+        float min_d;
+        int id;
+    };
+    struct HHeight
+    {
+        float f[6];
+        size_t xd, yd;
+        std::vector<float> data;
+        int id;
+        float *d_data = nullptr;
+    };
+
+    struct HCapt
+    {
+        float r_min, r_max, r_point;
+        int nlog2 = 0;
+        std::vector<float> tests;
+        std::vector<float> leaf_lo, leaf_hi;  // 3 floats per leaf
+        std::vector<uint32_t> leaf_start;     // per leaf + 1, in points
+        std::vector<float> points;            // xyz0 per afforded point (representative first)
+        float top_lo[3], top_hi[3];
+        int id;
+        float *d_tests = nullptr;
+        float4 *d_aabbs = nullptr;
+        float4 *d_points = nullptr;
+    };
+
+    float finite_or_neg_inf(float v)
+    {
+        // a degenerate capsule gives NaN; the reference then never breaks out of the sweep at it
+        return std::isnan(v) ? -std::numeric_limits<float>::infinity() : v;
+    }
+
+    // -- CAPT build -------------------------------------------------------------------------
+    struct Vol
+    {
+        float lo[3], hi[3];
+        float distsq(const float *p) const
+        {
+            float s = 0.F;
+            for (int k = 0; k < 3; ++k)
+            {
+                const float d = p[k] - std::min(std::max(p[k], lo[k]), hi[k]);
+                s += d * d;
+            }
+            return s;
+        }
+        void extend(const float *p)
+        {
+            for (int k = 0; k < 3; ++k)
+            {
+                lo[k] = std::min(lo[k], p[k]);
+                hi[k] = std::max(hi[k], p[k]);
+            }
+        }
+    };
+
+    struct CaptBuilder
+    {
+        HCapt &t;
+        const std::vector<float> &pts;  // padded to 2^nlog2 points with +inf
+        std::vector<uint32_t> argsort;
+        float max_l2, min_l2;
+
+        void subdivide(uint32_t begin, uint32_t count, uint32_t i, std::vector<uint32_t> afford, Vol vol, int d)
+        {
+            if (count == 1)
+            {
+                const float *rep = &pts[3 * argsort[begin]];
+                Vol aabb{{rep[0], rep[1], rep[2]}, {rep[0], rep[1], rep[2]}};
+                if (std::isfinite(rep[0]))
+                {
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        t.top_lo[k] = std::min(t.top_lo[k], rep[k]);
+                        t.top_hi[k] = std::max(t.top_hi[k], rep[k]);
+                    }
+                    t.points.insert(t.points.end(), {rep[0], rep[1], rep[2], 0.F});
+                    // cell entirely inside the smallest query ball around its representative:
+                    // the representative alone decides (capt.hh:39-46,150)
+                    const float d0 = std::max(rep[0] - vol.lo[0], vol.hi[0] - rep[0]);
+                    const float d1 = std::max(rep[1] - vol.lo[1], vol.hi[1] - rep[1]);
+                    const float d2 = std::max(rep[2] - vol.lo[2], vol.hi[2] - rep[2]);
+                    if (!((d0 * d0 + d1 * d1 + d2 * d2) <= min_l2))
+                    {
+                        for (const uint32_t id : afford)
+                        {
+                            const float *p = &pts[3 * id];
+                            if (vol.distsq(p) <= max_l2)
+                            {
+                                aabb.extend(p);
+                                t.points.insert(t.points.end(), {p[0], p[1], p[2], 0.F});
+                            }
+                        }
+                    }
+                }
+                t.leaf_lo.insert(t.leaf_lo.end(), aabb.lo, aabb.lo + 3);
+                t.leaf_hi.insert(t.leaf_hi.end(), aabb.hi, aabb.hi + 3);
+                t.leaf_start.push_back(static_cast<uint32_t>(t.points.size() / 4));
+                return;
+            }
+
+            // median split on axis d (capt.hh:106-119)
+            std::sort(
+                argsort.begin() + begin,
+                argsort.begin() + begin + count,
+                [&](uint32_t a, uint32_t b) { return pts[3 * a + d] < pts[3 * b + d]; });
+            const uint32_t middle = begin + count / 2;
+            const float test = static_cast<float>((pts[3 * argsort[middle - 1] + d] + pts[3 * argsort[middle] + d]) / 2.0);
+            t.tests[i] = test;
+
+            const uint32_t half = count / 2;
+            Vol lo_vol = vol, hi_vol = vol;
+            lo_vol.hi[d] = test;
+            hi_vol.lo[d] = test;
+
+            std::vector<uint32_t> lo_afford, hi_afford;
+            lo_afford.reserve(afford.size() + half);
+            hi_afford.reserve(afford.size() + half);
+            for (const uint32_t idx : afford)
+            {
+                if (pts[3 * idx + d] <= test + t.r_max)
+                {
+                    lo_afford.push_back(idx);
+                }
+                if (pts[3 * idx + d] >= test - t.r_max)
+                {
+                    hi_afford.push_back(idx);
+                }
+            }
+            // points of the sibling half that may reach into this half: the reference scans each
+            // half from its FIRST (smallest) element while the predicate holds (capt.hh:232-246)
+            uint32_t new_hi = begin, new_lo = begin + half;
+            while (new_hi < begin + half && pts[3 * argsort[new_hi] + d] >= test - t.r_max &&
+                   std::isfinite(pts[3 * argsort[new_hi] + d]))
+            {
+                ++new_hi;
+            }
+            while (new_lo < begin + count && pts[3 * argsort[new_lo] + d] <= test + t.r_max &&
+                   std::isfinite(pts[3 * argsort[new_lo] + d]))
+            {
+                ++new_lo;
+            }
+            hi_afford.insert(hi_afford.end(), argsort.begin() + begin, argsort.begin() + new_hi);
+            lo_afford.insert(lo_afford.end(), argsort.begin() + begin + half, argsort.begin() + new_lo);
+            afford.clear();
+            afford.shrink_to_fit();
+
+            const int nd = (d + 1) % 3;
+            subdivide(begin, half, 2 * i + 1, std::move(lo_afford), lo_vol, nd);
+            subdivide(begin + half, half, 2 * i + 2, std::move(hi_afford), hi_vol, nd);
+        }
+    };
+
+    void capt_build(HCapt &t, const float *points, size_t n, float r_min, float r_max, float r_point)
+    {
+        t.r_min = r_min, t.r_max = r_max, t.r_point = r_point;
+        const float max_l1 = r_max + r_point;
+        t.nlog2 = 0;
+        while ((size_t(1) << t.nlog2) < n)
+        {
+            t.nlog2++;
+        }
+        const size_t pow2 = size_t(1) << t.nlog2;
+        const float inf = std::numeric_limits<float>::infinity();
+        std::vector<float> pts(points, points + 3 * n);
+        pts.resize(3 * pow2, inf);
+        for (int k = 0; k < 3; ++k)
+        {
+            t.top_lo[k] = inf;
+            t.top_hi[k] = -inf;
+        }
+        t.tests.assign(pow2 - 1, std::numeric_limits<float>::quiet_NaN());
+        t.leaf_start.assign(1, 0);
+        CaptBuilder b{t, pts, {}, max_l1 * max_l1, (r_min + r_point) * (r_min + r_point)};
+        b.argsort.resize(pow2);
+        std::iota(b.argsort.begin(), b.argsort.end(), 0u);
+        b.subdivide(0, static_cast<uint32_t>(pow2), 0, {}, Vol{{-inf, -inf, -inf}, {inf, inf, inf}}, 0);
+    }
+}  // namespace
+
+struct vmv_env
+{
+    std::vector<HSphere> spheres;
+    std::vector<HCapsule> capsules, z_capsules;
+    std::vector<HCuboid> cuboids, z_cuboids;
+    std::vector<HHeight> heightfields;
+    std::vector<HCapt> capts;
+    bool has_attachment = false;
+    float attach_tf[12];  // row-major 3x4
+    std::vector<float> attach_spheres;
+    int next_id = 0;
+
+    bool committed = false;
+    int device = -1;
+    std::vector<uint32_t> blob;
+    float *d_blob = nullptr;
+    std::vector<void *> owned;  // device allocations referenced from the blob
+
+    void release_device()
+    {
+        for (void *p : owned)
+        {
+            cudaFree(p);
+        }
+        owned.clear();
+        if (d_blob)
+        {
+            cudaFree(d_blob);
+            d_blob = nullptr;
+        }
+        committed = false;
+    }
+};
+
+namespace
+{
+    template <typename T>
+    void sort_by_min_distance(std::vector<T> &v)
+    {
+        std::stable_sort(v.begin(), v.end(), [](const T &a, const T &b) { return a.min_d < b.min_d; });
+    }
+
+    uint32_t f2u(float f)
+    {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        return u;
+    }
+
+    template <typename T>
+    int upload(vmv_env *env, const std::vector<T> &host, T *&dev)
+    {
+        void *p = nullptr;
+        const size_t bytes = std::max<size_t>(16, host.size() * sizeof(T));
+        VMV_CUDA(cudaMalloc(&p, bytes));
+        env->owned.push_back(p);
+        if (!host.empty())
+        {
+            VMV_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+        }
+        dev = static_cast<T *>(p);
+        return VMV_OK;
+    }
+
+    int pack_and_upload(vmv_env *env)
+    {
+        env->release_device();
+        VMV_CUDA(cudaGetDevice(&env->device));
+
+        // device-side arrays first (their addresses go into the blob)
+        for (auto &h : env->heightfields)
+        {
+            // one padding row + one element: the reference's clamp admits index == xd*yd + xd
+            std::vector<float> padded(h.data);
+            padded.resize(h.xd * (h.yd + 1) + h.xd + 1, 0.F);
+            int rc = upload(env, padded, h.d_data);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
+        for (auto &t : env->capts)
+        {
+            int rc = upload(env, t.tests, t.d_tests);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            const size_t leaves = t.leaf_start.size() - 1;
+            std::vector<float4> aabbs(2 * leaves);
+            for (size_t z = 0; z < leaves; ++z)
+            {
+                float s, e;
+                const uint32_t us = t.leaf_start[z], ue = t.leaf_start[z + 1];
+                std::memcpy(&s, &us, 4);
+                std::memcpy(&e, &ue, 4);
+                aabbs[2 * z] = make_float4(t.leaf_lo[3 * z], t.leaf_lo[3 * z + 1], t.leaf_lo[3 * z + 2], t.leaf_hi[3 * z]);
+                aabbs[2 * z + 1] = make_float4(t.leaf_hi[3 * z + 1], t.leaf_hi[3 * z + 2], s, e);
+            }
+            rc = upload(env, aabbs, t.d_aabbs);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            std::vector<float4> pts(t.points.size() / 4);
+            std::memcpy(pts.data(), t.points.data(), t.points.size() * sizeof(float));
+            rc = upload(env, pts, t.d_points);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
+
+        std::vector<uint32_t> &B = env->blob;
+        B.assign(sizeof(vmv::EnvHeader) / 4, 0u);
+        auto align4 = [&]()
+        {
+            while (B.size() % 4)
+            {
+                B.push_back(0u);
+            }
+        };
+        auto pf = [&](float v) { B.push_back(f2u(v)); };
+        vmv::EnvHeader H{};
+
+        H.n_spheres = static_cast<uint32_t>(env->spheres.size());
+        H.off_spheres = static_cast<uint32_t>(B.size());
+        for (const auto &s : env->spheres)
+        {
+            pf(s.x), pf(s.y), pf(s.z), pf(s.r), pf(s.min_d), pf(0), pf(0), pf(0);
+        }
+        H.n_capsules = static_cast<uint32_t>(env->capsules.size());
+        H.off_capsules = static_cast<uint32_t>(B.size());
+        for (const auto &c : env->capsules)
+        {
+            pf(c.x1), pf(c.y1), pf(c.z1), pf(c.r), pf(c.xv), pf(c.yv), pf(c.zv), pf(c.rdv), pf(c.min_d), pf(0), pf(0), pf(0);
+        }
+        H.n_zcapsules = static_cast<uint32_t>(env->z_capsules.size());
+        H.off_zcapsules = static_cast<uint32_t>(B.size());
+        for (const auto &c : env->z_capsules)
+        {
+            pf(c.x1), pf(c.y1), pf(c.z1), pf(c.r), pf(c.zv), pf(c.rdv), pf(c.min_d), pf(0);
+        }
+        H.n_cuboids = static_cast<uint32_t>(env->cuboids.size());
+        H.off_cuboids = static_cast<uint32_t>(B.size());
+        for (const auto &c : env->cuboids)
+        {
+            const float *f = c.f;
+            pf(f[0]), pf(f[1]), pf(f[2]), pf(f[12]);
+            pf(f[3]), pf(f[4]), pf(f[5]), pf(f[13]);
+            pf(f[6]), pf(f[7]), pf(f[8]), pf(f[14]);
+            pf(f[9]), pf(f[10]), pf(f[11]), pf(c.min_d);
+        }
+        H.n_zcuboids = static_cast<uint32_t>(env->z_cuboids.size());
+        H.off_zcuboids = static_cast<uint32_t>(B.size());
+        for (const auto &c : env->z_cuboids)
+        {
+            const float *f = c.f;
+            pf(f[0]), pf(f[1]), pf(f[2]), pf(c.min_d);
+            pf(f[3]), pf(f[4]), pf(f[6]), pf(f[7]);
+            pf(f[12]), pf(f[13]), pf(f[14]), pf(0);
+        }
+        H.n_heightfields = static_cast<uint32_t>(env->heightfields.size());
+        H.off_heightfields = static_cast<uint32_t>(B.size());
+        for (const auto &h : env->heightfields)
+        {
+            const unsigned long long addr = reinterpret_cast<unsigned long long>(h.d_data);
+            pf(h.f[0]), pf(h.f[1]), pf(h.f[2]), pf(h.f[3]);
+            pf(h.f[4]), pf(h.f[5]), pf(static_cast<float>(h.xd)), pf(static_cast<float>(h.yd));
+            pf(static_cast<float>(h.xd / 2)), pf(static_cast<float>(h.yd / 2));
+            B.push_back(static_cast<uint32_t>(addr & 0xffffffffu));
+            B.push_back(static_cast<uint32_t>(addr >> 32));
+        }
+        H.n_capts = static_cast<uint32_t>(env->capts.size());
+        align4();
+        H.off_capts = static_cast<uint32_t>(B.size());
+        for (const auto &t : env->capts)
+        {
+            vmv::CaptRec r{};
+            r.r_point = t.r_point;
+            r.nlog2 = static_cast<uint32_t>(t.nlog2);
+            r.n_tests = static_cast<uint32_t>(t.tests.size());
+            for (int k = 0; k < 3; ++k)
+            {
+                r.lo[k] = t.top_lo[k];
+                r.hi[k] = t.top_hi[k];
+            }
+            r.tests = t.d_tests;
+            r.aabbs = t.d_aabbs;
+            r.points = t.d_points;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(&r);
+            B.insert(B.end(), w, w + vmv::kCaptRec);
+        }
+        H.n_attach = env->has_attachment ? static_cast<uint32_t>(env->attach_spheres.size() / 4) : 0u;
+        align4();
+        H.off_attach = static_cast<uint32_t>(B.size());
+        B.push_back(H.n_attach), B.push_back(0), B.push_back(0), B.push_back(0);
+        if (env->has_attachment)
+        {
+            for (float v : env->attach_spheres)
+            {
+                pf(v);
+            }
+        }
+        align4();
+        std::memcpy(B.data(), &H, sizeof(H));
+
+        VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&env->d_blob), B.size() * 4));
+        VMV_CUDA(cudaMemcpy(env->d_blob, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+        env->committed = true;
+        return VMV_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // launches
+    // ---------------------------------------------------------------------------------------
+    int sm_count()
+    {
+        static int cached[kMaxDevices] = {0};
+        int device = 0;
+        cudaGetDevice(&device);
+        if (device < kMaxDevices && cached[device] == 0)
+        {
+            cudaDeviceGetAttribute(&cached[device], cudaDevAttrMultiProcessorCount, device);
+        }
+        return device < kMaxDevices ? std::max(1, cached[device]) : 148;
+    }
+
+    int make_launch_env(const RobotHost &r, const vmv_env *env, vmv::LaunchEnv &le)
+    {
+        if (env == nullptr || !env->committed)
+        {
+            return fail(VMV_ERR_STATE, "environment is not committed (call vmv_env_commit)");
+        }
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        if (device != env->device)
+        {
+            return fail(VMV_ERR_STATE, "environment was committed on another device");
+        }
+        le.blob = env->d_blob;
+        le.blob_bytes = static_cast<uint32_t>(env->blob.size() * 4);
+        // attach_tf = ee_tf(robot) * attachment offset
+        const float *E = r.ee_tf;
+        float A[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        if (env->has_attachment)
+        {
+            std::memcpy(A, env->attach_tf, sizeof(A));
+        }
+        for (int i = 0; i < 3; ++i)
+        {
+            for (int j = 0; j < 4; ++j)
+            {
+                float s = E[4 * i] * A[j] + E[4 * i + 1] * A[4 + j] + E[4 * i + 2] * A[8 + j];
+                le.attach_tf[4 * i + j] = (j == 3) ? s + E[4 * i + 3] : s;
+            }
+        }
+        return VMV_OK;
+    }
+
+    constexpr uint32_t kMaxSmem = 227 * 1024;
+
+    template <typename R, int BLOCK>
+    int launch_configs(const vmv::RobotDev &rd, const vmv::LaunchEnv &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
+    {
+        using M = typename R::Model;
+        const vmv::SmemLayout<M, BLOCK> L(le.blob_bytes);
+        if (L.total > kMaxSmem)
+        {
+            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
+        }
+        auto kernel = vmv::k_validate_configs<R, BLOCK>;
+        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
+        const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
+        kernel<<<grid, BLOCK, L.total, s>>>(rd, le, q, n, bits);
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        return VMV_OK;
+    }
+
+    template <typename R, int BLOCK>
+    int launch_edges(
+        const vmv::RobotDev &rd,
+        const vmv::LaunchEnv &le,
+        const float *a,
+        const float *b,
+        const uint32_t *pairs,
+        size_t n,
+        float resolution,
+        uint32_t *bits,
+        cudaStream_t s)
+    {
+        using M = typename R::Model;
+        const vmv::SmemLayout<M, BLOCK> L(le.blob_bytes);
+        if (L.total > kMaxSmem)
+        {
+            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
+        }
+        const size_t rounds = (n + 31) / 32;  // one warp-round per verdict word
+        const size_t blocks_needed = (rounds + BLOCK / 32 - 1) / (BLOCK / 32);
+        const int per_sm = std::max<int>(1, static_cast<int>(kMaxSmem / std::max<uint32_t>(L.total, 1)));
+        const unsigned grid = static_cast<unsigned>(std::min<size_t>(blocks_needed, static_cast<size_t>(sm_count()) * per_sm * 4));
+        if (pairs != nullptr)
+        {
+            auto kernel = vmv::k_validate_edges<R, BLOCK, true>;
+            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
+            kernel<<<grid, BLOCK, L.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+        }
+        else
+        {
+            auto kernel = vmv::k_validate_edges<R, BLOCK, false>;
+            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
+            kernel<<<grid, BLOCK, L.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+        }
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        return VMV_OK;
+    }
+
+    template <typename R>
+    int launch_fk(const vmv::RobotDev &rd, const float *q, size_t n, float *out, cudaStream_t s)
+    {
+        constexpr int BLOCK = 128;
+        const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
+        vmv::k_sphere_fk<R, BLOCK><<<grid, BLOCK, 0, s>>>(rd, q, n, out);
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        return VMV_OK;
+    }
+
+    bool valid_robot(int robot)
+    {
+        return robot >= 0 && robot < VMV_N_ROBOTS;
+    }
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C"
+{
+    const char *vmv_last_error(void)
+    {
+        return g_error.c_str();
+    }
+
+    const char *vmv_version(void)
+    {
+        return "vamp_mvt_b200 0.1 (sm_100a)";
+    }
+
+    int vmv_device_count(void)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+        return n;
+    }
+
+    int vmv_set_device(int device)
+    {
+        VMV_CUDA(cudaSetDevice(device));
+        return VMV_OK;
+    }
+
+    int vmv_robot_id(const char *name)
+    {
+        for (int i = 0; i < VMV_N_ROBOTS; ++i)
+        {
+            if (name != nullptr && std::strcmp(name, g_robots[i].name) == 0)
+            {
+                return i;
+            }
+        }
+        return fail(VMV_ERR_ARG, "unknown robot");
+    }
+
+    const char *vmv_robot_name(int robot)
+    {
+        return valid_robot(robot) ? g_robots[robot].name : nullptr;
+    }
+
+    int vmv_robot_dof(int robot)
+    {
+        return valid_robot(robot) ? g_robots[robot].dof : fail(VMV_ERR_ARG, "unknown robot");
+    }
+
+    int vmv_robot_n_spheres(int robot)
+    {
+        return valid_robot(robot) ? g_robots[robot].n_spheres : fail(VMV_ERR_ARG, "unknown robot");
+    }
+
+    int vmv_robot_resolution(int robot)
+    {
+        return valid_robot(robot) ? g_robots[robot].resolution : fail(VMV_ERR_ARG, "unknown robot");
+    }
+
+    int vmv_robot_bounds(int robot, float *lower, float *range)
+    {
+        if (!valid_robot(robot) || lower == nullptr || range == nullptr)
+        {
+            return fail(VMV_ERR_ARG, "vmv_robot_bounds: bad argument");
+        }
+        std::memcpy(lower, g_robots[robot].lower, g_robots[robot].dof * sizeof(float));
+        std::memcpy(range, g_robots[robot].range, g_robots[robot].dof * sizeof(float));
+        return VMV_OK;
+    }
+
+    vmv_env *vmv_env_create(void)
+    {
+        return new (std::nothrow) vmv_env();
+    }
+
+    void vmv_env_destroy(vmv_env *env)
+    {
+        if (env != nullptr)
+        {
+            env->release_device();
+            delete env;
+        }
+    }
+
+    int vmv_env_add_spheres(vmv_env *env, const float *f, size_t n)
+    {
+        if (env == nullptr || (f == nullptr && n > 0))
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_add_spheres: null argument");
+        }
+        for (size_t i = 0; i < n; ++i, f += 4)
+        {
+            HSphere s{f[0], f[1], f[2], f[3], 0.F, env->next_id++};
+            s.min_d = std::sqrt(s.x * s.x + s.y * s.y + s.z * s.z) - s.r;  // shapes.hh:238
+            env->spheres.push_back(s);
+        }
+        env->committed = false;
+        return VMV_OK;
+    }
+
+    int vmv_env_add_cuboids(vmv_env *env, const float *f, size_t n)
+    {
+        if (env == nullptr || (f == nullptr && n > 0))
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_add_cuboids: null argument");
+        }
+        for (size_t i = 0; i < n; ++i, f += 15)
+        {
+            HCuboid c{};
+            std::memcpy(c.f, f, sizeof(c.f));
+            c.id = env->next_id++;
+            // Cuboid::compute_min_distance, shapes.hh:52-67
+            const float x = f[0], y = f[1], z = f[2];
+            const float d1 = dot3(-x, -y, -z, f[3], f[4], f[5]);
+            const float d2 = dot3(-x, -y, -z, f[6], f[7], f[8]);
+            const float d3 = dot3(-x, -y, -z, f[9], f[10], f[11]);
+            const float v1 = clamp_ref(d1, -f[12], f[12]);
+            const float v2 = clamp_ref(d2, -f[13], f[13]);
+            const float v3 = clamp_ref(d3, -f[14], f[14]);
+            const float xn = x + f[3] * v1 + f[6] * v2 + f[9] * v3;
+            const float yn = y + f[4] * v1 + f[7] * v2 + f[10] * v3;
+            const float zn = z + f[5] * v1 + f[8] * v2 + f[11] * v3;
+            c.min_d = finite_or_neg_inf(std::sqrt(xn * xn + yn * yn + zn * zn));
+            // z-aligned iff axis_3_z == 1 (bindings/environment.cc:124)
+            (f[11] == 1.F ? env->z_cuboids : env->cuboids).push_back(c);
+        }
+        env->committed = false;
+        return VMV_OK;
+    }
+
+    int vmv_env_add_capsules(vmv_env *env, const float *f, size_t n)
+    {
+        if (env == nullptr || (f == nullptr && n > 0))
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_add_capsules: null argument");
+        }
+        for (size_t i = 0; i < n; ++i, f += 8)
+        {
+            HCapsule c{f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], 0.F, env->next_id++};
+            // Cylinder::compute_min_distance, shapes.hh:165-189
+            const float dot = clamp_ref(dot3(-c.x1, -c.y1, -c.z1, c.xv, c.yv, c.zv) * c.rdv, 0.F, 1.F);
+            const float xp = c.x1 + c.xv * dot, yp = c.y1 + c.yv * dot, zp = c.z1 + c.zv * dot;
+            float xo = -xp, yo = -yp, zo = -zp;
+            const float ol = std::sqrt(dot3(xo, yo, zo, xo, yo, zo));
+            xo = xo / ol, yo = yo / ol, zo = zo / ol;
+            const float ro = clamp_ref(ol, 0.F, c.r);
+            const float xn = xp + ro * xo, yn = yp + ro * yo, zn = zp + ro * zo;
+            c.min_d = finite_or_neg_inf(std::sqrt(xn * xn + yn * yn + zn * zn));
+            // z-aligned iff xv == 0 and yv == 0 (bindings/environment.cc:138)
+            ((c.xv == 0.F && c.yv == 0.F) ? env->z_capsules : env->capsules).push_back(c);
+        }
+        env->committed = false;
+        return VMV_OK;
+    }
+
+    int vmv_env_add_heightfield(vmv_env *env, const float *f6, size_t xd, size_t yd, const float *data)
+    {
+        if (env == nullptr || f6 == nullptr || data == nullptr || xd == 0 || yd == 0)
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_add_heightfield: bad argument");
+        }
+        HHeight h;
+        std::memcpy(h.f, f6, sizeof(h.f));
+        h.xd = xd, h.yd = yd;
+        h.data.assign(data, data + xd * yd);
+        h.id = env->next_id++;
+        env->heightfields.push_back(std::move(h));
+        env->committed = false;
+        return VMV_OK;
+    }
+
+    int vmv_env_add_capt(vmv_env *env, const float *pts, size_t n, float r_min, float r_max, float r_point)
+    {
+        if (env == nullptr || (pts == nullptr && n > 0))
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_add_capt: null argument");
+        }
+        HCapt t;
+        capt_build(t, pts, n, r_min, r_max, r_point);
+        t.id = env->next_id++;
+        env->capts.push_back(std::move(t));
+        env->committed = false;
+        return VMV_OK;
+    }
+
+    int vmv_env_attach(vmv_env *env, const float *tf12, const float *spheres, size_t n)
+    {
+        if (env == nullptr || tf12 == nullptr || (spheres == nullptr && n > 0))
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_attach: null argument");
+        }
+        for (int r = 0; r < 3; ++r)
+        {
+            for (int c = 0; c < 3; ++c)
+            {
+                env->attach_tf[4 * r + c] = tf12[3 + 3 * c + r];
+            }
+            env->attach_tf[4 * r + 3] = tf12[r];
+        }
+        env->attach_spheres.assign(spheres, spheres + 4 * n);
+        env->has_attachment = true;
+        env->committed = false;
+        return VMV_OK;
+    }
+
+    int vmv_env_detach(vmv_env *env)
+    {
+        if (env == nullptr)
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_detach: null argument");
+        }
+        env->has_attachment = false;
+        env->attach_spheres.clear();
+        env->committed = false;
+        return VMV_OK;
+    }
+
+    int vmv_env_commit(vmv_env *env)
+    {
+        if (env == nullptr)
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_commit: null argument");
+        }
+        sort_by_min_distance(env->spheres);
+        sort_by_min_distance(env->capsules);
+        sort_by_min_distance(env->z_capsules);
+        sort_by_min_distance(env->cuboids);
+        sort_by_min_distance(env->z_cuboids);
+        return pack_and_upload(env);
+    }
+
+    long vmv_env_dump(const vmv_env *env, int kind, float *out, size_t cap)
+    {
+        if (env == nullptr)
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_dump: null argument");
+        }
+        // dump reflects the order a commit would produce
+        vmv_env tmp;
+        tmp.spheres = env->spheres, tmp.capsules = env->capsules, tmp.z_capsules = env->z_capsules;
+        tmp.cuboids = env->cuboids, tmp.z_cuboids = env->z_cuboids;
+        sort_by_min_distance(tmp.spheres), sort_by_min_distance(tmp.capsules), sort_by_min_distance(tmp.z_capsules);
+        sort_by_min_distance(tmp.cuboids), sort_by_min_distance(tmp.z_cuboids);
+        size_t k = 0;
+        auto put = [&](float v)
+        {
+            if (k < cap && out != nullptr)
+            {
+                out[k] = v;
+            }
+            ++k;
+        };
+        switch (kind)
+        {
+            case 0:
+                for (const auto &s : tmp.spheres)
+                {
+                    put(s.x), put(s.y), put(s.z), put(s.r), put(s.min_d);
+                }
+                return static_cast<long>(tmp.spheres.size());
+            case 1:
+            case 2:
+            {
+                const auto &v = kind == 1 ? tmp.capsules : tmp.z_capsules;
+                for (const auto &c : v)
+                {
+                    put(c.x1), put(c.y1), put(c.z1), put(c.xv), put(c.yv), put(c.zv), put(c.r), put(c.rdv), put(c.min_d);
+                }
+                return static_cast<long>(v.size());
+            }
+            case 3:
+            case 4:
+            {
+                const auto &v = kind == 3 ? tmp.cuboids : tmp.z_cuboids;
+                for (const auto &c : v)
+                {
+                    for (float f : c.f)
+                    {
+                        put(f);
+                    }
+                    put(c.min_d);
+                }
+                return static_cast<long>(v.size());
+            }
+            default:
+                return fail(VMV_ERR_ARG, "vmv_env_dump: unknown kind");
+        }
+    }
+
+#define VMV_DISPATCH(robot, CALL)            \
+    switch (robot)                           \
+    {                                        \
+        case VMV_PANDA:                      \
+        {                                    \
+            using R = panda_robot;           \
+            constexpr int BLOCK = 128;       \
+            rc = CALL;                       \
+            break;                           \
+        }                                    \
+        case VMV_UR5:                        \
+        {                                    \
+            using R = ur5_robot;             \
+            constexpr int BLOCK = 128;       \
+            rc = CALL;                       \
+            break;                           \
+        }                                    \
+        case VMV_FETCH:                      \
+        {                                    \
+            using R = fetch_robot;           \
+            constexpr int BLOCK = 128;       \
+            rc = CALL;                       \
+            break;                           \
+        }                                    \
+        default:                             \
+        {                                    \
+            using R = baxter_robot;          \
+            constexpr int BLOCK = 64;        \
+            rc = CALL;                       \
+            break;                           \
+        }                                    \
+    }
+
+    int vmv_validate_configs_dev(int robot, const vmv_env *env, const float *d_q, size_t n, uint32_t *d_bits, void *stream)
+    {
+        if (!valid_robot(robot) || (n > 0 && (d_q == nullptr || d_bits == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_validate_configs_dev: bad argument");
+        }
+        vmv::LaunchEnv le{};
+        int rc = make_launch_env(g_robots[robot], env, le);
+        if (rc != VMV_OK || n == 0)
+        {
+            return rc;
+        }
+        vmv::RobotDev rd{};
+        rc = robot_tables(robot, rd);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        VMV_DISPATCH(robot, (launch_configs<R, BLOCK>(rd, le, d_q, n, d_bits, s)))
+        return rc;
+    }
+
+    static int edges_common(
+        int robot,
+        const vmv_env *env,
+        const float *d_a,
+        const float *d_b,
+        const uint32_t *d_pairs,
+        size_t n,
+        int resolution,
+        uint32_t *d_bits,
+        void *stream)
+    {
+        vmv::LaunchEnv le{};
+        int rc = make_launch_env(g_robots[robot], env, le);
+        if (rc != VMV_OK || n == 0)
+        {
+            return rc;
+        }
+        vmv::RobotDev rd{};
+        rc = robot_tables(robot, rd);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        const float res = static_cast<float>(resolution > 0 ? resolution : g_robots[robot].resolution);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        VMV_DISPATCH(robot, (launch_edges<R, BLOCK>(rd, le, d_a, d_b, d_pairs, n, res, d_bits, s)))
+        return rc;
+    }
+
+    int vmv_validate_edges_dev(int robot, const vmv_env *env, const float *d_a, const float *d_b, size_t n, int resolution, uint32_t *d_bits, void *stream)
+    {
+        if (!valid_robot(robot) || (n > 0 && (d_a == nullptr || d_b == nullptr || d_bits == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_validate_edges_dev: bad argument");
+        }
+        return edges_common(robot, env, d_a, d_b, nullptr, n, resolution, d_bits, stream);
+    }
+
+    int vmv_validate_edges_indexed_dev(int robot, const vmv_env *env, const float *d_vertices, size_t n_vertices, const uint32_t *d_pairs, size_t n_edges, int resolution, uint32_t *d_bits, void *stream)
+    {
+        (void)n_vertices;
+        if (!valid_robot(robot) || (n_edges > 0 && (d_vertices == nullptr || d_pairs == nullptr || d_bits == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed_dev: bad argument");
+        }
+        return edges_common(robot, env, d_vertices, nullptr, d_pairs, n_edges, resolution, d_bits, stream);
+    }
+
+    int vmv_sphere_fk_dev(int robot, const float *d_q, size_t n, float *d_xyzr, void *stream)
+    {
+        if (!valid_robot(robot) || (n > 0 && (d_q == nullptr || d_xyzr == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_sphere_fk_dev: bad argument");
+        }
+        if (n == 0)
+        {
+            return VMV_OK;
+        }
+        vmv::RobotDev rd{};
+        int rc = robot_tables(robot, rd);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        switch (robot)
+        {
+            case VMV_PANDA:
+                return launch_fk<panda_robot>(rd, d_q, n, d_xyzr, s);
+            case VMV_UR5:
+                return launch_fk<ur5_robot>(rd, d_q, n, d_xyzr, s);
+            case VMV_FETCH:
+                return launch_fk<fetch_robot>(rd, d_q, n, d_xyzr, s);
+            default:
+                return launch_fk<baxter_robot>(rd, d_q, n, d_xyzr, s);
+        }
+    }
+
+    // ---- host-buffer versions: H2D + kernel + D2H + sync ------------------------------------
+    namespace
+    {
+        struct DevBuf
+        {
+            void *p = nullptr;
+            ~DevBuf()
+            {
+                if (p)
+                {
+                    cudaFree(p);
+                }
+            }
+            int alloc(size_t bytes)
+            {
+                VMV_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+                return VMV_OK;
+            }
+        };
+    }  // namespace
+
+    int vmv_validate_configs(int robot, const vmv_env *env, const float *q, size_t n, uint32_t *bits)
+    {
+        if (!valid_robot(robot) || (n > 0 && (q == nullptr || bits == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_validate_configs: bad argument");
+        }
+        if (n == 0)
+        {
+            vmv::LaunchEnv probe{};
+            return make_launch_env(g_robots[robot], env, probe);
+        }
+        const size_t qbytes = n * g_robots[robot].dof * sizeof(float), wbytes = ((n + 31) / 32) * 4;
+        DevBuf dq, db;
+        int rc = dq.alloc(qbytes);
+        if (rc == VMV_OK)
+        {
+            rc = db.alloc(wbytes);
+        }
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, nullptr));
+        rc = vmv_validate_configs_dev(robot, env, static_cast<const float *>(dq.p), n, static_cast<uint32_t *>(db.p), nullptr);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpyAsync(bits, db.p, wbytes, cudaMemcpyDeviceToHost, nullptr));
+        VMV_CUDA(cudaStreamSynchronize(nullptr));
+        return VMV_OK;
+    }
+
+    int vmv_validate_edges(int robot, const vmv_env *env, const float *a, const float *b, size_t n, int resolution, uint32_t *bits)
+    {
+        if (!valid_robot(robot) || (n > 0 && (a == nullptr || b == nullptr || bits == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_validate_edges: bad argument");
+        }
+        if (n == 0)
+        {
+            vmv::LaunchEnv probe{};
+            return make_launch_env(g_robots[robot], env, probe);
+        }
+        const size_t qbytes = n * g_robots[robot].dof * sizeof(float), wbytes = ((n + 31) / 32) * 4;
+        DevBuf da, dbb, dw;
+        int rc = da.alloc(qbytes);
+        if (rc == VMV_OK)
+        {
+            rc = dbb.alloc(qbytes);
+        }
+        if (rc == VMV_OK)
+        {
+            rc = dw.alloc(wbytes);
+        }
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpyAsync(da.p, a, qbytes, cudaMemcpyHostToDevice, nullptr));
+        VMV_CUDA(cudaMemcpyAsync(dbb.p, b, qbytes, cudaMemcpyHostToDevice, nullptr));
+        rc = vmv_validate_edges_dev(
+            robot, env, static_cast<const float *>(da.p), static_cast<const float *>(dbb.p), n, resolution, static_cast<uint32_t *>(dw.p), nullptr);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpyAsync(bits, dw.p, wbytes, cudaMemcpyDeviceToHost, nullptr));
+        VMV_CUDA(cudaStreamSynchronize(nullptr));
+        return VMV_OK;
+    }
+
+    int vmv_sphere_fk(int robot, const float *q, size_t n, float *xyzr)
+    {
+        if (!valid_robot(robot) || (n > 0 && (q == nullptr || xyzr == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_sphere_fk: bad argument");
+        }
+        if (n == 0)
+        {
+            return VMV_OK;
+        }
+        const size_t qbytes = n * g_robots[robot].dof * sizeof(float);
+        const size_t obytes = n * g_robots[robot].n_spheres * 4 * sizeof(float);
+        DevBuf dq, dout;
+        int rc = dq.alloc(qbytes);
+        if (rc == VMV_OK)
+        {
+            rc = dout.alloc(obytes);
+        }
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, nullptr));
+        rc = vmv_sphere_fk_dev(robot, static_cast<const float *>(dq.p), n, static_cast<float *>(dout.p), nullptr);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpyAsync(xyzr, dout.p, obytes, cudaMemcpyDeviceToHost, nullptr));
+        VMV_CUDA(cudaStreamSynchronize(nullptr));
+        return VMV_OK;
+    }
+
+    int vmv_debug(int robot, const vmv_env *env, const float *q, int32_t *env_hits, size_t cap_env, size_t *n_env, int32_t *self_hits, size_t cap_self, size_t *n_self)
+    {
+        (void)robot, (void)env, (void)q, (void)env_hits, (void)cap_env, (void)n_env, (void)self_hits, (void)cap_self, (void)n_self;
+        return fail(VMV_ERR_STATE, "vmv_debug: not implemented yet");
+    }
+
+    void *vmv_dev_alloc(size_t bytes)
+    {
+        void *p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess)
+        {
+            g_error = "vmv_dev_alloc: cudaMalloc failed";
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+
+    void vmv_dev_free(void *p)
+    {
+        if (p)
+        {
+            cudaFree(p);
+        }
+    }
+
+    void *vmv_host_alloc_pinned(size_t bytes)
+    {
+        void *p = nullptr;
+        if (cudaMallocHost(&p, std::max<size_t>(bytes, 16)) != cudaSuccess)
+        {
+            g_error = "vmv_host_alloc_pinned: cudaMallocHost failed";
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+
+    void vmv_host_free_pinned(void *p)
+    {
+        if (p)
+        {
+            cudaFreeHost(p);
+        }
+    }
+
+    int vmv_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
+    {
+        VMV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+        return VMV_OK;
+    }
+
+    int vmv_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
+    {
+        VMV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+        return VMV_OK;
+    }
+
+    int vmv_stream_sync(void *stream)
+    {
+        VMV_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+        return VMV_OK;
+    }
+
+    uint64_t vmv_launch_count(void)
+    {
+        return g_launches.load();
+    }
+}

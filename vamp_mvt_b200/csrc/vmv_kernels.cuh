@@ -1,0 +1,607 @@
+// Validation kernels (sm_100a).  One thread = one robot state.
+//
+//   k_validate_configs : one configuration per thread                 (reference Robot::fkcc,
+//                        robots/panda.hh:5227, via validate_motion<Robot,8,1>)
+//   k_validate_edges   : one warp per edge, one lane per raked state  (reference validate_vector,
+//                        planning/validate.hh:24-67)
+//   k_sphere_fk        : fine sphere centres                          (reference Robot::sphere_fk)
+//
+// Structure of a state check (phases):
+//   A  straight-line FK of the moving rigid bodies (generated, gen/<robot>_fk.cuh); the 3x4 frames go
+//      to a per-thread stash in shared memory, laid out [entry][thread] (bank-conflict free);
+//   B  environment sweep as a task loop: every thread walks its own list of sphere tasks (bounding
+//      sphere of a link -> on hit its fine spheres, else skip to the next link) but all threads run
+//      the same loop body, so a warp stays converged no matter which link each lane is on;
+//   C  self collision: bounding pair test on the bounding centres saved during B, fine pairs on hit;
+//   D  attachment spheres (posed by the end-effector frame) against the environment and the links.
+//
+// The environment blob, the robot's task/link/pair tables and the stash live in dynamic shared
+// memory; the blob arrives by one TMA bulk copy that overlaps phase A.
+#pragma once
+#include "vmv_device.cuh"
+
+namespace vmv
+{
+    struct RobotDev
+    {
+        const SphereTask *tasks;  // kTasks
+        const LinkInfo *links;    // kLinks
+        const LinkPair *pairs;    // kPairs
+        const int *attach_links;  // kAttachLinks
+    };
+
+    struct LaunchEnv
+    {
+        const float *blob;    // device copy of the packed environment
+        uint32_t blob_bytes;  // multiple of 16
+        float attach_tf[12];  // end-effector frame (in its body) * attachment offset, row-major 3x4
+    };
+
+    // shared-memory carve-up, identical on host (size computation) and device
+    template <typename M, int BLOCK>
+    struct SmemLayout
+    {
+        static constexpr int kStashFrames = (M::kBodies - 1) * 12;
+        static constexpr int kStashBounds = M::kLinks * 3;
+
+        __host__ __device__ static constexpr uint32_t align16(uint32_t v)
+        {
+            return (v + 15u) & ~15u;
+        }
+
+        uint32_t off_tasks, off_links, off_pairs, off_attach, off_stash, total;
+
+        __host__ __device__ explicit SmemLayout(uint32_t blob_bytes)
+        {
+            uint32_t o = align16(blob_bytes);
+            off_tasks = o;
+            o += align16(M::kTasks * sizeof(SphereTask));
+            off_links = o;
+            o += align16(M::kLinks * sizeof(LinkInfo));
+            off_pairs = o;
+            o += align16((M::kPairs > 0 ? M::kPairs : 1) * sizeof(LinkPair));
+            off_attach = o;
+            o += align16((M::kAttachLinks > 0 ? M::kAttachLinks : 1) * sizeof(int));
+            off_stash = o;
+            o += (kStashFrames + kStashBounds) * BLOCK * sizeof(float);
+            total = o;
+        }
+    };
+
+    template <int BLOCK>
+    struct StashSink
+    {
+        float *base;  // already offset by threadIdx.x
+
+        template <int BODY, int K>
+        __device__ __forceinline__ void put(float v)
+        {
+            base[((BODY - 1) * 12 + K) * BLOCK] = v;
+        }
+    };
+
+    struct RegSink
+    {
+        // used by k_sphere_fk: frames stay in registers/local for an immediate read-back
+        float *f;
+
+        template <int BODY, int K>
+        __device__ __forceinline__ void put(float v)
+        {
+            f[(BODY - 1) * 12 + K] = v;
+        }
+    };
+
+    template <int BLOCK>
+    __device__ __forceinline__ void
+    task_centre(const SphereTask &t, const float *stash, float &x, float &y, float &z)
+    {
+        if (t.body == 0)
+        {
+            x = t.cx, y = t.cy, z = t.cz;
+        }
+        else
+        {
+            const float *F = stash + (t.body - 1) * 12 * BLOCK;
+            x = fmaf(F[0 * BLOCK], t.cx, fmaf(F[1 * BLOCK], t.cy, fmaf(F[2 * BLOCK], t.cz, F[3 * BLOCK])));
+            y = fmaf(F[4 * BLOCK], t.cx, fmaf(F[5 * BLOCK], t.cy, fmaf(F[6 * BLOCK], t.cz, F[7 * BLOCK])));
+            z = fmaf(F[8 * BLOCK], t.cx, fmaf(F[9 * BLOCK], t.cy, fmaf(F[10 * BLOCK], t.cz, F[11 * BLOCK])));
+        }
+    }
+
+    // Everything a thread needs to check states: pointers into shared memory.
+    template <typename M, int BLOCK>
+    struct BlockCtx
+    {
+        const float *env;
+        const SphereTask *tasks;
+        const LinkInfo *links;
+        const LinkPair *pairs;
+        const int *attach_links;
+        float *stash;   // frames, offset by threadIdx.x
+        float *bounds;  // bounding centres, offset by threadIdx.x
+    };
+
+    // Stage tables + environment.  Returns after issuing the copies; call ctx_wait() before phase B.
+    template <typename M, int BLOCK>
+    __device__ __forceinline__ BlockCtx<M, BLOCK>
+    ctx_begin(unsigned char *smem, uint64_t *bar, const RobotDev &robot, const LaunchEnv &env)
+    {
+        const SmemLayout<M, BLOCK> L(env.blob_bytes);
+        if (threadIdx.x == 0)
+        {
+            mbar_init(bar, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            tma_bulk_g2s(smem, env.blob, env.blob_bytes, bar);
+        }
+
+        // robot tables: a few KB, plain coalesced loads
+        {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + L.off_tasks);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(robot.tasks);
+            for (int i = threadIdx.x; i < M::kTasks * 8; i += BLOCK)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_links);
+            src = reinterpret_cast<const uint32_t *>(robot.links);
+            for (int i = threadIdx.x; i < M::kLinks * 4; i += BLOCK)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_pairs);
+            src = reinterpret_cast<const uint32_t *>(robot.pairs);
+            for (int i = threadIdx.x; i < M::kPairs * 2; i += BLOCK)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_attach);
+            src = reinterpret_cast<const uint32_t *>(robot.attach_links);
+            for (int i = threadIdx.x; i < M::kAttachLinks; i += BLOCK)
+            {
+                dst[i] = __ldg(src + i);
+            }
+        }
+
+        BlockCtx<M, BLOCK> c;
+        c.env = reinterpret_cast<const float *>(smem);
+        c.tasks = reinterpret_cast<const SphereTask *>(smem + L.off_tasks);
+        c.links = reinterpret_cast<const LinkInfo *>(smem + L.off_links);
+        c.pairs = reinterpret_cast<const LinkPair *>(smem + L.off_pairs);
+        c.attach_links = reinterpret_cast<const int *>(smem + L.off_attach);
+        c.stash = reinterpret_cast<float *>(smem + L.off_stash) + threadIdx.x;
+        c.bounds = c.stash + SmemLayout<M, BLOCK>::kStashFrames * BLOCK;
+        return c;
+    }
+
+    __device__ __forceinline__ void ctx_wait(uint64_t *bar)
+    {
+        __syncthreads();  // robot tables visible
+        mbar_wait(bar, 0);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // phases B, C, D for one state whose frames are in the stash.  `Vote` lets the edge kernel stop
+    // a whole warp as soon as any lane has found a collision.
+    // ------------------------------------------------------------------------------------------
+    struct NoVote
+    {
+        __device__ __forceinline__ bool stop(bool) const
+        {
+            return false;
+        }
+        __device__ __forceinline__ bool any(bool v) const
+        {
+            return v;
+        }
+        static constexpr bool kWarp = false;
+    };
+
+    struct WarpVote
+    {
+        // every lane of the warp calls these together
+        __device__ __forceinline__ bool stop(bool bad) const
+        {
+            return __any_sync(0xffffffffu, bad);
+        }
+        __device__ __forceinline__ bool any(bool v) const
+        {
+            return __any_sync(0xffffffffu, v);
+        }
+        static constexpr bool kWarp = true;
+    };
+
+    template <typename M, int BLOCK, typename Vote>
+    __device__ __forceinline__ bool
+    check_state(const BlockCtx<M, BLOCK> &c, const LaunchEnv &env, bool has_state, const Vote &vote)
+    {
+        bool bad = false;
+
+        // ---- B: environment -----------------------------------------------------------------
+        {
+            int ti = 0;
+            bool active = has_state;
+            while (vote.any(active))
+            {
+                if (active)
+                {
+                    const SphereTask t = c.tasks[ti];
+                    float x, y, z;
+                    task_centre<BLOCK>(t, c.stash, x, y, z);
+                    const bool hit = sphere_hits_env(c.env, x, y, z, t.r);
+                    if (t.skip >= 0)
+                    {
+                        float *b = c.bounds + t.link * 3 * BLOCK;
+                        b[0] = x, b[BLOCK] = y, b[2 * BLOCK] = z;
+                        ti = hit ? ti + 1 : t.skip;
+                    }
+                    else
+                    {
+                        bad = hit;
+                        ti = ti + 1;
+                    }
+                    active = (ti < M::kTasks) && !bad;
+                }
+                if (vote.stop(bad))
+                {
+                    return false;
+                }
+            }
+        }
+        if (!Vote::kWarp && bad)
+        {
+            return false;
+        }
+
+        // ---- C: self collision --------------------------------------------------------------
+        {
+            int pi = 0;
+            bool active = has_state && M::kPairs > 0;
+            while (vote.any(active))
+            {
+                if (active)
+                {
+                    const LinkPair p = c.pairs[pi];
+                    const LinkInfo la = c.links[p.a], lb = c.links[p.b];
+                    const float *ba = c.bounds + p.a * 3 * BLOCK, *bb = c.bounds + p.b * 3 * BLOCK;
+                    const float dx = ba[0] - bb[0], dy = ba[BLOCK] - bb[BLOCK], dz = ba[2 * BLOCK] - bb[2 * BLOCK];
+                    const float rs = c.tasks[la.bound_task].r + c.tasks[lb.bound_task].r;
+                    if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                    {
+                        // fine pairs (rare): spheres of link a against spheres of link b
+                        for (int i = 0; i < la.n_spheres && !bad; ++i)
+                        {
+                            const SphereTask ta = c.tasks[la.bound_task + 1 + i];
+                            float ax, ay, az;
+                            task_centre<BLOCK>(ta, c.stash, ax, ay, az);
+                            for (int j = 0; j < lb.n_spheres; ++j)
+                            {
+                                const SphereTask tb = c.tasks[lb.bound_task + 1 + j];
+                                float bx, by, bz;
+                                task_centre<BLOCK>(tb, c.stash, bx, by, bz);
+                                const float ex = ax - bx, ey = ay - by, ez = az - bz;
+                                const float rr = ta.r + tb.r;
+                                if (sign_set((ex * ex + ey * ey + ez * ez) - rr * rr))
+                                {
+                                    bad = true;
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                    pi = pi + 1;
+                    active = (pi < M::kPairs) && !bad;
+                }
+                if (vote.stop(bad))
+                {
+                    return false;
+                }
+            }
+        }
+        if (!Vote::kWarp && bad)
+        {
+            return false;
+        }
+
+        // ---- D: attachment (reference fkcc_attach, robots/panda.hh:15308-15440) --------------
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(c.env);
+        if (H.n_attach > 0)
+        {
+            if (has_state)
+            {
+                // T = F[ee_body] * attach_tf   (Attachment::pose, collision/attachments.hh:43-55)
+                float T[12];
+                {
+                    float F[12];
+                    if (M::kEeBody == 0)
+                    {
+#pragma unroll
+                        for (int k = 0; k < 12; ++k)
+                        {
+                            F[k] = (k % 5 == 0) ? 1.F : 0.F;
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int k = 0; k < 12; ++k)
+                        {
+                            F[k] = c.stash[((M::kEeBody - 1) * 12 + k) * BLOCK];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            float s = F[4 * i] * env.attach_tf[j] + F[4 * i + 1] * env.attach_tf[4 + j] +
+                                      F[4 * i + 2] * env.attach_tf[8 + j];
+                            T[4 * i + j] = (j == 3) ? s + F[4 * i + 3] : s;
+                        }
+                    }
+                }
+                const float4 *S = reinterpret_cast<const float4 *>(c.env + H.off_attach + kAttachHdr);
+                // attachment vs environment (validity.hh:259-276)
+                for (uint32_t i = 0; i < H.n_attach && !bad; ++i)
+                {
+                    const float4 s = S[i];
+                    const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
+                    const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
+                    const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
+                    bad = sphere_hits_env(c.env, x, y, z, s.w);
+                }
+                // attachment vs links, bounding sphere first (validity.hh:278-301)
+                for (int k = 0; k < M::kAttachLinks && !bad; ++k)
+                {
+                    const int l = c.attach_links[k];
+                    const LinkInfo li = c.links[l];
+                    const float *b = c.bounds + l * 3 * BLOCK;
+                    const float br = c.tasks[li.bound_task].r;
+                    bool near = false;
+                    for (uint32_t i = 0; i < H.n_attach && !near; ++i)
+                    {
+                        const float4 s = S[i];
+                        const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
+                        const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
+                        const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
+                        const float dx = b[0] - x, dy = b[BLOCK] - y, dz = b[2 * BLOCK] - z;
+                        const float rs = br + s.w;
+                        near = sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
+                    }
+                    if (!near)
+                    {
+                        continue;
+                    }
+                    for (int f = 0; f < li.n_spheres && !bad; ++f)
+                    {
+                        const SphereTask tf = c.tasks[li.bound_task + 1 + f];
+                        float fx, fy, fz;
+                        task_centre<BLOCK>(tf, c.stash, fx, fy, fz);
+                        for (uint32_t i = 0; i < H.n_attach; ++i)
+                        {
+                            const float4 s = S[i];
+                            const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
+                            const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
+                            const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
+                            const float dx = fx - x, dy = fy - y, dz = fz - z;
+                            const float rs = tf.r + s.w;
+                            if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                            {
+                                bad = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+            if (vote.stop(bad))
+            {
+                return false;
+            }
+        }
+
+        return !bad;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // kernels
+    // ------------------------------------------------------------------------------------------
+    template <typename R, int BLOCK>
+    __global__ void __launch_bounds__(BLOCK)
+        k_validate_configs(RobotDev robot, LaunchEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
+    {
+        using M = typename R::Model;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        BlockCtx<M, BLOCK> c = ctx_begin<M, BLOCK>(smem, &bar, robot, env);
+
+        const size_t i = static_cast<size_t>(blockIdx.x) * BLOCK + threadIdx.x;
+        const bool has = i < n;
+        float cfg[M::kDof];
+#pragma unroll
+        for (int j = 0; j < M::kDof; ++j)
+        {
+            cfg[j] = has ? __ldg(q + i * M::kDof + j) : 0.F;
+        }
+        StashSink<BLOCK> sink{c.stash};
+        R::frames(cfg, sink);
+
+        ctx_wait(&bar);
+        const bool valid = has && check_state<M, BLOCK>(c, env, has, NoVote{});
+        const uint32_t word = __ballot_sync(0xffffffffu, valid);
+        if ((threadIdx.x & 31) == 0 && has)
+        {
+            bits[i >> 5] = word;
+        }
+    }
+
+    // FloatVector<dim>::l2_norm() of (b - a) with the reference's summation order
+    // (vector/interface.hh:397-410, vector/avx.hh:441-452): rows of 8 lanes summed elementwise, then
+    // (l4+l0 + l6+l2) + (l5+l1 + l7+l3).
+    template <int DOF>
+    __device__ __forceinline__ float ref_l2_norm(const float (&v)[DOF])
+    {
+        float lane[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            lane[k] = 0.F;
+        }
+#pragma unroll
+        for (int k = 0; k < DOF; ++k)
+        {
+            const float sq = __fmul_rn(v[k], v[k]);
+            lane[k % 8] = (k < 8) ? sq : __fadd_rn(lane[k % 8], sq);
+        }
+        const float s0 = __fadd_rn(lane[4], lane[0]), s1 = __fadd_rn(lane[5], lane[1]);
+        const float s2 = __fadd_rn(lane[6], lane[2]), s3 = __fadd_rn(lane[7], lane[3]);
+        return __fsqrt_rn(__fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3)));
+    }
+
+    // One warp per edge.  The reference checks 8 "tines" at (t+1)/8 along the edge, then steps all of
+    // them back n-1 times by vector/(8n) (planning/validate.hh:31-64).  A warp covers 4 such steps
+    // (32 states) per pass; the edge is invalid as soon as any state is.
+    template <typename R, int BLOCK, bool INDEXED>
+    __global__ void __launch_bounds__(BLOCK) k_validate_edges(
+        RobotDev robot,
+        LaunchEnv env,
+        const float *__restrict__ a,
+        const float *__restrict__ b,
+        const uint32_t *__restrict__ pairs,
+        size_t n,
+        float resolution,
+        uint32_t *__restrict__ bits)
+    {
+        using M = typename R::Model;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        BlockCtx<M, BLOCK> c = ctx_begin<M, BLOCK>(smem, &bar, robot, env);
+        ctx_wait(&bar);
+
+        constexpr int WARPS = BLOCK / 32;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int tine = lane & 7, sub = lane >> 3;
+        const WarpVote vote{};
+
+        // each warp owns 32 consecutive edges per round so that lane e can publish the verdict word
+        for (size_t base = (static_cast<size_t>(blockIdx.x) * WARPS + warp) * 32; base < n;
+             base += static_cast<size_t>(gridDim.x) * WARPS * 32)
+        {
+            uint32_t word = 0;
+            const int count = static_cast<int>(min(static_cast<size_t>(32), n - base));
+            for (int e = 0; e < count; ++e)
+            {
+                const size_t edge = base + e;
+                const float *pa, *pb;
+                if (INDEXED)
+                {
+                    pa = a + static_cast<size_t>(__ldg(pairs + 2 * edge)) * M::kDof;
+                    pb = a + static_cast<size_t>(__ldg(pairs + 2 * edge + 1)) * M::kDof;
+                }
+                else
+                {
+                    pa = a + edge * M::kDof;
+                    pb = b + edge * M::kDof;
+                }
+                float start[M::kDof], vec[M::kDof];
+#pragma unroll
+                for (int j = 0; j < M::kDof; ++j)
+                {
+                    start[j] = __ldg(pa + j);
+                    vec[j] = __fsub_rn(__ldg(pb + j), start[j]);
+                }
+                const float dist = ref_l2_norm<M::kDof>(vec);
+                // n = max(ceil(distance / rake * resolution), 1)   (validate.hh:41)
+                const int steps = static_cast<int>(fmaxf(ceilf(__fmul_rn(__fdiv_rn(dist, 8.F), resolution)), 1.F));
+                const float pct = static_cast<float>(tine + 1) / 8.F;
+                const float denom = static_cast<float>(8 * steps);
+                float cfg[M::kDof], back[M::kDof];
+#pragma unroll
+                for (int j = 0; j < M::kDof; ++j)
+                {
+                    cfg[j] = fmaf(vec[j], pct, start[j]);
+                    back[j] = __fdiv_rn(vec[j], denom);
+                }
+                // this lane starts at step `sub`
+                for (int s = 0; s < sub && s < steps; ++s)
+                {
+#pragma unroll
+                    for (int j = 0; j < M::kDof; ++j)
+                    {
+                        cfg[j] = __fsub_rn(cfg[j], back[j]);
+                    }
+                }
+
+                bool edge_ok = true;
+                for (int step0 = 0; step0 < steps; step0 += 4)
+                {
+                    const bool has = (step0 + sub) < steps;
+                    StashSink<BLOCK> sink{c.stash};
+                    R::frames(cfg, sink);
+                    if (!check_state<M, BLOCK>(c, env, has, vote))
+                    {
+                        edge_ok = false;
+                        break;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+#pragma unroll
+                        for (int j = 0; j < M::kDof; ++j)
+                        {
+                            cfg[j] = __fsub_rn(cfg[j], back[j]);
+                        }
+                    }
+                }
+                word |= (edge_ok ? 1u : 0u) << e;
+            }
+            if (lane == 0)
+            {
+                bits[base >> 5] = word;
+            }
+        }
+    }
+
+    template <typename R, int BLOCK>
+    __global__ void __launch_bounds__(BLOCK)
+        k_sphere_fk(RobotDev robot, const float *__restrict__ q, size_t n, float *__restrict__ out)
+    {
+        using M = typename R::Model;
+        const size_t i = static_cast<size_t>(blockIdx.x) * BLOCK + threadIdx.x;
+        if (i >= n)
+        {
+            return;
+        }
+        float cfg[M::kDof];
+#pragma unroll
+        for (int j = 0; j < M::kDof; ++j)
+        {
+            cfg[j] = __ldg(q + i * M::kDof + j);
+        }
+        float F[(M::kBodies - 1) * 12];
+        RegSink sink{F};
+        R::frames(cfg, sink);
+        for (int t = 0; t < M::kTasks; ++t)
+        {
+            const SphereTask tk = robot.tasks[t];
+            if (tk.sphere < 0)
+            {
+                continue;
+            }
+            float x = tk.cx, y = tk.cy, z = tk.cz;
+            if (tk.body > 0)
+            {
+                const float *f = F + (tk.body - 1) * 12;
+                x = fmaf(f[0], tk.cx, fmaf(f[1], tk.cy, fmaf(f[2], tk.cz, f[3])));
+                y = fmaf(f[4], tk.cx, fmaf(f[5], tk.cy, fmaf(f[6], tk.cz, f[7])));
+                z = fmaf(f[8], tk.cx, fmaf(f[9], tk.cy, fmaf(f[10], tk.cz, f[11])));
+            }
+            float4 *o = reinterpret_cast<float4 *>(out + (i * M::kSpheres + tk.sphere) * 4);
+            *o = make_float4(x, y, z, tk.r);
+        }
+    }
+}  // namespace vmv
