@@ -134,6 +134,9 @@ extern "C"
     /* --- measurement helpers -------------------------------------------------------------------
      * number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
     uint64_t vmv_launch_count(void);
+    /* testing aid: 0 = automatic choice (default), 1 = force the generic per-thread kernel,
+     * 2 = force the block-cooperative kernel (fails with VMV_ERR_LIMIT when it does not apply) */
+    int vmv_force_kernel_path(int path);
 
 #ifdef __cplusplus
 }

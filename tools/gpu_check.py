@@ -24,7 +24,13 @@ def main():
             oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
             N = 20000
             q = scenes.random_configs(robot, N, seed=1)
+            from vamp_mvt_b200 import _lib
+            _lib.lib().vmv_force_kernel_path(1)
+            got1 = R.validate_batch(q, env)
+            _lib.lib().vmv_force_kernel_path(0)
             t = time.time(); got = R.validate_batch(q, env); tg = time.time() - t
+            if (got1 != got).any():
+                print("   !! v1/v2 kernels disagree on", int((got1 != got).sum()), "configs")
             want = O.validate_configs(oenv, q)
             mism = np.nonzero(got != want)[0]
             cl = O.min_clearance(oenv, q[mism]) if len(mism) else np.zeros(0)

@@ -514,6 +514,18 @@ def trace_frames(model):
     return tr, frames
 
 
+def trace_bounds(model, tr, frames):
+    """World-frame centre of every collision link's bounding sphere (3 node ids per link)."""
+    out = []
+    for l in model["links"]:
+        F = frames[l["body"]]
+        c = [tr.const(v) for v in l["bound"][:3]]
+        out.append(
+            [tr.add(tr.add(tr.add(tr.mul(F[i][0], c[0]), tr.mul(F[i][1], c[1])), tr.mul(F[i][2], c[2])), F[i][3]) for i in range(3)]
+        )
+    return out
+
+
 def emit_cuda(model, tr, frames):
     """Straight-line device code: computes every moving body's 3x4 frame and hands each of the 12
     entries to `sink(body, k, value)`; constant entries are passed as literals so the sink sees
@@ -532,10 +544,14 @@ def emit_cuda(model, tr, frames):
             need(a)
             need(b)
 
+    bounds = trace_bounds(model, tr, frames)
     for F in frames:
         for row in F:
             for n in row:
                 need(n)
+    for b3 in bounds:
+        for n in b3:
+            need(n)
 
     def lit(v):
         f = float(np.float32(v))
@@ -567,6 +583,9 @@ def emit_cuda(model, tr, frames):
         for row in F:
             for n in row:
                 uses[n] = uses.get(n, 0) + 1
+    for b3 in bounds:
+        for n in b3:
+            uses[n] = uses.get(n, 0) + 1
 
     fused = set()
     for n in sorted(needed):
@@ -631,6 +650,10 @@ def emit_cuda(model, tr, frames):
         for i in range(3):
             for j in range(4):
                 out.append(f"    sink.template put<{b}, {i * 4 + j}>({operand(F[i][j])});")
+    out.append("    // world-frame centres of the per-link bounding spheres")
+    for li, b3 in enumerate(bounds):
+        for ax in range(3):
+            out.append(f"    sink.template bound<{li}, {ax}>({operand(b3[ax])});")
     out.append("}")
     out.append("")
     out.append("}}  // namespace vmv::gen")
@@ -704,6 +727,17 @@ def emit_tables(model):
     if not model["self_pairs"]:
         out.append("    {0, 0},")
     out.append("};")
+    out.append("")
+    N = name.upper()
+    out.append("// X-macros for fully unrolled device code: LINKS(X) -> X(link, bound_radius, n_spheres, first_fine_task);")
+    out.append("// PAIRS(X) -> X(pair_index, link_a, link_b)")
+    out.append(f"#define VMV_{N}_LINKS(X) \\")
+    for li, l in enumerate(L):
+        out.append(f"    X({li}, {f(l['bound'][3])}, {len(l['spheres'])}, {btask[li] + 1}) \\")
+    out.append("")
+    out.append(f"#define VMV_{N}_PAIRS(X) \\")
+    for pi, (a, b) in enumerate(model["self_pairs"]):
+        out.append(f"    X({pi}, {a}, {b}) \\")
     out.append("")
     out.append(f"static const int {name}_attach_links_host[{max(1, len(model['attach_links']))}] = {{" + ", ".join(str(a) for a in (model["attach_links"] or [0])) + "};")
     ee = np.array(model["end_effector"]["T"]).reshape(-1)

@@ -66,6 +66,7 @@ def lib():
         L.vmv_memcpy_d2h.argtypes = [vp, vp, sz, vp]
         L.vmv_stream_sync.argtypes = [vp]
         L.vmv_launch_count.restype = C.c_uint64
+        L.vmv_force_kernel_path.argtypes = [i32]
         _lib = L
     return _lib
 

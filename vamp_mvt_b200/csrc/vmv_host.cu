@@ -15,7 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/vamp_b200.h"
-#include "vmv_kernels.cuh"
+#include "vmv_kernels_v2.cuh"
 
 #include "gen/panda_fk.cuh"
 #include "gen/ur5_fk.cuh"
@@ -64,7 +64,27 @@ namespace
         {                                                                             \
             vmv::gen::NAME##_frames(q, s);                                            \
         }                                                                             \
+        template <typename F>                                                         \
+        static __device__ __forceinline__ void for_each_link(F &&f)                   \
+        {                                                                             \
+            VMV_##NAME##_LINKS_DISPATCH                                               \
+        }                                                                             \
+        template <typename F>                                                         \
+        static __device__ __forceinline__ void for_each_pair(F &&f)                   \
+        {                                                                             \
+            VMV_##NAME##_PAIRS_DISPATCH                                               \
+        }                                                                             \
     };
+#define VMV_X_LINK(l, r, n, t) f(vmv::IC<l>{}, r, n, t);
+#define VMV_X_PAIR(p, a, b) f(vmv::IC<p>{}, vmv::IC<a>{}, vmv::IC<b>{});
+#define VMV_panda_LINKS_DISPATCH VMV_PANDA_LINKS(VMV_X_LINK)
+#define VMV_panda_PAIRS_DISPATCH VMV_PANDA_PAIRS(VMV_X_PAIR)
+#define VMV_ur5_LINKS_DISPATCH VMV_UR5_LINKS(VMV_X_LINK)
+#define VMV_ur5_PAIRS_DISPATCH VMV_UR5_PAIRS(VMV_X_PAIR)
+#define VMV_fetch_LINKS_DISPATCH VMV_FETCH_LINKS(VMV_X_LINK)
+#define VMV_fetch_PAIRS_DISPATCH VMV_FETCH_PAIRS(VMV_X_PAIR)
+#define VMV_baxter_LINKS_DISPATCH VMV_BAXTER_LINKS(VMV_X_LINK)
+#define VMV_baxter_PAIRS_DISPATCH VMV_BAXTER_PAIRS(VMV_X_PAIR)
     VMV_ROBOT(panda)
     VMV_ROBOT(ur5)
     VMV_ROBOT(fetch)
@@ -590,6 +610,9 @@ namespace
         }
         le.blob = env->d_blob;
         le.blob_bytes = static_cast<uint32_t>(env->blob.size() * 4);
+        le.n_objects = static_cast<uint32_t>(
+            env->spheres.size() + env->capsules.size() + env->z_capsules.size() + env->cuboids.size() + env->z_cuboids.size());
+        le.primitives_only = env->heightfields.empty() && env->capts.empty() && !env->has_attachment;
         // attach_tf = ee_tf(robot) * attachment offset
         const float *E = r.ee_tf;
         float A[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -610,10 +633,44 @@ namespace
 
     constexpr uint32_t kMaxSmem = 227 * 1024;
 
+    // 0: pick automatically; 1: generic per-thread kernel; 2: block-cooperative kernel
+    std::atomic<int> g_force_path{0};
+
+    template <typename R, int BLOCK>
+    int launch_configs_v2(const vmv::RobotDev &rd, const vmv::LaunchEnv &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
+    {
+        using M = typename R::Model;
+        const vmv::SmemLayoutV2<M, BLOCK> L(le.blob_bytes);
+        if (L.total > kMaxSmem)
+        {
+            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
+        }
+        auto kernel = vmv::k_validate_configs_v2<R, BLOCK>;
+        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
+        const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
+        kernel<<<grid, BLOCK, L.total, s>>>(rd, le, q, n, bits);
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        return VMV_OK;
+    }
+
     template <typename R, int BLOCK>
     int launch_configs(const vmv::RobotDev &rd, const vmv::LaunchEnv &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
     {
         using M = typename R::Model;
+        const int force = g_force_path.load();
+        if (force != 1 && le.primitives_only && le.n_objects <= 64)
+        {
+            const vmv::SmemLayoutV2<M, BLOCK> L2(le.blob_bytes);
+            if (L2.total <= kMaxSmem)
+            {
+                return launch_configs_v2<R, BLOCK>(rd, le, q, n, bits, s);
+            }
+        }
+        if (force == 2)
+        {
+            return fail(VMV_ERR_LIMIT, "block-cooperative kernel not applicable to this environment");
+        }
         const vmv::SmemLayout<M, BLOCK> L(le.blob_bytes);
         if (L.total > kMaxSmem)
         {
@@ -1113,6 +1170,10 @@ extern "C"
     }
 
     // ---- host-buffer versions: H2D + kernel + D2H + sync ------------------------------------
+    // The batch is cut into chunks that alternate between two streams so that the upload of chunk
+    // k+1 overlaps the kernel of chunk k (pinned host memory makes the copies truly asynchronous;
+    // pageable memory still works, staged by the driver).  Device scratch is a grow-only pool per
+    // device, so steady-state calls do not allocate.
     namespace
     {
         struct DevBuf
@@ -1131,6 +1192,46 @@ extern "C"
                 return VMV_OK;
             }
         };
+
+        struct HostPathPool
+        {
+            std::mutex mutex;
+            cudaStream_t streams[2] = {nullptr, nullptr};
+            void *buf[3] = {nullptr, nullptr, nullptr};
+            size_t cap[3] = {0, 0, 0};
+
+            int ensure(int which, size_t bytes)
+            {
+                if (cap[which] < bytes)
+                {
+                    if (buf[which])
+                    {
+                        VMV_CUDA(cudaFree(buf[which]));
+                        buf[which] = nullptr;
+                        cap[which] = 0;
+                    }
+                    const size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+                    VMV_CUDA(cudaMalloc(&buf[which], want));
+                    cap[which] = want;
+                }
+                return VMV_OK;
+            }
+
+            int init()
+            {
+                for (auto &st : streams)
+                {
+                    if (st == nullptr)
+                    {
+                        VMV_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                    }
+                }
+                return VMV_OK;
+            }
+        };
+        HostPathPool g_pools[kMaxDevices];
+
+        constexpr size_t kChunkUnits = size_t(1) << 17;  // multiple of 32: chunks own whole verdict words
     }  // namespace
 
     int vmv_validate_configs(int robot, const vmv_env *env, const float *q, size_t n, uint32_t *bits)
@@ -1144,25 +1245,41 @@ extern "C"
             vmv::LaunchEnv probe{};
             return make_launch_env(g_robots[robot], env, probe);
         }
-        const size_t qbytes = n * g_robots[robot].dof * sizeof(float), wbytes = ((n + 31) / 32) * 4;
-        DevBuf dq, db;
-        int rc = dq.alloc(qbytes);
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        HostPathPool &pool = g_pools[device % kMaxDevices];
+        std::lock_guard<std::mutex> lock(pool.mutex);
+        const size_t dof = g_robots[robot].dof;
+        int rc = pool.init();
         if (rc == VMV_OK)
         {
-            rc = db.alloc(wbytes);
+            rc = pool.ensure(0, n * dof * sizeof(float));
+        }
+        if (rc == VMV_OK)
+        {
+            rc = pool.ensure(2, ((n + 31) / 32) * 4);
         }
         if (rc != VMV_OK)
         {
             return rc;
         }
-        VMV_CUDA(cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, nullptr));
-        rc = vmv_validate_configs_dev(robot, env, static_cast<const float *>(dq.p), n, static_cast<uint32_t *>(db.p), nullptr);
-        if (rc != VMV_OK)
+        float *dq = static_cast<float *>(pool.buf[0]);
+        uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
+        int k = 0;
+        for (size_t off = 0; off < n; off += kChunkUnits, ++k)
         {
-            return rc;
+            const size_t cnt = std::min(kChunkUnits, n - off);
+            cudaStream_t st = pool.streams[k & 1];
+            VMV_CUDA(cudaMemcpyAsync(dq + off * dof, q + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
+            rc = vmv_validate_configs_dev(robot, env, dq + off * dof, cnt, dw + off / 32, st);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpyAsync(bits + off / 32, dw + off / 32, ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
         }
-        VMV_CUDA(cudaMemcpyAsync(bits, db.p, wbytes, cudaMemcpyDeviceToHost, nullptr));
-        VMV_CUDA(cudaStreamSynchronize(nullptr));
+        VMV_CUDA(cudaStreamSynchronize(pool.streams[0]));
+        VMV_CUDA(cudaStreamSynchronize(pool.streams[1]));
         return VMV_OK;
     }
 
@@ -1177,31 +1294,48 @@ extern "C"
             vmv::LaunchEnv probe{};
             return make_launch_env(g_robots[robot], env, probe);
         }
-        const size_t qbytes = n * g_robots[robot].dof * sizeof(float), wbytes = ((n + 31) / 32) * 4;
-        DevBuf da, dbb, dw;
-        int rc = da.alloc(qbytes);
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        HostPathPool &pool = g_pools[device % kMaxDevices];
+        std::lock_guard<std::mutex> lock(pool.mutex);
+        const size_t dof = g_robots[robot].dof;
+        int rc = pool.init();
         if (rc == VMV_OK)
         {
-            rc = dbb.alloc(qbytes);
+            rc = pool.ensure(0, n * dof * sizeof(float));
         }
         if (rc == VMV_OK)
         {
-            rc = dw.alloc(wbytes);
+            rc = pool.ensure(1, n * dof * sizeof(float));
+        }
+        if (rc == VMV_OK)
+        {
+            rc = pool.ensure(2, ((n + 31) / 32) * 4);
         }
         if (rc != VMV_OK)
         {
             return rc;
         }
-        VMV_CUDA(cudaMemcpyAsync(da.p, a, qbytes, cudaMemcpyHostToDevice, nullptr));
-        VMV_CUDA(cudaMemcpyAsync(dbb.p, b, qbytes, cudaMemcpyHostToDevice, nullptr));
-        rc = vmv_validate_edges_dev(
-            robot, env, static_cast<const float *>(da.p), static_cast<const float *>(dbb.p), n, resolution, static_cast<uint32_t *>(dw.p), nullptr);
-        if (rc != VMV_OK)
+        float *da = static_cast<float *>(pool.buf[0]);
+        float *db = static_cast<float *>(pool.buf[1]);
+        uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
+        const size_t chunk = kChunkUnits / 4;
+        int k = 0;
+        for (size_t off = 0; off < n; off += chunk, ++k)
         {
-            return rc;
+            const size_t cnt = std::min(chunk, n - off);
+            cudaStream_t st = pool.streams[k & 1];
+            VMV_CUDA(cudaMemcpyAsync(da + off * dof, a + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
+            VMV_CUDA(cudaMemcpyAsync(db + off * dof, b + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
+            rc = vmv_validate_edges_dev(robot, env, da + off * dof, db + off * dof, cnt, resolution, dw + off / 32, st);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpyAsync(bits + off / 32, dw + off / 32, ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
         }
-        VMV_CUDA(cudaMemcpyAsync(bits, dw.p, wbytes, cudaMemcpyDeviceToHost, nullptr));
-        VMV_CUDA(cudaStreamSynchronize(nullptr));
+        VMV_CUDA(cudaStreamSynchronize(pool.streams[0]));
+        VMV_CUDA(cudaStreamSynchronize(pool.streams[1]));
         return VMV_OK;
     }
 
@@ -1305,5 +1439,11 @@ extern "C"
     uint64_t vmv_launch_count(void)
     {
         return g_launches.load();
+    }
+
+    int vmv_force_kernel_path(int path)
+    {
+        g_force_path.store(path);
+        return VMV_OK;
     }
 }

@@ -35,6 +35,8 @@ namespace vmv
         const float *blob;    // device copy of the packed environment
         uint32_t blob_bytes;  // multiple of 16
         float attach_tf[12];  // end-effector frame (in its body) * attachment offset, row-major 3x4
+        uint32_t n_objects;   // spheres + capsules + cuboids
+        bool primitives_only; // no heightfield / pointcloud / attachment
     };
 
     // shared-memory carve-up, identical on host (size computation) and device
@@ -78,6 +80,11 @@ namespace vmv
         {
             base[((BODY - 1) * 12 + K) * BLOCK] = v;
         }
+
+        template <int LINK, int AXIS>
+        __device__ __forceinline__ void bound(float)
+        {
+        }
     };
 
     struct RegSink
@@ -89,6 +96,11 @@ namespace vmv
         __device__ __forceinline__ void put(float v)
         {
             f[(BODY - 1) * 12 + K] = v;
+        }
+
+        template <int LINK, int AXIS>
+        __device__ __forceinline__ void bound(float)
+        {
         }
     };
 

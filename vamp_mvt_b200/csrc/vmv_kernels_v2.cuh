@@ -1,0 +1,471 @@
+// Block-cooperative configuration kernel (sm_100a) for environments made of primitives
+// (spheres, capsules, cuboids; at most 64 objects, no heightfield / pointcloud / attachment --
+// those take the generic per-thread path in vmv_kernels.cuh).
+//
+// The reference walks, per configuration, link by link: bounding sphere vs every object, and on a hit
+// every fine sphere of the link vs every object again (robots/panda.hh:5629-6010), then the
+// self-collision pairs.  Per-thread that is badly divergent (a free configuration runs 11 sphere
+// sweeps, a cluttered one 70).  Here a block of BLOCK configurations goes through the phases
+// together and the data-dependent work is re-distributed over the threads of the block:
+//
+//   A   thread = configuration: straight-line FK; frames -> shared-memory stash, bounding-sphere
+//       centres stay in registers.
+//   B1  thread = configuration, loops are uniform: for every object (record loaded once), every
+//       link's bounding sphere is tested (fully unrolled over links, centres/radii in registers).
+//       Result: per link a 64-bit mask of the objects its bounding sphere touches.
+//   B2  work items = (configuration, fine sphere) for every link with a non-empty mask, written to a
+//       shared queue and processed BLOCK at a time.  A fine sphere is only tested against the
+//       objects in its link's mask: a fine sphere lies inside its link's bounding sphere, so it can
+//       touch nothing else.  Verdicts are unchanged (the reference's own early-outs are likewise
+//       conservative culls).
+//   C1  thread = configuration: the allowed link pairs, unrolled, on the register-resident bounding
+//       centres -> records (configuration, pair) for the pairs whose bounding spheres overlap.
+//   C2  one warp per record: the lanes pose the fine spheres of both links once, then split the
+//       |A| x |B| sphere pairs.
+#pragma once
+#include <type_traits>
+
+#include "vmv_kernels.cuh"
+
+namespace vmv
+{
+    template <int I>
+    using IC = std::integral_constant<int, I>;
+
+    // ---- primitive margins (reference collision/sphere_*.hh); sign bit set <=> collision ----
+    __device__ __forceinline__ float margin_sphere(const float4 a, float x, float y, float z, float r)
+    {
+        const float dx = a.x - x, dy = a.y - y, dz = a.z - z;
+        const float rs = a.w + r;
+        return (dx * dx + dy * dy + dz * dz) - rs * rs;
+    }
+
+    __device__ __forceinline__ float margin_capsule(const float4 a, const float4 v, float x, float y, float z, float r)
+    {
+        const float dot = (x - a.x) * v.x + (y - a.y) * v.y + (z - a.z) * v.z;
+        const float cdf = fminf(fmaxf(dot * v.w, 0.F), 1.F);
+        const float dx = x - (a.x + v.x * cdf), dy = y - (a.y + v.y * cdf), dz = z - (a.z + v.z * cdf);
+        const float rs = r + a.w;
+        return (dx * dx + dy * dy + dz * dz) - rs * rs;
+    }
+
+    __device__ __forceinline__ float margin_zcapsule(const float4 a, const float4 v, float x, float y, float z, float r)
+    {
+        const float dot = (z - a.z) * v.x;
+        const float cdf = fminf(fmaxf(dot * v.y, 0.F), 1.F);
+        const float dx = x - a.x, dy = y - a.y, dz = z - (a.z + v.x * cdf);
+        const float rs = r + a.w;
+        return (dx * dx + dy * dy + dz * dz) - rs * rs;
+    }
+
+    __device__ __forceinline__ float
+    margin_cuboid(const float4 c, const float4 a1, const float4 a2, const float4 a3, float x, float y, float z, float rsq)
+    {
+        const float xs = x - c.x, ys = y - c.y, zs = z - c.z;
+        const float e1 = fmaxf(fabsf(a1.x * xs + a1.y * ys + a1.z * zs) - c.w, 0.F);
+        const float e2 = fmaxf(fabsf(a2.x * xs + a2.y * ys + a2.z * zs) - a1.w, 0.F);
+        const float e3 = fmaxf(fabsf(a3.x * xs + a3.y * ys + a3.z * zs) - a2.w, 0.F);
+        return (e1 * e1 + e2 * e2 + e3 * e3) - rsq;
+    }
+
+    __device__ __forceinline__ float
+    margin_zcuboid(const float4 c, const float4 ax, const float4 h, float x, float y, float z, float rsq)
+    {
+        const float xs = x - c.x, ys = y - c.y, zs = z - c.z;
+        const float e1 = fmaxf(fabsf(ax.x * xs + ax.y * ys) - h.x, 0.F);
+        const float e2 = fmaxf(fabsf(ax.z * xs + ax.w * ys) - h.y, 0.F);
+        const float e3 = fmaxf(fabsf(zs) - h.z, 0.F);
+        return (e1 * e1 + e2 * e2 + e3 * e3) - rsq;
+    }
+
+    // exact test of one sphere against object `og` (index into the concatenation
+    // spheres | capsules | z-capsules | cuboids | z-cuboids, each sorted by min_distance)
+    __device__ __forceinline__ bool object_hit(const float *__restrict__ E, uint32_t og, float x, float y, float z, float r)
+    {
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
+        if (og < H.n_spheres)
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_spheres) + 2 * og;
+            return sign_set(margin_sphere(p[0], x, y, z, r));
+        }
+        og -= H.n_spheres;
+        if (og < H.n_capsules)
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_capsules) + 3 * og;
+            return sign_set(margin_capsule(p[0], p[1], x, y, z, r));
+        }
+        og -= H.n_capsules;
+        if (og < H.n_zcapsules)
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_zcapsules) + 2 * og;
+            return sign_set(margin_zcapsule(p[0], p[1], x, y, z, r));
+        }
+        og -= H.n_zcapsules;
+        if (og < H.n_cuboids)
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_cuboids) + 4 * og;
+            return sign_set(margin_cuboid(p[0], p[1], p[2], p[3], x, y, z, r * r));
+        }
+        og -= H.n_cuboids;
+        const float4 *p = reinterpret_cast<const float4 *>(E + H.off_zcuboids) + 3 * og;
+        return sign_set(margin_zcuboid(p[0], p[1], p[2], x, y, z, r * r));
+    }
+
+    // Sink of phase A: frames -> shared stash, bounding centres -> registers.
+    template <int BLOCK, int NLINKS>
+    struct StashBoundSink
+    {
+        float *base;  // stash, already offset by threadIdx.x
+        float b[NLINKS][3];
+
+        template <int BODY, int K>
+        __device__ __forceinline__ void put(float v)
+        {
+            base[((BODY - 1) * 12 + K) * BLOCK] = v;
+        }
+
+        template <int LINK, int AXIS>
+        __device__ __forceinline__ void bound(float v)
+        {
+            b[LINK][AXIS] = v;
+        }
+    };
+
+    template <typename M, int BLOCK>
+    struct SmemLayoutV2
+    {
+        static constexpr int kStashFrames = (M::kBodies - 1) * 12;
+        // work queues sized for the worst case (every link of every configuration hit), 16 bits each
+        static constexpr int kItemCap = BLOCK * M::kSpheres;
+        static constexpr int kPairCap = BLOCK * (M::kPairs > 0 ? M::kPairs : 1);
+        static_assert(BLOCK <= 128 && M::kPairs < 512 && M::kTasks < 256, "16-bit work-item encoding");
+        static constexpr int kWarps = BLOCK / 32;
+        static constexpr int kScratchPerWarp = 64;  // float4 slots for posed spheres in phase C2
+
+        uint32_t off_tasks, off_links, off_pairs, off_stash, off_masks, off_items, off_pairq, off_scratch, off_flags, total;
+
+        __host__ __device__ static constexpr uint32_t align16(uint32_t v)
+        {
+            return (v + 15u) & ~15u;
+        }
+
+        __host__ __device__ explicit SmemLayoutV2(uint32_t blob_bytes)
+        {
+            uint32_t o = align16(blob_bytes);
+            off_tasks = o;
+            o += align16(M::kTasks * sizeof(SphereTask));
+            off_links = o;
+            o += align16(M::kLinks * sizeof(LinkInfo));
+            off_pairs = o;
+            o += align16((M::kPairs > 0 ? M::kPairs : 1) * sizeof(LinkPair));
+            off_stash = o;
+            o += kStashFrames * BLOCK * sizeof(float);
+            off_masks = o;
+            o += M::kLinks * BLOCK * sizeof(unsigned long long);
+            off_items = o;
+            o += align16(kItemCap * sizeof(uint16_t));
+            off_pairq = o;
+            o += align16(kPairCap * sizeof(uint16_t));
+            off_scratch = o;
+            o += kWarps * kScratchPerWarp * sizeof(float4);
+            off_flags = o;
+            o += align16(BLOCK * sizeof(uint32_t)) + 16;
+            total = o;
+        }
+    };
+
+    template <typename R, int BLOCK>
+    __global__ void __launch_bounds__(BLOCK)
+        k_validate_configs_v2(RobotDev robot, LaunchEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
+    {
+        using M = typename R::Model;
+        using Lay = SmemLayoutV2<M, BLOCK>;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        const Lay L(env.blob_bytes);
+        const int tid = threadIdx.x;
+
+        if (tid == 0)
+        {
+            mbar_init(&bar, 1);
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            tma_bulk_g2s(smem, env.blob, env.blob_bytes, &bar);
+        }
+        {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + L.off_tasks);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(robot.tasks);
+            for (int i = tid; i < M::kTasks * 8; i += BLOCK)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_links);
+            src = reinterpret_cast<const uint32_t *>(robot.links);
+            for (int i = tid; i < M::kLinks * 4; i += BLOCK)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_pairs);
+            src = reinterpret_cast<const uint32_t *>(robot.pairs);
+            for (int i = tid; i < M::kPairs * 2; i += BLOCK)
+            {
+                dst[i] = __ldg(src + i);
+            }
+        }
+        const float *E = reinterpret_cast<const float *>(smem);
+        const SphereTask *tasks = reinterpret_cast<const SphereTask *>(smem + L.off_tasks);
+        const LinkInfo *links = reinterpret_cast<const LinkInfo *>(smem + L.off_links);
+        const LinkPair *pairs = reinterpret_cast<const LinkPair *>(smem + L.off_pairs);
+        float *stash = reinterpret_cast<float *>(smem + L.off_stash);
+        unsigned long long *masks = reinterpret_cast<unsigned long long *>(smem + L.off_masks);
+        uint16_t *items = reinterpret_cast<uint16_t *>(smem + L.off_items);
+        uint16_t *pairq = reinterpret_cast<uint16_t *>(smem + L.off_pairq);
+        float4 *scratch = reinterpret_cast<float4 *>(smem + L.off_scratch);
+        volatile uint32_t *invalid = reinterpret_cast<volatile uint32_t *>(smem + L.off_flags);
+        uint32_t *counters = reinterpret_cast<uint32_t *>(smem + L.off_flags + Lay::align16(BLOCK * sizeof(uint32_t)));
+        // counters[0] = number of fine items, counters[1] = number of pair records
+
+        // ---- A: FK ------------------------------------------------------------------------------
+        const size_t i = static_cast<size_t>(blockIdx.x) * BLOCK + tid;
+        const bool has = i < n;
+        float cfg[M::kDof];
+#pragma unroll
+        for (int j = 0; j < M::kDof; ++j)
+        {
+            cfg[j] = has ? __ldg(q + i * M::kDof + j) : 0.F;
+        }
+        StashBoundSink<BLOCK, M::kLinks> sink;
+        sink.base = stash + tid;
+        R::frames(cfg, sink);
+        invalid[tid] = has ? 0u : 1u;
+        if (tid < 2)
+        {
+            counters[tid] = 0;
+        }
+
+        __syncthreads();  // tables, flags, counters
+        mbar_wait(&bar, 0);
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
+
+        // ---- B1: bounding spheres vs every object, object-major, links unrolled ------------------
+        uint32_t mlo[M::kLinks], mhi[M::kLinks];
+#pragma unroll
+        for (int l = 0; l < M::kLinks; ++l)
+        {
+            mlo[l] = 0u, mhi[l] = 0u;
+        }
+        if (has)
+        {
+            uint32_t og = 0;
+            {
+                const float4 *p = reinterpret_cast<const float4 *>(E + H.off_spheres);
+                for (uint32_t k = 0; k < H.n_spheres; ++k, ++og)
+                {
+                    const float4 a = p[2 * k];
+                    const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
+                    R::for_each_link(
+                        [&](auto l, float br, int, int)
+                        {
+                            constexpr int li = decltype(l)::value;
+                            const bool hit = sign_set(margin_sphere(a, sink.b[li][0], sink.b[li][1], sink.b[li][2], br));
+                            mlo[li] |= hit ? blo : 0u;
+                            mhi[li] |= hit ? bhi : 0u;
+                        });
+                }
+            }
+            {
+                const float4 *p = reinterpret_cast<const float4 *>(E + H.off_capsules);
+                for (uint32_t k = 0; k < H.n_capsules; ++k, ++og)
+                {
+                    const float4 a = p[3 * k], v = p[3 * k + 1];
+                    const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
+                    R::for_each_link(
+                        [&](auto l, float br, int, int)
+                        {
+                            constexpr int li = decltype(l)::value;
+                            const bool hit = sign_set(margin_capsule(a, v, sink.b[li][0], sink.b[li][1], sink.b[li][2], br));
+                            mlo[li] |= hit ? blo : 0u;
+                            mhi[li] |= hit ? bhi : 0u;
+                        });
+                }
+            }
+            {
+                const float4 *p = reinterpret_cast<const float4 *>(E + H.off_zcapsules);
+                for (uint32_t k = 0; k < H.n_zcapsules; ++k, ++og)
+                {
+                    const float4 a = p[2 * k], v = p[2 * k + 1];
+                    const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
+                    R::for_each_link(
+                        [&](auto l, float br, int, int)
+                        {
+                            constexpr int li = decltype(l)::value;
+                            const bool hit = sign_set(margin_zcapsule(a, v, sink.b[li][0], sink.b[li][1], sink.b[li][2], br));
+                            mlo[li] |= hit ? blo : 0u;
+                            mhi[li] |= hit ? bhi : 0u;
+                        });
+                }
+            }
+            {
+                const float4 *p = reinterpret_cast<const float4 *>(E + H.off_cuboids);
+                for (uint32_t k = 0; k < H.n_cuboids; ++k, ++og)
+                {
+                    const float4 c = p[4 * k], a1 = p[4 * k + 1], a2 = p[4 * k + 2], a3 = p[4 * k + 3];
+                    const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
+                    R::for_each_link(
+                        [&](auto l, float br, int, int)
+                        {
+                            constexpr int li = decltype(l)::value;
+                            const bool hit =
+                                sign_set(margin_cuboid(c, a1, a2, a3, sink.b[li][0], sink.b[li][1], sink.b[li][2], br * br));
+                            mlo[li] |= hit ? blo : 0u;
+                            mhi[li] |= hit ? bhi : 0u;
+                        });
+                }
+            }
+            {
+                const float4 *p = reinterpret_cast<const float4 *>(E + H.off_zcuboids);
+                for (uint32_t k = 0; k < H.n_zcuboids; ++k, ++og)
+                {
+                    const float4 c = p[3 * k], ax = p[3 * k + 1], h = p[3 * k + 2];
+                    const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
+                    R::for_each_link(
+                        [&](auto l, float br, int, int)
+                        {
+                            constexpr int li = decltype(l)::value;
+                            const bool hit =
+                                sign_set(margin_zcuboid(c, ax, h, sink.b[li][0], sink.b[li][1], sink.b[li][2], br * br));
+                            mlo[li] |= hit ? blo : 0u;
+                            mhi[li] |= hit ? bhi : 0u;
+                        });
+                }
+            }
+
+            // enqueue fine-sphere items of the links whose bounding sphere touches something
+            R::for_each_link(
+                [&](auto l, float, int n_fine, int first_task)
+                {
+                    constexpr int li = decltype(l)::value;
+                    if ((mlo[li] | mhi[li]) != 0u)
+                    {
+                        masks[li * BLOCK + tid] = (static_cast<unsigned long long>(mhi[li]) << 32) | mlo[li];
+                        const uint32_t base = atomicAdd(&counters[0], static_cast<uint32_t>(n_fine));
+                        for (int k = 0; k < n_fine; ++k)
+                        {
+                            items[base + k] = static_cast<uint16_t>((tid << 8) | (first_task + k));
+                        }
+                    }
+                });
+        }
+        __syncthreads();
+
+        // ---- B2: fine spheres, one item per thread per round --------------------------------------
+        {
+            const uint32_t n_items = counters[0];
+            for (uint32_t it = tid; it < n_items; it += BLOCK)
+            {
+                const uint32_t item = items[it];
+                const int c = item >> 8;
+                if (invalid[c])
+                {
+                    continue;
+                }
+                const SphereTask t = tasks[item & 255u];
+                float x, y, z;
+                task_centre<BLOCK>(t, stash + c, x, y, z);
+                unsigned long long m = masks[t.link * BLOCK + c];
+                while (m != 0ull)
+                {
+                    const int o = __ffsll(static_cast<long long>(m)) - 1;
+                    m &= m - 1ull;
+                    if (object_hit(E, static_cast<uint32_t>(o), x, y, z, t.r))
+                    {
+                        invalid[c] = 1u;
+                        break;
+                    }
+                }
+            }
+        }
+
+        // ---- C1: allowed link pairs on the bounding spheres ---------------------------------------
+        if (has && !invalid[tid])
+        {
+            float brad[M::kLinks];
+            R::for_each_link([&](auto l, float br, int, int) { brad[decltype(l)::value] = br; });
+            R::for_each_pair(
+                [&](auto pi, auto la, auto lb)
+                {
+                    constexpr int a = decltype(la)::value, b = decltype(lb)::value;
+                    const float dx = sink.b[a][0] - sink.b[b][0], dy = sink.b[a][1] - sink.b[b][1], dz = sink.b[a][2] - sink.b[b][2];
+                    const float rs = brad[a] + brad[b];
+                    if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                    {
+                        const uint32_t slot = atomicAdd(&counters[1], 1u);
+                        pairq[slot] = static_cast<uint16_t>((tid << 9) | decltype(pi)::value);
+                    }
+                });
+        }
+        __syncthreads();
+
+        // ---- C2: fine sphere pairs, one warp per (configuration, pair) record ----------------------
+        {
+            const uint32_t n_rec = counters[1];
+            const int lane = tid & 31, warp = tid >> 5;
+            float4 *my = scratch + warp * Lay::kScratchPerWarp;
+            for (uint32_t r = warp; r < n_rec; r += Lay::kWarps)
+            {
+                const uint32_t rec = pairq[r];
+                const int c = rec >> 9;
+                if (invalid[c])
+                {
+                    continue;  // warp-uniform: every lane reads the same flag
+                }
+                const LinkPair p = pairs[rec & 0x1ffu];
+                const LinkInfo A = links[p.a], B = links[p.b];
+                const int na = A.n_spheres, nb = B.n_spheres;
+                bool hit = false;
+                // tile link b in chunks that fit the scratch next to all of link a's spheres
+                for (int b0 = 0; b0 < nb && !hit; b0 += Lay::kScratchPerWarp / 2)
+                {
+                    const int nbc = min(nb - b0, Lay::kScratchPerWarp / 2);
+                    for (int a0 = 0; a0 < na && !hit; a0 += Lay::kScratchPerWarp / 2)
+                    {
+                        const int nac = min(na - a0, Lay::kScratchPerWarp / 2);
+                        __syncwarp();
+                        for (int s = lane; s < nac + nbc; s += 32)
+                        {
+                            const int ti = s < nac ? A.bound_task + 1 + a0 + s : B.bound_task + 1 + b0 + (s - nac);
+                            const SphereTask t = tasks[ti];
+                            float x, y, z;
+                            task_centre<BLOCK>(t, stash + c, x, y, z);
+                            my[s] = make_float4(x, y, z, t.r);
+                        }
+                        __syncwarp();
+                        bool h = false;
+                        for (int k = lane; k < nac * nbc; k += 32)
+                        {
+                            const float4 sa = my[k / nbc], sb = my[nac + k % nbc];
+                            const float ex = sa.x - sb.x, ey = sa.y - sb.y, ez = sa.z - sb.z;
+                            const float rr = sa.w + sb.w;
+                            h |= sign_set((ex * ex + ey * ey + ez * ez) - rr * rr);
+                        }
+                        hit = __any_sync(0xffffffffu, h);
+                    }
+                }
+                if (hit && lane == 0)
+                {
+                    invalid[c] = 1u;
+                }
+            }
+        }
+        __syncthreads();
+
+        const bool valid = has && !invalid[tid];
+        const uint32_t word = __ballot_sync(0xffffffffu, valid);
+        if ((tid & 31) == 0 && has)
+        {
+            bits[i >> 5] = word;
+        }
+    }
+}  // namespace vmv
