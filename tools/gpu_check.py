@@ -24,6 +24,9 @@ def main():
             oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
             N = 20000
             q = scenes.random_configs(robot, N, seed=1)
+            # a quarter of the configurations leave the joint limits (exercises the unpruned self-collision path)
+            rng = np.random.default_rng(5)
+            q[: N // 4] += rng.uniform(-0.6, 0.6, size=(N // 4, q.shape[1])).astype(np.float32)
             from vamp_mvt_b200 import _lib
             _lib.lib().vmv_force_kernel_path(1)
             got1 = R.validate_batch(q, env)

@@ -351,6 +351,105 @@ def build_model(name, urdf_path, srdf_path):
     return model
 
 
+
+# --------------------------------------------------------------------------------------------
+# self-collision analysis: which sphere pairs can ever touch, which link pairs nearly always overlap
+# --------------------------------------------------------------------------------------------
+BOX_MARGIN = 0.02      # the pruned lists are valid for joints within [lower - m, upper + m]
+INLINE_FREQUENCY = 0.5  # link pairs whose bounding spheres overlap more often than this are checked
+                        # unconditionally (fine spheres, pruned list) by every thread
+
+
+def numeric_frames(model, q):
+    """Body frames for configurations q [N, dof] (float64) -> list of [N, 4, 4]."""
+    q = np.asarray(q, float)
+    N = len(q)
+    F = []
+    for b in model["bodies"]:
+        if b["parent"] < 0:
+            F.append(np.tile(np.eye(4), (N, 1, 1)))
+            continue
+        pre = np.vstack([np.array(b["T_pre"]), [0, 0, 0, 1]])
+        ax = np.array(b["axis"], float)
+        ax = ax / np.linalg.norm(ax)
+        v = q[:, b["dof"]]
+        J = np.tile(np.eye(4), (N, 1, 1))
+        if b["jtype"] == "revolute":
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            J[:, :3, :3] = np.eye(3) + np.sin(v)[:, None, None] * K + (1 - np.cos(v))[:, None, None] * (K @ K)
+        else:
+            J[:, :3, 3] = ax * v[:, None]
+        F.append(F[b["parent"]] @ pre @ J)
+    return F
+
+
+def body_chain(model, a, b):
+    """Bodies (with a joint) on the tree path between bodies a and b, split by side."""
+    def ancestors(x):
+        out = [x]
+        while model["bodies"][x]["parent"] >= 0:
+            x = model["bodies"][x]["parent"]
+            out.append(x)
+        return out
+
+    pa, pb = ancestors(a), ancestors(b)
+    common = next(x for x in pa if x in pb)
+    side_a = pa[: pa.index(common)]
+    side_b = pb[: pb.index(common)]
+    return side_a, side_b
+
+
+def analyze_self_pairs(model, seed=0):
+    rng = np.random.default_rng(seed)
+    L, Bd = model["links"], model["bodies"]
+    lo = np.array(model["lower"], float)
+    rg = np.array(model["range"], float)
+    q = lo + rg * rng.random((20000, model["dof"]))
+    F = numeric_frames(model, q)
+    centre = [(F[l["body"]] @ np.array(l["bound"][:3] + [1.0]))[:, :3] for l in L]
+    info = []
+    for a, b in model["self_pairs"]:
+        d = np.linalg.norm(centre[a] - centre[b], axis=1)
+        freq = float((d < L[a]["bound"][3] + L[b]["bound"][3]).mean())
+        side_a, side_b = body_chain(model, L[a]["body"], L[b]["body"])
+        chain = side_a + side_b
+        entry = dict(a=a, b=b, frequency=freq, chain_dofs=[Bd[x]["dof"] for x in chain], pruned=None)
+        if 1 <= len(chain) <= 2:
+            n = 4096 if len(chain) == 1 else 720
+            grids = []
+            for x in chain:
+                dof = Bd[x]["dof"]
+                grids.append(np.linspace(lo[dof] - BOX_MARGIN, lo[dof] + rg[dof] + BOX_MARGIN, n))
+            mesh = np.meshgrid(*grids, indexing="ij")
+            qq = np.zeros((mesh[0].size, model["dof"]))
+            for x, g in zip(chain, mesh):
+                qq[:, Bd[x]["dof"]] = g.ravel()
+            Fg = numeric_frames(model, qq)
+            Fa, Fb = Fg[L[a]["body"]], Fg[L[b]["body"]]
+            pa = [(Fa @ np.array(s[:3] + [1.0]))[:, :3] for s in L[a]["spheres"]]
+            pb = [(Fb @ np.array(s[:3] + [1.0]))[:, :3] for s in L[b]["spheres"]]
+            # Lipschitz slack: between grid nodes a sphere on the far side of joint k moves at most
+            # step_k/2 * (its distance from the joint origin) per axis of the grid
+            slack = 1e-4
+            for x, g in zip(chain, grids):
+                step = g[1] - g[0]
+                origin = Fg[x][:, :3, 3]
+                far = pa if x in side_a else pb
+                lever = max(float(np.linalg.norm(p - origin, axis=1).max()) for p in far) if Bd[x]["jtype"] == "revolute" else 1.0
+                slack += 0.5 * step * lever
+            keep = []
+            for i, sa in enumerate(L[a]["spheres"]):
+                for j, sb in enumerate(L[b]["spheres"]):
+                    dmin = float((np.linalg.norm(pa[i] - pb[j], axis=1)).min()) - (sa[3] + sb[3])
+                    if dmin < slack:
+                        keep.append([i, j])
+            entry["pruned"] = keep
+            entry["prune_slack"] = slack
+        entry["inline"] = bool(freq > INLINE_FREQUENCY and entry["pruned"] is not None)
+        info.append(entry)
+    return info
+
+
 # --------------------------------------------------------------------------------------------
 # symbolic tracer
 # --------------------------------------------------------------------------------------------
@@ -553,6 +652,34 @@ def emit_cuda(model, tr, frames):
         for n in b3:
             need(n)
 
+    # fine-sphere positions needed by the inline self-collision tests
+    sphere_nodes = {}
+
+    def sphere_pos(link, k):
+        key = (link, k)
+        if key not in sphere_nodes:
+            l = model["links"][link]
+            F = frames[l["body"]]
+            c = [tr.const(v) for v in l["spheres"][k][:3]]
+            sphere_nodes[key] = [
+                tr.add(tr.add(tr.add(tr.mul(F[i][0], c[0]), tr.mul(F[i][1], c[1])), tr.mul(F[i][2], c[2])), F[i][3])
+                for i in range(3)
+            ]
+        return sphere_nodes[key]
+
+    inline_tests = []  # (nodesA, nodesB, rs2 literal)
+    for e in model.get("self_pair_info", []):
+        if not e["inline"]:
+            continue
+        for i, j in e["pruned"]:
+            ra = model["links"][e["a"]]["spheres"][i][3]
+            rb = model["links"][e["b"]]["spheres"][j][3]
+            rs = np.float32(np.float32(ra) + np.float32(rb))
+            inline_tests.append((sphere_pos(e["a"], i), sphere_pos(e["b"], j), float(np.float32(rs * rs))))
+    for pa, pb, _ in inline_tests:
+        for n in pa + pb:
+            need(n)
+
     def lit(v):
         f = float(np.float32(v))
         s = repr(f)
@@ -585,6 +712,9 @@ def emit_cuda(model, tr, frames):
                 uses[n] = uses.get(n, 0) + 1
     for b3 in bounds:
         for n in b3:
+            uses[n] = uses.get(n, 0) + 1
+    for pa, pb, _ in inline_tests:
+        for n in pa + pb:
             uses[n] = uses.get(n, 0) + 1
 
     fused = set()
@@ -654,6 +784,26 @@ def emit_cuda(model, tr, frames):
     for li, b3 in enumerate(bounds):
         for ax in range(3):
             out.append(f"    sink.template bound<{li}, {ax}>({operand(b3[ax])});")
+    # pruned sphere-pair lists are valid inside the (slightly widened) joint box
+    box_dofs = sorted({d for e in model.get("self_pair_info", []) if e["pruned"] is not None for d in e["chain_dofs"]})
+    conds = []
+    for d in box_dofs:
+        lo_d = model["lower"][d] - BOX_MARGIN
+        hi_d = model["lower"][d] + model["range"][d] + BOX_MARGIN
+        conds.append(f"(q[{d}] >= {lit(lo_d)}) & (q[{d}] <= {lit(hi_d)})")
+    out.append("    // the statically pruned self-collision lists hold inside the joint limits (+ margin)")
+    out.append("    sink.in_box(" + (" & ".join(conds) if conds else "true") + ");")
+    out.append("    // link pairs whose bounding spheres (nearly) always overlap: kinematically feasible fine pairs, ungated")
+    out.append("    bool self_hit = false;")
+    for pa, pb, rs2 in inline_tests:
+        dx = f"({operand(pa[0])} - {operand(pb[0])})"
+        dy = f"({operand(pa[1])} - {operand(pb[1])})"
+        dz = f"({operand(pa[2])} - {operand(pb[2])})"
+        out.append(
+            f"    {{ const float dx = {dx}, dy = {dy}, dz = {dz}; "
+            f"self_hit |= vmv::sign_set(((dx * dx + dy * dy) + dz * dz) - {lit(rs2)}); }}"
+        )
+    out.append("    sink.self_inline(self_hit);")
     out.append("}")
     out.append("")
     out.append("}}  // namespace vmv::gen")
@@ -730,14 +880,36 @@ def emit_tables(model):
     out.append("")
     N = name.upper()
     out.append("// X-macros for fully unrolled device code: LINKS(X) -> X(link, bound_radius, n_spheres, first_fine_task);")
-    out.append("// PAIRS(X) -> X(pair_index, link_a, link_b)")
+    out.append("// PAIRS(X) -> X(pair_index, link_a, link_b, checked_inline)")
     out.append(f"#define VMV_{N}_LINKS(X) \\")
     for li, l in enumerate(L):
         out.append(f"    X({li}, {f(l['bound'][3])}, {len(l['spheres'])}, {btask[li] + 1}) \\")
     out.append("")
+    info = model.get("self_pair_info") or [dict(inline=False, pruned=None) for _ in model["self_pairs"]]
     out.append(f"#define VMV_{N}_PAIRS(X) \\")
     for pi, (a, b) in enumerate(model["self_pairs"]):
-        out.append(f"    X({pi}, {a}, {b}) \\")
+        out.append(f"    X({pi}, {a}, {b}, {1 if info[pi]['inline'] else 0}) \\")
+    out.append("")
+    # statically pruned sphere-pair lists (task indices), valid inside the joint box
+    lists, pinfo = [], []
+    for pi, (a, b) in enumerate(model["self_pairs"]):
+        e = info[pi]
+        if e["pruned"] is None:
+            pinfo.append((0, -1, 0))
+        else:
+            pinfo.append((len(lists), len(e["pruned"]), 1 if e["inline"] else 0))
+            for i, j in e["pruned"]:
+                lists.append((btask[a] + 1 + i, btask[b] + 1 + j))
+    out.append("// per pair: {offset into pair_lists, count (-1 = no pruned list: full cross product), inline flag}")
+    out.append(f"static const vmv::PairInfo {name}_pair_info_host[{max(1, len(pinfo))}] = {{")
+    for o, c, f_ in pinfo or [(0, -1, 0)]:
+        out.append(f"    {{{o}, {c}, {f_}}},")
+    out.append("};")
+    out.append(f"static const vmv::SpherePair {name}_pair_lists_host[{max(1, len(lists))}] = {{")
+    for ta, tb in lists or [(0, 0)]:
+        out.append(f"    {{{ta}, {tb}}},")
+    out.append("};")
+    out.append(f"static const int {name}_pair_lists_count = {len(lists)};")
     out.append("")
     out.append(f"static const int {name}_attach_links_host[{max(1, len(model['attach_links']))}] = {{" + ", ".join(str(a) for a in (model["attach_links"] or [0])) + "};")
     ee = np.array(model["end_effector"]["T"]).reshape(-1)
@@ -759,6 +931,7 @@ def main():
     for name in args.robots:
         res = Path(args.resources) / name
         model = build_model(name, res / f"{name}_spherized.urdf", res / f"{name}.srdf")
+        model["self_pair_info"] = analyze_self_pairs(model)
         tr, frames = trace_frames(model)
         code, stats = emit_cuda(model, tr, frames)
         model["fk_ops"] = stats

@@ -28,4 +28,16 @@ namespace vmv
     {
         int a, b;
     };
+
+    // Statically pruned fine-sphere pairs of a link pair (robot compiler: pairs that can touch for
+    // some joint values inside the joint limits); count < 0: no list, use the full cross product.
+    struct PairInfo
+    {
+        int offset, count, inline_checked;
+    };
+
+    struct SpherePair
+    {
+        uint8_t task_a, task_b;
+    };
 }  // namespace vmv

@@ -76,7 +76,7 @@ namespace
         }                                                                             \
     };
 #define VMV_X_LINK(l, r, n, t) f(vmv::IC<l>{}, r, n, t);
-#define VMV_X_PAIR(p, a, b) f(vmv::IC<p>{}, vmv::IC<a>{}, vmv::IC<b>{});
+#define VMV_X_PAIR(p, a, b, inl) f(vmv::IC<p>{}, vmv::IC<a>{}, vmv::IC<b>{}, vmv::IC<inl>{});
 #define VMV_panda_LINKS_DISPATCH VMV_PANDA_LINKS(VMV_X_LINK)
 #define VMV_panda_PAIRS_DISPATCH VMV_PANDA_PAIRS(VMV_X_PAIR)
 #define VMV_ur5_LINKS_DISPATCH VMV_UR5_LINKS(VMV_X_LINK)
@@ -101,6 +101,9 @@ namespace
         const vmv::LinkPair *pairs;
         const int *attach_links;
         const float *ee_tf;
+        const vmv::PairInfo *pair_info;
+        const vmv::SpherePair *pair_lists;
+        int n_pair_lists;
     };
 
 #define VMV_ROBOT_HOST(NAME)                                                                                  \
@@ -110,7 +113,8 @@ namespace
             vmv::gen::NAME##_model::kResolution, vmv::gen::NAME##_model::kAttachLinks,                        \
             vmv::gen::NAME##_model::kEeBody, vmv::gen::NAME##_lower, vmv::gen::NAME##_range,                  \
             vmv::gen::NAME##_tasks_host, vmv::gen::NAME##_links_host, vmv::gen::NAME##_pairs_host,            \
-            vmv::gen::NAME##_attach_links_host, vmv::gen::NAME##_ee_tf_host                                   \
+            vmv::gen::NAME##_attach_links_host, vmv::gen::NAME##_ee_tf_host, vmv::gen::NAME##_pair_info_host, \
+            vmv::gen::NAME##_pair_lists_host, vmv::gen::NAME##_pair_lists_count                               \
     }
     const RobotHost g_robots[VMV_N_ROBOTS] = {
         VMV_ROBOT_HOST(panda), VMV_ROBOT_HOST(ur5), VMV_ROBOT_HOST(fetch), VMV_ROBOT_HOST(baxter)};
@@ -153,6 +157,13 @@ namespace
             VMV_CUDA(cudaMalloc(&p, na * sizeof(int)));
             VMV_CUDA(cudaMemcpy(p, r.attach_links, na * sizeof(int), cudaMemcpyHostToDevice));
             t.dev.attach_links = static_cast<const int *>(p);
+            VMV_CUDA(cudaMalloc(&p, np * sizeof(vmv::PairInfo)));
+            VMV_CUDA(cudaMemcpy(p, r.pair_info, np * sizeof(vmv::PairInfo), cudaMemcpyHostToDevice));
+            t.dev.pair_info = static_cast<const vmv::PairInfo *>(p);
+            const int nl = std::max(1, r.n_pair_lists);
+            VMV_CUDA(cudaMalloc(&p, nl * sizeof(vmv::SpherePair)));
+            VMV_CUDA(cudaMemcpy(p, r.pair_lists, nl * sizeof(vmv::SpherePair), cudaMemcpyHostToDevice));
+            t.dev.pair_lists = static_cast<const vmv::SpherePair *>(p);
             t.ready = true;
         }
         out = t.dev;

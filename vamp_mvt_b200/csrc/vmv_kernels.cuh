@@ -28,6 +28,8 @@ namespace vmv
         const LinkInfo *links;    // kLinks
         const LinkPair *pairs;    // kPairs
         const int *attach_links;  // kAttachLinks
+        const PairInfo *pair_info;    // kPairs
+        const SpherePair *pair_lists; // statically pruned fine pairs (global memory)
     };
 
     struct LaunchEnv
@@ -85,6 +87,14 @@ namespace vmv
         __device__ __forceinline__ void bound(float)
         {
         }
+
+        __device__ __forceinline__ void in_box(bool)
+        {
+        }
+
+        __device__ __forceinline__ void self_inline(bool)
+        {
+        }
     };
 
     struct RegSink
@@ -100,6 +110,14 @@ namespace vmv
 
         template <int LINK, int AXIS>
         __device__ __forceinline__ void bound(float)
+        {
+        }
+
+        __device__ __forceinline__ void in_box(bool)
+        {
+        }
+
+        __device__ __forceinline__ void self_inline(bool)
         {
         }
     };

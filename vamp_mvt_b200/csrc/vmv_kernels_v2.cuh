@@ -129,6 +129,18 @@ namespace vmv
         {
             b[LINK][AXIS] = v;
         }
+
+        bool inbox, self_hit;
+
+        __device__ __forceinline__ void in_box(bool v)
+        {
+            inbox = v;
+        }
+
+        __device__ __forceinline__ void self_inline(bool v)
+        {
+            self_hit = v;
+        }
     };
 
     template <typename M, int BLOCK>
@@ -169,7 +181,7 @@ namespace vmv
             off_scratch = o;
             o += kWarps * kScratchPerWarp * sizeof(float4);
             off_flags = o;
-            o += align16(BLOCK * sizeof(uint32_t)) + 16;
+            o += 2 * align16(BLOCK * sizeof(uint32_t)) + 16;
             total = o;
         }
     };
@@ -224,7 +236,8 @@ namespace vmv
         uint16_t *pairq = reinterpret_cast<uint16_t *>(smem + L.off_pairq);
         float4 *scratch = reinterpret_cast<float4 *>(smem + L.off_scratch);
         volatile uint32_t *invalid = reinterpret_cast<volatile uint32_t *>(smem + L.off_flags);
-        uint32_t *counters = reinterpret_cast<uint32_t *>(smem + L.off_flags + Lay::align16(BLOCK * sizeof(uint32_t)));
+        volatile uint32_t *inbox = invalid + BLOCK;
+        uint32_t *counters = reinterpret_cast<uint32_t *>(smem + L.off_flags + 2 * Lay::align16(BLOCK * sizeof(uint32_t)));
         // counters[0] = number of fine items, counters[1] = number of pair records
 
         // ---- A: FK ------------------------------------------------------------------------------
@@ -239,7 +252,10 @@ namespace vmv
         StashBoundSink<BLOCK, M::kLinks> sink;
         sink.base = stash + tid;
         R::frames(cfg, sink);
-        invalid[tid] = has ? 0u : 1u;
+        // the ungated fine pairs of the always-overlapping link pairs were evaluated with the FK;
+        // their (pruned) list is only valid inside the joint box
+        invalid[tid] = (has && !(sink.inbox && sink.self_hit)) ? 0u : 1u;
+        inbox[tid] = sink.inbox ? 1u : 0u;
         if (tid < 2)
         {
             counters[tid] = 0;
@@ -394,9 +410,13 @@ namespace vmv
             float brad[M::kLinks];
             R::for_each_link([&](auto l, float br, int, int) { brad[decltype(l)::value] = br; });
             R::for_each_pair(
-                [&](auto pi, auto la, auto lb)
+                [&](auto pi, auto la, auto lb, auto inl)
                 {
                     constexpr int a = decltype(la)::value, b = decltype(lb)::value;
+                    if (decltype(inl)::value != 0 && sink.inbox)
+                    {
+                        return;  // already checked in phase A
+                    }
                     const float dx = sink.b[a][0] - sink.b[b][0], dy = sink.b[a][1] - sink.b[b][1], dz = sink.b[a][2] - sink.b[b][2];
                     const float rs = brad[a] + brad[b];
                     if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
@@ -425,6 +445,28 @@ namespace vmv
                 const LinkInfo A = links[p.a], B = links[p.b];
                 const int na = A.n_spheres, nb = B.n_spheres;
                 bool hit = false;
+                const PairInfo pinfo = robot.pair_info[rec & 0x1ffu];
+                if (pinfo.count >= 0 && inbox[c])
+                {
+                    // statically pruned list: one feasible sphere pair per lane
+                    bool h = false;
+                    for (int k = lane; k < pinfo.count; k += 32)
+                    {
+                        const SpherePair sp = robot.pair_lists[pinfo.offset + k];
+                        const SphereTask ta = tasks[sp.task_a], tb = tasks[sp.task_b];
+                        float ax, ay, az, bx, by, bz;
+                        task_centre<BLOCK>(ta, stash + c, ax, ay, az);
+                        task_centre<BLOCK>(tb, stash + c, bx, by, bz);
+                        const float ex = ax - bx, ey = ay - by, ez = az - bz;
+                        const float rr = ta.r + tb.r;
+                        h |= sign_set((ex * ex + ey * ey + ez * ez) - rr * rr);
+                    }
+                    if (__any_sync(0xffffffffu, h) && lane == 0)
+                    {
+                        invalid[c] = 1u;
+                    }
+                    continue;
+                }
                 // tile link b in chunks that fit the scratch next to all of link a's spheres
                 for (int b0 = 0; b0 < nb && !hit; b0 += Lay::kScratchPerWarp / 2)
                 {
