@@ -164,6 +164,7 @@ namespace
             VMV_CUDA(cudaMalloc(&p, nl * sizeof(vmv::SpherePair)));
             VMV_CUDA(cudaMemcpy(p, r.pair_lists, nl * sizeof(vmv::SpherePair), cudaMemcpyHostToDevice));
             t.dev.pair_lists = static_cast<const vmv::SpherePair *>(p);
+            t.dev.n_pair_lists = r.n_pair_lists;
             t.ready = true;
         }
         out = t.dev;

@@ -29,7 +29,8 @@ namespace vmv
         const LinkPair *pairs;    // kPairs
         const int *attach_links;  // kAttachLinks
         const PairInfo *pair_info;    // kPairs
-        const SpherePair *pair_lists; // statically pruned fine pairs (global memory)
+        const SpherePair *pair_lists; // statically pruned fine pairs
+        int n_pair_lists;
     };
 
     struct LaunchEnv

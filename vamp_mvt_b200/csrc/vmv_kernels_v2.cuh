@@ -151,10 +151,12 @@ namespace vmv
         static constexpr int kItemCap = BLOCK * M::kSpheres;
         static constexpr int kPairCap = BLOCK * (M::kPairs > 0 ? M::kPairs : 1);
         static_assert(BLOCK <= 128 && M::kPairs < 512 && M::kTasks < 256, "16-bit work-item encoding");
-        static constexpr int kWarps = BLOCK / 32;
-        static constexpr int kScratchPerWarp = 64;  // float4 slots for posed spheres in phase C2
+        static constexpr int kGroups = BLOCK / 8;     // phase C2 works in groups of 8 lanes
+        static constexpr int kScratchPerGroup = 32;   // float4 slots for posed spheres (16 + 16)
+        static constexpr int kMaxPairLists = 256;     // statically pruned sphere pairs kept in smem
 
-        uint32_t off_tasks, off_links, off_pairs, off_stash, off_masks, off_items, off_pairq, off_scratch, off_flags, total;
+        uint32_t off_tasks, off_links, off_pairs, off_pinfo, off_plists, off_stash, off_masks, off_items, off_pairq, off_scratch,
+            off_flags, total;
 
         __host__ __device__ static constexpr uint32_t align16(uint32_t v)
         {
@@ -170,6 +172,10 @@ namespace vmv
             o += align16(M::kLinks * sizeof(LinkInfo));
             off_pairs = o;
             o += align16((M::kPairs > 0 ? M::kPairs : 1) * sizeof(LinkPair));
+            off_pinfo = o;
+            o += align16((M::kPairs > 0 ? M::kPairs : 1) * sizeof(PairInfo));
+            off_plists = o;
+            o += align16(kMaxPairLists * sizeof(SpherePair));
             off_stash = o;
             o += kStashFrames * BLOCK * sizeof(float);
             off_masks = o;
@@ -179,7 +185,7 @@ namespace vmv
             off_pairq = o;
             o += align16(kPairCap * sizeof(uint16_t));
             off_scratch = o;
-            o += kWarps * kScratchPerWarp * sizeof(float4);
+            o += kGroups * kScratchPerGroup * sizeof(float4);
             off_flags = o;
             o += 2 * align16(BLOCK * sizeof(uint32_t)) + 16;
             total = o;
@@ -225,8 +231,22 @@ namespace vmv
             {
                 dst[i] = __ldg(src + i);
             }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_pinfo);
+            src = reinterpret_cast<const uint32_t *>(robot.pair_info);
+            for (int i = tid; i < M::kPairs * 3; i += BLOCK)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            uint16_t *dl = reinterpret_cast<uint16_t *>(smem + L.off_plists);
+            const uint16_t *sl = reinterpret_cast<const uint16_t *>(robot.pair_lists);
+            for (int i = tid; i < min(robot.n_pair_lists, Lay::kMaxPairLists); i += BLOCK)
+            {
+                dl[i] = __ldg(sl + i);
+            }
         }
         const float *E = reinterpret_cast<const float *>(smem);
+        const PairInfo *pinfos = reinterpret_cast<const PairInfo *>(smem + L.off_pinfo);
+        const SpherePair *plists = reinterpret_cast<const SpherePair *>(smem + L.off_plists);
         const SphereTask *tasks = reinterpret_cast<const SphereTask *>(smem + L.off_tasks);
         const LinkInfo *links = reinterpret_cast<const LinkInfo *>(smem + L.off_links);
         const LinkPair *pairs = reinterpret_cast<const LinkPair *>(smem + L.off_pairs);
@@ -428,31 +448,32 @@ namespace vmv
         }
         __syncthreads();
 
-        // ---- C2: fine sphere pairs, one warp per (configuration, pair) record ----------------------
+        // ---- C2: fine sphere pairs, one group of 8 lanes per (configuration, pair) record ---------
+        // (four records in flight per warp: the work per record is a short chain of dependent
+        // shared-memory reads, so concurrency across records is what hides the latency)
         {
             const uint32_t n_rec = counters[1];
-            const int lane = tid & 31, warp = tid >> 5;
-            float4 *my = scratch + warp * Lay::kScratchPerWarp;
-            for (uint32_t r = warp; r < n_rec; r += Lay::kWarps)
+            const int lane = tid & 31, gl = tid & 7, group = tid >> 3;
+            const uint32_t gmask = 0xffu << (lane & 24);
+            float4 *my = scratch + group * Lay::kScratchPerGroup;
+            constexpr int HALF = Lay::kScratchPerGroup / 2;
+            for (uint32_t r = group; r < n_rec; r += Lay::kGroups)
             {
                 const uint32_t rec = pairq[r];
                 const int c = rec >> 9;
                 if (invalid[c])
                 {
-                    continue;  // warp-uniform: every lane reads the same flag
+                    continue;  // group-uniform
                 }
-                const LinkPair p = pairs[rec & 0x1ffu];
-                const LinkInfo A = links[p.a], B = links[p.b];
-                const int na = A.n_spheres, nb = B.n_spheres;
-                bool hit = false;
-                const PairInfo pinfo = robot.pair_info[rec & 0x1ffu];
-                if (pinfo.count >= 0 && inbox[c])
+                const int pair = rec & 0x1ffu;
+                const PairInfo pinfo = pinfos[pair];
+                bool h = false;
+                if (pinfo.count >= 0 && inbox[c] && pinfo.offset + pinfo.count <= Lay::kMaxPairLists)
                 {
                     // statically pruned list: one feasible sphere pair per lane
-                    bool h = false;
-                    for (int k = lane; k < pinfo.count; k += 32)
+                    for (int k = gl; k < pinfo.count; k += 8)
                     {
-                        const SpherePair sp = robot.pair_lists[pinfo.offset + k];
+                        const SpherePair sp = plists[pinfo.offset + k];
                         const SphereTask ta = tasks[sp.task_a], tb = tasks[sp.task_b];
                         float ax, ay, az, bx, by, bz;
                         task_centre<BLOCK>(ta, stash + c, ax, ay, az);
@@ -461,41 +482,43 @@ namespace vmv
                         const float rr = ta.r + tb.r;
                         h |= sign_set((ex * ex + ey * ey + ez * ez) - rr * rr);
                     }
-                    if (__any_sync(0xffffffffu, h) && lane == 0)
-                    {
-                        invalid[c] = 1u;
-                    }
-                    continue;
                 }
-                // tile link b in chunks that fit the scratch next to all of link a's spheres
-                for (int b0 = 0; b0 < nb && !hit; b0 += Lay::kScratchPerWarp / 2)
+                else
                 {
-                    const int nbc = min(nb - b0, Lay::kScratchPerWarp / 2);
-                    for (int a0 = 0; a0 < na && !hit; a0 += Lay::kScratchPerWarp / 2)
+                    // full cross product, tiled HALF x HALF through the group's scratch
+                    const LinkPair p = pairs[pair];
+                    const LinkInfo A = links[p.a], B = links[p.b];
+                    for (int a0 = 0; a0 < A.n_spheres; a0 += HALF)
                     {
-                        const int nac = min(na - a0, Lay::kScratchPerWarp / 2);
-                        __syncwarp();
-                        for (int s = lane; s < nac + nbc; s += 32)
+                        const int nac = min(A.n_spheres - a0, HALF);
+                        for (int b0 = 0; b0 < B.n_spheres; b0 += HALF)
                         {
-                            const int ti = s < nac ? A.bound_task + 1 + a0 + s : B.bound_task + 1 + b0 + (s - nac);
-                            const SphereTask t = tasks[ti];
-                            float x, y, z;
-                            task_centre<BLOCK>(t, stash + c, x, y, z);
-                            my[s] = make_float4(x, y, z, t.r);
+                            const int nbc = min(B.n_spheres - b0, HALF);
+                            __syncwarp(gmask);
+                            for (int sidx = gl; sidx < nac + nbc; sidx += 8)
+                            {
+                                const int ti = sidx < nac ? A.bound_task + 1 + a0 + sidx : B.bound_task + 1 + b0 + (sidx - nac);
+                                const SphereTask t = tasks[ti];
+                                float x, y, z;
+                                task_centre<BLOCK>(t, stash + c, x, y, z);
+                                my[sidx < nac ? sidx : HALF + (sidx - nac)] = make_float4(x, y, z, t.r);
+                            }
+                            __syncwarp(gmask);
+                            for (int ia = 0; ia < nac; ++ia)
+                            {
+                                const float4 sa = my[ia];
+                                for (int ib = gl; ib < nbc; ib += 8)
+                                {
+                                    const float4 sb = my[HALF + ib];
+                                    const float ex = sa.x - sb.x, ey = sa.y - sb.y, ez = sa.z - sb.z;
+                                    const float rr = sa.w + sb.w;
+                                    h |= sign_set((ex * ex + ey * ey + ez * ez) - rr * rr);
+                                }
+                            }
                         }
-                        __syncwarp();
-                        bool h = false;
-                        for (int k = lane; k < nac * nbc; k += 32)
-                        {
-                            const float4 sa = my[k / nbc], sb = my[nac + k % nbc];
-                            const float ex = sa.x - sb.x, ey = sa.y - sb.y, ez = sa.z - sb.z;
-                            const float rr = sa.w + sb.w;
-                            h |= sign_set((ex * ex + ey * ey + ez * ez) - rr * rr);
-                        }
-                        hit = __any_sync(0xffffffffu, h);
                     }
                 }
-                if (hit && lane == 0)
+                if (h)
                 {
                     invalid[c] = 1u;
                 }
