@@ -1,0 +1,289 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle, the committed golden vectors and
+-- where oracle/_ref travelled to the box -- the reference's own compiled code.
+
+Bar (BASELINE.json north_star): verdicts bit-exact except for units whose minimum signed clearance
+lies within 1e-5 m of zero (counted and asserted to be the only mismatches); FK sphere centres
+within 1e-5 m."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import vamp_mvt_b200 as vmv
+from oracle import pyoracle as po
+from tests import scenes
+from vamp_mvt_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+ROBOTS = ["panda", "ur5", "fetch", "baxter"]
+KEEP_OUT = {"panda": 0.0, "ur5": 0.0, "fetch": 0.45, "baxter": 0.5}
+BAND = 1e-5  # metres
+KINDS = {0: "spheres", 1: "cuboids", 2: "capsules"}
+
+
+def assert_verdicts(robot, oracle, oenv, q, got, want, what):
+    bad = np.nonzero(got != want)[0]
+    if len(bad):
+        clear = oracle.min_clearance(oenv, q[bad])
+        assert np.abs(clear).max() <= BAND, f"{robot} {what}: {len(bad)} mismatches, clearances {clear}"
+    return len(bad)
+
+
+def scenes_for(robot):
+    named = [(f"random{s}", scenes.random_scene(s, keep_out=KEEP_OUT[robot])) for s in (0, 2, 5)] + [("empty", {"order": []})]
+    if robot == "panda":
+        named += [("cage", scenes.sphere_cage()), ("table", scenes.table_shelf_scene()), ("box", scenes.box_scene())]
+    return named
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_sphere_fk(robot):
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    q = scenes.random_configs(robot, 5000, seed=1)
+    got, want = R.fk_batch(q), O.sphere_fk(q)
+    assert np.linalg.norm(got[..., :3] - want[..., :3], axis=-1).max() < 2e-6  # bar: 1e-5 m
+    assert np.array_equal(got[..., 3], want[..., 3])
+    single = R.fk(q[0])
+    assert len(single) == R.n_spheres() and abs(single[3].x - want[0, 3, 0]) < 2e-6
+
+
+@pytest.mark.parametrize("path", [1, 0], ids=["per_thread_kernel", "auto_kernel"])
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_config_verdicts(robot, path):
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    ref = po.Ref(robot) if po.ref_available() else None
+    _lib.lib().vmv_force_kernel_path(path)
+    try:
+        for name, sc in scenes_for(robot):
+            env = scenes.build_product_env(sc)
+            oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+            q = scenes.random_configs(robot, 30000, seed=3)
+            # a quarter outside the joint limits: the statically pruned self-collision lists do not apply there
+            q[:7500] += np.random.default_rng(9).uniform(-0.6, 0.6, size=(7500, q.shape[1])).astype(np.float32)
+            got = R.validate_batch(q, env)
+            assert_verdicts(robot, O, oenv, q, got, O.validate_configs(oenv, q), f"{name} configs vs oracle")
+            if ref is not None:
+                renv = po.add_scene(po.RefEnv(), scenes.packed(sc))
+                assert_verdicts(robot, O, oenv, q, got, ref.validate_configs(renv, q, threads=8), f"{name} configs vs reference")
+    finally:
+        _lib.lib().vmv_force_kernel_path(0)
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_edge_verdicts(robot):
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    ref = po.Ref(robot) if po.ref_available() else None
+    for name, sc in scenes_for(robot):
+        env = scenes.build_product_env(sc)
+        oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+        a, b = scenes.random_edges(robot, 6000, seed=4)
+        got = R.validate_motion_batch(a, b, env)
+        want = O.validate_edges(oenv, a, b)
+        # an edge mismatch must come from a state inside the clearance band: allow only a handful
+        assert (got != want).sum() <= 2, (robot, name, int((got != want).sum()))
+        if ref is not None:
+            renv = po.add_scene(po.RefEnv(), scenes.packed(sc))
+            assert (got != ref.validate_edges(renv, a, b, threads=8)).sum() <= 2, (robot, name)
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_golden_vectors(robot):
+    d = np.load(GOLDEN / f"{robot}.npz")
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    fk = R.fk_batch(d["q"][:64])
+    assert np.linalg.norm(fk[..., :3] - d["fk"][..., :3], axis=-1).max() < 2e-6
+    for name in d["scene_names"]:
+        env = vmv.Environment()
+        packed = {k: d[f"{name}_{k}"] for k in ("spheres", "cuboids", "capsules")}
+        L = _lib.lib()
+        for kind, i in d[f"{name}_order"]:
+            row = np.ascontiguousarray(packed[KINDS[int(kind)]][int(i)], dtype=np.float32)
+            fn = {0: L.vmv_env_add_spheres, 1: L.vmv_env_add_cuboids, 2: L.vmv_env_add_capsules}[int(kind)]
+            _lib.check(fn(env._h, _lib.ptr(row), 1))
+        env._dirty = True
+        oenv = po.OracleEnv()
+        po.add_scene(oenv, {**{k: list(v) for k, v in packed.items()}, "order": [(KINDS[int(k)], int(i)) for k, i in d[f"{name}_order"]]})
+        got = R.validate_batch(d["q"], env)
+        assert_verdicts(robot, O, oenv, d["q"], got, d[f"{name}_valid"], f"golden {name}")
+        assert (R.validate_motion_batch(d["a"], d["b"], env) != d[f"{name}_edge_valid"]).sum() == 0
+
+
+def test_sphere_cage_known_answers():
+    # reference scripts/sphere_cage_example.py:10-31,67 (BASELINE config 1)
+    env = scenes.build_product_env(scenes.sphere_cage())
+    assert vmv.panda.validate(scenes.CAGE_A, env) is True
+    assert vmv.panda.validate(scenes.CAGE_B, env) is True
+    assert vmv.panda.validate_motion(scenes.CAGE_A, scenes.CAGE_B, env) is False
+    assert vmv.panda.validate(scenes.CAGE_A) is True  # default: empty environment
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 129, 1000, 4097])
+def test_ragged_batch_sizes(n):
+    env = scenes.build_product_env(scenes.table_shelf_scene())
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.table_shelf_scene()))
+    O = po.Oracle("panda")
+    q = scenes.random_configs("panda", max(n, 1), seed=n)[:n]
+    got = vmv.panda.validate_batch(q, env)
+    assert got.shape == (n,)
+    if n:
+        assert np.array_equal(got, O.validate_configs(oenv, q))
+        a, b = scenes.random_edges("panda", n, seed=n)
+        ge = vmv.panda.validate_motion_batch(a, b, env)
+        assert (ge != O.validate_edges(oenv, a, b)).sum() == 0
+
+
+def test_full_size_properties():
+    """BASELINE size (2^20 configs): properties that need no oracle pass over the whole batch."""
+    n = 1 << 20
+    env = scenes.build_product_env(scenes.table_shelf_scene())
+    q = scenes.random_configs("panda", n, seed=0)
+    v = vmv.panda.validate_batch(q, env)
+    # idempotence
+    assert np.array_equal(v, vmv.panda.validate_batch(q, env))
+    # a verdict does not depend on the unit's position in the batch or on its block-mates
+    perm = np.random.default_rng(0).permutation(n)
+    assert np.array_equal(vmv.panda.validate_batch(q[perm], env), v[perm])
+    # both kernels agree on every unit
+    _lib.lib().vmv_force_kernel_path(1)
+    try:
+        v1 = vmv.panda.validate_batch(q[: 1 << 18], env)
+    finally:
+        _lib.lib().vmv_force_kernel_path(0)
+    assert np.array_equal(v1, v[: 1 << 18])
+    # monotonicity: removing every obstacle can only make configurations valid
+    v_empty = vmv.panda.validate_batch(q, vmv.Environment())
+    assert not np.any(v & ~v_empty)
+    # a zero-length edge is the configuration check (validate.hh:70-77 with vector = 0)
+    sub = q[: 1 << 16]
+    assert np.array_equal(vmv.panda.validate_motion_batch(sub, sub, env), v[: 1 << 16])
+    # oracle spot check on a slice of the big batch
+    O = po.Oracle("panda")
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.table_shelf_scene()))
+    sl = slice(500000, 520000)
+    assert_verdicts("panda", O, oenv, q[sl], v[sl], O.validate_configs(oenv, q[sl]), "2^20 slice")
+
+
+def test_edges_full_size_properties():
+    n = 1 << 18
+    env = scenes.build_product_env(scenes.box_scene())
+    a, b = scenes.random_edges("panda", n, seed=0)
+    e = vmv.panda.validate_motion_batch(a, b, env)
+    assert np.array_equal(e, vmv.panda.validate_motion_batch(a, b, env))
+    # the last tine of the first rake block is the goal itself: a valid edge has a valid goal
+    vb = vmv.panda.validate_batch(b, env)
+    assert not np.any(e & ~vb)
+    O = po.Oracle("panda")
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.box_scene()))
+    assert (e[:5000] != O.validate_edges(oenv, a[:5000], b[:5000])).sum() <= 1
+
+
+@pytest.mark.parametrize("robot", ["panda", "fetch", "ur5"])
+def test_capt_pointcloud_and_heightfield(robot):
+    """BASELINE config 4 at test size: CAPT pointcloud + heightfield in one environment."""
+    rng = np.random.default_rng(3)
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    m = O.model
+    pts = np.concatenate(
+        [
+            rng.uniform([0.3, -0.6, 0.0], [0.9, 0.6, 0.02], size=(6000, 3)),
+            rng.normal([0.5, 0.3, 0.6], 0.05, size=(2500, 3)),
+            rng.uniform([-0.8, -0.8, 0.0], [0.8, 0.8, 1.2], size=(500, 3)),
+        ]
+    ).astype(np.float32)
+    pts = pts[np.hypot(pts[:, 0], pts[:, 1]) > (0.5 if robot == "fetch" else 0.3)]
+    xd, yd = 64, 48
+    data = (0.5 * rng.random((yd, xd)) ** 3).astype(np.float32)
+    yy, xx = np.mgrid[0:yd, 0:xd]
+    data[np.hypot(xx - xd / 2, yy - yd / 2) < 12] = 0.0
+    env, oenv = vmv.Environment(), po.OracleEnv()
+    env.add_capt_pointcloud(pts, m["min_radius"], m["max_radius"], vmv.POINT_RADIUS)
+    oenv.add_capt(pts, m["min_radius"], m["max_radius"], vmv.POINT_RADIUS)
+    hf = vmv.make_heightfield([0, 0, -0.25], [0.05, 0.05, 1.0], [xd, yd], data)
+    env.add_heightfield(hf)
+    oenv.add_heightfield(hf.packed(), xd, yd, data.reshape(-1))
+    q = scenes.random_configs(robot, 8000, seed=21)
+    got, want = R.validate_batch(q, env), O.validate_configs(oenv, q)
+    assert 0.02 < want.mean() < 0.98
+    assert (got != want).sum() <= 2, int((got != want).sum())
+    if po.ref_available():
+        renv = po.RefEnv()
+        renv.add_capt(pts, m["min_radius"], m["max_radius"], vmv.POINT_RADIUS)
+        renv.add_heightfield(hf.packed(), xd, yd, data.reshape(-1))
+        assert (got != po.Ref(robot).validate_configs(renv, q, threads=8)).sum() <= 2
+    a, b = scenes.random_edges(robot, 1500, seed=22)
+    assert (R.validate_motion_batch(a, b, env) != O.validate_edges(oenv, a, b)).sum() <= 1
+
+
+@pytest.mark.parametrize("robot", ["panda", "ur5", "fetch"])
+def test_attachment(robot):
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    sc = scenes.random_scene(2, keep_out=KEEP_OUT[robot])
+    env = scenes.build_product_env(sc)
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+    tf = np.eye(4, dtype=np.float32)
+    tf[:3, 3] = [0.0, 0.0, 0.08]
+    att = vmv.Attachment(tf)
+    att.add_spheres([vmv.Sphere([0, 0, 0], 0.04), vmv.Sphere([0, 0, 0.06], 0.03), vmv.Sphere([0.03, 0, 0.1], 0.025)])
+    env.attach(att)
+    oenv.attach(att.packed_tf12(), att.packed_spheres())
+    q = scenes.random_configs(robot, 10000, seed=41)
+    got, want = R.validate_batch(q, env), O.validate_configs(oenv, q)
+    assert (got != want).sum() <= 2
+    env.detach()
+    oenv.detach()
+    assert (R.validate_batch(q, env) != got).any()
+    assert_verdicts(robot, O, oenv, q, R.validate_batch(q, env), O.validate_configs(oenv, q), "detached")
+
+
+def test_indexed_edges_and_device_api():
+    """PRM-style indexed edge sets through the device-pointer entry points (config 5 format)."""
+    L = _lib.lib()
+    env = scenes.build_product_env(scenes.box_scene())
+    O = po.Oracle("panda")
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.box_scene()))
+    V = scenes.random_configs("panda", 2000, seed=8)
+    rng = np.random.default_rng(8)
+    pairs = rng.integers(0, len(V), size=(5000, 2)).astype(np.uint32)
+    dV, dP = L.vmv_dev_alloc(V.nbytes), L.vmv_dev_alloc(pairs.nbytes)
+    dB = L.vmv_dev_alloc((len(pairs) + 31) // 32 * 4)
+    _lib.check(L.vmv_memcpy_h2d(dV, _lib.ptr(V), V.nbytes, None))
+    _lib.check(L.vmv_memcpy_h2d(dP, _lib.ptr(pairs), pairs.nbytes, None))
+    before = L.vmv_launch_count()
+    _lib.check(L.vmv_validate_edges_indexed_dev(vmv.panda.id, env.handle, dV, len(V), dP, len(pairs), 0, dB, None))
+    assert L.vmv_launch_count() == before + 1
+    words = np.zeros((len(pairs) + 31) // 32, np.uint32)
+    _lib.check(L.vmv_memcpy_d2h(_lib.ptr(words), dB, words.nbytes, None))
+    _lib.check(L.vmv_stream_sync(None))
+    got = _lib.unpack_bits(words, len(pairs))
+    want = O.validate_edges(oenv, V[pairs[:, 0]], V[pairs[:, 1]])
+    assert (got != want).sum() <= 1
+    for p in (dV, dP, dB):
+        L.vmv_dev_free(p)
+
+
+def test_uncommitted_environment_is_an_error():
+    L = _lib.lib()
+    h = L.vmv_env_create()
+    q = np.zeros(7, np.float32)
+    w = np.zeros(1, np.uint32)
+    assert L.vmv_validate_configs(vmv.panda.id, h, _lib.ptr(q), 1, _lib.ptr(w)) == -3  # VMV_ERR_STATE
+    assert b"not committed" in L.vmv_last_error()
+    L.vmv_env_destroy(h)
+
+
+def test_debug_attribution():
+    env = scenes.build_product_env(scenes.table_shelf_scene())
+    O = po.Oracle("panda")
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.table_shelf_scene()))
+    names = [shape.name for _, shape in scenes.table_shelf_scene()["order"]]
+    q = scenes.random_configs("panda", 60, seed=61)
+    for i in range(len(q)):
+        per_sphere, self_pairs = vmv.panda.debug(q[i], env)
+        eh, sh = O.debug(oenv, q[i])
+        want = [[] for _ in range(59)]
+        for s, obj in eh:
+            want[s].append(names[obj])
+        assert [sorted(x) for x in per_sphere] == [sorted(x) for x in want]
+        assert sorted(self_pairs) == sorted(map(tuple, sh.tolist()))

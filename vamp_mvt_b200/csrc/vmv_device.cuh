@@ -154,7 +154,9 @@ namespace vmv
     // min_distance >= |p| + r.  The reference evaluates |p| with a 12-bit rsqrt and so sometimes
     // stops one object early or late; we use a (slightly inflated) accurate bound, so the set of
     // objects we test is a superset of every object that can actually touch the sphere.
-    __device__ __forceinline__ bool sphere_hits_env(const float *__restrict__ E, float x, float y, float z, float r)
+    // r_pc is the radius used for pointcloud queries (see check_state: a link's bounding sphere is
+    // queried with its exact, un-inflated radius there).
+    __device__ __forceinline__ bool sphere_hits_env(const float *__restrict__ E, float x, float y, float z, float r, float r_pc)
     {
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
         const float ext = fmaf(__fsqrt_rn(fmaf(x, x, fmaf(y, y, z * z))), 1.0000002f, r);
@@ -283,7 +285,7 @@ namespace vmv
         for (uint32_t i = 0; i < H.n_capts; ++i)
         {
             const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * i);
-            if (capt_collides(t, x, y, z, r))
+            if (capt_collides(t, x, y, z, r_pc))
             {
                 return true;
             }

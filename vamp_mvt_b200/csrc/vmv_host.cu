@@ -396,6 +396,7 @@ struct vmv_env
     int device = -1;
     std::vector<uint32_t> blob;
     float *d_blob = nullptr;
+    int *d_object_ids = nullptr;  // packed object index -> insertion id (vmv_debug)
     std::vector<void *> owned;  // device allocations referenced from the blob
 
     void release_device()
@@ -587,6 +588,20 @@ namespace
         align4();
         std::memcpy(B.data(), &H, sizeof(H));
 
+        {
+            std::vector<int> ids;
+            for (const auto &o : env->spheres) ids.push_back(o.id);
+            for (const auto &o : env->capsules) ids.push_back(o.id);
+            for (const auto &o : env->z_capsules) ids.push_back(o.id);
+            for (const auto &o : env->cuboids) ids.push_back(o.id);
+            for (const auto &o : env->z_cuboids) ids.push_back(o.id);
+            for (const auto &o : env->heightfields) ids.push_back(o.id);
+            int rc = upload(env, ids, env->d_object_ids);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
         VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&env->d_blob), B.size() * 4));
         VMV_CUDA(cudaMemcpy(env->d_blob, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
         env->committed = true;
@@ -1386,8 +1401,77 @@ extern "C"
 
     int vmv_debug(int robot, const vmv_env *env, const float *q, int32_t *env_hits, size_t cap_env, size_t *n_env, int32_t *self_hits, size_t cap_self, size_t *n_self)
     {
-        (void)robot, (void)env, (void)q, (void)env_hits, (void)cap_env, (void)n_env, (void)self_hits, (void)cap_self, (void)n_self;
-        return fail(VMV_ERR_STATE, "vmv_debug: not implemented yet");
+        if (!valid_robot(robot) || q == nullptr || n_env == nullptr || n_self == nullptr || (cap_env > 0 && env_hits == nullptr) ||
+            (cap_self > 0 && self_hits == nullptr))
+        {
+            return fail(VMV_ERR_ARG, "vmv_debug: bad argument");
+        }
+        vmv::LaunchEnv le{};
+        int rc = make_launch_env(g_robots[robot], env, le);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        vmv::RobotDev rd{};
+        rc = robot_tables(robot, rd);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        const size_t dof = g_robots[robot].dof;
+        DevBuf dq, de, ds, dc;
+        rc = dq.alloc(dof * sizeof(float));
+        rc = rc == VMV_OK ? de.alloc(2 * cap_env * sizeof(int32_t)) : rc;
+        rc = rc == VMV_OK ? ds.alloc(2 * cap_self * sizeof(int32_t)) : rc;
+        rc = rc == VMV_OK ? dc.alloc(2 * sizeof(uint32_t)) : rc;
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpy(dq.p, q, dof * sizeof(float), cudaMemcpyHostToDevice));
+        VMV_CUDA(cudaMemset(dc.p, 0, 2 * sizeof(uint32_t)));
+        constexpr int BLOCK = 64;
+#define VMV_DEBUG_LAUNCH(RT)                                                                                                  \
+    {                                                                                                                         \
+        const vmv::SmemLayout<RT::Model, BLOCK> L(le.blob_bytes);                                                             \
+        if (L.total > kMaxSmem)                                                                                               \
+        {                                                                                                                     \
+            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");                                    \
+        }                                                                                                                     \
+        auto kernel = vmv::k_debug<RT, BLOCK>;                                                                                \
+        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));       \
+        kernel<<<1, BLOCK, L.total, nullptr>>>(                                                                               \
+            rd, le, static_cast<const float *>(dq.p), env->d_object_ids, static_cast<int32_t *>(de.p),                        \
+            static_cast<uint32_t>(cap_env), static_cast<int32_t *>(ds.p), static_cast<uint32_t>(cap_self),                    \
+            static_cast<uint32_t *>(dc.p));                                                                                   \
+    }
+        switch (robot)
+        {
+            case VMV_PANDA:
+                VMV_DEBUG_LAUNCH(panda_robot) break;
+            case VMV_UR5:
+                VMV_DEBUG_LAUNCH(ur5_robot) break;
+            case VMV_FETCH:
+                VMV_DEBUG_LAUNCH(fetch_robot) break;
+            default:
+                VMV_DEBUG_LAUNCH(baxter_robot) break;
+        }
+#undef VMV_DEBUG_LAUNCH
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        uint32_t counts[2] = {0, 0};
+        VMV_CUDA(cudaMemcpy(counts, dc.p, sizeof(counts), cudaMemcpyDeviceToHost));
+        *n_env = counts[0];
+        *n_self = counts[1];
+        if (cap_env > 0)
+        {
+            VMV_CUDA(cudaMemcpy(env_hits, de.p, 2 * std::min<size_t>(cap_env, counts[0]) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        }
+        if (cap_self > 0)
+        {
+            VMV_CUDA(cudaMemcpy(self_hits, ds.p, 2 * std::min<size_t>(cap_self, counts[1]) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        }
+        return VMV_OK;
     }
 
     void *vmv_dev_alloc(size_t bytes)

@@ -228,6 +228,10 @@ namespace vmv
         {
             return v;
         }
+        __device__ __forceinline__ bool rake_any(bool v) const
+        {
+            return v;
+        }
         static constexpr bool kWarp = false;
     };
 
@@ -242,6 +246,12 @@ namespace vmv
         {
             return __any_sync(0xffffffffu, v);
         }
+        // OR over the 8 lanes that hold the tines of one rake block
+        __device__ __forceinline__ bool rake_any(bool v) const
+        {
+            const uint32_t b = __ballot_sync(0xffffffffu, v);
+            return ((b >> ((threadIdx.x & 31) & 24)) & 0xffu) != 0u;
+        }
         static constexpr bool kWarp = true;
     };
 
@@ -252,17 +262,34 @@ namespace vmv
         bool bad = false;
 
         // ---- B: environment -----------------------------------------------------------------
+        // Pointcloud queries are not conservative for a bounding sphere (its radius exceeds the
+        // tree's r_max, reference capt.hh:428-512 queried from robots/panda.hh:5633), so with a
+        // pointcloud in the environment the hierarchy is part of the verdict and is reproduced as
+        // the reference runs it: the un-inflated bounding radius, and "any lane of the rake block
+        // hits" decides whether the block's fine spheres are swept (robots/panda.hh:5634-5645).
+        const bool collective = Vote::kWarp && reinterpret_cast<const EnvHeader *>(c.env)->n_capts > 0;
         {
             int ti = 0;
             bool active = has_state;
             while (vote.any(active))
             {
+                bool hit = false;
+                SphereTask t{};
+                float x = 0.F, y = 0.F, z = 0.F;
                 if (active)
                 {
-                    const SphereTask t = c.tasks[ti];
-                    float x, y, z;
+                    t = c.tasks[ti];
                     task_centre<BLOCK>(t, c.stash, x, y, z);
-                    const bool hit = sphere_hits_env(c.env, x, y, z, t.r);
+                    hit = sphere_hits_env(c.env, x, y, z, t.r, t.skip >= 0 ? t.r - 1e-6f : t.r);
+                }
+                if (collective)
+                {
+                    // lanes of a rake block walk the task list in lock step, so this is the block's bounding verdict
+                    const bool block_hit = vote.rake_any(hit && t.skip >= 0);
+                    hit = (active && t.skip >= 0) ? block_hit : hit;
+                }
+                if (active)
+                {
                     if (t.skip >= 0)
                     {
                         float *b = c.bounds + t.link * 3 * BLOCK;
@@ -383,7 +410,7 @@ namespace vmv
                     const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
                     const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
                     const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
-                    bad = sphere_hits_env(c.env, x, y, z, s.w);
+                    bad = sphere_hits_env(c.env, x, y, z, s.w, s.w);
                 }
                 // attachment vs links, bounding sphere first (validity.hh:278-301)
                 for (int k = 0; k < M::kAttachLinks && !bad; ++k)
@@ -633,6 +660,166 @@ namespace vmv
             }
             float4 *o = reinterpret_cast<float4 *>(out + (i * M::kSpheres + tk.sphere) * 4);
             *o = make_float4(x, y, z, tk.r);
+        }
+    }
+
+    // Robot::fkcc_debug for ONE configuration (reference robots/panda.hh:468-5224): every fine sphere
+    // against every object with the early-outs of sphere_environment_get_collisions
+    // (collision/validity.hh:160-257: primitives and heightfields, no pointclouds) and every allowed
+    // sphere pair, non-hierarchical.  One block; thread s owns fine-sphere task s.
+    template <typename R, int BLOCK>
+    __global__ void __launch_bounds__(BLOCK) k_debug(
+        RobotDev robot,
+        LaunchEnv env,
+        const float *__restrict__ q,
+        const int *__restrict__ object_ids,
+        int32_t *__restrict__ env_hits,
+        uint32_t cap_env,
+        int32_t *__restrict__ self_hits,
+        uint32_t cap_self,
+        uint32_t *__restrict__ counts)
+    {
+        using M = typename R::Model;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        BlockCtx<M, BLOCK> c = ctx_begin<M, BLOCK>(smem, &bar, robot, env);
+        float cfg[M::kDof];
+#pragma unroll
+        for (int j = 0; j < M::kDof; ++j)
+        {
+            cfg[j] = __ldg(q + j);
+        }
+        StashSink<BLOCK> sink{c.stash};
+        R::frames(cfg, sink);  // every thread poses the same robot into its own stash column
+        ctx_wait(&bar);
+        const float *E = c.env;
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
+
+        auto report = [&](int sphere, uint32_t packed_index)
+        {
+            const uint32_t slot = atomicAdd(&counts[0], 1u);
+            if (slot < cap_env)
+            {
+                env_hits[2 * slot] = sphere;
+                env_hits[2 * slot + 1] = object_ids[packed_index];
+            }
+        };
+
+        for (int ti = threadIdx.x; ti < M::kTasks; ti += BLOCK)
+        {
+            const SphereTask t = c.tasks[ti];
+            if (t.sphere < 0)
+            {
+                continue;
+            }
+            float x, y, z;
+            task_centre<BLOCK>(t, c.stash, x, y, z);
+            const float r = t.r, rsq = r * r;
+            const float ext = fmaf(__fsqrt_rn(fmaf(x, x, fmaf(y, y, z * z))), 1.0000002f, r);
+            uint32_t base = 0;
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_spheres);
+            for (uint32_t i = 0; i < H.n_spheres && E[H.off_spheres + kSphereRec * i + 4] < ext; ++i)
+            {
+                const float4 a = p[2 * i];
+                const float dx = a.x - x, dy = a.y - y, dz = a.z - z, rs = a.w + r;
+                if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                {
+                    report(t.sphere, base + i);
+                }
+            }
+            base += H.n_spheres;
+            p = reinterpret_cast<const float4 *>(E + H.off_capsules);
+            for (uint32_t i = 0; i < H.n_capsules && E[H.off_capsules + kCapsuleRec * i + 8] < ext; ++i)
+            {
+                const float4 a = p[3 * i], v = p[3 * i + 1];
+                const float dot = (x - a.x) * v.x + (y - a.y) * v.y + (z - a.z) * v.z;
+                const float cdf = fminf(fmaxf(dot * v.w, 0.F), 1.F);
+                const float dx = x - (a.x + v.x * cdf), dy = y - (a.y + v.y * cdf), dz = z - (a.z + v.z * cdf), rs = r + a.w;
+                if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                {
+                    report(t.sphere, base + i);
+                }
+            }
+            base += H.n_capsules;
+            p = reinterpret_cast<const float4 *>(E + H.off_zcapsules);
+            for (uint32_t i = 0; i < H.n_zcapsules && p[2 * i + 1].z < ext; ++i)
+            {
+                const float4 a = p[2 * i], v = p[2 * i + 1];
+                const float cdf = fminf(fmaxf((z - a.z) * v.x * v.y, 0.F), 1.F);
+                const float dx = x - a.x, dy = y - a.y, dz = z - (a.z + v.x * cdf), rs = r + a.w;
+                if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                {
+                    report(t.sphere, base + i);
+                }
+            }
+            base += H.n_zcapsules;
+            p = reinterpret_cast<const float4 *>(E + H.off_cuboids);
+            for (uint32_t i = 0; i < H.n_cuboids && p[4 * i + 3].w < ext; ++i)
+            {
+                const float4 cc = p[4 * i], a1 = p[4 * i + 1], a2 = p[4 * i + 2], a3 = p[4 * i + 3];
+                const float xs = x - cc.x, ys = y - cc.y, zs = z - cc.z;
+                const float e1 = fmaxf(fabsf(a1.x * xs + a1.y * ys + a1.z * zs) - cc.w, 0.F);
+                const float e2 = fmaxf(fabsf(a2.x * xs + a2.y * ys + a2.z * zs) - a1.w, 0.F);
+                const float e3 = fmaxf(fabsf(a3.x * xs + a3.y * ys + a3.z * zs) - a2.w, 0.F);
+                if (sign_set((e1 * e1 + e2 * e2 + e3 * e3) - rsq))
+                {
+                    report(t.sphere, base + i);
+                }
+            }
+            base += H.n_cuboids;
+            p = reinterpret_cast<const float4 *>(E + H.off_zcuboids);
+            for (uint32_t i = 0; i < H.n_zcuboids && p[3 * i].w < ext; ++i)
+            {
+                const float4 cc = p[3 * i], ax = p[3 * i + 1], h = p[3 * i + 2];
+                const float xs = x - cc.x, ys = y - cc.y, zs = z - cc.z;
+                const float e1 = fmaxf(fabsf(ax.x * xs + ax.y * ys) - h.x, 0.F);
+                const float e2 = fmaxf(fabsf(ax.z * xs + ax.w * ys) - h.y, 0.F);
+                const float e3 = fmaxf(fabsf(zs) - h.z, 0.F);
+                if (sign_set((e1 * e1 + e2 * e2 + e3 * e3) - rsq))
+                {
+                    report(t.sphere, base + i);
+                }
+            }
+            base += H.n_zcuboids;
+            for (uint32_t i = 0; i < H.n_heightfields; ++i)
+            {
+                const float4 *hp = reinterpret_cast<const float4 *>(E + H.off_heightfields + kHeightRec * i);
+                const float4 a = hp[0], b = hp[1], cc = hp[2];
+                const float xi = floorf(fminf(fmaxf(fmaf(a.w, a.x - x, cc.x), 0.F), b.z));
+                const float yi = floorf(fminf(fmaxf(fmaf(b.x, a.y - y, cc.y), 0.F), b.w));
+                const int index = __float2int_rn(fmaf(yi, b.z, xi));
+                const float *data = reinterpret_cast<const float *>(
+                    (static_cast<unsigned long long>(__float_as_uint(cc.w)) << 32) | __float_as_uint(cc.z));
+                if (sign_set(z - r - fmaf(b.y, __ldg(data + index), a.z)))
+                {
+                    report(t.sphere, base + i);
+                }
+            }
+        }
+
+        // allowed sphere pairs, flattened over the link pairs
+        for (int pi = 0; pi < M::kPairs; ++pi)
+        {
+            const LinkPair lp = c.pairs[pi];
+            const LinkInfo A = c.links[lp.a], B = c.links[lp.b];
+            for (int k = threadIdx.x; k < A.n_spheres * B.n_spheres; k += BLOCK)
+            {
+                const SphereTask ta = c.tasks[A.bound_task + 1 + k / B.n_spheres];
+                const SphereTask tb = c.tasks[B.bound_task + 1 + k % B.n_spheres];
+                float ax, ay, az, bx, by, bz;
+                task_centre<BLOCK>(ta, c.stash, ax, ay, az);
+                task_centre<BLOCK>(tb, c.stash, bx, by, bz);
+                const float ex = ax - bx, ey = ay - by, ez = az - bz, rr = ta.r + tb.r;
+                if (sign_set((ex * ex + ey * ey + ez * ez) - rr * rr))
+                {
+                    const uint32_t slot = atomicAdd(&counts[1], 1u);
+                    if (slot < cap_self)
+                    {
+                        self_hits[2 * slot] = ta.sphere;
+                        self_hits[2 * slot + 1] = tb.sphere;
+                    }
+                }
+            }
         }
     }
 }  // namespace vmv
