@@ -730,6 +730,36 @@ namespace
         {
             return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
         }
+        const int force = g_force_path.load();
+        if (BLOCK == 128 && force != 1 && le.primitives_only && le.n_objects <= 64)
+        {
+            const vmv::SmemLayoutV2<M, 128> L2(le.blob_bytes);
+            if (L2.total <= kMaxSmem)
+            {
+                const size_t chunks = (n + 31) / 32;
+                const int per_sm2 = std::max<int>(1, static_cast<int>(kMaxSmem / std::max<uint32_t>(L2.total + 4096, 1)));
+                const unsigned grid2 = static_cast<unsigned>(std::min<size_t>(chunks, static_cast<size_t>(sm_count()) * per_sm2 * 8));
+                if (pairs != nullptr)
+                {
+                    auto kernel = vmv::k_validate_edges_v2<R, 128, true>;
+                    VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L2.total)));
+                    kernel<<<grid2, 128, L2.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+                }
+                else
+                {
+                    auto kernel = vmv::k_validate_edges_v2<R, 128, false>;
+                    VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L2.total)));
+                    kernel<<<grid2, 128, L2.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+                }
+                g_launches++;
+                VMV_CUDA(cudaGetLastError());
+                return VMV_OK;
+            }
+        }
+        if (force == 2)
+        {
+            return fail(VMV_ERR_LIMIT, "block-cooperative kernel not applicable to this environment");
+        }
         const size_t rounds = (n + 31) / 32;  // one warp-round per verdict word
         const size_t blocks_needed = (rounds + BLOCK / 32 - 1) / (BLOCK / 32);
         const int per_sm = std::max<int>(1, static_cast<int>(kMaxSmem / std::max<uint32_t>(L.total, 1)));

@@ -192,17 +192,37 @@ namespace vmv
         }
     };
 
+    // Everything the phases need, as pointers into the block's shared memory.
     template <typename R, int BLOCK>
-    __global__ void __launch_bounds__(BLOCK)
-        k_validate_configs_v2(RobotDev robot, LaunchEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
+    struct V2Ctx
+    {
+        const float *E;
+        const PairInfo *pinfos;
+        const SpherePair *plists;
+        const SphereTask *tasks;
+        const LinkInfo *links;
+        const LinkPair *pairs;
+        float *stash;
+        unsigned long long *masks;
+        uint16_t *items;
+        uint16_t *pairq;
+        float4 *scratch;
+        volatile uint32_t *invalid;  // [BLOCK] result of a pass: 1 = state in collision (or no state)
+        volatile uint32_t *inbox;    // [BLOCK]
+        uint32_t *counters;          // [0] fine items, [1] pair records
+        uint64_t *bar;
+    };
+
+    // Issue the environment TMA copy and stage the robot tables.  Data is ready after a
+    // __syncthreads() and mbar_wait(bar, 0) -- v2_pass does both after its FK phase.
+    template <typename R, int BLOCK>
+    __device__ __forceinline__ V2Ctx<R, BLOCK> v2_stage(unsigned char *smem, uint64_t *barp, const RobotDev &robot, const LaunchEnv &env)
     {
         using M = typename R::Model;
         using Lay = SmemLayoutV2<M, BLOCK>;
-        extern __shared__ __align__(128) unsigned char smem[];
-        __shared__ uint64_t bar;
         const Lay L(env.blob_bytes);
         const int tid = threadIdx.x;
-
+        uint64_t &bar = *barp;
         if (tid == 0)
         {
             mbar_init(&bar, 1);
@@ -244,31 +264,50 @@ namespace vmv
                 dl[i] = __ldg(sl + i);
             }
         }
-        const float *E = reinterpret_cast<const float *>(smem);
-        const PairInfo *pinfos = reinterpret_cast<const PairInfo *>(smem + L.off_pinfo);
-        const SpherePair *plists = reinterpret_cast<const SpherePair *>(smem + L.off_plists);
-        const SphereTask *tasks = reinterpret_cast<const SphereTask *>(smem + L.off_tasks);
-        const LinkInfo *links = reinterpret_cast<const LinkInfo *>(smem + L.off_links);
-        const LinkPair *pairs = reinterpret_cast<const LinkPair *>(smem + L.off_pairs);
-        float *stash = reinterpret_cast<float *>(smem + L.off_stash);
-        unsigned long long *masks = reinterpret_cast<unsigned long long *>(smem + L.off_masks);
-        uint16_t *items = reinterpret_cast<uint16_t *>(smem + L.off_items);
-        uint16_t *pairq = reinterpret_cast<uint16_t *>(smem + L.off_pairq);
-        float4 *scratch = reinterpret_cast<float4 *>(smem + L.off_scratch);
-        volatile uint32_t *invalid = reinterpret_cast<volatile uint32_t *>(smem + L.off_flags);
-        volatile uint32_t *inbox = invalid + BLOCK;
-        uint32_t *counters = reinterpret_cast<uint32_t *>(smem + L.off_flags + 2 * Lay::align16(BLOCK * sizeof(uint32_t)));
-        // counters[0] = number of fine items, counters[1] = number of pair records
+        V2Ctx<R, BLOCK> X;
+        X.E = reinterpret_cast<const float *>(smem);
+        X.pinfos = reinterpret_cast<const PairInfo *>(smem + L.off_pinfo);
+        X.plists = reinterpret_cast<const SpherePair *>(smem + L.off_plists);
+        X.tasks = reinterpret_cast<const SphereTask *>(smem + L.off_tasks);
+        X.links = reinterpret_cast<const LinkInfo *>(smem + L.off_links);
+        X.pairs = reinterpret_cast<const LinkPair *>(smem + L.off_pairs);
+        X.stash = reinterpret_cast<float *>(smem + L.off_stash);
+        X.masks = reinterpret_cast<unsigned long long *>(smem + L.off_masks);
+        X.items = reinterpret_cast<uint16_t *>(smem + L.off_items);
+        X.pairq = reinterpret_cast<uint16_t *>(smem + L.off_pairq);
+        X.scratch = reinterpret_cast<float4 *>(smem + L.off_scratch);
+        X.invalid = reinterpret_cast<volatile uint32_t *>(smem + L.off_flags);
+        X.inbox = X.invalid + BLOCK;
+        X.counters = reinterpret_cast<uint32_t *>(smem + L.off_flags + 2 * Lay::align16(BLOCK * sizeof(uint32_t)));
+        X.bar = barp;
+        return X;
+    }
+
+    // One pass: up to BLOCK states (one per thread; `has` false = idle lane) through phases A..C2.
+    // Must be called by every thread of the block.  On return X.invalid[tid] holds the verdict of
+    // this thread's state and all shared-memory traffic of the pass is complete.
+    template <typename R, int BLOCK>
+    __device__ __forceinline__ void v2_pass(const V2Ctx<R, BLOCK> &X, const float (&cfg)[R::Model::kDof], const bool has)
+    {
+        using M = typename R::Model;
+        using Lay = SmemLayoutV2<M, BLOCK>;
+        const int tid = threadIdx.x;
+        const float *E = X.E;
+        const PairInfo *pinfos = X.pinfos;
+        const SpherePair *plists = X.plists;
+        const SphereTask *tasks = X.tasks;
+        const LinkInfo *links = X.links;
+        const LinkPair *pairs = X.pairs;
+        float *stash = X.stash;
+        unsigned long long *masks = X.masks;
+        uint16_t *items = X.items;
+        uint16_t *pairq = X.pairq;
+        float4 *scratch = X.scratch;
+        volatile uint32_t *invalid = X.invalid;
+        volatile uint32_t *inbox = X.inbox;
+        uint32_t *counters = X.counters;
 
         // ---- A: FK ------------------------------------------------------------------------------
-        const size_t i = static_cast<size_t>(blockIdx.x) * BLOCK + tid;
-        const bool has = i < n;
-        float cfg[M::kDof];
-#pragma unroll
-        for (int j = 0; j < M::kDof; ++j)
-        {
-            cfg[j] = has ? __ldg(q + i * M::kDof + j) : 0.F;
-        }
         StashBoundSink<BLOCK, M::kLinks> sink;
         sink.base = stash + tid;
         R::frames(cfg, sink);
@@ -282,7 +321,7 @@ namespace vmv
         }
 
         __syncthreads();  // tables, flags, counters
-        mbar_wait(&bar, 0);
+        mbar_wait(X.bar, 0);
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
 
         // ---- B1: bounding spheres vs every object, object-major, links unrolled ------------------
@@ -526,11 +565,175 @@ namespace vmv
         }
         __syncthreads();
 
-        const bool valid = has && !invalid[tid];
+    }
+
+    template <typename R, int BLOCK>
+    __global__ void __launch_bounds__(BLOCK)
+        k_validate_configs_v2(RobotDev robot, LaunchEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
+    {
+        using M = typename R::Model;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        const V2Ctx<R, BLOCK> X = v2_stage<R, BLOCK>(smem, &bar, robot, env);
+        const int tid = threadIdx.x;
+        const size_t i = static_cast<size_t>(blockIdx.x) * BLOCK + tid;
+        const bool has = i < n;
+        float cfg[M::kDof];
+#pragma unroll
+        for (int j = 0; j < M::kDof; ++j)
+        {
+            cfg[j] = has ? __ldg(q + i * M::kDof + j) : 0.F;
+        }
+        v2_pass<R, BLOCK>(X, cfg, has);
+        const bool valid = has && !X.invalid[tid];
         const uint32_t word = __ballot_sync(0xffffffffu, valid);
         if ((tid & 31) == 0 && has)
         {
             bits[i >> 5] = word;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // Edges, block-cooperative.  A block takes 32 edges (one verdict word) at a time.  The states of
+    // an edge are the reference's rake blocks (planning/validate.hh:31-64): block s holds the 8 tines
+    // (t+1)/8 stepped back s times by vector/(8n).  Each pass checks 16 rake blocks = 128 states; blocks
+    // are handed out round-robin over the edges still alive, so an edge found invalid drops its
+    // remaining blocks -- the counterpart of the reference's early return.
+    // ------------------------------------------------------------------------------------------
+    template <typename R, int BLOCK, bool INDEXED>
+    __global__ void __launch_bounds__(BLOCK) k_validate_edges_v2(
+        RobotDev robot,
+        LaunchEnv env,
+        const float *__restrict__ a,
+        const float *__restrict__ b,
+        const uint32_t *__restrict__ pairs,
+        size_t n,
+        float resolution,
+        uint32_t *__restrict__ bits)
+    {
+        using M = typename R::Model;
+        static_assert(BLOCK == 128, "16 rake blocks of 8 tines per pass");
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        __shared__ float s_start[32][M::kDof], s_vec[32][M::kDof];
+        __shared__ int s_steps[32], s_next[32], s_dead[32];
+        __shared__ int s_slot_edge[16], s_slot_step[16], s_nslots;
+        const V2Ctx<R, BLOCK> X = v2_stage<R, BLOCK>(smem, &bar, robot, env);
+        const int tid = threadIdx.x, lane = tid & 31;
+        const size_t n_chunks = (n + 31) / 32;
+
+        for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
+        {
+            __syncthreads();
+            if (tid < 32)
+            {
+                const size_t edge = chunk * 32 + tid;
+                int steps = 0;
+                if (edge < n)
+                {
+                    const float *pa, *pb;
+                    if (INDEXED)
+                    {
+                        pa = a + static_cast<size_t>(__ldg(pairs + 2 * edge)) * M::kDof;
+                        pb = a + static_cast<size_t>(__ldg(pairs + 2 * edge + 1)) * M::kDof;
+                    }
+                    else
+                    {
+                        pa = a + edge * M::kDof;
+                        pb = b + edge * M::kDof;
+                    }
+                    float vec[M::kDof];
+#pragma unroll
+                    for (int j = 0; j < M::kDof; ++j)
+                    {
+                        const float st = __ldg(pa + j);
+                        vec[j] = __fsub_rn(__ldg(pb + j), st);
+                        s_start[tid][j] = st;
+                        s_vec[tid][j] = vec[j];
+                    }
+                    const float dist = ref_l2_norm<M::kDof>(vec);
+                    // n = max(ceil(distance / rake * resolution), 1)   (validate.hh:41)
+                    steps = static_cast<int>(fmaxf(ceilf(__fmul_rn(__fdiv_rn(dist, 8.F), resolution)), 1.F));
+                }
+                s_steps[tid] = steps;
+                s_next[tid] = 0;
+                s_dead[tid] = 0;
+            }
+            __syncthreads();
+
+            while (true)
+            {
+                // ---- hand out up to 16 rake blocks, round-robin over the live edges (warp 0) ------
+                if (tid < 32)
+                {
+                    const int rem = s_dead[tid] ? 0 : s_steps[tid] - s_next[tid];
+                    int base = 0, got = 0;
+                    for (int r = 0; base < 16; ++r)
+                    {
+                        const uint32_t m = __ballot_sync(0xffffffffu, rem > r);
+                        if (m == 0u)
+                        {
+                            break;
+                        }
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (rem > r && pos < 16)
+                        {
+                            s_slot_edge[pos] = tid;
+                            s_slot_step[pos] = s_next[tid] + r;
+                            ++got;
+                        }
+                        base += __popc(m);
+                    }
+                    s_next[tid] += got;
+                    if (tid == 0)
+                    {
+                        s_nslots = min(base, 16);
+                    }
+                }
+                __syncthreads();
+                const int nslots = s_nslots;
+                if (nslots == 0)
+                {
+                    break;
+                }
+                const int slot = tid >> 3, tine = tid & 7;
+                const bool has = slot < nslots;
+                const int e = has ? s_slot_edge[slot] : 0;
+                const int step = has ? s_slot_step[slot] : 0;
+                float cfg[M::kDof];
+                {
+                    const float pct = static_cast<float>(tine + 1) / 8.F;
+                    const float denom = static_cast<float>(8 * s_steps[e]);
+#pragma unroll
+                    for (int j = 0; j < M::kDof; ++j)
+                    {
+                        const float v = s_vec[e][j];
+                        const float back = __fdiv_rn(v, denom);
+                        float c = fmaf(v, pct, s_start[e][j]);
+                        for (int k = 0; k < step; ++k)
+                        {
+                            c = __fsub_rn(c, back);
+                        }
+                        cfg[j] = c;
+                    }
+                }
+                v2_pass<R, BLOCK>(X, cfg, has);
+                if (has && X.invalid[tid])
+                {
+                    s_dead[e] = 1;
+                }
+                __syncthreads();
+            }
+
+            if (tid < 32)
+            {
+                const bool ok = s_steps[tid] > 0 && !s_dead[tid];
+                const uint32_t word = __ballot_sync(0xffffffffu, ok);
+                if (tid == 0)
+                {
+                    bits[chunk] = word;
+                }
+            }
         }
     }
 }  // namespace vmv
