@@ -79,6 +79,7 @@ ROBOTS = {
 }
 
 BOUND_MARGIN = 1e-6  # metres added to our enclosing spheres so they are strictly conservative
+BOX_MARGIN = 0.02  # rad / m: static analyses hold for joints within [lower - m, upper + m]
 
 
 # --------------------------------------------------------------------------------------------
@@ -293,6 +294,35 @@ def build_model(name, urdf_path, srdf_path):
         )
         sphere_index += len(sph)
 
+    # Static reach: an upper bound, valid for ANY revolute joint values, on how far from the world
+    # origin a link's bounding sphere can extend (triangle inequality along the chain).  Prismatic
+    # joints contribute their largest in-limit travel (+ margin); the kernels only use the bound for
+    # states whose prismatic joints are inside that range (sink.reach_ok).
+    def reach(bi, p):
+        """max over all revolute joint values of |world position| of point p fixed in body bi:
+        the point sweeps a circle about the joint axis; circle centre c is fixed in the parent's
+        frame, so reach <= reach(parent, c) + circle radius (triangle inequality, level by level)."""
+        bd = bodies[bi]
+        p = np.asarray(p, float)
+        if bd["parent"] < 0:
+            return float(np.linalg.norm(p))
+        ax = np.array(bd["axis"], float)
+        ax = ax / np.linalg.norm(ax)
+        T = bd["T_pre"]
+        if bd["jtype"] == "prismatic":
+            d = bd["dof"]
+            mid = 0.5 * (lower[d] + upper[d])
+            half = 0.5 * (upper[d] - lower[d]) + BOX_MARGIN
+            c = T[:3, :3] @ (p + mid * ax) + T[:3, 3]
+            return reach(bd["parent"], c) + half
+        c_local = (p @ ax) * ax
+        rho = float(np.linalg.norm(p - c_local))
+        c = T[:3, :3] @ c_local + T[:3, 3]
+        return reach(bd["parent"], c) + rho
+
+    for c in clinks:
+        c["reach"] = float(reach(c["body"], c["bound"][:3]) + c["bound"][3] + 1e-4)
+
     names = [c["name"] for c in clinks]
     disabled = disabled | {frozenset(p) for p in cfg.get("extra_disabled", [])}
     pairs = []
@@ -355,7 +385,6 @@ def build_model(name, urdf_path, srdf_path):
 # --------------------------------------------------------------------------------------------
 # self-collision analysis: which sphere pairs can ever touch, which link pairs nearly always overlap
 # --------------------------------------------------------------------------------------------
-BOX_MARGIN = 0.02      # the pruned lists are valid for joints within [lower - m, upper + m]
 INLINE_FREQUENCY = 0.5  # link pairs whose bounding spheres overlap more often than this are checked
                         # unconditionally (fine spheres, pruned list) by every thread
 
@@ -793,6 +822,14 @@ def emit_cuda(model, tr, frames):
         conds.append(f"(q[{d}] >= {lit(lo_d)}) & (q[{d}] <= {lit(hi_d)})")
     out.append("    // the statically pruned self-collision lists hold inside the joint limits (+ margin)")
     out.append("    sink.in_box(" + (" & ".join(conds) if conds else "true") + ");")
+    pris = [b for b in model["bodies"] if b["jtype"] == "prismatic"]
+    rconds = []
+    for b in pris:
+        d = b["dof"]
+        lim = max(abs(model["lower"][d]), abs(model["lower"][d] + model["range"][d])) + BOX_MARGIN
+        rconds.append(f"(fabsf(q[{d}]) <= {lit(lim)})")
+    out.append("    // the static per-link reach bounds assume prismatic joints inside their limits")
+    out.append("    sink.reach_ok(" + (" & ".join(rconds) if rconds else "true") + ");")
     out.append("    // link pairs whose bounding spheres (nearly) always overlap: kinematically feasible fine pairs, ungated")
     out.append("    bool self_hit = false;")
     for pa, pb, rs2 in inline_tests:
@@ -879,11 +916,11 @@ def emit_tables(model):
     out.append("};")
     out.append("")
     N = name.upper()
-    out.append("// X-macros for fully unrolled device code: LINKS(X) -> X(link, bound_radius, n_spheres, first_fine_task);")
+    out.append("// X-macros for fully unrolled device code: LINKS(X) -> X(link, bound_radius, n_spheres, first_fine_task, reach);")
     out.append("// PAIRS(X) -> X(pair_index, link_a, link_b, checked_inline)")
     out.append(f"#define VMV_{N}_LINKS(X) \\")
     for li, l in enumerate(L):
-        out.append(f"    X({li}, {f(l['bound'][3])}, {len(l['spheres'])}, {btask[li] + 1}) \\")
+        out.append(f"    X({li}, {f(l['bound'][3])}, {len(l['spheres'])}, {btask[li] + 1}, {f(l['reach'])}) \\")
     out.append("")
     info = model.get("self_pair_info") or [dict(inline=False, pruned=None) for _ in model["self_pairs"]]
     out.append(f"#define VMV_{N}_PAIRS(X) \\")

@@ -75,7 +75,7 @@ namespace
             VMV_##NAME##_PAIRS_DISPATCH                                               \
         }                                                                             \
     };
-#define VMV_X_LINK(l, r, n, t) f(vmv::IC<l>{}, r, n, t);
+#define VMV_X_LINK(l, r, n, t, reach) f(vmv::IC<l>{}, r, n, t, reach);
 #define VMV_X_PAIR(p, a, b, inl) f(vmv::IC<p>{}, vmv::IC<a>{}, vmv::IC<b>{}, vmv::IC<inl>{});
 #define VMV_panda_LINKS_DISPATCH VMV_PANDA_LINKS(VMV_X_LINK)
 #define VMV_panda_PAIRS_DISPATCH VMV_PANDA_PAIRS(VMV_X_PAIR)

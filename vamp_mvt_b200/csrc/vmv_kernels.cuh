@@ -42,11 +42,20 @@ namespace vmv
         bool primitives_only; // no heightfield / pointcloud / attachment
     };
 
+    // A body frame is a rigid transform [R | t] (row-major 3x4, K = 4*row + col).  The stash keeps the
+    // first two columns of R and t (9 floats); the third column is their cross product.
+    static constexpr int kFrameFloats = 9;
+
+    __host__ __device__ constexpr int frame_slot(int k)
+    {
+        return (k / 4) * 3 + ((k % 4) == 3 ? 2 : (k % 4));
+    }
+
     // shared-memory carve-up, identical on host (size computation) and device
     template <typename M, int BLOCK>
     struct SmemLayout
     {
-        static constexpr int kStashFrames = (M::kBodies - 1) * 12;
+        static constexpr int kStashFrames = (M::kBodies - 1) * kFrameFloats;
         static constexpr int kStashBounds = M::kLinks * 3;
 
         __host__ __device__ static constexpr uint32_t align16(uint32_t v)
@@ -81,7 +90,10 @@ namespace vmv
         template <int BODY, int K>
         __device__ __forceinline__ void put(float v)
         {
-            base[((BODY - 1) * 12 + K) * BLOCK] = v;
+            if (K % 4 != 2)
+            {
+                base[((BODY - 1) * kFrameFloats + frame_slot(K)) * BLOCK] = v;
+            }
         }
 
         template <int LINK, int AXIS>
@@ -90,6 +102,10 @@ namespace vmv
         }
 
         __device__ __forceinline__ void in_box(bool)
+        {
+        }
+
+        __device__ __forceinline__ void reach_ok(bool)
         {
         }
 
@@ -118,6 +134,10 @@ namespace vmv
         {
         }
 
+        __device__ __forceinline__ void reach_ok(bool)
+        {
+        }
+
         __device__ __forceinline__ void self_inline(bool)
         {
         }
@@ -133,10 +153,17 @@ namespace vmv
         }
         else
         {
-            const float *F = stash + (t.body - 1) * 12 * BLOCK;
-            x = fmaf(F[0 * BLOCK], t.cx, fmaf(F[1 * BLOCK], t.cy, fmaf(F[2 * BLOCK], t.cz, F[3 * BLOCK])));
-            y = fmaf(F[4 * BLOCK], t.cx, fmaf(F[5 * BLOCK], t.cy, fmaf(F[6 * BLOCK], t.cz, F[7 * BLOCK])));
-            z = fmaf(F[8 * BLOCK], t.cx, fmaf(F[9 * BLOCK], t.cy, fmaf(F[10 * BLOCK], t.cz, F[11 * BLOCK])));
+            const float *F = stash + (t.body - 1) * kFrameFloats * BLOCK;
+            const float r00 = F[0 * BLOCK], r01 = F[1 * BLOCK], tx = F[2 * BLOCK];
+            const float r10 = F[3 * BLOCK], r11 = F[4 * BLOCK], ty = F[5 * BLOCK];
+            const float r20 = F[6 * BLOCK], r21 = F[7 * BLOCK], tz = F[8 * BLOCK];
+            // third column of a rotation = first x second
+            const float r02 = fmaf(r10, r21, -(r20 * r11));
+            const float r12 = fmaf(r20, r01, -(r00 * r21));
+            const float r22 = fmaf(r00, r11, -(r10 * r01));
+            x = fmaf(r00, t.cx, fmaf(r01, t.cy, fmaf(r02, t.cz, tx)));
+            y = fmaf(r10, t.cx, fmaf(r11, t.cy, fmaf(r12, t.cz, ty)));
+            z = fmaf(r20, t.cx, fmaf(r21, t.cy, fmaf(r22, t.cz, tz)));
         }
     }
 
@@ -387,8 +414,11 @@ namespace vmv
 #pragma unroll
                         for (int k = 0; k < 12; ++k)
                         {
-                            F[k] = c.stash[((M::kEeBody - 1) * 12 + k) * BLOCK];
+                            F[k] = (k % 4 == 2) ? 0.F : c.stash[((M::kEeBody - 1) * kFrameFloats + frame_slot(k)) * BLOCK];
                         }
+                        F[2] = fmaf(F[4], F[9], -(F[8] * F[5]));
+                        F[6] = fmaf(F[8], F[1], -(F[0] * F[9]));
+                        F[10] = fmaf(F[0], F[5], -(F[4] * F[1]));
                     }
 #pragma unroll
                     for (int i = 0; i < 3; ++i)

@@ -121,7 +121,10 @@ namespace vmv
         template <int BODY, int K>
         __device__ __forceinline__ void put(float v)
         {
-            base[((BODY - 1) * 12 + K) * BLOCK] = v;
+            if (K % 4 != 2)
+            {
+                base[((BODY - 1) * kFrameFloats + frame_slot(K)) * BLOCK] = v;
+            }
         }
 
         template <int LINK, int AXIS>
@@ -130,7 +133,12 @@ namespace vmv
             b[LINK][AXIS] = v;
         }
 
-        bool inbox, self_hit;
+        bool inbox, self_hit, reach_valid;
+
+        __device__ __forceinline__ void reach_ok(bool v)
+        {
+            reach_valid = v;
+        }
 
         __device__ __forceinline__ void in_box(bool v)
         {
@@ -146,7 +154,7 @@ namespace vmv
     template <typename M, int BLOCK>
     struct SmemLayoutV2
     {
-        static constexpr int kStashFrames = (M::kBodies - 1) * 12;
+        static constexpr int kStashFrames = (M::kBodies - 1) * kFrameFloats;
         // work queues sized for the worst case (every link of every configuration hit), 16 bits each
         static constexpr int kItemCap = BLOCK * M::kSpheres;
         static constexpr int kPairCap = BLOCK * (M::kPairs > 0 ? M::kPairs : 1);
@@ -178,14 +186,17 @@ namespace vmv
             o += align16(kMaxPairLists * sizeof(SpherePair));
             off_stash = o;
             o += kStashFrames * BLOCK * sizeof(float);
+            // the B-phase queues (masks, items) and the C-phase queues (pair records, scratch) are never
+            // live at the same time: they share one region
             off_masks = o;
-            o += M::kLinks * BLOCK * sizeof(unsigned long long);
-            off_items = o;
-            o += align16(kItemCap * sizeof(uint16_t));
+            uint32_t b_bytes = M::kLinks * BLOCK * sizeof(unsigned long long);
+            off_items = o + b_bytes;
+            b_bytes += align16(kItemCap * sizeof(uint16_t));
             off_pairq = o;
-            o += align16(kPairCap * sizeof(uint16_t));
-            off_scratch = o;
-            o += kGroups * kScratchPerGroup * sizeof(float4);
+            uint32_t c_bytes = align16(kPairCap * sizeof(uint16_t));
+            off_scratch = o + c_bytes;
+            c_bytes += kGroups * kScratchPerGroup * sizeof(float4);
+            o += b_bytes > c_bytes ? b_bytes : c_bytes;
             off_flags = o;
             o += 2 * align16(BLOCK * sizeof(uint32_t)) + 16;
             total = o;
@@ -341,9 +352,13 @@ namespace vmv
                     const float4 a = p[2 * k];
                     const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
                     R::for_each_link(
-                        [&](auto l, float br, int, int)
+                        [&](auto l, float br, int, int, float reach)
                         {
                             constexpr int li = decltype(l)::value;
+                            if (!((E[H.off_spheres + kSphereRec * k + 4]) < reach) && sink.reach_valid)
+                            {
+                                return;  // out of this link's reach for every configuration
+                            }
                             const bool hit = sign_set(margin_sphere(a, sink.b[li][0], sink.b[li][1], sink.b[li][2], br));
                             mlo[li] |= hit ? blo : 0u;
                             mhi[li] |= hit ? bhi : 0u;
@@ -357,9 +372,13 @@ namespace vmv
                     const float4 a = p[3 * k], v = p[3 * k + 1];
                     const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
                     R::for_each_link(
-                        [&](auto l, float br, int, int)
+                        [&](auto l, float br, int, int, float reach)
                         {
                             constexpr int li = decltype(l)::value;
+                            if (!((E[H.off_capsules + kCapsuleRec * k + 8]) < reach) && sink.reach_valid)
+                            {
+                                return;  // out of this link's reach for every configuration
+                            }
                             const bool hit = sign_set(margin_capsule(a, v, sink.b[li][0], sink.b[li][1], sink.b[li][2], br));
                             mlo[li] |= hit ? blo : 0u;
                             mhi[li] |= hit ? bhi : 0u;
@@ -373,9 +392,13 @@ namespace vmv
                     const float4 a = p[2 * k], v = p[2 * k + 1];
                     const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
                     R::for_each_link(
-                        [&](auto l, float br, int, int)
+                        [&](auto l, float br, int, int, float reach)
                         {
                             constexpr int li = decltype(l)::value;
+                            if (!((v.z) < reach) && sink.reach_valid)
+                            {
+                                return;  // out of this link's reach for every configuration
+                            }
                             const bool hit = sign_set(margin_zcapsule(a, v, sink.b[li][0], sink.b[li][1], sink.b[li][2], br));
                             mlo[li] |= hit ? blo : 0u;
                             mhi[li] |= hit ? bhi : 0u;
@@ -389,9 +412,13 @@ namespace vmv
                     const float4 c = p[4 * k], a1 = p[4 * k + 1], a2 = p[4 * k + 2], a3 = p[4 * k + 3];
                     const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
                     R::for_each_link(
-                        [&](auto l, float br, int, int)
+                        [&](auto l, float br, int, int, float reach)
                         {
                             constexpr int li = decltype(l)::value;
+                            if (!((a3.w) < reach) && sink.reach_valid)
+                            {
+                                return;  // out of this link's reach for every configuration
+                            }
                             const bool hit =
                                 sign_set(margin_cuboid(c, a1, a2, a3, sink.b[li][0], sink.b[li][1], sink.b[li][2], br * br));
                             mlo[li] |= hit ? blo : 0u;
@@ -406,9 +433,13 @@ namespace vmv
                     const float4 c = p[3 * k], ax = p[3 * k + 1], h = p[3 * k + 2];
                     const uint32_t blo = og < 32 ? 1u << og : 0u, bhi = og < 32 ? 0u : 1u << (og - 32);
                     R::for_each_link(
-                        [&](auto l, float br, int, int)
+                        [&](auto l, float br, int, int, float reach)
                         {
                             constexpr int li = decltype(l)::value;
+                            if (!((c.w) < reach) && sink.reach_valid)
+                            {
+                                return;  // out of this link's reach for every configuration
+                            }
                             const bool hit =
                                 sign_set(margin_zcuboid(c, ax, h, sink.b[li][0], sink.b[li][1], sink.b[li][2], br * br));
                             mlo[li] |= hit ? blo : 0u;
@@ -419,7 +450,7 @@ namespace vmv
 
             // enqueue fine-sphere items of the links whose bounding sphere touches something
             R::for_each_link(
-                [&](auto l, float, int n_fine, int first_task)
+                [&](auto l, float, int n_fine, int first_task, float)
                 {
                     constexpr int li = decltype(l)::value;
                     if ((mlo[li] | mhi[li]) != 0u)
@@ -463,11 +494,13 @@ namespace vmv
             }
         }
 
+        __syncthreads();  // the C-phase queues reuse the B-phase queues' memory
+
         // ---- C1: allowed link pairs on the bounding spheres ---------------------------------------
         if (has && !invalid[tid])
         {
             float brad[M::kLinks];
-            R::for_each_link([&](auto l, float br, int, int) { brad[decltype(l)::value] = br; });
+            R::for_each_link([&](auto l, float br, int, int, float) { brad[decltype(l)::value] = br; });
             R::for_each_pair(
                 [&](auto pi, auto la, auto lb, auto inl)
                 {
