@@ -1,0 +1,116 @@
+#!/usr/bin/env python3
+"""Secondary workloads of BASELINE.json, measured on one GPU (device-resident inputs, CUDA events via
+the library's own stream sync + host timer around >= 5 back-to-back launches):
+
+  C4  Fetch and UR5 FK+CC vs a CAPT pointcloud of 100k synthetic points plus a 256x256 heightfield
+  C5  PRM-style roadmap edge validation, 10^8 Panda edges as (u32,u32) index pairs into a vertex table
+
+Usage: bench_extra.py [c4] [c5] [--edges N]
+Prints one JSON line per workload."""
+import json
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+
+import vamp_mvt_b200 as vmv
+from tests import scenes
+from vamp_mvt_b200 import _lib
+
+L = _lib.lib()
+
+
+def synth_pointcloud(n, keep_out, seed=0):
+    """Surface samples of a synthetic table/shelf/wall scene, in the spirit of src/vamp/pointcloud.py."""
+    rng = np.random.default_rng(seed)
+    parts = [
+        rng.uniform([0.35, -0.8, 0.38], [1.1, 0.8, 0.40], size=(n * 4 // 10, 3)),   # table top
+        rng.uniform([-0.4, 0.75, 0.0], [0.6, 0.78, 1.4], size=(n * 3 // 10, 3)),     # wall / shelf back
+        rng.normal([0.7, 0.2, 0.55], [0.06, 0.06, 0.1], size=(n * 2 // 10, 3)),     # object on the table
+        rng.uniform([-1.2, -1.2, 0.0], [1.2, 1.2, 0.02], size=(n - n * 9 // 10, 3)),  # floor
+    ]
+    p = np.concatenate(parts).astype(np.float32)
+    return p[np.hypot(p[:, 0], p[:, 1]) > keep_out]
+
+
+def time_launches(fn, reps=5):
+    fn()
+    _lib.check(L.vmv_stream_sync(None))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    _lib.check(L.vmv_stream_sync(None))
+    return (time.perf_counter() - t0) / reps
+
+
+def c4():
+    for robot, keep in (("fetch", 0.55), ("ur5", 0.3)):
+        R = getattr(vmv, robot)
+        rmin, rmax = R.min_max_radii()
+        pts = synth_pointcloud(100_000, keep)
+        env = vmv.Environment()
+        build_ns = env.add_capt_pointcloud(pts, rmin, rmax, vmv.POINT_RADIUS)
+        rng = np.random.default_rng(1)
+        xd = yd = 256
+        data = (0.15 * rng.random((yd, xd)) ** 4).astype(np.float32)
+        yy, xx = np.mgrid[0:yd, 0:xd]
+        data[np.hypot(xx - xd / 2, yy - yd / 2) < 40] = 0.0
+        env.add_heightfield(vmv.make_heightfield([0, 0, -0.3], [0.02, 0.02, 1.0], [xd, yd], data))
+        n = 1 << 18
+        q = scenes.random_configs(robot, n, seed=0)
+        dq, db = L.vmv_dev_alloc(q.nbytes), L.vmv_dev_alloc((n + 31) // 32 * 4)
+        _lib.check(L.vmv_memcpy_h2d(dq, _lib.ptr(q), q.nbytes, None))
+        h = env.handle
+        t = time_launches(lambda: _lib.check(L.vmv_validate_configs_dev(R.id, h, dq, n, db, None)))
+        words = np.zeros((n + 31) // 32, np.uint32)
+        _lib.check(L.vmv_memcpy_d2h(_lib.ptr(words), db, words.nbytes, None))
+        _lib.check(L.vmv_stream_sync(None))
+        print(json.dumps({"workload": f"C4 {robot}: 2^18 configs vs CAPT({len(pts)} pts) + 256x256 heightfield",
+                          "value": n / t, "unit": "configs/s", "ms": t * 1e3, "capt_build_ms": build_ns / 1e6,
+                          "valid_fraction": float(_lib.unpack_bits(words, n).mean())}), flush=True)
+        L.vmv_dev_free(dq), L.vmv_dev_free(db)
+
+
+def c5(n_edges):
+    R = vmv.panda
+    env = scenes.build_product_env(scenes.table_shelf_scene())
+    rng = np.random.default_rng(5)
+    # vertex table: clusters of nearby valid configurations (PRM neighbourhoods)
+    n_clusters, per = 1 << 14, 64
+    centres = scenes.random_configs("panda", n_clusters, seed=5)
+    V = (centres[:, None, :] + rng.normal(0, 0.12, size=(n_clusters, per, 7)).astype(np.float32)).reshape(-1, 7)
+    lo = np.array(R.lower_bounds(), np.float32)
+    hi = np.array(R.upper_bounds(), np.float32)
+    V = np.clip(V, lo, hi).astype(np.float32)
+    valid = R.validate_batch(V, env)
+    # edges: pairs inside a cluster whose two vertices are valid
+    c = rng.integers(0, n_clusters, size=n_edges, dtype=np.int64)
+    i = rng.integers(0, per, size=n_edges, dtype=np.int64)
+    j = (i + rng.integers(1, per, size=n_edges, dtype=np.int64)) % per
+    pairs = np.stack([c * per + i, c * per + j], axis=1).astype(np.uint32)
+    keep = valid[pairs[:, 0]] & valid[pairs[:, 1]]
+    pairs = np.ascontiguousarray(pairs[keep])
+    n = len(pairs)
+    dV, dP, dB = L.vmv_dev_alloc(V.nbytes), L.vmv_dev_alloc(pairs.nbytes), L.vmv_dev_alloc((n + 31) // 32 * 4)
+    _lib.check(L.vmv_memcpy_h2d(dV, _lib.ptr(V), V.nbytes, None))
+    _lib.check(L.vmv_memcpy_h2d(dP, _lib.ptr(pairs), pairs.nbytes, None))
+    h = env.handle
+    t = time_launches(lambda: _lib.check(L.vmv_validate_edges_indexed_dev(R.id, h, dV, len(V), dP, n, 0, dB, None)), reps=3)
+    words = np.zeros((n + 31) // 32, np.uint32)
+    _lib.check(L.vmv_memcpy_d2h(_lib.ptr(words), dB, words.nbytes, None))
+    _lib.check(L.vmv_stream_sync(None))
+    d = np.linalg.norm(V[pairs[:100000, 0]] - V[pairs[:100000, 1]], axis=1)
+    print(json.dumps({"workload": f"C5: {n} PRM-style Panda edges (index pairs into {len(V)} vertices), table/shelf scene",
+                      "value": n / t, "unit": "edges/s", "ms": t * 1e3, "mean_edge_length_rad": float(d.mean()),
+                      "valid_fraction": float(_lib.unpack_bits(words, n).mean())}), flush=True)
+
+
+if __name__ == "__main__":
+    what = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c4", "c5"]
+    n_edges = int(sys.argv[sys.argv.index("--edges") + 1]) if "--edges" in sys.argv else 100_000_000
+    if "c4" in what:
+        c4()
+    if "c5" in what:
+        c5(n_edges)

@@ -8,7 +8,9 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libvamp_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("VMV_LIB", str(HERE / "libvamp_b200.so")))
 
 OK = 0
 

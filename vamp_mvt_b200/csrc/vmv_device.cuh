@@ -97,52 +97,81 @@ namespace vmv
     }
 
     // ------------------------------------------------------------------------------------------
-    // CAPT query for one sphere (reference collision/capt.hh:428-512, one lane)
+    // CAPT query (reference collision/capt.hh:428-512), warp-cooperative.
+    // Called by whichever lanes of the warp currently have a query (the converged group,
+    // __activemask()).  Each lane does its own top-AABB reject, Eytzinger descent and leaf-AABB test;
+    // the affordance lists of the lanes that survive are then scanned ONE LIST AT A TIME BY THE WHOLE
+    // GROUP: up to 32 lanes x 128-bit loads = 512 contiguous bytes per step, and a ballot ends the
+    // scan at the first chunk with a hit.
     // ------------------------------------------------------------------------------------------
-    __device__ __forceinline__ bool capt_collides(const CaptRec &t, float x, float y, float z, float r)
+    __device__ __forceinline__ bool capt_collides_warp(const CaptRec &t, float x, float y, float z, float r, bool active)
     {
-        // top-level AABB reject uses r, not r + r_point (capt.hh:431-438)
-        if (!((x + r >= t.lo[0]) & (x - r <= t.hi[0]) & (y + r >= t.lo[1]) & (y - r <= t.hi[1]) & (z + r >= t.lo[2]) &
-              (z - r <= t.hi[2])))
+        const uint32_t group = __activemask();
+        const int lane = threadIdx.x & 31;
+        const int rank = __popc(group & ((1u << lane) - 1u));  // position of this lane inside the group
+        const int gsize = __popc(group);
+        bool need = false;
+        uint32_t start = 0, end = 0;
+        float rc_sq = 0.F;
+        if (active)
         {
-            return false;
-        }
-
-        const float c[3] = {x, y, z};
-        uint32_t idx = 0;
-        int k = 0;
-        for (uint32_t i = 0; i < t.nlog2; ++i)
-        {
-            const float split = __ldg(t.tests + idx);
-            const float v = (k == 0) ? c[0] : ((k == 1) ? c[1] : c[2]);
-            idx = 2 * idx + 1 + (v >= split ? 1u : 0u);
-            k = (k == 2) ? 0 : k + 1;
-        }
-
-        const uint32_t leaf = idx - t.n_tests;
-        const float rr = r + t.r_point;
-        const float rc_sq = rr * rr;
-        const float4 b0 = __ldg(t.aabbs + 2 * leaf);
-        const float4 b1 = __ldg(t.aabbs + 2 * leaf + 1);
-        const float d0 = x - fminf(fmaxf(x, b0.x), b0.w);
-        const float d1 = y - fminf(fmaxf(y, b0.y), b1.x);
-        const float d2 = z - fminf(fmaxf(z, b0.z), b1.y);
-        if (!(d0 * d0 + d1 * d1 + d2 * d2 <= rc_sq))
-        {
-            return false;
-        }
-
-        const uint32_t start = __float_as_uint(b1.z), end = __float_as_uint(b1.w);
-        for (uint32_t i = start; i < end; ++i)
-        {
-            const float4 p = __ldg(t.points + i);
-            const float ex = p.x - x, ey = p.y - y, ez = p.z - z;
-            if (ex * ex + ey * ey + ez * ez <= rc_sq)
+            // top-level AABB reject uses r, not r + r_point (capt.hh:431-438)
+            const bool inb = (x + r >= t.lo[0]) & (x - r <= t.hi[0]) & (y + r >= t.lo[1]) & (y - r <= t.hi[1]) &
+                             (z + r >= t.lo[2]) & (z - r <= t.hi[2]);
+            if (inb)
             {
-                return true;
+                uint32_t idx = 0;
+                int k = 0;
+                for (uint32_t i = 0; i < t.nlog2; ++i)
+                {
+                    const float split = __ldg(t.tests + idx);
+                    const float v = (k == 0) ? x : ((k == 1) ? y : z);
+                    idx = 2 * idx + 1 + (v >= split ? 1u : 0u);
+                    k = (k == 2) ? 0 : k + 1;
+                }
+                const uint32_t leaf = idx - t.n_tests;
+                const float rr = r + t.r_point;
+                rc_sq = rr * rr;
+                const float4 b0 = __ldg(t.aabbs + 2 * leaf);
+                const float4 b1 = __ldg(t.aabbs + 2 * leaf + 1);
+                const float d0 = x - fminf(fmaxf(x, b0.x), b0.w);
+                const float d1 = y - fminf(fmaxf(y, b0.y), b1.x);
+                const float d2 = z - fminf(fmaxf(z, b0.z), b1.y);
+                need = d0 * d0 + d1 * d1 + d2 * d2 <= rc_sq;
+                start = __float_as_uint(b1.z);
+                end = __float_as_uint(b1.w);
             }
         }
-        return false;
+
+        bool hit = false;
+        uint32_t pending = __ballot_sync(group, need);
+        while (pending != 0u)
+        {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1u;
+            const uint32_t s = __shfl_sync(group, start, src), e = __shfl_sync(group, end, src);
+            const float qx = __shfl_sync(group, x, src), qy = __shfl_sync(group, y, src);
+            const float qz = __shfl_sync(group, z, src), qr = __shfl_sync(group, rc_sq, src);
+            bool found = false;
+            for (uint32_t base = s; base < e; base += gsize)
+            {
+                const uint32_t i = base + rank;
+                bool h = false;
+                if (i < e)
+                {
+                    const float4 p = __ldg(t.points + i);
+                    const float ex = p.x - qx, ey = p.y - qy, ez = p.z - qz;
+                    h = ex * ex + ey * ey + ez * ez <= qr;
+                }
+                if (__any_sync(group, h))
+                {
+                    found = true;
+                    break;
+                }
+            }
+            hit = (lane == src) ? found : hit;
+        }
+        return hit;
     }
 
     // ------------------------------------------------------------------------------------------
@@ -156,7 +185,8 @@ namespace vmv
     // objects we test is a superset of every object that can actually touch the sphere.
     // r_pc is the radius used for pointcloud queries (see check_state: a link's bounding sphere is
     // queried with its exact, un-inflated radius there).
-    __device__ __forceinline__ bool sphere_hits_env(const float *__restrict__ E, float x, float y, float z, float r, float r_pc)
+    // spheres, capsules, cuboids and heightfields for one sphere (no warp-level operations)
+    __device__ __forceinline__ bool sphere_hits_primitives(const float *__restrict__ E, float x, float y, float z, float r)
     {
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
         const float ext = fmaf(__fsqrt_rn(fmaf(x, x, fmaf(y, y, z * z))), 1.0000002f, r);
@@ -282,16 +312,30 @@ namespace vmv
             }
         }
 
+        return false;
+    }
+
+    // May be called by any subset of a warp's lanes; lanes that arrive together cooperate on the
+    // pointcloud scans (`active` false = lane has no sphere but helps scanning).
+    __device__ __forceinline__ bool
+    sphere_hits_env(const float *__restrict__ E, float x, float y, float z, float r, float r_pc, bool active)
+    {
+        bool hit = false;
+        if (active)
+        {
+            hit = sphere_hits_primitives(E, x, y, z, r);
+        }
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
         for (uint32_t i = 0; i < H.n_capts; ++i)
         {
             const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * i);
-            if (capt_collides(t, x, y, z, r_pc))
+            // lanes that already collided skip the query but keep the warp's loop structure
+            if (capt_collides_warp(t, x, y, z, r_pc, active && !hit))
             {
-                return true;
+                hit = true;
             }
         }
-
-        return false;
+        return hit;
     }
 
     // ------------------------------------------------------------------------------------------

@@ -307,7 +307,7 @@ namespace vmv
                 {
                     t = c.tasks[ti];
                     task_centre<BLOCK>(t, c.stash, x, y, z);
-                    hit = sphere_hits_env(c.env, x, y, z, t.r, t.skip >= 0 ? t.r - 1e-6f : t.r);
+                    hit = sphere_hits_env(c.env, x, y, z, t.r, t.skip >= 0 ? t.r - 1e-6f : t.r, true);
                 }
                 if (collective)
                 {
@@ -344,7 +344,7 @@ namespace vmv
         // ---- C: self collision --------------------------------------------------------------
         {
             int pi = 0;
-            bool active = has_state && M::kPairs > 0;
+            bool active = has_state && !bad && M::kPairs > 0;
             while (vote.any(active))
             {
                 if (active)
@@ -395,93 +395,90 @@ namespace vmv
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(c.env);
         if (H.n_attach > 0)
         {
-            if (has_state)
+            // T = F[ee_body] * attach_tf   (Attachment::pose, collision/attachments.hh:43-55)
+            float T[12];
             {
-                // T = F[ee_body] * attach_tf   (Attachment::pose, collision/attachments.hh:43-55)
-                float T[12];
+                float F[12];
+                if (M::kEeBody == 0 || !has_state)
                 {
-                    float F[12];
-                    if (M::kEeBody == 0)
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
                     {
-#pragma unroll
-                        for (int k = 0; k < 12; ++k)
-                        {
-                            F[k] = (k % 5 == 0) ? 1.F : 0.F;
-                        }
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int k = 0; k < 12; ++k)
-                        {
-                            F[k] = (k % 4 == 2) ? 0.F : c.stash[((M::kEeBody - 1) * kFrameFloats + frame_slot(k)) * BLOCK];
-                        }
-                        F[2] = fmaf(F[4], F[9], -(F[8] * F[5]));
-                        F[6] = fmaf(F[8], F[1], -(F[0] * F[9]));
-                        F[10] = fmaf(F[0], F[5], -(F[4] * F[1]));
-                    }
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-                    {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                        {
-                            float s = F[4 * i] * env.attach_tf[j] + F[4 * i + 1] * env.attach_tf[4 + j] +
-                                      F[4 * i + 2] * env.attach_tf[8 + j];
-                            T[4 * i + j] = (j == 3) ? s + F[4 * i + 3] : s;
-                        }
+                        F[k] = (k % 5 == 0) ? 1.F : 0.F;
                     }
                 }
-                const float4 *S = reinterpret_cast<const float4 *>(c.env + H.off_attach + kAttachHdr);
-                // attachment vs environment (validity.hh:259-276)
-                for (uint32_t i = 0; i < H.n_attach && !bad; ++i)
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                    {
+                        F[k] = (k % 4 == 2) ? 0.F : c.stash[((M::kEeBody - 1) * kFrameFloats + frame_slot(k)) * BLOCK];
+                    }
+                    F[2] = fmaf(F[4], F[9], -(F[8] * F[5]));
+                    F[6] = fmaf(F[8], F[1], -(F[0] * F[9]));
+                    F[10] = fmaf(F[0], F[5], -(F[4] * F[1]));
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        float s = F[4 * i] * env.attach_tf[j] + F[4 * i + 1] * env.attach_tf[4 + j] +
+                                  F[4 * i + 2] * env.attach_tf[8 + j];
+                        T[4 * i + j] = (j == 3) ? s + F[4 * i + 3] : s;
+                    }
+                }
+            }
+            const float4 *S = reinterpret_cast<const float4 *>(c.env + H.off_attach + kAttachHdr);
+            // attachment vs environment (validity.hh:259-276)
+            for (uint32_t i = 0; i < H.n_attach && has_state && !bad; ++i)
+            {
+                const float4 s = S[i];
+                const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
+                const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
+                const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
+                bad = sphere_hits_env(c.env, x, y, z, s.w, s.w, true);
+            }
+            // attachment vs links, bounding sphere first (validity.hh:278-301); per lane
+            for (int k = 0; k < M::kAttachLinks && has_state && !bad; ++k)
+            {
+                const int l = c.attach_links[k];
+                const LinkInfo li = c.links[l];
+                const float *b = c.bounds + l * 3 * BLOCK;
+                const float br = c.tasks[li.bound_task].r;
+                bool near = false;
+                for (uint32_t i = 0; i < H.n_attach && !near; ++i)
                 {
                     const float4 s = S[i];
                     const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
                     const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
                     const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
-                    bad = sphere_hits_env(c.env, x, y, z, s.w, s.w);
+                    const float dx = b[0] - x, dy = b[BLOCK] - y, dz = b[2 * BLOCK] - z;
+                    const float rs = br + s.w;
+                    near = sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
                 }
-                // attachment vs links, bounding sphere first (validity.hh:278-301)
-                for (int k = 0; k < M::kAttachLinks && !bad; ++k)
+                if (!near)
                 {
-                    const int l = c.attach_links[k];
-                    const LinkInfo li = c.links[l];
-                    const float *b = c.bounds + l * 3 * BLOCK;
-                    const float br = c.tasks[li.bound_task].r;
-                    bool near = false;
-                    for (uint32_t i = 0; i < H.n_attach && !near; ++i)
+                    continue;
+                }
+                for (int f = 0; f < li.n_spheres && !bad; ++f)
+                {
+                    const SphereTask tf = c.tasks[li.bound_task + 1 + f];
+                    float fx, fy, fz;
+                    task_centre<BLOCK>(tf, c.stash, fx, fy, fz);
+                    for (uint32_t i = 0; i < H.n_attach; ++i)
                     {
                         const float4 s = S[i];
                         const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
                         const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
                         const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
-                        const float dx = b[0] - x, dy = b[BLOCK] - y, dz = b[2 * BLOCK] - z;
-                        const float rs = br + s.w;
-                        near = sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
-                    }
-                    if (!near)
-                    {
-                        continue;
-                    }
-                    for (int f = 0; f < li.n_spheres && !bad; ++f)
-                    {
-                        const SphereTask tf = c.tasks[li.bound_task + 1 + f];
-                        float fx, fy, fz;
-                        task_centre<BLOCK>(tf, c.stash, fx, fy, fz);
-                        for (uint32_t i = 0; i < H.n_attach; ++i)
+                        const float dx = fx - x, dy = fy - y, dz = fz - z;
+                        const float rs = tf.r + s.w;
+                        if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
                         {
-                            const float4 s = S[i];
-                            const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
-                            const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
-                            const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
-                            const float dx = fx - x, dy = fy - y, dz = fz - z;
-                            const float rs = tf.r + s.w;
-                            if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
-                            {
-                                bad = true;
-                                break;
-                            }
+                            bad = true;
+                            break;
                         }
                     }
                 }
@@ -499,7 +496,7 @@ namespace vmv
     // kernels
     // ------------------------------------------------------------------------------------------
     template <typename R, int BLOCK>
-    __global__ void __launch_bounds__(BLOCK)
+    __global__ void __maxnreg__(128)
         k_validate_configs(RobotDev robot, LaunchEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
     {
         using M = typename R::Model;
@@ -554,7 +551,7 @@ namespace vmv
     // them back n-1 times by vector/(8n) (planning/validate.hh:31-64).  A warp covers 4 such steps
     // (32 states) per pass; the edge is invalid as soon as any state is.
     template <typename R, int BLOCK, bool INDEXED>
-    __global__ void __launch_bounds__(BLOCK) k_validate_edges(
+    __global__ void __maxnreg__(128) k_validate_edges(
         RobotDev robot,
         LaunchEnv env,
         const float *__restrict__ a,
