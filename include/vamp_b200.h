@@ -135,7 +135,8 @@ extern "C"
      * number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
     uint64_t vmv_launch_count(void);
     /* testing aid: 0 = automatic choice (default), 1 = force the generic per-thread kernel,
-     * 2 = force the block-cooperative kernel (fails with VMV_ERR_LIMIT when it does not apply) */
+     * 2 = force the block-cooperative kernel, 3 = force the grid-culled kernel (2 and 3 fail with
+     * VMV_ERR_LIMIT when they do not apply to the environment) */
     int vmv_force_kernel_path(int path);
 
 #ifdef __cplusplus

@@ -49,7 +49,7 @@ def test_sphere_fk(robot):
     assert len(single) == R.n_spheres() and abs(single[3].x - want[0, 3, 0]) < 2e-6
 
 
-@pytest.mark.parametrize("path", [1, 0], ids=["per_thread_kernel", "auto_kernel"])
+@pytest.mark.parametrize("path", [1, 2, 3, 0], ids=["per_thread_kernel", "block_kernel", "grid_kernel", "auto_kernel"])
 @pytest.mark.parametrize("robot", ROBOTS)
 def test_config_verdicts(robot, path):
     R, O = getattr(vmv, robot), po.Oracle(robot)
@@ -57,6 +57,8 @@ def test_config_verdicts(robot, path):
     _lib.lib().vmv_force_kernel_path(path)
     try:
         for name, sc in scenes_for(robot):
+            if path == 3 and not sc["order"]:
+                continue  # nothing to rasterise: the grid-culled kernel does not apply
             env = scenes.build_product_env(sc)
             oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
             q = scenes.random_configs(robot, 30000, seed=3)
@@ -71,8 +73,17 @@ def test_config_verdicts(robot, path):
         _lib.lib().vmv_force_kernel_path(0)
 
 
+@pytest.mark.parametrize("path", [2, 0], ids=["block_kernel", "auto_kernel"])
 @pytest.mark.parametrize("robot", ROBOTS)
-def test_edge_verdicts(robot):
+def test_edge_verdicts(robot, path):
+    try:
+        _lib.lib().vmv_force_kernel_path(path if robot != "baxter" else 0)  # baxter edges have no block kernel
+        _edge_verdicts(robot)
+    finally:
+        _lib.lib().vmv_force_kernel_path(0)
+
+
+def _edge_verdicts(robot):
     R, O = getattr(vmv, robot), po.Oracle(robot)
     ref = po.Ref(robot) if po.ref_available() else None
     for name, sc in scenes_for(robot):
@@ -250,6 +261,8 @@ def test_indexed_edges_and_device_api():
     dB = L.vmv_dev_alloc((len(pairs) + 31) // 32 * 4)
     _lib.check(L.vmv_memcpy_h2d(dV, _lib.ptr(V), V.nbytes, None))
     _lib.check(L.vmv_memcpy_h2d(dP, _lib.ptr(pairs), pairs.nbytes, None))
+    # first use of the environment with this robot also rasterises it (one extra launch, once)
+    _lib.check(L.vmv_validate_edges_indexed_dev(vmv.panda.id, env.handle, dV, len(V), dP, len(pairs), 0, dB, None))
     before = L.vmv_launch_count()
     _lib.check(L.vmv_validate_edges_indexed_dev(vmv.panda.id, env.handle, dV, len(V), dP, len(pairs), 0, dB, None))
     assert L.vmv_launch_count() == before + 1

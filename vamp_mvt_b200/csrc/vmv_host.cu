@@ -16,6 +16,7 @@
 
 #include "../../include/vamp_b200.h"
 #include "vmv_kernels_v2.cuh"
+#include "vmv_kernels_v3.cuh"
 
 #include "gen/panda_fk.cuh"
 #include "gen/ur5_fk.cuh"
@@ -91,6 +92,33 @@ namespace
     VMV_ROBOT(baxter)
 #undef VMV_ROBOT
 
+#define VMV_X_MAXREACH(l, r, n, t, reach) m = (reach) > m ? (reach) : m;
+    float panda_max_reach()
+    {
+        float m = 0.F;
+        VMV_PANDA_LINKS(VMV_X_MAXREACH)
+        return m;
+    }
+    float ur5_max_reach()
+    {
+        float m = 0.F;
+        VMV_UR5_LINKS(VMV_X_MAXREACH)
+        return m;
+    }
+    float fetch_max_reach()
+    {
+        float m = 0.F;
+        VMV_FETCH_LINKS(VMV_X_MAXREACH)
+        return m;
+    }
+    float baxter_max_reach()
+    {
+        float m = 0.F;
+        VMV_BAXTER_LINKS(VMV_X_MAXREACH)
+        return m;
+    }
+#undef VMV_X_MAXREACH
+
     struct RobotHost
     {
         const char *name;
@@ -104,6 +132,7 @@ namespace
         const vmv::PairInfo *pair_info;
         const vmv::SpherePair *pair_lists;
         int n_pair_lists;
+        float max_reach;  // farthest any link's bounding sphere extends from the world origin
     };
 
 #define VMV_ROBOT_HOST(NAME)                                                                                  \
@@ -114,7 +143,7 @@ namespace
             vmv::gen::NAME##_model::kEeBody, vmv::gen::NAME##_lower, vmv::gen::NAME##_range,                  \
             vmv::gen::NAME##_tasks_host, vmv::gen::NAME##_links_host, vmv::gen::NAME##_pairs_host,            \
             vmv::gen::NAME##_attach_links_host, vmv::gen::NAME##_ee_tf_host, vmv::gen::NAME##_pair_info_host, \
-            vmv::gen::NAME##_pair_lists_host, vmv::gen::NAME##_pair_lists_count                               \
+            vmv::gen::NAME##_pair_lists_host, vmv::gen::NAME##_pair_lists_count, NAME##_max_reach()           \
     }
     const RobotHost g_robots[VMV_N_ROBOTS] = {
         VMV_ROBOT_HOST(panda), VMV_ROBOT_HOST(ur5), VMV_ROBOT_HOST(fetch), VMV_ROBOT_HOST(baxter)};
@@ -399,8 +428,33 @@ struct vmv_env
     int *d_object_ids = nullptr;  // packed object index -> insertion id (vmv_debug)
     std::vector<void *> owned;  // device allocations referenced from the blob
 
+    // grid-culled path (vmv_kernels_v3.cuh): rounded-box records of all primitives and, per robot,
+    // the voxel table of candidate masks (built on first use with that robot)
+    std::vector<float> uobjs;  // kObjRec floats per object, packed order
+    float4 *d_uobjs = nullptr;
+    struct GridCache
+    {
+        bool ready = false;
+        bool usable = false;
+        vmv::GridDev dev{};
+        void *mem = nullptr;
+        float build_ms = 0.F;
+        size_t bytes = 0;
+    };
+    mutable std::mutex grid_mutex;
+    mutable GridCache grids[VMV_N_ROBOTS];
+
     void release_device()
     {
+        for (auto &g : grids)
+        {
+            if (g.mem)
+            {
+                cudaFree(g.mem);
+            }
+            g = GridCache{};
+        }
+        d_uobjs = nullptr;  // freed through `owned`
         for (void *p : owned)
         {
             cudaFree(p);
@@ -443,6 +497,106 @@ namespace
         }
         dev = static_cast<T *>(p);
         return VMV_OK;
+    }
+
+    // Every primitive as a rounded box {centre, rho}{axis_i, half extent_i} (vmv_kernels_v3.cuh), in
+    // the packed order spheres | capsules | z-capsules | cuboids | z-cuboids.
+    void build_rounded_boxes(vmv_env *env)
+    {
+        std::vector<float> &U = env->uobjs;
+        U.clear();
+        auto rec = [&](const double c[3], double rho, const double a[3][3], const double h[3])
+        {
+            U.push_back(static_cast<float>(c[0])), U.push_back(static_cast<float>(c[1])), U.push_back(static_cast<float>(c[2]));
+            U.push_back(static_cast<float>(rho));
+            for (int i = 0; i < 3; ++i)
+            {
+                U.push_back(static_cast<float>(a[i][0])), U.push_back(static_cast<float>(a[i][1])), U.push_back(static_cast<float>(a[i][2]));
+                U.push_back(static_cast<float>(h[i]));
+            }
+        };
+        const double I[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        const double Z[3] = {0, 0, 0};
+        for (const auto &s : env->spheres)
+        {
+            const double c[3] = {s.x, s.y, s.z};
+            rec(c, s.r, I, Z);
+        }
+        auto capsule = [&](const HCapsule &k)
+        {
+            const double v[3] = {k.xv, k.yv, k.zv};
+            const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            if (!(len > 1e-12) || !std::isfinite(len))
+            {
+                // degenerate segment: the clamped projection of the reference stays at the first end point
+                const double c[3] = {k.x1, k.y1, k.z1};
+                rec(c, k.r, I, Z);
+                return;
+            }
+            double a[3][3];
+            for (int j = 0; j < 3; ++j)
+            {
+                a[0][j] = v[j] / len;
+            }
+            // any orthonormal complement of a[0]
+            int m = 0;
+            for (int j = 1; j < 3; ++j)
+            {
+                if (std::fabs(a[0][j]) < std::fabs(a[0][m]))
+                {
+                    m = j;
+                }
+            }
+            double e[3] = {0, 0, 0};
+            e[m] = 1.0;
+            double d = a[0][m];
+            double n2 = 0;
+            for (int j = 0; j < 3; ++j)
+            {
+                a[1][j] = e[j] - d * a[0][j];
+                n2 += a[1][j] * a[1][j];
+            }
+            n2 = std::sqrt(n2);
+            for (int j = 0; j < 3; ++j)
+            {
+                a[1][j] /= n2;
+            }
+            a[2][0] = a[0][1] * a[1][2] - a[0][2] * a[1][1];
+            a[2][1] = a[0][2] * a[1][0] - a[0][0] * a[1][2];
+            a[2][2] = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+            const double c[3] = {k.x1 + 0.5 * v[0], k.y1 + 0.5 * v[1], k.z1 + 0.5 * v[2]};
+            const double h[3] = {0.5 * len, 0, 0};
+            rec(c, k.r, a, h);
+        };
+        for (const auto &k : env->capsules)
+        {
+            capsule(k);
+        }
+        for (const auto &k : env->z_capsules)
+        {
+            capsule(k);
+        }
+        auto cuboid = [&](const HCuboid &b)
+        {
+            const float *f = b.f;
+            const double c[3] = {f[0], f[1], f[2]};
+            const double a[3][3] = {{f[3], f[4], f[5]}, {f[6], f[7], f[8]}, {f[9], f[10], f[11]}};
+            const double h[3] = {f[12], f[13], f[14]};
+            rec(c, 0.0, a, h);
+        };
+        for (const auto &b : env->cuboids)
+        {
+            cuboid(b);
+        }
+        for (const auto &b : env->z_cuboids)
+        {
+            // the z-aligned test reads only the xy parts of axes 1, 2 and takes axis 3 = z
+            // (collision/sphere_cuboid.hh:35-52)
+            HCuboid zb = b;
+            zb.f[5] = 0.F, zb.f[8] = 0.F;
+            zb.f[9] = 0.F, zb.f[10] = 0.F, zb.f[11] = 1.F;
+            cuboid(zb);
+        }
     }
 
     int pack_and_upload(vmv_env *env)
@@ -604,6 +758,16 @@ namespace
         }
         VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&env->d_blob), B.size() * 4));
         VMV_CUDA(cudaMemcpy(env->d_blob, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+        {
+            build_rounded_boxes(env);
+            std::vector<float4> recs(env->uobjs.size() / 4);
+            std::memcpy(recs.data(), env->uobjs.data(), env->uobjs.size() * sizeof(float));
+            int rc = upload(env, recs, env->d_uobjs);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
         env->committed = true;
         return VMV_OK;
     }
@@ -676,6 +840,253 @@ namespace
         VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
         const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
         kernel<<<grid, BLOCK, L.total, s>>>(rd, le, q, n, bits);
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        return VMV_OK;
+    }
+
+    // ---- grid-culled path ---------------------------------------------------------------------
+    constexpr size_t kGridMinConfigs = 4096;  // smaller batches do not amortise a table build
+    constexpr size_t kGridMinEdges = 256;
+    constexpr size_t kGridMaxVoxels = 400000;
+
+    struct RobotGridInfo
+    {
+        bool ready = false;
+        float class_r[vmv::kGridClasses];
+        unsigned char link_class[vmv::kGridMaxLinks];
+        float reach;
+        uint32_t max_fine;
+    };
+    RobotGridInfo g_grid_info[VMV_N_ROBOTS];
+
+    // Radius classes of a robot's link bounding spheres: the partition of the sorted radii into at
+    // most kGridClasses groups that minimises the total over-estimate (class radius - link radius).
+    const RobotGridInfo &robot_grid_info(int robot)
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        RobotGridInfo &gi = g_grid_info[robot];
+        if (gi.ready)
+        {
+            return gi;
+        }
+        const RobotHost &r = g_robots[robot];
+        const int n = r.n_links;
+        std::vector<int> order(n);
+        std::iota(order.begin(), order.end(), 0);
+        auto rad = [&](int l) { return r.tasks[r.links[l].bound_task].r; };
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return rad(a) < rad(b); });
+        constexpr int K = vmv::kGridClasses;
+        const double inf = 1e30;
+        std::vector<std::vector<double>> dp(K + 1, std::vector<double>(n + 1, inf));
+        std::vector<std::vector<int>> cut(K + 1, std::vector<int>(n + 1, 0));
+        dp[0][0] = 0;
+        for (int g = 1; g <= K; ++g)
+        {
+            for (int j = 1; j <= n; ++j)
+            {
+                for (int i = g - 1; i < j; ++i)
+                {
+                    if (dp[g - 1][i] >= inf)
+                    {
+                        continue;
+                    }
+                    double cost = 0;
+                    for (int k = i; k < j; ++k)
+                    {
+                        cost += rad(order[j - 1]) - rad(order[k]);
+                    }
+                    if (dp[g - 1][i] + cost < dp[g][j])
+                    {
+                        dp[g][j] = dp[g - 1][i] + cost;
+                        cut[g][j] = i;
+                    }
+                }
+            }
+        }
+        int groups = std::min(K, n);
+        for (int k = 0; k < K; ++k)
+        {
+            gi.class_r[k] = 0.F;
+        }
+        int j = n;
+        for (int g = groups; g >= 1; --g)
+        {
+            const int i = cut[g][j];
+            gi.class_r[g - 1] = rad(order[j - 1]);
+            for (int k = i; k < j; ++k)
+            {
+                gi.link_class[order[k]] = static_cast<unsigned char>(g - 1);
+            }
+            j = i;
+        }
+        for (int k = groups; k < K; ++k)
+        {
+            gi.class_r[k] = gi.class_r[groups - 1];
+        }
+        gi.max_fine = 1;
+        for (int l = 0; l < n; ++l)
+        {
+            gi.max_fine = std::max<uint32_t>(gi.max_fine, static_cast<uint32_t>(r.links[l].n_spheres));
+        }
+        gi.reach = r.max_reach;
+        gi.ready = true;
+        return gi;
+    }
+
+    // The voxel table of `env` for `robot` (built once, synchronously, on first use).  ok = false when
+    // the path does not apply (no primitives, more than 64 of them, other content in the environment).
+    int grid_launch_env(int robot, const vmv_env *env, vmv::LaunchEnvV3 &out, bool &ok)
+    {
+        ok = false;
+        const size_t n_obj = env->uobjs.size() / vmv::kObjRec;
+        if (n_obj == 0 || n_obj > 64 || !env->heightfields.empty() || !env->capts.empty() || env->has_attachment)
+        {
+            return VMV_OK;
+        }
+        const RobotGridInfo &gi = robot_grid_info(robot);
+        std::lock_guard<std::mutex> lock(env->grid_mutex);
+        vmv_env::GridCache &gc = env->grids[robot];
+        if (!gc.ready)
+        {
+            gc.ready = true;
+            gc.usable = false;
+            const float r_max = *std::max_element(gi.class_r, gi.class_r + vmv::kGridClasses);
+            // region: bounding box of the objects grown by r_max (a centre outside it is farther than
+            // r_max from every object), clipped to the cube the robot can reach
+            const float grow = r_max + 1e-3F;
+            double lo[3] = {1e30, 1e30, 1e30}, hi[3] = {-1e30, -1e30, -1e30};
+            bool finite = true;
+            for (size_t k = 0; k < n_obj; ++k)
+            {
+                const float *u = env->uobjs.data() + k * vmv::kObjRec;
+                for (int j = 0; j < 3; ++j)
+                {
+                    const double ext = std::fabs(u[4 + j]) * u[7] + std::fabs(u[8 + j]) * u[11] + std::fabs(u[12 + j]) * u[15] + u[3] + grow;
+                    lo[j] = std::min(lo[j], u[j] - ext);
+                    hi[j] = std::max(hi[j], u[j] + ext);
+                    finite = finite && std::isfinite(ext) && std::isfinite(u[j]);
+                }
+            }
+            if (!finite)
+            {
+                return VMV_OK;
+            }
+            bool empty = false;
+            for (int j = 0; j < 3; ++j)
+            {
+                lo[j] = std::max<double>(lo[j], -gi.reach);
+                hi[j] = std::min<double>(hi[j], gi.reach);
+                empty = empty || !(hi[j] > lo[j]);
+            }
+            if (empty)
+            {
+                // nothing within reach: a 1-voxel table of empty masks far away
+                lo[0] = lo[1] = lo[2] = 1e6;
+                hi[0] = hi[1] = hi[2] = 1e6 + 1;
+            }
+            double h = 0.04;
+            int nx, ny, nz;
+            while (true)
+            {
+                nx = std::max(1, static_cast<int>(std::ceil((hi[0] - lo[0]) / h)));
+                ny = std::max(1, static_cast<int>(std::ceil((hi[1] - lo[1]) / h)));
+                nz = std::max(1, static_cast<int>(std::ceil((hi[2] - lo[2]) / h)));
+                if (static_cast<size_t>(nx) * ny * nz <= kGridMaxVoxels)
+                {
+                    break;
+                }
+                h *= 1.15;
+            }
+            const size_t n_vox = static_cast<size_t>(nx) * ny * nz;
+            gc.bytes = n_vox * vmv::kGridClasses * sizeof(unsigned long long);
+            VMV_CUDA(cudaMalloc(&gc.mem, gc.bytes));
+            cudaEvent_t e0, e1;
+            VMV_CUDA(cudaEventCreate(&e0));
+            VMV_CUDA(cudaEventCreate(&e1));
+            VMV_CUDA(cudaEventRecord(e0, nullptr));
+            vmv::k_build_grid<<<static_cast<unsigned>((n_vox + 127) / 128), 128>>>(
+                env->d_uobjs, static_cast<uint32_t>(n_obj), static_cast<float>(lo[0]), static_cast<float>(lo[1]), static_cast<float>(lo[2]),
+                static_cast<float>(h), nx, ny, nz, gi.class_r[0], gi.class_r[1], gi.class_r[2], gi.class_r[3],
+                static_cast<unsigned long long *>(gc.mem));
+            g_launches++;
+            VMV_CUDA(cudaGetLastError());
+            VMV_CUDA(cudaEventRecord(e1, nullptr));
+            VMV_CUDA(cudaEventSynchronize(e1));
+            VMV_CUDA(cudaEventElapsedTime(&gc.build_ms, e0, e1));
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            gc.dev.masks = static_cast<const unsigned long long *>(gc.mem);
+            gc.dev.x0 = static_cast<float>(lo[0]), gc.dev.y0 = static_cast<float>(lo[1]), gc.dev.z0 = static_cast<float>(lo[2]);
+            gc.dev.inv_h = static_cast<float>(1.0 / h);
+            gc.dev.nx = nx, gc.dev.ny = ny, gc.dev.nz = nz;
+            gc.dev.all_mask = n_obj >= 64 ? ~0ull : ((1ull << n_obj) - 1ull);
+            std::memcpy(gc.dev.link_class, gi.link_class, sizeof(gc.dev.link_class));
+            gc.usable = true;
+        }
+        if (!gc.usable)
+        {
+            return VMV_OK;
+        }
+        out.objs = env->d_uobjs;
+        out.n_objects = static_cast<uint32_t>(n_obj);
+        out.max_fine = gi.max_fine;
+        out.grid = gc.dev;
+        ok = true;
+        return VMV_OK;
+    }
+
+    template <typename R, int BLOCK>
+    int launch_configs_v3(const vmv::RobotDev &rd, const vmv::LaunchEnvV3 &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
+    {
+        using M = typename R::Model;
+        const vmv::SmemLayoutV3<M, BLOCK> L(le.n_objects, le.max_fine);
+        if (L.total > kMaxSmem)
+        {
+            return fail(VMV_ERR_LIMIT, "robot tables too large for the grid-culled kernel");
+        }
+        auto kernel = vmv::k_validate_configs_v3<R, BLOCK>;
+        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
+        const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
+        kernel<<<grid, BLOCK, L.total, s>>>(rd, le, q, n, bits);
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        return VMV_OK;
+    }
+
+    template <typename R>
+    int launch_edges_v3(
+        const vmv::RobotDev &rd,
+        const vmv::LaunchEnvV3 &le,
+        const float *a,
+        const float *b,
+        const uint32_t *pairs,
+        size_t n,
+        float resolution,
+        uint32_t *bits,
+        cudaStream_t s)
+    {
+        using M = typename R::Model;
+        const vmv::SmemLayoutV3<M, 128> L(le.n_objects, le.max_fine);
+        if (L.total + 4096 > kMaxSmem)
+        {
+            return fail(VMV_ERR_LIMIT, "robot tables too large for the grid-culled kernel");
+        }
+        const size_t chunks = (n + 31) / 32;
+        const int per_sm = std::max<int>(1, static_cast<int>(kMaxSmem / std::max<uint32_t>(L.total + 4096, 1)));
+        const unsigned grid = static_cast<unsigned>(std::min<size_t>(chunks, static_cast<size_t>(sm_count()) * per_sm * 8));
+        if (pairs != nullptr)
+        {
+            auto kernel = vmv::k_validate_edges_v3<R, 128, true>;
+            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
+            kernel<<<grid, 128, L.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+        }
+        else
+        {
+            auto kernel = vmv::k_validate_edges_v3<R, 128, false>;
+            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
+            kernel<<<grid, 128, L.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+        }
         g_launches++;
         VMV_CUDA(cudaGetLastError());
         return VMV_OK;
@@ -1144,6 +1555,29 @@ extern "C"
             return rc;
         }
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const int force = g_force_path.load();
+        if ((force == 0 && n >= kGridMinConfigs) || force == 3)
+        {
+            vmv::LaunchEnvV3 l3{};
+            bool ok = false;
+            rc = grid_launch_env(robot, env, l3, ok);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            if (ok)
+            {
+                VMV_DISPATCH(robot, (launch_configs_v3<R, BLOCK>(rd, l3, d_q, n, d_bits, s)))
+                if (rc != VMV_ERR_LIMIT || force == 3)
+                {
+                    return rc;
+                }
+            }
+            else if (force == 3)
+            {
+                return fail(VMV_ERR_LIMIT, "grid-culled kernel not applicable to this environment");
+            }
+        }
         VMV_DISPATCH(robot, (launch_configs<R, BLOCK>(rd, le, d_q, n, d_bits, s)))
         return rc;
     }
@@ -1173,6 +1607,29 @@ extern "C"
         }
         const float res = static_cast<float>(resolution > 0 ? resolution : g_robots[robot].resolution);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const int force = g_force_path.load();
+        if ((force == 0 && n >= kGridMinEdges) || force == 3)
+        {
+            vmv::LaunchEnvV3 l3{};
+            bool ok = false;
+            rc = grid_launch_env(robot, env, l3, ok);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            if (ok)
+            {
+                VMV_DISPATCH(robot, (launch_edges_v3<R>(rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
+                if (rc != VMV_ERR_LIMIT || force == 3)
+                {
+                    return rc;
+                }
+            }
+            else if (force == 3)
+            {
+                return fail(VMV_ERR_LIMIT, "grid-culled kernel not applicable to this environment");
+            }
+        }
         VMV_DISPATCH(robot, (launch_edges<R, BLOCK>(rd, le, d_a, d_b, d_pairs, n, res, d_bits, s)))
         return rc;
     }
