@@ -17,6 +17,7 @@
 #include "../../include/vamp_b200.h"
 #include "vmv_kernels_v2.cuh"
 #include "vmv_kernels_v3.cuh"
+#include "vmv_kernels_v4.cuh"
 
 #include "gen/panda_fk.cuh"
 #include "gen/ur5_fk.cuh"
@@ -436,6 +437,7 @@ struct vmv_env
     {
         bool ready = false;
         bool usable = false;
+        bool wide = false;  // 64-bit masks (more than 32 objects), else 32-bit
         vmv::GridDev dev{};
         void *mem = nullptr;
         float build_ms = 0.F;
@@ -936,9 +938,10 @@ namespace
 
     // The voxel table of `env` for `robot` (built once, synchronously, on first use).  ok = false when
     // the path does not apply (no primitives, more than 64 of them, other content in the environment).
-    int grid_launch_env(int robot, const vmv_env *env, vmv::LaunchEnvV3 &out, bool &ok)
+    int grid_launch_env(int robot, const vmv_env *env, vmv::LaunchEnvV3 &out, bool &ok, bool &wide)
     {
         ok = false;
+        wide = false;
         const size_t n_obj = env->uobjs.size() / vmv::kObjRec;
         if (n_obj == 0 || n_obj > 64 || !env->heightfields.empty() || !env->capts.empty() || env->has_attachment)
         {
@@ -999,16 +1002,27 @@ namespace
                 h *= 1.15;
             }
             const size_t n_vox = static_cast<size_t>(nx) * ny * nz;
-            gc.bytes = n_vox * vmv::kGridClasses * sizeof(unsigned long long);
+            gc.wide = n_obj > 32;
+            gc.bytes = n_vox * vmv::kGridClasses * (gc.wide ? sizeof(unsigned long long) : sizeof(uint32_t));
             VMV_CUDA(cudaMalloc(&gc.mem, gc.bytes));
             cudaEvent_t e0, e1;
             VMV_CUDA(cudaEventCreate(&e0));
             VMV_CUDA(cudaEventCreate(&e1));
             VMV_CUDA(cudaEventRecord(e0, nullptr));
-            vmv::k_build_grid<<<static_cast<unsigned>((n_vox + 127) / 128), 128>>>(
-                env->d_uobjs, static_cast<uint32_t>(n_obj), static_cast<float>(lo[0]), static_cast<float>(lo[1]), static_cast<float>(lo[2]),
-                static_cast<float>(h), nx, ny, nz, gi.class_r[0], gi.class_r[1], gi.class_r[2], gi.class_r[3],
-                static_cast<unsigned long long *>(gc.mem));
+            if (gc.wide)
+            {
+                vmv::k_build_grid_t<unsigned long long><<<static_cast<unsigned>((n_vox + 127) / 128), 128>>>(
+                    env->d_uobjs, static_cast<uint32_t>(n_obj), static_cast<float>(lo[0]), static_cast<float>(lo[1]), static_cast<float>(lo[2]),
+                    static_cast<float>(h), nx, ny, nz, gi.class_r[0], gi.class_r[1], gi.class_r[2], gi.class_r[3],
+                    static_cast<unsigned long long *>(gc.mem));
+            }
+            else
+            {
+                vmv::k_build_grid_t<uint32_t><<<static_cast<unsigned>((n_vox + 127) / 128), 128>>>(
+                    env->d_uobjs, static_cast<uint32_t>(n_obj), static_cast<float>(lo[0]), static_cast<float>(lo[1]), static_cast<float>(lo[2]),
+                    static_cast<float>(h), nx, ny, nz, gi.class_r[0], gi.class_r[1], gi.class_r[2], gi.class_r[3],
+                    static_cast<uint32_t *>(gc.mem));
+            }
             g_launches++;
             VMV_CUDA(cudaGetLastError());
             VMV_CUDA(cudaEventRecord(e1, nullptr));
@@ -1032,30 +1046,80 @@ namespace
         out.n_objects = static_cast<uint32_t>(n_obj);
         out.max_fine = gi.max_fine;
         out.grid = gc.dev;
+        wide = gc.wide;
         ok = true;
         return VMV_OK;
     }
 
-    template <typename R, int BLOCK>
-    int launch_configs_v3(const vmv::RobotDev &rd, const vmv::LaunchEnvV3 &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
+    // Launch geometry of the warp-autonomous kernels: the number of warps per block that maximises
+    // the warps resident per SM (shared memory = block-shared tables + one slice per warp), and a
+    // persistent grid of that many blocks per SM.
+    template <typename K>
+    int v4_geometry(K kernel, uint32_t shared_bytes, uint32_t warp_bytes, int max_threads, size_t units, int &warps, unsigned &grid, uint32_t &smem)
     {
-        using M = typename R::Model;
-        const vmv::SmemLayoutV3<M, BLOCK> L(le.n_objects, le.max_fine);
-        if (L.total > kMaxSmem)
+        int best_w = 0, best_blocks = 0;
+        constexpr uint32_t kMaxDynamic = kMaxSmem - 1024;  // the opt-in limit counts static shared memory too
+        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynamic)));
+        for (int w = 1; w <= max_threads / 32; ++w)
+        {
+            const size_t bytes = static_cast<size_t>(shared_bytes) + static_cast<size_t>(w) * warp_bytes;
+            if (bytes > kMaxDynamic)
+            {
+                break;
+            }
+            int blocks = 0;
+            VMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, w * 32, bytes));
+            if (blocks * w > best_blocks * best_w || (blocks * w == best_blocks * best_w && blocks > 0))
+            {
+                best_w = w;
+                best_blocks = blocks;
+            }
+        }
+        if (best_w == 0 || best_blocks == 0)
         {
             return fail(VMV_ERR_LIMIT, "robot tables too large for the grid-culled kernel");
         }
-        auto kernel = vmv::k_validate_configs_v3<R, BLOCK>;
-        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
-        const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
-        kernel<<<grid, BLOCK, L.total, s>>>(rd, le, q, n, bits);
+        warps = best_w;
+        smem = shared_bytes + static_cast<uint32_t>(best_w) * warp_bytes;
+        const size_t tiles = (units + 31) / 32;
+        const size_t blocks_needed = (tiles + best_w - 1) / best_w;
+        grid = static_cast<unsigned>(std::min<size_t>(blocks_needed, static_cast<size_t>(sm_count()) * best_blocks));
+        return VMV_OK;
+    }
+
+    template <typename R>
+    struct V4Tune
+    {
+        static constexpr int kMaxThreads = 256, kMinBlocks = 2;  // <= 128 registers
+    };
+    template <>
+    struct V4Tune<baxter_robot>
+    {
+        static constexpr int kMaxThreads = 128, kMinBlocks = 2;  // <= 255 registers
+    };
+
+    template <typename R, typename MaskT>
+    int launch_configs_v4(const vmv::RobotDev &rd, const vmv::LaunchEnvV3 &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
+    {
+        using M = typename R::Model;
+        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine);
+        auto kernel = vmv::k_validate_configs_v4<R, MaskT, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
+        int warps = 0;
+        unsigned grid = 0;
+        uint32_t smem = 0;
+        int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kMaxThreads, n, warps, grid, smem);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        kernel<<<grid, warps * 32, smem, s>>>(rd, le, q, n, bits);
         g_launches++;
         VMV_CUDA(cudaGetLastError());
         return VMV_OK;
     }
 
-    template <typename R>
-    int launch_edges_v3(
+    template <typename R, typename MaskT>
+    int launch_edges_v4(
         const vmv::RobotDev &rd,
         const vmv::LaunchEnvV3 &le,
         const float *a,
@@ -1067,25 +1131,29 @@ namespace
         cudaStream_t s)
     {
         using M = typename R::Model;
-        const vmv::SmemLayoutV3<M, 128> L(le.n_objects, le.max_fine);
-        if (L.total + 4096 > kMaxSmem)
-        {
-            return fail(VMV_ERR_LIMIT, "robot tables too large for the grid-culled kernel");
-        }
-        const size_t chunks = (n + 31) / 32;
-        const int per_sm = std::max<int>(1, static_cast<int>(kMaxSmem / std::max<uint32_t>(L.total + 4096, 1)));
-        const unsigned grid = static_cast<unsigned>(std::min<size_t>(chunks, static_cast<size_t>(sm_count()) * per_sm * 8));
+        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine);
+        int warps = 0;
+        unsigned grid = 0;
+        uint32_t smem = 0;
         if (pairs != nullptr)
         {
-            auto kernel = vmv::k_validate_edges_v3<R, 128, true>;
-            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
-            kernel<<<grid, 128, L.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, true, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
+            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kMaxThreads, n, warps, grid, smem);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits);
         }
         else
         {
-            auto kernel = vmv::k_validate_edges_v3<R, 128, false>;
-            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
-            kernel<<<grid, 128, L.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, false, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
+            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kMaxThreads, n, warps, grid, smem);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits);
         }
         g_launches++;
         VMV_CUDA(cudaGetLastError());
@@ -1559,15 +1627,22 @@ extern "C"
         if ((force == 0 && n >= kGridMinConfigs) || force == 3)
         {
             vmv::LaunchEnvV3 l3{};
-            bool ok = false;
-            rc = grid_launch_env(robot, env, l3, ok);
+            bool ok = false, wide = false;
+            rc = grid_launch_env(robot, env, l3, ok, wide);
             if (rc != VMV_OK)
             {
                 return rc;
             }
             if (ok)
             {
-                VMV_DISPATCH(robot, (launch_configs_v3<R, BLOCK>(rd, l3, d_q, n, d_bits, s)))
+                if (wide)
+                {
+                    VMV_DISPATCH(robot, (launch_configs_v4<R, unsigned long long>(rd, l3, d_q, n, d_bits, s)))
+                }
+                else
+                {
+                    VMV_DISPATCH(robot, (launch_configs_v4<R, uint32_t>(rd, l3, d_q, n, d_bits, s)))
+                }
                 if (rc != VMV_ERR_LIMIT || force == 3)
                 {
                     return rc;
@@ -1611,15 +1686,22 @@ extern "C"
         if ((force == 0 && n >= kGridMinEdges) || force == 3)
         {
             vmv::LaunchEnvV3 l3{};
-            bool ok = false;
-            rc = grid_launch_env(robot, env, l3, ok);
+            bool ok = false, wide = false;
+            rc = grid_launch_env(robot, env, l3, ok, wide);
             if (rc != VMV_OK)
             {
                 return rc;
             }
             if (ok)
             {
-                VMV_DISPATCH(robot, (launch_edges_v3<R>(rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
+                if (wide)
+                {
+                    VMV_DISPATCH(robot, (launch_edges_v4<R, unsigned long long>(rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
+                }
+                else
+                {
+                    VMV_DISPATCH(robot, (launch_edges_v4<R, uint32_t>(rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
+                }
                 if (rc != VMV_ERR_LIMIT || force == 3)
                 {
                     return rc;

@@ -1,0 +1,685 @@
+// Warp-autonomous grid-culled kernels (sm_100a) for environments made of primitives (at most 64
+// objects).  Same algorithm as vmv_kernels_v3.cuh -- voxel table of candidate masks, rounded-box
+// records, exact tests only on candidates -- but the unit of cooperation is the warp, not the block:
+//
+//   * a warp owns 32 states per pass and a private slice of shared memory (frame stash, masks,
+//     work queues); phases are separated by __syncwarp() only, so the 16-18 resident warps of an SM
+//     drift apart and overlap each other's latencies instead of meeting at block barriers;
+//   * queues are filled with ballot / prefix-sum positions (no shared-memory atomics); the verdict
+//     mask of the 32 states is a warp-uniform register, merged with redux.sync after every round;
+//   * blocks are persistent: the environment records (one TMA bulk copy) and the robot tables are
+//     staged once per block, then each warp strides over its tiles;
+//   * shared memory per warp is ~11-13 KB (Panda), which is what bounds residency.
+//
+// Phase order inside a pass: A (FK, lane = state) -> voxel-table loads issued -> C1 (link-pair bounding
+// tests -> records) -> C2 (records, lane = record) -> B0 (consume the loads: candidate masks, Q1) ->
+// B1 (lane = (state, link) item: exact bounding test, fine items -> Q2) -> B2 (lane = fine item).
+// The self-collision phases sit between the issue and the use of the table loads and cover their
+// L2 latency.
+#pragma once
+#include "vmv_kernels_v3.cuh"
+
+namespace vmv
+{
+    static constexpr uint32_t kFullWarp = 0xffffffffu;
+
+    template <typename MaskT>
+    __device__ __forceinline__ int mask_pop_lowest(MaskT &m);
+
+    template <>
+    __device__ __forceinline__ int mask_pop_lowest<uint32_t>(uint32_t &m)
+    {
+        const int o = __ffs(static_cast<int>(m)) - 1;
+        m &= m - 1u;
+        return o;
+    }
+
+    template <>
+    __device__ __forceinline__ int mask_pop_lowest<unsigned long long>(unsigned long long &m)
+    {
+        const int o = __ffsll(static_cast<long long>(m)) - 1;
+        m &= m - 1ull;
+        return o;
+    }
+
+    template <typename MaskT>
+    __global__ void __launch_bounds__(128) k_build_grid_t(
+        const float4 *__restrict__ objs,
+        uint32_t n_objects,
+        float x0,
+        float y0,
+        float z0,
+        float h,
+        int nx,
+        int ny,
+        int nz,
+        float r0,
+        float r1,
+        float r2,
+        float r3,
+        MaskT *__restrict__ out)
+    {
+        const size_t n_vox = static_cast<size_t>(nx) * ny * nz;
+        const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (v >= n_vox)
+        {
+            return;
+        }
+        const int ix = static_cast<int>(v % nx), iy = static_cast<int>((v / nx) % ny), iz = static_cast<int>(v / (static_cast<size_t>(nx) * ny));
+        const float x = x0 + (ix + 0.5F) * h, y = y0 + (iy + 0.5F) * h, z = z0 + (iz + 0.5F) * h;
+        const float slack = 0.8660255F * h + 1e-4F;
+        MaskT m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        for (uint32_t k = 0; k < n_objects; ++k)
+        {
+            const float4 c = __ldg(objs + 4 * k), a1 = __ldg(objs + 4 * k + 1), a2 = __ldg(objs + 4 * k + 2), a3 = __ldg(objs + 4 * k + 3);
+            const float xs = x - c.x, ys = y - c.y, zs = z - c.z;
+            const float e1 = fmaxf(fabsf(a1.x * xs + a1.y * ys + a1.z * zs) - a1.w, 0.F);
+            const float e2 = fmaxf(fabsf(a2.x * xs + a2.y * ys + a2.z * zs) - a2.w, 0.F);
+            const float e3 = fmaxf(fabsf(a3.x * xs + a3.y * ys + a3.z * zs) - a3.w, 0.F);
+            const float d = sqrtf(e1 * e1 + e2 * e2 + e3 * e3) - c.w - slack;
+            const MaskT bit = static_cast<MaskT>(1) << k;
+            // !(d > r) also keeps an object whose record is not finite
+            m0 |= !(d > r0) ? bit : 0;
+            m1 |= !(d > r1) ? bit : 0;
+            m2 |= !(d > r2) ? bit : 0;
+            m3 |= !(d > r3) ? bit : 0;
+        }
+        MaskT *o = out + v * kGridClasses;
+        o[0] = m0, o[1] = m1, o[2] = m2, o[3] = m3;
+    }
+
+    template <typename MaskT>
+    __device__ __forceinline__ MaskT grid_lookup_t(const GridDev &G, float x, float y, float z, int cls)
+    {
+        const int ix = __float2int_rd((x - G.x0) * G.inv_h);
+        const int iy = __float2int_rd((y - G.y0) * G.inv_h);
+        const int iz = __float2int_rd((z - G.z0) * G.inv_h);
+        // outside the table = farther than the largest class radius from every object
+        const bool in = (static_cast<unsigned>(ix) < static_cast<unsigned>(G.nx)) & (static_cast<unsigned>(iy) < static_cast<unsigned>(G.ny)) &
+                        (static_cast<unsigned>(iz) < static_cast<unsigned>(G.nz));
+        if (!in)
+        {
+            // a centre that is not finite also lands here (its index saturates): give it every object
+            return (fabsf(x) < 1e30F && fabsf(y) < 1e30F && fabsf(z) < 1e30F) ? static_cast<MaskT>(0) : static_cast<MaskT>(G.all_mask);
+        }
+        const uint32_t idx = ((static_cast<uint32_t>(iz) * G.ny + iy) * G.nx + ix) * kGridClasses + cls;
+        return __ldg(reinterpret_cast<const MaskT *>(G.masks) + idx);
+    }
+
+    template <typename M, typename MaskT>
+    struct SmemLayoutV4
+    {
+        static constexpr int kStashFrames = (M::kBodies - 1) * kFrameFloats;
+        static constexpr int kPairChunk = 64;  // link pairs per C1 round (bounds the record queue)
+        static constexpr int kPairCap = 32 * (M::kPairs < 1 ? 1 : (M::kPairs < kPairChunk ? M::kPairs : kPairChunk));
+        static constexpr int kMaxPairLists = 256;
+        static_assert(M::kPairs < 2048 && M::kTasks < 2048 && M::kLinks <= kGridMaxLinks, "16-bit work-item encoding");
+
+        // block-shared part, then one private slice per warp
+        uint32_t off_tasks, off_links, off_pairs, off_pinfo, off_plists, shared_bytes;
+        uint32_t w_stash, w_masks, w_q1, w_q2, w_pairq, warp_bytes, q2_cap;
+
+        __host__ __device__ static constexpr uint32_t align16(uint32_t v)
+        {
+            return (v + 15u) & ~15u;
+        }
+
+        __host__ __device__ SmemLayoutV4(uint32_t n_objects, uint32_t max_fine)
+        {
+            uint32_t o = align16(n_objects * kObjRec * 4);
+            off_tasks = o;
+            o += align16(M::kTasks * sizeof(SphereTask));
+            off_links = o;
+            o += align16(M::kLinks * sizeof(LinkInfo));
+            off_pairs = o;
+            o += align16((M::kPairs > 0 ? M::kPairs : 1) * sizeof(LinkPair));
+            off_pinfo = o;
+            o += align16((M::kPairs > 0 ? M::kPairs : 1) * sizeof(PairInfo));
+            off_plists = o;
+            o += align16(kMaxPairLists * sizeof(SpherePair));
+            shared_bytes = (o + 127u) & ~127u;
+
+            uint32_t w = 0;
+            w_stash = w;
+            w += kStashFrames * 32 * sizeof(float);
+            // the record queue of C1/C2 is dead before B0 writes masks and Q1: same memory
+            w_masks = w;
+            uint32_t b = M::kLinks * 32 * sizeof(MaskT);
+            w_q1 = w + b;
+            b += align16(M::kLinks * 32 * sizeof(uint16_t));
+            w_q2 = w + b;
+            q2_cap = 32u * max_fine;
+            b += align16(q2_cap * sizeof(uint16_t));
+            w_pairq = w;
+            const uint32_t c = align16(kPairCap * sizeof(uint16_t));
+            w += b > c ? b : c;
+            warp_bytes = (w + 127u) & ~127u;
+        }
+
+        __host__ __device__ uint32_t total(uint32_t warps) const
+        {
+            return shared_bytes + warps * warp_bytes;
+        }
+    };
+
+    template <typename R, typename MaskT>
+    struct V4Ctx
+    {
+        const float4 *objs;
+        const PairInfo *pinfos;
+        const SpherePair *plists;
+        const SphereTask *tasks;
+        const LinkInfo *links;
+        const LinkPair *pairs;
+        float *stash;  // this warp's [entry][32]
+        MaskT *masks;  // this warp's [link][32]
+        uint16_t *q1, *q2, *pairq;
+        uint32_t q2_cap;
+    };
+
+    // Block-level staging (once per persistent block) and this warp's slice.
+    template <typename R, typename MaskT>
+    __device__ __forceinline__ V4Ctx<R, MaskT> v4_stage(unsigned char *smem, uint64_t *barp, const RobotDev &robot, const LaunchEnvV3 &env)
+    {
+        using M = typename R::Model;
+        using Lay = SmemLayoutV4<M, MaskT>;
+        const Lay L(env.n_objects, env.max_fine);
+        const int tid = threadIdx.x, nthr = blockDim.x;
+        if (tid == 0)
+        {
+            mbar_init(barp, 1);
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            tma_bulk_g2s(smem, env.objs, env.n_objects * kObjRec * 4, barp);
+        }
+        {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(smem + L.off_tasks);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(robot.tasks);
+            for (int i = tid; i < M::kTasks * 8; i += nthr)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_links);
+            src = reinterpret_cast<const uint32_t *>(robot.links);
+            for (int i = tid; i < M::kLinks * 4; i += nthr)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_pairs);
+            src = reinterpret_cast<const uint32_t *>(robot.pairs);
+            for (int i = tid; i < M::kPairs * 2; i += nthr)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_pinfo);
+            src = reinterpret_cast<const uint32_t *>(robot.pair_info);
+            for (int i = tid; i < M::kPairs * 3; i += nthr)
+            {
+                dst[i] = __ldg(src + i);
+            }
+            uint16_t *dl = reinterpret_cast<uint16_t *>(smem + L.off_plists);
+            const uint16_t *sl = reinterpret_cast<const uint16_t *>(robot.pair_lists);
+            for (int i = tid; i < min(robot.n_pair_lists, Lay::kMaxPairLists); i += nthr)
+            {
+                dl[i] = __ldg(sl + i);
+            }
+        }
+        __syncthreads();
+        mbar_wait(barp, 0);
+
+        unsigned char *mine = smem + L.shared_bytes + (tid >> 5) * L.warp_bytes;
+        V4Ctx<R, MaskT> X;
+        X.objs = reinterpret_cast<const float4 *>(smem);
+        X.pinfos = reinterpret_cast<const PairInfo *>(smem + L.off_pinfo);
+        X.plists = reinterpret_cast<const SpherePair *>(smem + L.off_plists);
+        X.tasks = reinterpret_cast<const SphereTask *>(smem + L.off_tasks);
+        X.links = reinterpret_cast<const LinkInfo *>(smem + L.off_links);
+        X.pairs = reinterpret_cast<const LinkPair *>(smem + L.off_pairs);
+        X.stash = reinterpret_cast<float *>(mine + L.w_stash);
+        X.masks = reinterpret_cast<MaskT *>(mine + L.w_masks);
+        X.q1 = reinterpret_cast<uint16_t *>(mine + L.w_q1);
+        X.q2 = reinterpret_cast<uint16_t *>(mine + L.w_q2);
+        X.pairq = reinterpret_cast<uint16_t *>(mine + L.w_pairq);
+        X.q2_cap = L.q2_cap;
+        return X;
+    }
+
+    // C2: one lane per (state, pair) record.  Returns the states found in self collision.
+    template <typename R, typename MaskT>
+    __device__ __forceinline__ uint32_t
+    v4_pair_records(const V4Ctx<R, MaskT> &X, uint32_t n_rec, uint32_t invalid, uint32_t inbox_mask)
+    {
+        using Lay = SmemLayoutV4<typename R::Model, MaskT>;
+        const int lane = threadIdx.x & 31;
+        uint32_t hits = 0u;
+        for (uint32_t r = lane; r < n_rec; r += 32)
+        {
+            const uint32_t rec = X.pairq[r];
+            const int c = rec & 31u;
+            if ((invalid >> c) & 1u)
+            {
+                continue;
+            }
+            const int pair = rec >> 5;
+            const PairInfo pinfo = X.pinfos[pair];
+            const float *st = X.stash + c;
+            bool h = false;
+            if (pinfo.count >= 0 && ((inbox_mask >> c) & 1u) && pinfo.offset + pinfo.count <= Lay::kMaxPairLists)
+            {
+                // statically pruned list of the sphere pairs that can touch inside the joint box
+                for (int k = 0; k < pinfo.count; ++k)
+                {
+                    const SpherePair sp = X.plists[pinfo.offset + k];
+                    const SphereTask ta = X.tasks[sp.task_a], tb = X.tasks[sp.task_b];
+                    float ax, ay, az, bx, by, bz;
+                    task_centre<32>(ta, st, ax, ay, az);
+                    task_centre<32>(tb, st, bx, by, bz);
+                    const float ex = ax - bx, ey = ay - by, ez = az - bz;
+                    const float rr = ta.r + tb.r;
+                    h |= sign_set((ex * ex + ey * ey + ez * ez) - rr * rr);
+                }
+            }
+            else
+            {
+                // the link with fewer spheres (A) is posed into registers four spheres at a time; the
+                // other link's spheres stream past, filtered by A's bounding sphere
+                const LinkPair p = X.pairs[pair];
+                LinkInfo A = X.links[p.a], B = X.links[p.b];
+                if (A.n_spheres > B.n_spheres)
+                {
+                    const LinkInfo t = A;
+                    A = B;
+                    B = t;
+                }
+                const BodyFrame<32> FA(A.body, st), FB(B.body, st);
+                const float4 tba = *reinterpret_cast<const float4 *>(&X.tasks[A.bound_task]);
+                float gx, gy, gz;
+                FA.pose(tba.x, tba.y, tba.z, gx, gy, gz);
+                for (int a0 = 0; a0 < A.n_spheres && !h; a0 += 4)
+                {
+                    float ax[4], ay[4], az[4], ar[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        if (a0 + k < A.n_spheres)
+                        {
+                            const float4 ta = *reinterpret_cast<const float4 *>(&X.tasks[A.bound_task + 1 + a0 + k]);
+                            FA.pose(ta.x, ta.y, ta.z, ax[k], ay[k], az[k]);
+                            ar[k] = ta.w;
+                        }
+                        else
+                        {
+                            ax[k] = 1e18F, ay[k] = 1e18F, az[k] = 1e18F, ar[k] = 0.F;  // never touches
+                        }
+                    }
+                    for (int jb = 0; jb < B.n_spheres; ++jb)
+                    {
+                        const float4 tb = *reinterpret_cast<const float4 *>(&X.tasks[B.bound_task + 1 + jb]);
+                        float bx, by, bz;
+                        FB.pose(tb.x, tb.y, tb.z, bx, by, bz);
+                        const float fx = bx - gx, fy = by - gy, fz = bz - gz;
+                        const float fr = tb.w + tba.w;
+                        if (!sign_set((fx * fx + fy * fy + fz * fz) - fr * fr))
+                        {
+                            continue;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float ex = ax[k] - bx, ey = ay[k] - by, ez = az[k] - bz;
+                            const float rr = ar[k] + tb.w;
+                            h |= sign_set((ex * ex + ey * ey + ez * ez) - rr * rr);
+                        }
+                    }
+                }
+            }
+            hits |= h ? (1u << c) : 0u;
+        }
+        return __reduce_or_sync(kFullWarp, hits);
+    }
+
+    // B2: one lane per fine-sphere item, against its link's hit mask.  Returns the colliding states.
+    template <typename R, typename MaskT>
+    __device__ __forceinline__ uint32_t v4_fine_items(const V4Ctx<R, MaskT> &X, uint32_t n2, uint32_t invalid)
+    {
+        const int lane = threadIdx.x & 31;
+        for (uint32_t base = 0; base < n2; base += 32)
+        {
+            const uint32_t it = base + lane;
+            uint32_t hit = 0u;
+            if (it < n2)
+            {
+                const uint32_t item = X.q2[it];
+                const int c = item & 31u;
+                if (!((invalid >> c) & 1u))
+                {
+                    const SphereTask t = X.tasks[item >> 5];
+                    float x, y, z;
+                    task_centre<32>(t, X.stash + c, x, y, z);
+                    MaskT m = X.masks[t.link * 32 + c];
+                    while (m != 0)
+                    {
+                        const int o = mask_pop_lowest<MaskT>(m);
+                        if (sign_set(margin_obj(X.objs + 4 * o, x, y, z, t.r)))
+                        {
+                            hit = 1u << c;
+                            break;
+                        }
+                    }
+                }
+            }
+            invalid |= __reduce_or_sync(kFullWarp, hit);
+        }
+        return invalid;
+    }
+
+    // One pass over 32 states (lane = state in the dense phases).  Returns the warp-uniform mask of
+    // invalid states (lanes without a state count as invalid).
+    template <typename R, typename MaskT>
+    __device__ __forceinline__ uint32_t v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const float (&cfg)[R::Model::kDof], const bool has)
+    {
+        using M = typename R::Model;
+        using Lay = SmemLayoutV4<M, MaskT>;
+        const int lane = threadIdx.x & 31;
+        const uint32_t lt = (1u << lane) - 1u;
+
+        // ---- A: FK ------------------------------------------------------------------------------
+        StashBoundSink<32, M::kLinks> sink;
+        sink.base = X.stash + lane;
+        R::frames(cfg, sink);
+        const bool live = has && !(sink.inbox && sink.self_hit);
+        uint32_t invalid = ~__ballot_sync(kFullWarp, live);
+        const uint32_t inbox_mask = __ballot_sync(kFullWarp, sink.inbox);
+
+        // ---- voxel-table loads (consumed in B0, after the self-collision phases) -----------------
+        MaskT cand[M::kLinks];
+        R::for_each_link(
+            [&](auto l, float, int, int, float)
+            {
+                constexpr int li = decltype(l)::value;
+                cand[li] = !live ? static_cast<MaskT>(0)
+                                 : (sink.reach_valid ? grid_lookup_t<MaskT>(G, sink.b[li][0], sink.b[li][1], sink.b[li][2], G.link_class[li])
+                                                     : static_cast<MaskT>(G.all_mask));
+            });
+        __syncwarp();  // stash complete
+
+        // ---- C1: allowed link pairs on the bounding spheres -> records; C2 per chunk of pairs -----
+        if (M::kPairs > 0)
+        {
+            float brad[M::kLinks];
+            R::for_each_link([&](auto l, float br, int, int, float) { brad[decltype(l)::value] = br; });
+            uint32_t n_rec = 0u;
+            R::for_each_pair(
+                [&](auto pi, auto la, auto lb, auto inl)
+                {
+                    constexpr int a = decltype(la)::value, b = decltype(lb)::value, p = decltype(pi)::value;
+                    const float dx = sink.b[a][0] - sink.b[b][0], dy = sink.b[a][1] - sink.b[b][1], dz = sink.b[a][2] - sink.b[b][2];
+                    const float rs = brad[a] + brad[b];
+                    // pairs checked inline in phase A (inside the joint box) are skipped
+                    const bool hit = live && !(decltype(inl)::value != 0 && sink.inbox) && sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
+                    const uint32_t m = __ballot_sync(kFullWarp, hit);
+                    if (hit)
+                    {
+                        X.pairq[n_rec + __popc(m & lt)] = static_cast<uint16_t>(lane | (p << 5));
+                    }
+                    n_rec += __popc(m);
+                    if ((p + 1) % Lay::kPairChunk == 0 && p + 1 < M::kPairs)
+                    {
+                        __syncwarp();
+                        invalid |= v4_pair_records<R, MaskT>(X, n_rec, invalid, inbox_mask);
+                        __syncwarp();
+                        n_rec = 0u;
+                    }
+                });
+            __syncwarp();
+            invalid |= v4_pair_records<R, MaskT>(X, n_rec, invalid, inbox_mask);
+            __syncwarp();  // the record queue's memory is reused below
+        }
+
+        // ---- B0: candidate masks -> (state, link) items -------------------------------------------
+        uint32_t n1 = 0u;
+        {
+            const bool alive = !((invalid >> lane) & 1u);
+            R::for_each_link(
+                [&](auto l, float, int, int, float)
+                {
+                    constexpr int li = decltype(l)::value;
+                    const bool nz = alive && cand[li] != 0;
+                    const uint32_t m = __ballot_sync(kFullWarp, nz);
+                    if (nz)
+                    {
+                        X.masks[li * 32 + lane] = cand[li];
+                        X.q1[n1 + __popc(m & lt)] = static_cast<uint16_t>(lane | (li << 5));
+                    }
+                    n1 += __popc(m);
+                });
+        }
+        __syncwarp();
+
+        // ---- B1: bounding spheres vs their candidates; fine items -> Q2; B2 when Q2 fills ---------
+        uint32_t n2 = 0u;
+        for (uint32_t base = 0; base < n1; base += 32)
+        {
+            const uint32_t it = base + lane;
+            uint32_t cnt = 0u, first = 0u;
+            int c = 0;
+            if (it < n1)
+            {
+                const uint32_t item = X.q1[it];
+                c = item & 31u;
+                const int l = item >> 5;
+                if (!((invalid >> c) & 1u))
+                {
+                    const LinkInfo L = X.links[l];
+                    const SphereTask t = X.tasks[L.bound_task];
+                    float x, y, z;
+                    task_centre<32>(t, X.stash + c, x, y, z);
+                    MaskT m = X.masks[l * 32 + c], hit = 0;
+                    while (m != 0)
+                    {
+                        const int o = mask_pop_lowest<MaskT>(m);
+                        if (sign_set(margin_obj(X.objs + 4 * o, x, y, z, t.r)))
+                        {
+                            hit |= static_cast<MaskT>(1) << o;
+                        }
+                    }
+                    if (hit != 0)
+                    {
+                        X.masks[l * 32 + c] = hit;
+                        cnt = static_cast<uint32_t>(L.n_spheres);
+                        first = static_cast<uint32_t>(L.bound_task + 1);
+                    }
+                }
+            }
+            // exclusive prefix sum of cnt over the lanes
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t v = __shfl_up_sync(kFullWarp, incl, d);
+                incl += (lane >= d) ? v : 0u;
+            }
+            const uint32_t total = __shfl_sync(kFullWarp, incl, 31);
+            if (n2 + total > X.q2_cap)
+            {
+                __syncwarp();
+                invalid = v4_fine_items<R, MaskT>(X, n2, invalid);
+                __syncwarp();
+                n2 = 0u;
+            }
+            const uint32_t at = n2 + incl - cnt;
+            for (uint32_t k = 0; k < cnt; ++k)
+            {
+                X.q2[at + k] = static_cast<uint16_t>(c | ((first + k) << 5));
+            }
+            n2 += total;
+        }
+        __syncwarp();
+        invalid = v4_fine_items<R, MaskT>(X, n2, invalid);
+        __syncwarp();  // all reads of this pass's stash and queues are done
+        return invalid;
+    }
+
+    // Persistent blocks of blockDim.x / 32 autonomous warps; tile t = states [32 t, 32 t + 32).
+    template <typename R, typename MaskT, int MAXT, int MINB>
+    __global__ void __launch_bounds__(MAXT, MINB)
+        k_validate_configs_v4(RobotDev robot, const __grid_constant__ LaunchEnvV3 env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
+    {
+        using M = typename R::Model;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        const V4Ctx<R, MaskT> X = v4_stage<R, MaskT>(smem, &bar, robot, env);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        const size_t n_tiles = (n + 31) / 32;
+        const size_t stride = static_cast<size_t>(gridDim.x) * warps;
+        for (size_t tile = static_cast<size_t>(blockIdx.x) * warps + warp; tile < n_tiles; tile += stride)
+        {
+            const size_t i = tile * 32 + lane;
+            const bool has = i < n;
+            float cfg[M::kDof];
+#pragma unroll
+            for (int j = 0; j < M::kDof; ++j)
+            {
+                cfg[j] = has ? __ldg(q + i * M::kDof + j) : 0.F;
+            }
+            const uint32_t invalid = v4_pass<R, MaskT>(X, env.grid, cfg, has);
+            if (lane == 0)
+            {
+                bits[tile] = ~invalid;
+            }
+        }
+    }
+
+    // Edges.  A warp owns a chunk of 32 edges (one verdict word): lane e keeps edge e's start, vector
+    // and rake-step count in registers.  Every pass checks 4 rake blocks (8 tines each) of the
+    // reference's schedule (planning/validate.hh:31-64), handed out round-robin over the edges still
+    // alive, so an edge found invalid drops its remaining blocks -- the reference's early return.
+    template <typename R, typename MaskT, bool INDEXED, int MAXT, int MINB>
+    __global__ void __launch_bounds__(MAXT, MINB) k_validate_edges_v4(
+        RobotDev robot,
+        const __grid_constant__ LaunchEnvV3 env,
+        const float *__restrict__ a,
+        const float *__restrict__ b,
+        const uint32_t *__restrict__ pairs,
+        size_t n,
+        float resolution,
+        uint32_t *__restrict__ bits)
+    {
+        using M = typename R::Model;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        const V4Ctx<R, MaskT> X = v4_stage<R, MaskT>(smem, &bar, robot, env);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        const size_t n_chunks = (n + 31) / 32;
+        const size_t stride = static_cast<size_t>(gridDim.x) * warps;
+        const int my_slot = lane >> 3, tine = lane & 7;
+        const float pct = static_cast<float>(tine + 1) / 8.F;
+
+        for (size_t chunk = static_cast<size_t>(blockIdx.x) * warps + warp; chunk < n_chunks; chunk += stride)
+        {
+            const size_t edge = chunk * 32 + lane;
+            float start[M::kDof], vec[M::kDof];
+            int steps = 0;
+            if (edge < n)
+            {
+                const float *pa, *pb;
+                if (INDEXED)
+                {
+                    pa = a + static_cast<size_t>(__ldg(pairs + 2 * edge)) * M::kDof;
+                    pb = a + static_cast<size_t>(__ldg(pairs + 2 * edge + 1)) * M::kDof;
+                }
+                else
+                {
+                    pa = a + edge * M::kDof;
+                    pb = b + edge * M::kDof;
+                }
+#pragma unroll
+                for (int j = 0; j < M::kDof; ++j)
+                {
+                    start[j] = __ldg(pa + j);
+                    vec[j] = __fsub_rn(__ldg(pb + j), start[j]);
+                }
+                const float dist = ref_l2_norm<M::kDof>(vec);
+                // n = max(ceil(distance / rake * resolution), 1)   (validate.hh:41)
+                steps = static_cast<int>(fmaxf(ceilf(__fmul_rn(__fdiv_rn(dist, 8.F), resolution)), 1.F));
+            }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < M::kDof; ++j)
+                {
+                    start[j] = 0.F, vec[j] = 0.F;
+                }
+            }
+            int next = 0;
+            bool dead = false;
+
+            while (true)
+            {
+                // hand out up to 4 rake blocks: round r takes the r-th pending block of every live edge
+                const int rem = dead ? 0 : steps - next;
+                int n_slots = 0, got = 0, owner = 0, round = 0;
+                for (int r = 0; n_slots < 4; ++r)
+                {
+                    uint32_t m = __ballot_sync(kFullWarp, rem > r);
+                    if (m == 0u)
+                    {
+                        break;
+                    }
+                    while (m != 0u && n_slots < 4)
+                    {
+                        const int o = __ffs(static_cast<int>(m)) - 1;
+                        m &= m - 1u;
+                        if (n_slots == my_slot)
+                        {
+                            owner = o, round = r;
+                        }
+                        got += (o == lane) ? 1 : 0;
+                        ++n_slots;
+                    }
+                }
+                if (n_slots == 0)
+                {
+                    break;
+                }
+                const bool has = my_slot < n_slots;
+                const int step = __shfl_sync(kFullWarp, next, owner) + round;
+                const int e_steps = __shfl_sync(kFullWarp, steps, owner);
+                next += got;
+                float cfg[M::kDof];
+                {
+                    const float denom = static_cast<float>(8 * e_steps);
+#pragma unroll
+                    for (int j = 0; j < M::kDof; ++j)
+                    {
+                        const float v = __shfl_sync(kFullWarp, vec[j], owner);
+                        const float st = __shfl_sync(kFullWarp, start[j], owner);
+                        const float back = __fdiv_rn(v, denom);
+                        float c = fmaf(v, pct, st);
+                        for (int k = 0; k < step; ++k)
+                        {
+                            c = __fsub_rn(c, back);
+                        }
+                        cfg[j] = has ? c : 0.F;
+                    }
+                }
+                const uint32_t invalid = v4_pass<R, MaskT>(X, env.grid, cfg, has);
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                {
+                    const int o = __shfl_sync(kFullWarp, owner, 8 * p);
+                    const bool bad = p < n_slots && ((invalid >> (8 * p)) & 0xffu) != 0u;
+                    dead = dead || (bad && o == lane);
+                }
+            }
+
+            const uint32_t word = __ballot_sync(kFullWarp, steps > 0 && !dead);
+            if (lane == 0)
+            {
+                bits[chunk] = word;
+            }
+        }
+    }
+}  // namespace vmv
