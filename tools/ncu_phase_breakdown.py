@@ -51,7 +51,7 @@ if len(sys.argv) > 3:
     ph = collections.OrderedDict()
     for (f, l), a in agg.items():
         name = f
-        if f == "vmv_kernels_v2.cuh":
+        if f == (sys.argv[4] if len(sys.argv) > 4 else "vmv_kernels_v2.cuh"):
             name = "v2:other"
             for n, lo, hi in ranges:
                 if lo <= l <= hi:

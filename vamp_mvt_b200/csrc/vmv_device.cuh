@@ -87,7 +87,13 @@ namespace vmv
         return __uint_as_float(__float_as_uint(r) ^ sign);
     }
 
+    // not inlined: a robot's FK calls it once per joint, and the straight-line FK bodies are already
+    // large enough to pressure the instruction cache when warps run out of step
+#ifdef VMV_SINCOS_INLINE
     __device__ __forceinline__ void sincos_f32(float x, float &s, float &c)
+#else
+    __device__ __noinline__ void sincos_f32(float x, float &s, float &c)
+#endif
     {
         s = ref_sin(x);
         // cos(x) = sin(x + pi/2), wrapped by 2 pi when the sum reaches pi (interface.hh:451-458)

@@ -1090,7 +1090,11 @@ namespace
     template <typename R>
     struct V4Tune
     {
+#if defined(VMV_V4_MAXT) && defined(VMV_V4_MINB)
+        static constexpr int kMaxThreads = VMV_V4_MAXT, kMinBlocks = VMV_V4_MINB;
+#else
         static constexpr int kMaxThreads = 256, kMinBlocks = 2;  // <= 128 registers
+#endif
     };
     template <>
     struct V4Tune<baxter_robot>
@@ -1118,6 +1122,28 @@ namespace
         return VMV_OK;
     }
 
+    // work counters of the persistent edge kernels: a ring per device, one slot per launch, zeroed
+    // on the launch's stream
+    constexpr int kCounterSlots = 256;
+    unsigned int *g_counters[kMaxDevices] = {nullptr};
+    std::atomic<unsigned> g_counter_next{0};
+
+    int next_counter(cudaStream_t s, unsigned int *&out)
+    {
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        {
+            std::lock_guard<std::mutex> lock(g_mutex);
+            if (g_counters[device] == nullptr)
+            {
+                VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&g_counters[device]), kCounterSlots * sizeof(unsigned int)));
+            }
+        }
+        out = g_counters[device] + (g_counter_next++ % kCounterSlots);
+        VMV_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned int), s));
+        return VMV_OK;
+    }
+
     template <typename R, typename MaskT>
     int launch_edges_v4(
         const vmv::RobotDev &rd,
@@ -1135,6 +1161,14 @@ namespace
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
+        unsigned int *counter = nullptr;
+        {
+            int rc = next_counter(s, counter);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
         if (pairs != nullptr)
         {
             auto kernel = vmv::k_validate_edges_v4<R, MaskT, true, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
@@ -1143,7 +1177,7 @@ namespace
             {
                 return rc;
             }
-            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits, counter);
         }
         else
         {
@@ -1153,7 +1187,7 @@ namespace
             {
                 return rc;
             }
-            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits);
+            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits, counter);
         }
         g_launches++;
         VMV_CUDA(cudaGetLastError());
@@ -1571,6 +1605,16 @@ extern "C"
         }
     }
 
+#ifdef VMV_DEV_PANDA_ONLY
+    // development builds (kernel A/B timing): one robot, a quarter of the compile time
+#define VMV_DISPATCH(robot, CALL)       \
+    {                                   \
+        using R = panda_robot;          \
+        constexpr int BLOCK = 128;      \
+        (void)BLOCK;                    \
+        rc = CALL;                      \
+    }
+#else
 #define VMV_DISPATCH(robot, CALL)            \
     switch (robot)                           \
     {                                        \
@@ -1603,6 +1647,7 @@ extern "C"
             break;                           \
         }                                    \
     }
+#endif
 
     int vmv_validate_configs_dev(int robot, const vmv_env *env, const float *d_q, size_t n, uint32_t *d_bits, void *stream)
     {

@@ -106,6 +106,29 @@ namespace vmv
         return __ldg(reinterpret_cast<const MaskT *>(G.masks) + idx);
     }
 
+    // Append one item per set bit of every lane's `bits` to a warp-private queue: item = lane |
+    // (base + bit) << 5, positions from an exclusive prefix sum over the lanes.  Returns the new fill.
+    __device__ __forceinline__ uint32_t warp_append_bits(uint16_t *queue, uint32_t fill, uint32_t bits, uint32_t base)
+    {
+        const int lane = threadIdx.x & 31;
+        const uint32_t cnt = static_cast<uint32_t>(__popc(bits));
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t v = __shfl_up_sync(kFullWarp, incl, d);
+            incl += (lane >= d) ? v : 0u;
+        }
+        uint32_t at = fill + incl - cnt;
+        while (bits != 0u)
+        {
+            const uint32_t b = static_cast<uint32_t>(__ffs(static_cast<int>(bits)) - 1);
+            bits &= bits - 1u;
+            queue[at++] = static_cast<uint16_t>(lane | ((base + b) << 5));
+        }
+        return fill + __shfl_sync(kFullWarp, incl, 31);
+    }
+
     template <typename M, typename MaskT>
     struct SmemLayoutV4
     {
@@ -148,7 +171,7 @@ namespace vmv
             w_q1 = w + b;
             b += align16(M::kLinks * 32 * sizeof(uint16_t));
             w_q2 = w + b;
-            q2_cap = 32u * max_fine;
+            q2_cap = 2u * 32u * max_fine;  // two B1 rounds (the common case) fit without a flush in between
             b += align16(q2_cap * sizeof(uint16_t));
             w_pairq = w;
             const uint32_t c = align16(kPairCap * sizeof(uint16_t));
@@ -174,7 +197,7 @@ namespace vmv
         float *stash;  // this warp's [entry][32]
         MaskT *masks;  // this warp's [link][32]
         uint16_t *q1, *q2, *pairq;
-        uint32_t q2_cap;
+        uint32_t q2_cap, round_cap;  // Q2 capacity; most fine items one B1 round can add (32 * max_fine)
     };
 
     // Block-level staging (once per persistent block) and this warp's slice.
@@ -243,6 +266,7 @@ namespace vmv
         X.q2 = reinterpret_cast<uint16_t *>(mine + L.w_q2);
         X.pairq = reinterpret_cast<uint16_t *>(mine + L.w_pairq);
         X.q2_cap = L.q2_cap;
+        X.round_cap = 32u * env.max_fine;
         return X;
     }
 
@@ -410,7 +434,7 @@ namespace vmv
         {
             float brad[M::kLinks];
             R::for_each_link([&](auto l, float br, int, int, float) { brad[decltype(l)::value] = br; });
-            uint32_t n_rec = 0u;
+            uint32_t n_rec = 0u, word = 0u;
             R::for_each_pair(
                 [&](auto pi, auto la, auto lb, auto inl)
                 {
@@ -418,19 +442,19 @@ namespace vmv
                     const float dx = sink.b[a][0] - sink.b[b][0], dy = sink.b[a][1] - sink.b[b][1], dz = sink.b[a][2] - sink.b[b][2];
                     const float rs = brad[a] + brad[b];
                     // pairs checked inline in phase A (inside the joint box) are skipped
-                    const bool hit = live && !(decltype(inl)::value != 0 && sink.inbox) && sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
-                    const uint32_t m = __ballot_sync(kFullWarp, hit);
-                    if (hit)
+                    const bool hit = !(decltype(inl)::value != 0 && sink.inbox) && sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
+                    word |= hit ? (1u << (p & 31)) : 0u;
+                    if constexpr ((p & 31) == 31 || p + 1 == M::kPairs)
                     {
-                        X.pairq[n_rec + __popc(m & lt)] = static_cast<uint16_t>(lane | (p << 5));
-                    }
-                    n_rec += __popc(m);
-                    if ((p + 1) % Lay::kPairChunk == 0 && p + 1 < M::kPairs)
-                    {
-                        __syncwarp();
-                        invalid |= v4_pair_records<R, MaskT>(X, n_rec, invalid, inbox_mask);
-                        __syncwarp();
-                        n_rec = 0u;
+                        n_rec = warp_append_bits(X.pairq, n_rec, live ? word : 0u, p & ~31);
+                        word = 0u;
+                        if constexpr ((p + 1) % Lay::kPairChunk == 0 && p + 1 < M::kPairs)
+                        {
+                            __syncwarp();
+                            invalid |= v4_pair_records<R, MaskT>(X, n_rec, invalid, inbox_mask);
+                            __syncwarp();
+                            n_rec = 0u;
+                        }
                     }
                 });
             __syncwarp();
@@ -442,83 +466,86 @@ namespace vmv
         uint32_t n1 = 0u;
         {
             const bool alive = !((invalid >> lane) & 1u);
+            uint32_t word = 0u;
             R::for_each_link(
                 [&](auto l, float, int, int, float)
                 {
                     constexpr int li = decltype(l)::value;
-                    const bool nz = alive && cand[li] != 0;
-                    const uint32_t m = __ballot_sync(kFullWarp, nz);
-                    if (nz)
+                    if (cand[li] != 0)
                     {
                         X.masks[li * 32 + lane] = cand[li];
-                        X.q1[n1 + __popc(m & lt)] = static_cast<uint16_t>(lane | (li << 5));
+                        word |= 1u << (li & 31);
                     }
-                    n1 += __popc(m);
+                    if constexpr ((li & 31) == 31 || li + 1 == M::kLinks)
+                    {
+                        n1 = warp_append_bits(X.q1, n1, alive ? word : 0u, li & ~31);
+                        word = 0u;
+                    }
                 });
         }
         __syncwarp();
 
-        // ---- B1: bounding spheres vs their candidates; fine items -> Q2; B2 when Q2 fills ---------
-        uint32_t n2 = 0u;
-        for (uint32_t base = 0; base < n1; base += 32)
+        // ---- B1: bounding spheres vs their candidates, fine items -> Q2; B2 whenever the next
+        //      round might overflow Q2 and at the end ------------------------------------------------
         {
-            const uint32_t it = base + lane;
-            uint32_t cnt = 0u, first = 0u;
-            int c = 0;
-            if (it < n1)
+            uint32_t base = 0u;
+            do
             {
-                const uint32_t item = X.q1[it];
-                c = item & 31u;
-                const int l = item >> 5;
-                if (!((invalid >> c) & 1u))
+                uint32_t n2 = 0u;
+                while (base < n1 && n2 + X.round_cap <= X.q2_cap)
                 {
-                    const LinkInfo L = X.links[l];
-                    const SphereTask t = X.tasks[L.bound_task];
-                    float x, y, z;
-                    task_centre<32>(t, X.stash + c, x, y, z);
-                    MaskT m = X.masks[l * 32 + c], hit = 0;
-                    while (m != 0)
+                    const uint32_t it = base + lane;
+                    uint32_t cnt = 0u, first = 0u;
+                    int c = 0;
+                    if (it < n1)
                     {
-                        const int o = mask_pop_lowest<MaskT>(m);
-                        if (sign_set(margin_obj(X.objs + 4 * o, x, y, z, t.r)))
+                        const uint32_t item = X.q1[it];
+                        c = item & 31u;
+                        const int l = item >> 5;
+                        if (!((invalid >> c) & 1u))
                         {
-                            hit |= static_cast<MaskT>(1) << o;
+                            const LinkInfo L = X.links[l];
+                            const SphereTask t = X.tasks[L.bound_task];
+                            float x, y, z;
+                            task_centre<32>(t, X.stash + c, x, y, z);
+                            MaskT m = X.masks[l * 32 + c], hit = 0;
+                            while (m != 0)
+                            {
+                                const int o = mask_pop_lowest<MaskT>(m);
+                                if (sign_set(margin_obj(X.objs + 4 * o, x, y, z, t.r)))
+                                {
+                                    hit |= static_cast<MaskT>(1) << o;
+                                }
+                            }
+                            if (hit != 0)
+                            {
+                                X.masks[l * 32 + c] = hit;
+                                cnt = static_cast<uint32_t>(L.n_spheres);
+                                first = static_cast<uint32_t>(L.bound_task + 1);
+                            }
                         }
                     }
-                    if (hit != 0)
-                    {
-                        X.masks[l * 32 + c] = hit;
-                        cnt = static_cast<uint32_t>(L.n_spheres);
-                        first = static_cast<uint32_t>(L.bound_task + 1);
-                    }
-                }
-            }
-            // exclusive prefix sum of cnt over the lanes
-            uint32_t incl = cnt;
+                    // exclusive prefix sum of cnt over the lanes
+                    uint32_t incl = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                const uint32_t v = __shfl_up_sync(kFullWarp, incl, d);
-                incl += (lane >= d) ? v : 0u;
-            }
-            const uint32_t total = __shfl_sync(kFullWarp, incl, 31);
-            if (n2 + total > X.q2_cap)
-            {
+                    for (int d = 1; d < 32; d <<= 1)
+                    {
+                        const uint32_t v = __shfl_up_sync(kFullWarp, incl, d);
+                        incl += (lane >= d) ? v : 0u;
+                    }
+                    const uint32_t at = n2 + incl - cnt;
+                    for (uint32_t k = 0; k < cnt; ++k)
+                    {
+                        X.q2[at + k] = static_cast<uint16_t>(c | ((first + k) << 5));
+                    }
+                    n2 += __shfl_sync(kFullWarp, incl, 31);
+                    base += 32u;
+                }
                 __syncwarp();
                 invalid = v4_fine_items<R, MaskT>(X, n2, invalid);
-                __syncwarp();
-                n2 = 0u;
-            }
-            const uint32_t at = n2 + incl - cnt;
-            for (uint32_t k = 0; k < cnt; ++k)
-            {
-                X.q2[at + k] = static_cast<uint16_t>(c | ((first + k) << 5));
-            }
-            n2 += total;
+                __syncwarp();  // all reads of the queues (and, at the end, of this pass's stash) are done
+            } while (base < n1);
         }
-        __syncwarp();
-        invalid = v4_fine_items<R, MaskT>(X, n2, invalid);
-        __syncwarp();  // all reads of this pass's stash and queues are done
         return invalid;
     }
 
@@ -565,20 +592,32 @@ namespace vmv
         const uint32_t *__restrict__ pairs,
         size_t n,
         float resolution,
-        uint32_t *__restrict__ bits)
+        uint32_t *__restrict__ bits,
+        unsigned int *__restrict__ next_chunk)
     {
         using M = typename R::Model;
         extern __shared__ __align__(128) unsigned char smem[];
         __shared__ uint64_t bar;
         const V4Ctx<R, MaskT> X = v4_stage<R, MaskT>(smem, &bar, robot, env);
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        const int lane = threadIdx.x & 31;
         const size_t n_chunks = (n + 31) / 32;
-        const size_t stride = static_cast<size_t>(gridDim.x) * warps;
         const int my_slot = lane >> 3, tine = lane & 7;
         const float pct = static_cast<float>(tine + 1) / 8.F;
 
-        for (size_t chunk = static_cast<size_t>(blockIdx.x) * warps + warp; chunk < n_chunks; chunk += stride)
+        // chunks cost anything from one pass to dozens (edge lengths, early exits): warps draw them
+        // from a device-wide counter (zeroed by the host before the launch)
+        while (true)
         {
+            unsigned int ticket = 0u;
+            if (lane == 0)
+            {
+                ticket = atomicAdd(next_chunk, 1u);
+            }
+            const size_t chunk = __shfl_sync(kFullWarp, ticket, 0);
+            if (chunk >= n_chunks)
+            {
+                break;
+            }
             const size_t edge = chunk * 32 + lane;
             float start[M::kDof], vec[M::kDof];
             int steps = 0;
