@@ -325,10 +325,20 @@ def main() -> int:
         peak_tflops = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
         achieved = flops_per_config * N_CONFIGS / (kernel_ms * 1e-3) / 1e12
         bytes_per_launch = N_CONFIGS * (dof * 4 + 1 / 8)
+        # DRAM bytes per launch and pipe activity of the same kernel on the same workload, from the
+        # committed `ncu --set full` capture (profiles/): a number taken under the profiler, reported
+        # as such, never mixed into the timings
+        captured = {}
+        try:
+            captured = json.loads((REPO / "profiles" / "kernel_metrics.json").read_text()).get("k_validate_configs_v4", {})
+        except Exception:
+            pass
         roofline = {
             "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-            "traffic": None,
-            "kernel": "k_validate_configs<panda,128>", "kernel_ms": kernel_ms,
+            "traffic": captured.get("dram_bytes_per_launch"),
+            "traffic_source": captured.get("capture"),
+            "pipe_fma_pct_of_peak": captured.get("pipe_fma_pct"), "pipe_alu_pct_of_peak": captured.get("pipe_alu_pct"),
+            "kernel": "k_validate_configs_v4<panda, u32 masks> (vmv_kernels_v4.cuh)", "kernel_ms": kernel_ms,
             "algorithmic_flops_per_config": flops_per_config,
             "peak_source": f"FP32 pipe: {n_sm} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (clocks.max.sm); no tensor-core work on this path",
             "hbm": {"algorithmic_bytes_per_launch": bytes_per_launch,

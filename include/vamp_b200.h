@@ -78,6 +78,10 @@ extern "C"
     int vmv_env_add_heightfield(vmv_env *env, const float *f6, size_t xd, size_t yd, const float *data);
     /* CAPT(points, r_min, r_max, r_point): capt.hh:299-369 (add_capt_pointcloud, environment.cc:150-160) */
     int vmv_env_add_capt(vmv_env *env, const float *points_xyz, size_t n, float r_min, float r_max, float r_point);
+    /* MVT(points, r_min, r_max, workspace_aabb_min, workspace_aabb_max, r_point): mvt.hh:146-170
+     * (add_mvt_pointcloud, environment.cc:163-176).  The grid is cubic, floor(workspace x-width /
+     * r_max) cells per axis (mvt.hh:437-446); points outside the workspace are clamped into it. */
+    int vmv_env_add_mvt(vmv_env *env, const float *points_xyz, size_t n, float r_min, float r_max, const float *aabb_min_xyz, const float *aabb_max_xyz, float r_point);
     /* Attachment(tf) + add_spheres (attachments.hh:12-56, environment.cc:177-181).  tf12 =
      * translation(3) followed by the 3x3 rotation in column-major order (vector/math.hh:39-51). */
     int vmv_env_attach(vmv_env *env, const float *tf12, const float *spheres_xyzr, size_t n);

@@ -98,6 +98,8 @@ class Counters(C.Structure):
             "t_self",
             "capt_queries",
             "capt_points",
+            "mvt_queries",
+            "mvt_points",
         )
     ]
 
@@ -185,6 +187,19 @@ class _EnvBase:
             self.h, _fp(p), C.c_size_t(len(p)), C.c_float(r_min), C.c_float(r_max), C.c_float(r_point)
         )
 
+    def add_mvt(self, points, r_min, r_max, aabb_min, aabb_max, r_point):
+        p = _f32(points).reshape(-1, 3)
+        getattr(self.lib, self.prefix + "env_add_mvt")(
+            self.h,
+            _fp(p),
+            C.c_size_t(len(p)),
+            C.c_float(r_min),
+            C.c_float(r_max),
+            _fp(_f32(aabb_min)),
+            _fp(_f32(aabb_max)),
+            C.c_float(r_point),
+        )
+
     def attach(self, tf12, spheres):
         s = _f32(spheres).reshape(-1, 4)
         getattr(self.lib, self.prefix + "env_attach")(self.h, _fp(_f32(tf12)), _fp(s), C.c_size_t(len(s)))
@@ -212,18 +227,6 @@ class RefEnv(_EnvBase):
     def __init__(self):
         super().__init__(ref_lib())
 
-    def add_mvt(self, points, r_min, r_max, aabb_min, aabb_max, r_point):
-        p = _f32(points).reshape(-1, 3)
-        self.lib.ref_env_add_mvt(
-            self.h,
-            _fp(p),
-            C.c_size_t(len(p)),
-            C.c_float(r_min),
-            C.c_float(r_max),
-            _fp(_f32(aabb_min)),
-            _fp(_f32(aabb_max)),
-            C.c_float(r_point),
-        )
 
 
 def add_scene(env, scene: dict):

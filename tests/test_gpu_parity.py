@@ -227,6 +227,44 @@ def test_capt_pointcloud_and_heightfield(robot):
     assert (R.validate_motion_batch(a, b, env) != O.validate_edges(oenv, a, b)).sum() <= 1
 
 
+@pytest.mark.parametrize("robot", ["panda", "fetch", "ur5"])
+def test_mvt_pointcloud(robot):
+    """Multi-level Voxel Table pointcloud (reference collision/mvt.hh) next to primitives: configs and
+    edges against the oracle and, where it travelled, the compiled reference."""
+    rng = np.random.default_rng(6)
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    m = O.model
+    # a small cloud: the reference sizes its voxel pools for 10 % occupied cells (mvt.hh:455-513) and
+    # aborts beyond that
+    pts = np.concatenate(
+        [
+            rng.uniform([0.3, -0.6, 0.0], [0.9, 0.6, 0.02], size=(1500, 3)),
+            rng.normal([0.5, 0.3, 0.6], 0.05, size=(700, 3)),
+            rng.uniform([-0.8, -0.8, 0.0], [0.8, 0.8, 1.2], size=(300, 3)),
+        ]
+    ).astype(np.float32)
+    pts = pts[np.hypot(pts[:, 0], pts[:, 1]) > (0.5 if robot == "fetch" else 0.3)]
+    # one point per 2.5 cm cell: the reference's voxels have a fixed capacity (mvt.hh:455-457)
+    _, keep = np.unique(np.floor(pts / 0.025).astype(np.int64), axis=0, return_index=True)
+    pts = pts[np.sort(keep)]
+    lo, hi = [-1.5, -1.5, -0.5], [1.5, 1.5, 2.5]
+    sc = scenes.random_scene(7, n_spheres=2, n_cuboids=2, n_capsules=1, keep_out=max(KEEP_OUT[robot], 0.4))
+    env = scenes.build_product_env(sc)
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+    env.add_mvt_pointcloud(pts, m["min_radius"], m["max_radius"], lo, hi, vmv.POINT_RADIUS)
+    oenv.add_mvt(pts, m["min_radius"], m["max_radius"], lo, hi, vmv.POINT_RADIUS)
+    q = scenes.random_configs(robot, 8000, seed=25)
+    got, want = R.validate_batch(q, env), O.validate_configs(oenv, q)
+    assert 0.02 < want.mean() < 0.98
+    assert (got != want).sum() <= 2, int((got != want).sum())
+    if po.ref_available():
+        renv = po.add_scene(po.RefEnv(), scenes.packed(sc))
+        renv.add_mvt(pts, m["min_radius"], m["max_radius"], lo, hi, vmv.POINT_RADIUS)
+        assert (got != po.Ref(robot).validate_configs(renv, q, threads=8)).sum() <= 2
+    a, b = scenes.random_edges(robot, 1500, seed=26)
+    assert (R.validate_motion_batch(a, b, env) != O.validate_edges(oenv, a, b)).sum() <= 1
+
+
 @pytest.mark.parametrize("robot", ["panda", "ur5", "fetch"])
 def test_attachment(robot):
     R, O = getattr(vmv, robot), po.Oracle(robot)

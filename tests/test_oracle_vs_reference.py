@@ -110,6 +110,39 @@ def test_capt_pointcloud(robot):
     assert (o.validate_edges(eo, a, b) != r.validate_edges(er, a, b, threads=4)).sum() <= 1
 
 
+@pytest.mark.parametrize("robot", ["panda", "fetch"])
+def test_mvt_pointcloud(robot):
+    """Multi-level Voxel Table (collision/mvt.hh): the oracle's dense-cell restatement against the
+    reference's three-level pointer tables, through the full hierarchy (bounding spheres larger
+    than r_max are queried with the +-1 voxel clamp, as the reference does)."""
+    rng = np.random.default_rng(5)
+    o, r = po.Oracle(robot), po.Ref(robot)
+    m = o.model
+    pts = np.concatenate(
+        [
+            rng.uniform([0.3, -0.6, 0.0], [0.9, 0.6, 0.02], size=(1500, 3)),
+            rng.normal([0.5, 0.3, 0.6], 0.05, size=(700, 3)),
+            rng.uniform([-0.8, -0.8, 0.0], [0.8, 0.8, 1.2], size=(300, 3)),
+        ]
+    ).astype(np.float32)
+    pts = pts[np.hypot(pts[:, 0], pts[:, 1]) > (0.5 if robot == "fetch" else 0.25)]
+    lo, hi = [-1.5, -1.5, -0.5], [1.5, 1.5, 2.5]
+    pts = pts[np.all((pts > lo) & (pts < hi), axis=1)]
+    # the reference's voxels hold at most (r_max / 0.02)^3 points (mvt.hh:455-457, it expects a
+    # filtered cloud): keep one point per 2.5 cm cell
+    _, keep = np.unique(np.floor(pts / 0.025).astype(np.int64), axis=0, return_index=True)
+    pts = pts[np.sort(keep)]
+    eo, er = po.OracleEnv(), po.RefEnv()
+    for e in (eo, er):
+        e.add_mvt(pts, m["min_radius"], m["max_radius"], lo, hi, 0.0025)
+    q = scenes.random_configs(robot, 3000, seed=23)
+    vo, vr = o.validate_configs(eo, q), r.validate_configs(er, q, threads=4)
+    assert 0.02 < vr.mean() < 0.98
+    assert (vo != vr).sum() <= 2, int((vo != vr).sum())
+    a, b = scenes.random_edges(robot, 600, seed=24)
+    assert (o.validate_edges(eo, a, b) != r.validate_edges(er, a, b, threads=4)).sum() <= 1
+
+
 def test_heightfield():
     rng = np.random.default_rng(4)
     xd, yd = 64, 48

@@ -44,6 +44,7 @@ def lib():
         L.vmv_env_add_capsules.argtypes = [vp, vp, sz]
         L.vmv_env_add_heightfield.argtypes = [vp, vp, sz, sz, vp]
         L.vmv_env_add_capt.argtypes = [vp, vp, sz, f32, f32, f32]
+        L.vmv_env_add_mvt.argtypes = [vp, vp, sz, f32, f32, vp, vp, f32]
         L.vmv_env_attach.argtypes = [vp, vp, vp, sz]
         L.vmv_env_detach.argtypes = [vp]
         L.vmv_env_commit.argtypes = [vp]

@@ -25,6 +25,7 @@ namespace vmv
         uint32_t n_zcuboids, n_heightfields, n_capts, n_attach;
         uint32_t off_spheres, off_capsules, off_zcapsules, off_cuboids;
         uint32_t off_zcuboids, off_heightfields, off_capts, off_attach;
+        uint32_t n_mvts, off_mvts, pad0, pad1;
     };
 
     static constexpr int kSphereRec = 8;     // {x y z r}{min_d 0 0 0}
@@ -50,6 +51,28 @@ namespace vmv
         const void *pad3;
     };
     static_assert(sizeof(CaptRec) == kCaptRec * 4, "CaptRec layout");
+
+    // Multi-level Voxel Table (reference collision/mvt.hh).  The reference's three sparse pointer
+    // levels (X -> Y -> Z -> voxel index) address a cube of grid_width^3 cells; in HBM that is one
+    // dense u32 array (a missing Y or Z table is a run of empty cells), per voxel two float4
+    // {bbox lo, bbox hi.x}{bbox hi.y, hi.z, start, count}, and the points as float4, grouped by voxel.
+    static constexpr int kMvtRec = 24;
+    struct MvtRec
+    {
+        float r_point, inv_scale;
+        uint32_t grid_width, pad0;
+        float ws_min[3];
+        float pad1;
+        float g_min[3];
+        float pad2;
+        float g_max[3];
+        float pad3;
+        const uint32_t *cells;
+        const float4 *voxels;
+        const float4 *points;
+        const void *pad4;
+    };
+    static_assert(sizeof(MvtRec) == kMvtRec * 4, "MvtRec layout");
 
     __device__ __forceinline__ bool sign_set(float v)
     {
@@ -178,6 +201,66 @@ namespace vmv
             hit = (lane == src) ? found : hit;
         }
         return hit;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // MVT query (reference collision/mvt.hh:205-276; collides_simd :279-403 is this per lane): the
+    // voxels within +-min(1, q / cell) of the centre's cell, bbox-culled, then every point.  The +-1
+    // clamp is part of the semantics: a link's bounding sphere wider than a cell does not see points
+    // two cells away, and then its fine spheres are not swept -- as in the reference.
+    // ------------------------------------------------------------------------------------------
+    __device__ __forceinline__ int mvt_cell(float v)
+    {
+        // static_cast<uint16_t>(float) on clamped arguments: truncation (negative stays 0)
+        return v <= 0.F ? 0 : (v >= 65535.F ? 65535 : static_cast<int>(v));
+    }
+
+    __device__ __forceinline__ bool mvt_collides(const MvtRec &t, float x, float y, float z, float r)
+    {
+        const float q = r + t.r_point, q2 = q * q;
+        if (x + q < t.g_min[0] || x - q > t.g_max[0] || y + q < t.g_min[1] || y - q > t.g_max[1] || z + q < t.g_min[2] ||
+            z - q > t.g_max[2])
+        {
+            return false;
+        }
+        const float gq = fminf(1.F, q * t.inv_scale);
+        const float top = static_cast<float>(t.grid_width - 1);
+        const float gx = (x - t.ws_min[0]) * t.inv_scale, gy = (y - t.ws_min[1]) * t.inv_scale, gz = (z - t.ws_min[2]) * t.inv_scale;
+        const int x0 = mvt_cell(fmaxf(0.F, gx - gq)), x1 = mvt_cell(fminf(top, gx + gq));
+        const int y0 = mvt_cell(fmaxf(0.F, gy - gq)), y1 = mvt_cell(fminf(top, gy + gq));
+        const int z0 = mvt_cell(fmaxf(0.F, gz - gq)), z1 = mvt_cell(fminf(top, gz + gq));
+        const size_t gw = t.grid_width;
+        for (int vx = x0; vx <= x1; ++vx)
+        {
+            for (int vy = y0; vy <= y1; ++vy)
+            {
+                for (int vz = z0; vz <= z1; ++vz)
+                {
+                    const uint32_t v = __ldg(t.cells + (static_cast<size_t>(vx) * gw + vy) * gw + vz);
+                    if (v == 0xffffffffu)
+                    {
+                        continue;
+                    }
+                    const float4 b0 = __ldg(t.voxels + 2 * static_cast<size_t>(v));
+                    const float4 b1 = __ldg(t.voxels + 2 * static_cast<size_t>(v) + 1);
+                    if (x + q < b0.x || x - q > b0.w || y + q < b0.y || y - q > b1.x || z + q < b0.z || z - q > b1.y)
+                    {
+                        continue;
+                    }
+                    const uint32_t s = __float_as_uint(b1.z), e = s + __float_as_uint(b1.w);
+                    for (uint32_t i = s; i < e; ++i)
+                    {
+                        const float4 p = __ldg(t.points + i);
+                        const float dx = x - p.x, dy = y - p.y, dz = z - p.z;
+                        if (dx * dx + dy * dy + dz * dz <= q2)
+                        {
+                            return true;
+                        }
+                    }
+                }
+            }
+        }
+        return false;
     }
 
     // ------------------------------------------------------------------------------------------
@@ -337,6 +420,14 @@ namespace vmv
             const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * i);
             // lanes that already collided skip the query but keep the warp's loop structure
             if (capt_collides_warp(t, x, y, z, r_pc, active && !hit))
+            {
+                hit = true;
+            }
+        }
+        for (uint32_t i = 0; i < H.n_mvts; ++i)
+        {
+            const MvtRec &t = *reinterpret_cast<const MvtRec *>(E + H.off_mvts + kMvtRec * i);
+            if (active && !hit && mvt_collides(t, x, y, z, r_pc))
             {
                 hit = true;
             }

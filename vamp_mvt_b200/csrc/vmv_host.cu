@@ -256,6 +256,121 @@ namespace
         float4 *d_points = nullptr;
     };
 
+    // Multi-level Voxel Table, host build (reference collision/mvt.hh:146-170, 437-446, 531-604)
+    struct HMvt
+    {
+        float r_min, r_max, r_point;
+        float ws_min[3], ws_max[3];
+        float g_min[3], g_max[3];
+        float inv_scale = 0.F;
+        uint32_t grid_width = 0;
+        std::vector<uint32_t> cells;   // grid_width^3, 0xffffffff = empty
+        std::vector<float4> voxels;    // 2 per voxel
+        std::vector<float4> points;    // grouped by voxel
+        int id;
+        uint32_t *d_cells = nullptr;
+        float4 *d_voxels = nullptr;
+        float4 *d_points = nullptr;
+    };
+
+    inline int mvt_cell_host(float v)
+    {
+        return v <= 0.F ? 0 : (v >= 65535.F ? 65535 : static_cast<int>(v));
+    }
+
+    int mvt_build(HMvt &t, const float *pts, size_t n, float r_min, float r_max, const float *ws_min, const float *ws_max, float r_point)
+    {
+        t.r_min = r_min, t.r_max = r_max, t.r_point = r_point;
+        for (int k = 0; k < 3; ++k)
+        {
+            t.ws_min[k] = ws_min[k], t.ws_max[k] = ws_max[k];
+            // initialize_empty_bounds (mvt.hh:428-435): an empty table rejects every query
+            t.g_min[k] = std::numeric_limits<float>::max();
+            t.g_max[k] = std::numeric_limits<float>::lowest();
+        }
+        if (n == 0)
+        {
+            return VMV_OK;
+        }
+        const float width = ws_max[0] - ws_min[0];
+        // configure_grid (mvt.hh:437-446)
+        const float cells_f = std::floor(width / r_max);
+        if (!(cells_f >= 1.F) || !std::isfinite(cells_f))
+        {
+            return -1;
+        }
+        const uint32_t gw = static_cast<uint32_t>(std::min(cells_f, 65535.F));
+        if (static_cast<size_t>(gw) * gw * gw > (size_t(1) << 26))
+        {
+            return -2;
+        }
+        t.grid_width = gw;
+        t.inv_scale = static_cast<float>(gw) / width;
+        t.cells.assign(static_cast<size_t>(gw) * gw * gw, 0xffffffffu);
+        std::vector<uint32_t> voxel_of(n), count;
+        const float top = static_cast<float>(gw - 1);
+        for (size_t i = 0; i < n; ++i)
+        {
+            // build_spatial_grid (mvt.hh:531-588): clamp into the grid, voxels numbered by first insertion
+            const float *p = pts + 3 * i;
+            const uint32_t vx = mvt_cell_host(std::min(std::max((p[0] - ws_min[0]) * t.inv_scale, 0.F), top));
+            const uint32_t vy = mvt_cell_host(std::min(std::max((p[1] - ws_min[1]) * t.inv_scale, 0.F), top));
+            const uint32_t vz = mvt_cell_host(std::min(std::max((p[2] - ws_min[2]) * t.inv_scale, 0.F), top));
+            uint32_t &cell = t.cells[(static_cast<size_t>(vx) * gw + vy) * gw + vz];
+            if (cell == 0xffffffffu)
+            {
+                cell = static_cast<uint32_t>(count.size());
+                count.push_back(0);
+            }
+            voxel_of[i] = cell;
+            count[cell]++;
+        }
+        const size_t nv = count.size();
+        std::vector<uint32_t> start(nv + 1, 0), fill(nv, 0);
+        for (size_t v = 0; v < nv; ++v)
+        {
+            start[v + 1] = start[v] + count[v];
+        }
+        std::vector<float> bb(6 * nv);
+        t.points.assign(n, make_float4(0, 0, 0, 0));
+        for (size_t i = 0; i < n; ++i)
+        {
+            const uint32_t v = voxel_of[i];
+            const float *p = pts + 3 * i;
+            float *b = bb.data() + 6 * v;
+            if (fill[v] == 0)
+            {
+                b[0] = b[3] = p[0], b[1] = b[4] = p[1], b[2] = b[5] = p[2];
+            }
+            else
+            {
+                for (int k = 0; k < 3; ++k)
+                {
+                    b[k] = std::min(b[k], p[k]);
+                    b[3 + k] = std::max(b[3 + k], p[k]);
+                }
+            }
+            t.points[start[v] + fill[v]++] = make_float4(p[0], p[1], p[2], 0.F);
+        }
+        t.voxels.resize(2 * nv);
+        for (size_t v = 0; v < nv; ++v)
+        {
+            const float *b = bb.data() + 6 * v;
+            float s, c;
+            std::memcpy(&s, &start[v], 4);
+            std::memcpy(&c, &count[v], 4);
+            t.voxels[2 * v] = make_float4(b[0], b[1], b[2], b[3]);
+            t.voxels[2 * v + 1] = make_float4(b[4], b[5], s, c);
+            for (int k = 0; k < 3; ++k)
+            {
+                // compute_global_bounds (mvt.hh:590-604)
+                t.g_min[k] = std::min(t.g_min[k], b[k]);
+                t.g_max[k] = std::max(t.g_max[k], b[3 + k]);
+            }
+        }
+        return VMV_OK;
+    }
+
     float finite_or_neg_inf(float v)
     {
         // a degenerate capsule gives NaN; the reference then never breaks out of the sweep at it
@@ -417,6 +532,7 @@ struct vmv_env
     std::vector<HCuboid> cuboids, z_cuboids;
     std::vector<HHeight> heightfields;
     std::vector<HCapt> capts;
+    std::vector<HMvt> mvts;
     bool has_attachment = false;
     float attach_tf[12];  // row-major 3x4
     std::vector<float> attach_spheres;
@@ -650,6 +766,23 @@ namespace
             }
         }
 
+        for (auto &t : env->mvts)
+        {
+            int rc = upload(env, t.cells, t.d_cells);
+            if (rc == VMV_OK)
+            {
+                rc = upload(env, t.voxels, t.d_voxels);
+            }
+            if (rc == VMV_OK)
+            {
+                rc = upload(env, t.points, t.d_points);
+            }
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
+
         std::vector<uint32_t> &B = env->blob;
         B.assign(sizeof(vmv::EnvHeader) / 4, 0u);
         auto align4 = [&]()
@@ -730,6 +863,27 @@ namespace
             const uint32_t *w = reinterpret_cast<const uint32_t *>(&r);
             B.insert(B.end(), w, w + vmv::kCaptRec);
         }
+        H.n_mvts = static_cast<uint32_t>(env->mvts.size());
+        align4();
+        H.off_mvts = static_cast<uint32_t>(B.size());
+        for (const auto &t : env->mvts)
+        {
+            vmv::MvtRec r{};
+            r.r_point = t.r_point;
+            r.inv_scale = t.inv_scale;
+            r.grid_width = t.grid_width;
+            for (int k = 0; k < 3; ++k)
+            {
+                r.ws_min[k] = t.ws_min[k];
+                r.g_min[k] = t.g_min[k];
+                r.g_max[k] = t.g_max[k];
+            }
+            r.cells = t.d_cells;
+            r.voxels = t.d_voxels;
+            r.points = t.d_points;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(&r);
+            B.insert(B.end(), w, w + vmv::kMvtRec);
+        }
         H.n_attach = env->has_attachment ? static_cast<uint32_t>(env->attach_spheres.size() / 4) : 0u;
         align4();
         H.off_attach = static_cast<uint32_t>(B.size());
@@ -805,7 +959,7 @@ namespace
         le.blob_bytes = static_cast<uint32_t>(env->blob.size() * 4);
         le.n_objects = static_cast<uint32_t>(
             env->spheres.size() + env->capsules.size() + env->z_capsules.size() + env->cuboids.size() + env->z_cuboids.size());
-        le.primitives_only = env->heightfields.empty() && env->capts.empty() && !env->has_attachment;
+        le.primitives_only = env->heightfields.empty() && env->capts.empty() && env->mvts.empty() && !env->has_attachment;
         // attach_tf = ee_tf(robot) * attachment offset
         const float *E = r.ee_tf;
         float A[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -943,7 +1097,7 @@ namespace
         ok = false;
         wide = false;
         const size_t n_obj = env->uobjs.size() / vmv::kObjRec;
-        if (n_obj == 0 || n_obj > 64 || !env->heightfields.empty() || !env->capts.empty() || env->has_attachment)
+        if (n_obj == 0 || n_obj > 64 || !env->heightfields.empty() || !env->capts.empty() || !env->mvts.empty() || env->has_attachment)
         {
             return VMV_OK;
         }
@@ -1497,6 +1651,28 @@ extern "C"
         capt_build(t, pts, n, r_min, r_max, r_point);
         t.id = env->next_id++;
         env->capts.push_back(std::move(t));
+        env->committed = false;
+        return VMV_OK;
+    }
+
+    int vmv_env_add_mvt(vmv_env *env, const float *pts, size_t n, float r_min, float r_max, const float *aabb_min, const float *aabb_max, float r_point)
+    {
+        if (env == nullptr || (n > 0 && pts == nullptr) || aabb_min == nullptr || aabb_max == nullptr || !(r_max > 0.F))
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_add_mvt: bad argument");
+        }
+        HMvt t;
+        const int rc = mvt_build(t, pts, n, r_min, r_max, aabb_min, aabb_max, r_point);
+        if (rc == -1)
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_add_mvt: workspace narrower than r_max");
+        }
+        if (rc == -2)
+        {
+            return fail(VMV_ERR_LIMIT, "vmv_env_add_mvt: more than 2^26 grid cells");
+        }
+        t.id = env->next_id++;
+        env->mvts.push_back(std::move(t));
         env->committed = false;
         return VMV_OK;
     }

@@ -294,7 +294,8 @@ namespace vmv
         // pointcloud in the environment the hierarchy is part of the verdict and is reproduced as
         // the reference runs it: the un-inflated bounding radius, and "any lane of the rake block
         // hits" decides whether the block's fine spheres are swept (robots/panda.hh:5634-5645).
-        const bool collective = Vote::kWarp && reinterpret_cast<const EnvHeader *>(c.env)->n_capts > 0;
+        const bool collective = Vote::kWarp && (reinterpret_cast<const EnvHeader *>(c.env)->n_capts > 0 ||
+                                                reinterpret_cast<const EnvHeader *>(c.env)->n_mvts > 0);
         {
             int ti = 0;
             bool active = has_state;

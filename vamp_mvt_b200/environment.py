@@ -64,6 +64,16 @@ class Environment:
         self._dirty = True
         return time.perf_counter_ns() - t0
 
+    def add_mvt_pointcloud(self, points, r_min: float, r_max: float, aabb_min, aabb_max, r_point: float) -> int:
+        """Multi-level Voxel Table pointcloud (environment.cc:163-176); returns the build time in ns."""
+        p = _lib.f32(points).reshape(-1, 3)
+        lo, hi = _lib.f32(aabb_min).reshape(3), _lib.f32(aabb_max).reshape(3)
+        t0 = time.perf_counter_ns()
+        _lib.check(self._L.vmv_env_add_mvt(self._h, _lib.ptr(p), len(p), r_min, r_max, _lib.ptr(lo), _lib.ptr(hi), r_point))
+        self.names.append("")
+        self._dirty = True
+        return time.perf_counter_ns() - t0
+
     # upstream VAMP calls this add_pointcloud; the fork splits it into capt / mvt
     add_pointcloud = add_capt_pointcloud
 
