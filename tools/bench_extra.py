@@ -6,6 +6,9 @@ the library's own stream sync + host timer around >= 5 back-to-back launches):
   C5  PRM-style roadmap edge validation, 10^8 Panda edges as (u32,u32) index pairs into a vertex table
 
 Usage: bench_extra.py [c4] [c5] [--edges N]
+       python -m torch.distributed.run --nproc-per-node N ... bench_extra.py c5 --edges N
+           C5 sharded over N GPUs (contiguous word-aligned shards, one NCCL all-gather of the
+           verdict bitmask inside the timed region, device timing, max over ranks)
 Prints one JSON line per workload."""
 import json
 import sys
@@ -73,7 +76,7 @@ def c4():
         L.vmv_dev_free(dq), L.vmv_dev_free(db)
 
 
-def c5(n_edges):
+def c5_inputs(n_edges):
     R = vmv.panda
     env = scenes.build_product_env(scenes.table_shelf_scene())
     rng = np.random.default_rng(5)
@@ -91,7 +94,17 @@ def c5(n_edges):
     j = (i + rng.integers(1, per, size=n_edges, dtype=np.int64)) % per
     pairs = np.stack([c * per + i, c * per + j], axis=1).astype(np.uint32)
     keep = valid[pairs[:, 0]] & valid[pairs[:, 1]]
-    pairs = np.ascontiguousarray(pairs[keep])
+    return env, V, np.ascontiguousarray(pairs[keep])
+
+
+def c5(n_edges):
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        return c5_sharded(n_edges)
+    R = vmv.panda
+    env, V, pairs = c5_inputs(n_edges)
     n = len(pairs)
     dV, dP, dB = L.vmv_dev_alloc(V.nbytes), L.vmv_dev_alloc(pairs.nbytes), L.vmv_dev_alloc((n + 31) // 32 * 4)
     _lib.check(L.vmv_memcpy_h2d(dV, _lib.ptr(V), V.nbytes, None))
@@ -103,8 +116,62 @@ def c5(n_edges):
     _lib.check(L.vmv_stream_sync(None))
     d = np.linalg.norm(V[pairs[:100000, 0]] - V[pairs[:100000, 1]], axis=1)
     print(json.dumps({"workload": f"C5: {n} PRM-style Panda edges (index pairs into {len(V)} vertices), table/shelf scene",
-                      "value": n / t, "unit": "edges/s", "ms": t * 1e3, "mean_edge_length_rad": float(d.mean()),
+                      "value": n / t, "unit": "edges/s", "ms": t * 1e3, "n_gpus": 1, "mean_edge_length_rad": float(d.mean()),
                       "valid_fraction": float(_lib.unpack_bits(words, n).mean())}), flush=True)
+
+
+def c5_sharded(n_edges):
+    """Every rank builds the same roadmap (seeded), validates its contiguous word-aligned shard of
+    the edge list and takes part in ONE all-gather of verdict words (NCCL); strong scaling."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from vamp_mvt_b200 import sharding
+
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.check(L.vmv_set_device(local))
+    R = vmv.panda
+    env, V, pairs = c5_inputs(n_edges)
+    n = len(pairs)
+    lo, hi = sharding.shard_bounds(n, rank, world)
+    per = sharding.words_per_rank(n, world)
+    dV = torch.from_numpy(V).cuda()
+    dP = torch.from_numpy(pairs[lo:hi].view(np.int32)).cuda()
+    local_words = torch.zeros(per, dtype=torch.int32, device="cuda")
+    gathered = torch.zeros(per * world, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    h = env.handle
+
+    def step():
+        _lib.check(L.vmv_validate_edges_indexed_dev(R.id, h, dV.data_ptr(), len(V), dP.data_ptr(), hi - lo, 0, local_words.data_ptr(), stream))
+        dist.all_gather_into_tensor(gathered, local_words)
+
+    for _ in range(2):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        words = gathered.cpu().numpy().view(np.uint32)[: (n + 31) // 32]
+        print(json.dumps({"workload": f"C5: {n} PRM-style Panda edges (index pairs into {len(V)} vertices), table/shelf scene",
+                          "value": n / (ms * 1e-3), "unit": "edges/s", "ms": ms, "n_gpus": world, "scaling": "strong",
+                          "collective": f"one NCCL all_gather of {per * 4} bytes per rank per step",
+                          "valid_fraction": float(_lib.unpack_bits(words, n).mean())}), flush=True)
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

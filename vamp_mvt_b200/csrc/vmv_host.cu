@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -1208,30 +1209,59 @@ namespace
     // Launch geometry of the warp-autonomous kernels: the number of warps per block that maximises
     // the warps resident per SM (shared memory = block-shared tables + one slice per warp), and a
     // persistent grid of that many blocks per SM.
+    // The search runs once per (kernel, shared-memory shape, device) and is cached: the occupancy
+    // queries cost more host time than a launch.
+    struct V4Geometry
+    {
+        const void *kernel;
+        uint32_t shared_bytes, warp_bytes;
+        int device, warps, blocks_per_sm;
+    };
+    std::vector<V4Geometry> g_v4_geometry;
+
     template <typename K>
     int v4_geometry(K kernel, uint32_t shared_bytes, uint32_t warp_bytes, int max_threads, size_t units, int &warps, unsigned &grid, uint32_t &smem)
     {
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        const void *key = reinterpret_cast<const void *>(kernel);
         int best_w = 0, best_blocks = 0;
-        constexpr uint32_t kMaxDynamic = kMaxSmem - 1024;  // the opt-in limit counts static shared memory too
-        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynamic)));
-        for (int w = 1; w <= max_threads / 32; ++w)
         {
-            const size_t bytes = static_cast<size_t>(shared_bytes) + static_cast<size_t>(w) * warp_bytes;
-            if (bytes > kMaxDynamic)
+            std::lock_guard<std::mutex> lock(g_mutex);
+            for (const auto &g : g_v4_geometry)
             {
-                break;
-            }
-            int blocks = 0;
-            VMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, w * 32, bytes));
-            if (blocks * w > best_blocks * best_w || (blocks * w == best_blocks * best_w && blocks > 0))
-            {
-                best_w = w;
-                best_blocks = blocks;
+                if (g.kernel == key && g.shared_bytes == shared_bytes && g.warp_bytes == warp_bytes && g.device == device)
+                {
+                    best_w = g.warps, best_blocks = g.blocks_per_sm;
+                    break;
+                }
             }
         }
-        if (best_w == 0 || best_blocks == 0)
+        if (best_w == 0)
         {
-            return fail(VMV_ERR_LIMIT, "robot tables too large for the grid-culled kernel");
+            constexpr uint32_t kMaxDynamic = kMaxSmem - 1024;  // the opt-in limit counts static shared memory too
+            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynamic)));
+            for (int w = 1; w <= max_threads / 32; ++w)
+            {
+                const size_t bytes = static_cast<size_t>(shared_bytes) + static_cast<size_t>(w) * warp_bytes;
+                if (bytes > kMaxDynamic)
+                {
+                    break;
+                }
+                int blocks = 0;
+                VMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, w * 32, bytes));
+                if (blocks * w > best_blocks * best_w || (blocks * w == best_blocks * best_w && blocks > 0))
+                {
+                    best_w = w;
+                    best_blocks = blocks;
+                }
+            }
+            if (best_w == 0 || best_blocks == 0)
+            {
+                return fail(VMV_ERR_LIMIT, "robot tables too large for the grid-culled kernel");
+            }
+            std::lock_guard<std::mutex> lock(g_mutex);
+            g_v4_geometry.push_back({key, shared_bytes, warp_bytes, device, best_w, best_blocks});
         }
         warps = best_w;
         smem = shared_bytes + static_cast<uint32_t>(best_w) * warp_bytes;
@@ -2048,7 +2078,17 @@ extern "C"
         };
         HostPathPool g_pools[kMaxDevices];
 
-        constexpr size_t kChunkUnits = size_t(1) << 17;  // multiple of 32: chunks own whole verdict words
+        // multiple of 32: chunks own whole verdict words.  VMV_CHUNK_LOG2 overrides (tuning aid).
+        size_t chunk_units()
+        {
+            static const size_t v = []
+            {
+                const char *e = std::getenv("VMV_CHUNK_LOG2");
+                const int lg = e ? std::atoi(e) : 18;
+                return size_t(1) << std::min(std::max(lg, 10), 26);
+            }();
+            return v;
+        }
     }  // namespace
 
     int vmv_validate_configs(int robot, const vmv_env *env, const float *q, size_t n, uint32_t *bits)
@@ -2083,9 +2123,10 @@ extern "C"
         float *dq = static_cast<float *>(pool.buf[0]);
         uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
         int k = 0;
-        for (size_t off = 0; off < n; off += kChunkUnits, ++k)
+        const size_t chunk_cfg = chunk_units();
+        for (size_t off = 0; off < n; off += chunk_cfg, ++k)
         {
-            const size_t cnt = std::min(kChunkUnits, n - off);
+            const size_t cnt = std::min(chunk_cfg, n - off);
             cudaStream_t st = pool.streams[k & 1];
             VMV_CUDA(cudaMemcpyAsync(dq + off * dof, q + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
             rc = vmv_validate_configs_dev(robot, env, dq + off * dof, cnt, dw + off / 32, st);
@@ -2136,7 +2177,7 @@ extern "C"
         float *da = static_cast<float *>(pool.buf[0]);
         float *db = static_cast<float *>(pool.buf[1]);
         uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
-        const size_t chunk = kChunkUnits / 4;
+        const size_t chunk = chunk_units() / 4;
         int k = 0;
         for (size_t off = 0; off < n; off += chunk, ++k)
         {
