@@ -25,7 +25,7 @@ namespace vmv
         uint32_t n_zcuboids, n_heightfields, n_capts, n_attach;
         uint32_t off_spheres, off_capsules, off_zcapsules, off_cuboids;
         uint32_t off_zcuboids, off_heightfields, off_capts, off_attach;
-        uint32_t n_mvts, off_mvts, pad0, pad1;
+        uint32_t n_mvts, off_mvts, off_cloud_grid, pad1;  // off_cloud_grid = 0: no clearance grid
     };
 
     static constexpr int kSphereRec = 8;     // {x y z r}{min_d 0 0 0}
@@ -73,6 +73,72 @@ namespace vmv
         const void *pad4;
     };
     static_assert(sizeof(MvtRec) == kMvtRec * 4, "MvtRec layout");
+
+    // Clearance grid of the pointclouds (CAPT and MVT together): per voxel a lower bound of the
+    // distance from any position inside the voxel to the nearest cloud point.  A pointcloud query can
+    // only answer "collision" on an actual point within r + r_point of the centre (capt.hh:494-509,
+    // mvt.hh:383-397), so a sphere whose clearance bound exceeds that radius skips the tree descent /
+    // voxel walk altogether -- the verdict is the one the query would have returned.
+    static constexpr int kCloudGridRec = 12;
+    struct CloudGridRec
+    {
+        float x0, y0, z0, inv_h;
+        int nx, ny, nz;
+        float outside;      // clearance bound for positions outside the table
+        float r_point_max;  // largest r_point of any cloud
+        float pad0;
+        const float *cells;
+    };
+    static_assert(sizeof(CloudGridRec) == kCloudGridRec * 4, "CloudGridRec layout");
+
+    __device__ __forceinline__ float cloud_clearance(const CloudGridRec &g, float x, float y, float z)
+    {
+        const int ix = __float2int_rd((x - g.x0) * g.inv_h);
+        const int iy = __float2int_rd((y - g.y0) * g.inv_h);
+        const int iz = __float2int_rd((z - g.z0) * g.inv_h);
+        const bool in = (static_cast<unsigned>(ix) < static_cast<unsigned>(g.nx)) & (static_cast<unsigned>(iy) < static_cast<unsigned>(g.ny)) &
+                        (static_cast<unsigned>(iz) < static_cast<unsigned>(g.nz));
+        if (!in)
+        {
+            // a centre that is not finite lands here too: no claim about it
+            return (fabsf(x) < 1e30F && fabsf(y) < 1e30F && fabsf(z) < 1e30F) ? g.outside : 0.F;
+        }
+        return __ldg(g.cells + (static_cast<size_t>(iz) * g.ny + iy) * g.nx + ix);
+    }
+
+    // thread = voxel; the points stream through shared memory
+    __global__ void __launch_bounds__(256) k_build_cloud_grid(
+        const float4 *__restrict__ points, uint32_t n_points, float x0, float y0, float z0, float h, int nx, int ny, int nz, float *__restrict__ out)
+    {
+        __shared__ float4 tile[1024];
+        const size_t n_vox = static_cast<size_t>(nx) * ny * nz;
+        const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        const int ix = static_cast<int>(v % nx), iy = static_cast<int>((v / nx) % ny), iz = static_cast<int>(v / (static_cast<size_t>(nx) * ny));
+        const float x = x0 + (ix + 0.5F) * h, y = y0 + (iy + 0.5F) * h, z = z0 + (iz + 0.5F) * h;
+        float best = 3.0e38F;
+        for (uint32_t base = 0; base < n_points; base += 1024)
+        {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x)
+            {
+                tile[i] = base + i < n_points ? __ldg(points + base + i) : make_float4(1e18F, 1e18F, 1e18F, 0.F);
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int i = 0; i < 1024; ++i)
+            {
+                const float4 p = tile[i];
+                const float dx = p.x - x, dy = p.y - y, dz = p.z - z;
+                best = fminf(best, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            }
+        }
+        if (v < n_vox)
+        {
+            // distance from the voxel centre minus the half diagonal (and rounding slack): a lower
+            // bound for every position inside the voxel
+            out[v] = fmaxf(sqrtf(best) * 0.99999F - 0.8660255F * h - 1e-4F, 0.F);
+        }
+    }
 
     __device__ __forceinline__ bool sign_set(float v)
     {
@@ -415,11 +481,22 @@ namespace vmv
             hit = sphere_hits_primitives(E, x, y, z, r);
         }
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
+        if (H.n_capts + H.n_mvts == 0)
+        {
+            return hit;
+        }
+        // no cloud point within reach: every pointcloud query would answer "no"
+        bool query = active && !hit;
+        if (H.off_cloud_grid != 0 && query)
+        {
+            const CloudGridRec &g = *reinterpret_cast<const CloudGridRec *>(E + H.off_cloud_grid);
+            query = !(cloud_clearance(g, x, y, z) > r_pc + g.r_point_max);
+        }
         for (uint32_t i = 0; i < H.n_capts; ++i)
         {
             const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * i);
-            // lanes that already collided skip the query but keep the warp's loop structure
-            if (capt_collides_warp(t, x, y, z, r_pc, active && !hit))
+            // lanes without a query keep the warp's loop structure (they help scanning)
+            if (capt_collides_warp(t, x, y, z, r_pc, query && !hit))
             {
                 hit = true;
             }
@@ -427,7 +504,7 @@ namespace vmv
         for (uint32_t i = 0; i < H.n_mvts; ++i)
         {
             const MvtRec &t = *reinterpret_cast<const MvtRec *>(E + H.off_mvts + kMvtRec * i);
-            if (active && !hit && mvt_collides(t, x, y, z, r_pc))
+            if (query && !hit && mvt_collides(t, x, y, z, r_pc))
             {
                 hit = true;
             }

@@ -17,7 +17,6 @@
 
 #include "../../include/vamp_b200.h"
 #include "vmv_kernels_v2.cuh"
-#include "vmv_kernels_v3.cuh"
 #include "vmv_kernels_v4.cuh"
 
 #include "gen/panda_fk.cuh"
@@ -534,6 +533,9 @@ struct vmv_env
     std::vector<HHeight> heightfields;
     std::vector<HCapt> capts;
     std::vector<HMvt> mvts;
+    std::vector<float> cloud_xyz;  // every point of every pointcloud (clearance grid, vmv_device.cuh)
+    float cloud_r_point_max = 0.F;
+    float cloud_grid_ms = 0.F;
     bool has_attachment = false;
     float attach_tf[12];  // row-major 3x4
     std::vector<float> attach_spheres;
@@ -546,7 +548,7 @@ struct vmv_env
     int *d_object_ids = nullptr;  // packed object index -> insertion id (vmv_debug)
     std::vector<void *> owned;  // device allocations referenced from the blob
 
-    // grid-culled path (vmv_kernels_v3.cuh): rounded-box records of all primitives and, per robot,
+    // grid-culled path (vmv_grid.cuh, vmv_kernels_v4.cuh): rounded-box records of all primitives and, per robot,
     // the voxel table of candidate masks (built on first use with that robot)
     std::vector<float> uobjs;  // kObjRec floats per object, packed order
     float4 *d_uobjs = nullptr;
@@ -618,7 +620,7 @@ namespace
         return VMV_OK;
     }
 
-    // Every primitive as a rounded box {centre, rho}{axis_i, half extent_i} (vmv_kernels_v3.cuh), in
+    // Every primitive as a rounded box {centre, rho}{axis_i, half extent_i} (vmv_grid.cuh), in
     // the packed order spheres | capsules | z-capsules | cuboids | z-cuboids.
     void build_rounded_boxes(vmv_env *env)
     {
@@ -716,6 +718,83 @@ namespace
             zb.f[9] = 0.F, zb.f[10] = 0.F, zb.f[11] = 1.F;
             cuboid(zb);
         }
+    }
+
+    // Clearance grid of all pointcloud points (vmv_device.cuh: cloud_clearance).  The table covers the
+    // points' bounding box grown by kCloudReach; outside it every cloud point is farther than that.
+    constexpr float kCloudReach = 0.5F;
+    constexpr size_t kCloudMaxVoxels = 1u << 20;
+
+    int build_cloud_grid(vmv_env *env, vmv::CloudGridRec &g)
+    {
+        const size_t n = env->cloud_xyz.size() / 3;
+        float lo[3] = {3e38F, 3e38F, 3e38F}, hi[3] = {-3e38F, -3e38F, -3e38F};
+        std::vector<float4> pts(n);
+        for (size_t i = 0; i < n; ++i)
+        {
+            const float *p = env->cloud_xyz.data() + 3 * i;
+            if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2]))
+            {
+                return VMV_OK;  // no grid: every query runs
+            }
+            for (int k = 0; k < 3; ++k)
+            {
+                lo[k] = std::min(lo[k], p[k]);
+                hi[k] = std::max(hi[k], p[k]);
+            }
+            pts[i] = make_float4(p[0], p[1], p[2], 0.F);
+        }
+        double h = 0.03;
+        int dim[3];
+        while (true)
+        {
+            size_t vox = 1;
+            for (int k = 0; k < 3; ++k)
+            {
+                dim[k] = std::max(1, static_cast<int>(std::ceil((hi[k] - lo[k] + 2.0 * kCloudReach) / h)));
+                vox *= static_cast<size_t>(dim[k]);
+            }
+            if (vox <= kCloudMaxVoxels)
+            {
+                break;
+            }
+            h *= 1.15;
+        }
+        const size_t n_vox = static_cast<size_t>(dim[0]) * dim[1] * dim[2];
+        float4 *d_pts = nullptr;
+        float *d_cells = nullptr;
+        int rc = upload(env, pts, d_pts);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        {
+            void *p = nullptr;
+            VMV_CUDA(cudaMalloc(&p, n_vox * sizeof(float)));
+            env->owned.push_back(p);
+            d_cells = static_cast<float *>(p);
+        }
+        cudaEvent_t e0, e1;
+        VMV_CUDA(cudaEventCreate(&e0));
+        VMV_CUDA(cudaEventCreate(&e1));
+        VMV_CUDA(cudaEventRecord(e0, nullptr));
+        vmv::k_build_cloud_grid<<<static_cast<unsigned>((n_vox + 255) / 256), 256>>>(
+            d_pts, static_cast<uint32_t>(n), lo[0] - kCloudReach, lo[1] - kCloudReach, lo[2] - kCloudReach, static_cast<float>(h), dim[0], dim[1],
+            dim[2], d_cells);
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        VMV_CUDA(cudaEventRecord(e1, nullptr));
+        VMV_CUDA(cudaEventSynchronize(e1));
+        VMV_CUDA(cudaEventElapsedTime(&env->cloud_grid_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        g.x0 = lo[0] - kCloudReach, g.y0 = lo[1] - kCloudReach, g.z0 = lo[2] - kCloudReach;
+        g.inv_h = static_cast<float>(1.0 / h);
+        g.nx = dim[0], g.ny = dim[1], g.nz = dim[2];
+        g.outside = kCloudReach - static_cast<float>(h) - 1e-3F;
+        g.r_point_max = env->cloud_r_point_max;
+        g.cells = d_cells;
+        return VMV_OK;
     }
 
     int pack_and_upload(vmv_env *env)
@@ -884,6 +963,23 @@ namespace
             r.points = t.d_points;
             const uint32_t *w = reinterpret_cast<const uint32_t *>(&r);
             B.insert(B.end(), w, w + vmv::kMvtRec);
+        }
+        H.off_cloud_grid = 0;
+        if (!env->cloud_xyz.empty())
+        {
+            vmv::CloudGridRec g{};
+            int rc = build_cloud_grid(env, g);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            if (g.cells != nullptr)
+            {
+                align4();
+                H.off_cloud_grid = static_cast<uint32_t>(B.size());
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(&g);
+                B.insert(B.end(), w, w + vmv::kCloudGridRec);
+            }
         }
         H.n_attach = env->has_attachment ? static_cast<uint32_t>(env->attach_spheres.size() / 4) : 0u;
         align4();
@@ -1093,7 +1189,7 @@ namespace
 
     // The voxel table of `env` for `robot` (built once, synchronously, on first use).  ok = false when
     // the path does not apply (no primitives, more than 64 of them, other content in the environment).
-    int grid_launch_env(int robot, const vmv_env *env, vmv::LaunchEnvV3 &out, bool &ok, bool &wide)
+    int grid_launch_env(int robot, const vmv_env *env, vmv::GridEnv &out, bool &ok, bool &wide)
     {
         ok = false;
         wide = false;
@@ -1287,7 +1383,7 @@ namespace
     };
 
     template <typename R, typename MaskT>
-    int launch_configs_v4(const vmv::RobotDev &rd, const vmv::LaunchEnvV3 &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
+    int launch_configs_v4(const vmv::RobotDev &rd, const vmv::GridEnv &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
     {
         using M = typename R::Model;
         const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine);
@@ -1331,7 +1427,7 @@ namespace
     template <typename R, typename MaskT>
     int launch_edges_v4(
         const vmv::RobotDev &rd,
-        const vmv::LaunchEnvV3 &le,
+        const vmv::GridEnv &le,
         const float *a,
         const float *b,
         const uint32_t *pairs,
@@ -1681,6 +1777,8 @@ extern "C"
         capt_build(t, pts, n, r_min, r_max, r_point);
         t.id = env->next_id++;
         env->capts.push_back(std::move(t));
+        env->cloud_xyz.insert(env->cloud_xyz.end(), pts, pts + 3 * n);
+        env->cloud_r_point_max = std::max(env->cloud_r_point_max, r_point);
         env->committed = false;
         return VMV_OK;
     }
@@ -1703,6 +1801,8 @@ extern "C"
         }
         t.id = env->next_id++;
         env->mvts.push_back(std::move(t));
+        env->cloud_xyz.insert(env->cloud_xyz.end(), pts, pts + 3 * n);
+        env->cloud_r_point_max = std::max(env->cloud_r_point_max, r_point);
         env->committed = false;
         return VMV_OK;
     }
@@ -1877,7 +1977,7 @@ extern "C"
         const int force = g_force_path.load();
         if ((force == 0 && n >= kGridMinConfigs) || force == 3)
         {
-            vmv::LaunchEnvV3 l3{};
+            vmv::GridEnv l3{};
             bool ok = false, wide = false;
             rc = grid_launch_env(robot, env, l3, ok, wide);
             if (rc != VMV_OK)
@@ -1936,7 +2036,7 @@ extern "C"
         const int force = g_force_path.load();
         if ((force == 0 && n >= kGridMinEdges) || force == 3)
         {
-            vmv::LaunchEnvV3 l3{};
+            vmv::GridEnv l3{};
             bool ok = false, wide = false;
             rc = grid_launch_env(robot, env, l3, ok, wide);
             if (rc != VMV_OK)

@@ -1,6 +1,6 @@
 // Warp-autonomous grid-culled kernels (sm_100a) for environments made of primitives (at most 64
-// objects).  Same algorithm as vmv_kernels_v3.cuh -- voxel table of candidate masks, rounded-box
-// records, exact tests only on candidates -- but the unit of cooperation is the warp, not the block:
+// objects).  Broad phase: the voxel table of candidate masks and the rounded-box records of
+// vmv_grid.cuh; exact tests only on candidates.  The unit of cooperation is the warp, not the block:
 //
 //   * a warp owns 32 states per pass and a private slice of shared memory (frame stash, masks,
 //     work queues); phases are separated by __syncwarp() only, so the 16-18 resident warps of an SM
@@ -17,7 +17,7 @@
 // The self-collision phases sit between the issue and the use of the table loads and cover their
 // L2 latency.
 #pragma once
-#include "vmv_kernels_v3.cuh"
+#include "vmv_grid.cuh"
 
 namespace vmv
 {
@@ -40,70 +40,6 @@ namespace vmv
         const int o = __ffsll(static_cast<long long>(m)) - 1;
         m &= m - 1ull;
         return o;
-    }
-
-    template <typename MaskT>
-    __global__ void __launch_bounds__(128) k_build_grid_t(
-        const float4 *__restrict__ objs,
-        uint32_t n_objects,
-        float x0,
-        float y0,
-        float z0,
-        float h,
-        int nx,
-        int ny,
-        int nz,
-        float r0,
-        float r1,
-        float r2,
-        float r3,
-        MaskT *__restrict__ out)
-    {
-        const size_t n_vox = static_cast<size_t>(nx) * ny * nz;
-        const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-        if (v >= n_vox)
-        {
-            return;
-        }
-        const int ix = static_cast<int>(v % nx), iy = static_cast<int>((v / nx) % ny), iz = static_cast<int>(v / (static_cast<size_t>(nx) * ny));
-        const float x = x0 + (ix + 0.5F) * h, y = y0 + (iy + 0.5F) * h, z = z0 + (iz + 0.5F) * h;
-        const float slack = 0.8660255F * h + 1e-4F;
-        MaskT m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-        for (uint32_t k = 0; k < n_objects; ++k)
-        {
-            const float4 c = __ldg(objs + 4 * k), a1 = __ldg(objs + 4 * k + 1), a2 = __ldg(objs + 4 * k + 2), a3 = __ldg(objs + 4 * k + 3);
-            const float xs = x - c.x, ys = y - c.y, zs = z - c.z;
-            const float e1 = fmaxf(fabsf(a1.x * xs + a1.y * ys + a1.z * zs) - a1.w, 0.F);
-            const float e2 = fmaxf(fabsf(a2.x * xs + a2.y * ys + a2.z * zs) - a2.w, 0.F);
-            const float e3 = fmaxf(fabsf(a3.x * xs + a3.y * ys + a3.z * zs) - a3.w, 0.F);
-            const float d = sqrtf(e1 * e1 + e2 * e2 + e3 * e3) - c.w - slack;
-            const MaskT bit = static_cast<MaskT>(1) << k;
-            // !(d > r) also keeps an object whose record is not finite
-            m0 |= !(d > r0) ? bit : 0;
-            m1 |= !(d > r1) ? bit : 0;
-            m2 |= !(d > r2) ? bit : 0;
-            m3 |= !(d > r3) ? bit : 0;
-        }
-        MaskT *o = out + v * kGridClasses;
-        o[0] = m0, o[1] = m1, o[2] = m2, o[3] = m3;
-    }
-
-    template <typename MaskT>
-    __device__ __forceinline__ MaskT grid_lookup_t(const GridDev &G, float x, float y, float z, int cls)
-    {
-        const int ix = __float2int_rd((x - G.x0) * G.inv_h);
-        const int iy = __float2int_rd((y - G.y0) * G.inv_h);
-        const int iz = __float2int_rd((z - G.z0) * G.inv_h);
-        // outside the table = farther than the largest class radius from every object
-        const bool in = (static_cast<unsigned>(ix) < static_cast<unsigned>(G.nx)) & (static_cast<unsigned>(iy) < static_cast<unsigned>(G.ny)) &
-                        (static_cast<unsigned>(iz) < static_cast<unsigned>(G.nz));
-        if (!in)
-        {
-            // a centre that is not finite also lands here (its index saturates): give it every object
-            return (fabsf(x) < 1e30F && fabsf(y) < 1e30F && fabsf(z) < 1e30F) ? static_cast<MaskT>(0) : static_cast<MaskT>(G.all_mask);
-        }
-        const uint32_t idx = ((static_cast<uint32_t>(iz) * G.ny + iy) * G.nx + ix) * kGridClasses + cls;
-        return __ldg(reinterpret_cast<const MaskT *>(G.masks) + idx);
     }
 
     // Append one item per set bit of every lane's `bits` to a warp-private queue: item = lane |
@@ -202,7 +138,7 @@ namespace vmv
 
     // Block-level staging (once per persistent block) and this warp's slice.
     template <typename R, typename MaskT>
-    __device__ __forceinline__ V4Ctx<R, MaskT> v4_stage(unsigned char *smem, uint64_t *barp, const RobotDev &robot, const LaunchEnvV3 &env)
+    __device__ __forceinline__ V4Ctx<R, MaskT> v4_stage(unsigned char *smem, uint64_t *barp, const RobotDev &robot, const GridEnv &env)
     {
         using M = typename R::Model;
         using Lay = SmemLayoutV4<M, MaskT>;
@@ -551,7 +487,7 @@ namespace vmv
     // Persistent blocks of blockDim.x / 32 autonomous warps; tile t = states [32 t, 32 t + 32).
     template <typename R, typename MaskT, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB)
-        k_validate_configs_v4(RobotDev robot, const __grid_constant__ LaunchEnvV3 env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
+        k_validate_configs_v4(RobotDev robot, const __grid_constant__ GridEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
     {
         using M = typename R::Model;
         extern __shared__ __align__(128) unsigned char smem[];
@@ -587,7 +523,7 @@ namespace vmv
     template <typename R, typename MaskT, bool INDEXED, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB) k_validate_edges_v4(
         RobotDev robot,
-        const __grid_constant__ LaunchEnvV3 env,
+        const __grid_constant__ GridEnv env,
         const float *__restrict__ a,
         const float *__restrict__ b,
         const uint32_t *__restrict__ pairs,
