@@ -73,6 +73,39 @@ def test_config_verdicts(robot, path):
         _lib.lib().vmv_force_kernel_path(0)
 
 
+@pytest.mark.parametrize("robot", ["panda", "fetch"])
+def test_grid_kernel_wide_masks_and_ragged_sizes(robot):
+    """The grid-culled kernels with more than 32 objects (64-bit candidate masks), batch sizes that
+    are not multiples of 32, and the fall-back above 64 objects."""
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    L = _lib.lib()
+    keep = max(KEEP_OUT[robot], 0.3)
+    for n_obj, seed in ((48, 11), (64, 12), (80, 13)):
+        sc = scenes.random_scene(seed, n_spheres=n_obj // 4, n_cuboids=n_obj // 2, n_capsules=n_obj - n_obj // 4 - n_obj // 2,
+                                 lo=(-1.2, -1.2, -0.2), hi=(1.2, 1.2, 1.4), keep_out=keep)
+        env = scenes.build_product_env(sc)
+        oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+        for n in (4097, 20011):
+            q = scenes.random_configs(robot, n, seed=seed)
+            L.vmv_force_kernel_path(3 if n_obj <= 64 else 0)
+            try:
+                got = R.validate_batch(q, env)
+            finally:
+                L.vmv_force_kernel_path(0)
+            assert_verdicts(robot, O, oenv, q, got, O.validate_configs(oenv, q), f"{n_obj} objects, n={n}")
+        a, b = scenes.random_edges(robot, 2049, seed=seed)
+        got = R.validate_motion_batch(a, b, env)
+        assert (got != O.validate_edges(oenv, a, b)).sum() <= 2
+    if robot == "panda":
+        # above 64 objects the grid-culled kernel must refuse when forced
+        L.vmv_force_kernel_path(3)
+        try:
+            with pytest.raises(_lib.VmvError):
+                R.validate_batch(scenes.random_configs(robot, 5000, seed=1), env)
+        finally:
+            L.vmv_force_kernel_path(0)
+
+
 @pytest.mark.parametrize("path", [2, 0], ids=["block_kernel", "auto_kernel"])
 @pytest.mark.parametrize("robot", ROBOTS)
 def test_edge_verdicts(robot, path):
