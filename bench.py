@@ -121,7 +121,7 @@ def reference_arm(args) -> int:
     line = {"impl": "reference", "metric": "panda_collision_checked_configs_per_sec", "unit": "configs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: 2^20 random Panda configs vs synthetic MBM-style table/shelf scene (12 cuboids + 4 cylinders)",
+            "config": {"workload": "C2: 2^20 random Panda configs vs synthetic MBM-style table/shelf scene (13 cuboids + 4 cylinders)",
                        "robot": ROBOT, "n_configs": N_CONFIGS}}
     if po.ref_available():
         ref = po.Ref(ROBOT)
@@ -379,7 +379,7 @@ def main() -> int:
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": "C2: 2^20 random Panda configs vs synthetic MBM-style table/shelf scene (12 cuboids + 4 cylinders)",
+            "workload": "C2: 2^20 random Panda configs vs synthetic MBM-style table/shelf scene (13 cuboids + 4 cylinders)",
             "robot": ROBOT, "n_configs_per_gpu": N_CONFIGS, "valid_fraction": valid_fraction,
             "l2": f"steps rotate through {N_BATCHES} distinct resident batches ({N_BATCHES * N_CONFIGS * dof * 4 / 1e6:.0f} MB > 126 MB L2)",
             "parallelism": f"dp{world}: independent shards per GPU" + ("" if world == 1 or args.no_gather else " + NCCL all_gather of verdict bitmasks"),

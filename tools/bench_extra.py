@@ -174,8 +174,35 @@ def c5_sharded(n_edges):
     dist.destroy_process_group()
 
 
+def robots():
+    """All four robots on one primitives scene (15 objects): device-resident configs and edges."""
+    for robot, keep in (("panda", 0.0), ("ur5", 0.0), ("fetch", 0.45), ("baxter", 0.5)):
+        R = getattr(vmv, robot)
+        env = scenes.build_product_env(scenes.random_scene(2, keep_out=keep))
+        h = env.handle
+        n, ne = 1 << 20, 1 << 17
+        q = scenes.random_configs(robot, n, seed=0)
+        a, b = scenes.random_edges(robot, ne, seed=0)
+        dq, db = L.vmv_dev_alloc(q.nbytes), L.vmv_dev_alloc((n + 31) // 32 * 4)
+        da, dbb = L.vmv_dev_alloc(a.nbytes), L.vmv_dev_alloc(b.nbytes)
+        for d, hst in ((dq, q), (da, a), (dbb, b)):
+            _lib.check(L.vmv_memcpy_h2d(d, _lib.ptr(hst), hst.nbytes, None))
+        tc = time_launches(lambda: _lib.check(L.vmv_validate_configs_dev(R.id, h, dq, n, db, None)), reps=10)
+        words = np.zeros((n + 31) // 32, np.uint32)
+        _lib.check(L.vmv_memcpy_d2h(_lib.ptr(words), db, words.nbytes, None))
+        _lib.check(L.vmv_stream_sync(None))
+        vc = float(_lib.unpack_bits(words, n).mean())
+        te = time_launches(lambda: _lib.check(L.vmv_validate_edges_dev(R.id, h, da, dbb, ne, 0, db, None)), reps=5)
+        print(json.dumps({"workload": f"{robot}: 2^20 configs / 2^17 edges vs random scene (15 primitives)",
+                          "configs_per_s": n / tc, "edges_per_s": ne / te, "valid_fraction": vc}), flush=True)
+        for d in (dq, db, da, dbb):
+            L.vmv_dev_free(d)
+
+
 if __name__ == "__main__":
     what = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c4", "c5"]
+    if "robots" in what:
+        robots()
     n_edges = int(sys.argv[sys.argv.index("--edges") + 1]) if "--edges" in sys.argv else 100_000_000
     if "c4" in what:
         c4()
