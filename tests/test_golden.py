@@ -46,3 +46,37 @@ def test_sphere_cage_golden():
     assert o.validate_configs(env, q).tolist() == [True, True]
     assert o.validate_edges(env, q[:1], q[1:]).tolist() == [False]
     assert np.abs(o.sphere_fk(q[:1])[0] - d["fk_a"]).max() < 2e-6
+
+
+# ---- MotionBenchMaker problems shipped with the reference (resources/panda/problems.tar.bz2) ----------
+def mbm_problems():
+    """Yields (set name, index, packed scene dict, start, goal, ref valid_start, ref valid_goal, classic)
+    from tests/golden/mbm_panda.npz (tools/make_mbm_golden.py: the reference's converter rules and the
+    reference's own verdicts)."""
+    d = np.load(GOLDEN / "mbm_panda.npz")
+    kinds = {0: "spheres", 1: "cuboids", 2: "capsules"}
+    for k in range(len(d["start"])):
+        lo, hi = d["offsets"][k], d["offsets"][k + 1]
+        scene = {"spheres": [], "cuboids": [], "capsules": [], "order": []}
+        for kind, i in d["order"][lo:hi]:
+            name = kinds[int(kind)]
+            scene["order"].append((name, len(scene[name])))
+            scene[name].append(d[name][int(i)])
+        yield (str(d["sets"][d["set_id"][k]]), int(d["index"][k]), scene, d["start"][k], d["goal"][k],
+               bool(d["valid_start"][k]), bool(d["valid_goal"][k]), bool(d["classic"][k]))
+
+
+def test_mbm_problems_oracle_matches_reference_and_published_count():
+    """All 1300 Panda MBM problems: the oracle's verdict for every start and goal equals the
+    reference's, and the seven classic sets give the published 699 valid of 700
+    (reference resources/README.md:146)."""
+    oracle = po.Oracle("panda")
+    n = valid_classic = n_classic = 0
+    for name, index, scene, start, goal, vs, vg, classic in mbm_problems():
+        env = po.add_scene(po.OracleEnv(), scene)
+        got = oracle.validate_configs(env, np.stack([start, goal]))
+        assert (bool(got[0]), bool(got[1])) == (vs, vg), (name, index)
+        n += 1
+        n_classic += classic
+        valid_classic += classic and vs and vg
+    assert n == 1300 and n_classic == 700 and valid_classic == 699

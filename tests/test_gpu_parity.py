@@ -371,3 +371,40 @@ def test_debug_attribution():
             want[s].append(names[obj])
         assert [sorted(x) for x in per_sphere] == [sorted(x) for x in want]
         assert sorted(self_pairs) == sorted(map(tuple, sh.tolist()))
+
+
+def _product_env_from_packed(scene):
+    """Environment from packed shape fields (the golden fixtures store what the reference stores)."""
+    L = _lib.lib()
+    env = vmv.Environment()
+    fn = {"spheres": L.vmv_env_add_spheres, "cuboids": L.vmv_env_add_cuboids, "capsules": L.vmv_env_add_capsules}
+    for kind, i in scene["order"]:
+        row = np.ascontiguousarray(scene[kind][i], dtype=np.float32)
+        _lib.check(fn[kind](env._h, _lib.ptr(row), 1))
+    env._dirty = True
+    return env
+
+
+def test_mbm_problems_match_reference():
+    """Every start and goal of the 1300 Panda MotionBenchMaker problems the reference ships
+    (tests/golden/mbm_panda.npz: reference verdicts, 699 / 700 valid on the classic sets as published in
+    the reference's resources/README.md:146), through the C ABI; then the grid-culled kernels on a real
+    scene of every problem set with 20 k random configurations and 4 k edges against the oracle."""
+    from tests.test_golden import mbm_problems
+
+    O = po.Oracle("panda")
+    valid_classic = 0
+    seen = set()
+    for name, index, scene, start, goal, vs, vg, classic in mbm_problems():
+        env = _product_env_from_packed(scene)
+        got = vmv.panda.validate_batch(np.stack([start, goal]), env)
+        assert (bool(got[0]), bool(got[1])) == (vs, vg), (name, index)
+        valid_classic += classic and bool(got[0]) and bool(got[1])
+        if name not in seen:
+            seen.add(name)
+            oenv = po.add_scene(po.OracleEnv(), scene)
+            q = scenes.random_configs("panda", 20000, seed=index + 1)
+            assert_verdicts("panda", O, oenv, q, vmv.panda.validate_batch(q, env), O.validate_configs(oenv, q), f"MBM {name}")
+            a, b = scenes.random_edges("panda", 4000, seed=index + 2)
+            assert (vmv.panda.validate_motion_batch(a, b, env) != O.validate_edges(oenv, a, b)).sum() <= 2, name
+    assert valid_classic == 699 and len(seen) == 13
