@@ -294,8 +294,26 @@ def main() -> int:
             t = torch.tensor([ems], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
+        # the same through the host-buffer call (pinned host endpoints, H2D + kernel + D2H inside)
+        pa, pb = torch.from_numpy(a_h).pin_memory(), torch.from_numpy(b_h).pin_memory()
+        pe = torch.zeros((N_EDGES + 31) // 32, dtype=torch.int32).pin_memory()
+        run_h = lambda: _lib.check(L.vmv_validate_edges(robot.id, hb, pa.data_ptr(), pb.data_ptr(), N_EDGES, 0, pe.data_ptr()))
+        for _ in range(2):
+            run_h()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            run_h()
+        barrier()
+        e2e_edges_s = (time.perf_counter() - t0) / reps
+        if world > 1:
+            t = torch.tensor([e2e_edges_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_edges_s = float(t.item())
         edges = {"workload": "C3: 2^18 Panda edges (|b-a| ~ U(0.25,2) rad), resolution 32, synthetic box scene",
                  "value": world * N_EDGES / (ems * 1e-3), "unit": "edges/s", "ms_per_step": ems,
+                 "e2e": {"value": world * N_EDGES / e2e_edges_s, "unit": "edges/s", "h2d_bytes_per_step": 2 * N_EDGES * dof * 4,
+                         "d2h_bytes_per_step": (N_EDGES + 31) // 32 * 4, "api": "vmv_validate_edges (host pointers, pinned)"},
                  "valid_fraction": float(np.unpackbits(ebits.cpu().numpy().view(np.uint8)).mean())}
 
     if rank != 0:
@@ -355,6 +373,11 @@ def main() -> int:
                 cpu_baseline = {"value": N_CONFIGS / t, "unit": "configs/s", "cores": threads, "kind": "reference",
                                 "sample": f"one full 2^20-config batch (same inputs as the GPU step), best of 3, {threads} threads; "
                                           "reference AVX2 code compiled in place (oracle/_ref)"}
+                if edges is not None:
+                    benv = po.add_scene(po.RefEnv(), scenes.packed(scenes.box_scene()))
+                    te = ref.time_edges(benv, a_h, b_h, threads, reps=2)
+                    edges["cpu_baseline"] = {"value": N_EDGES / te, "unit": "edges/s", "cores": threads, "kind": "reference",
+                                             "sample": f"the same 2^18 edges, best of 2, {threads} threads"}
             else:
                 sub = host_batches[0][: 1 << 18]
                 t0 = time.perf_counter()
