@@ -120,6 +120,13 @@ extern "C"
     int vmv_sphere_fk_dev(int robot, const float *d_q, size_t n, float *d_xyzr, void *stream);
     int vmv_sphere_fk(int robot, const float *q, size_t n, float *xyzr);
 
+    /* Helper::filter_self_from_pointcloud (bindings/robot_helper.hh:284-322;
+     * vamp.<robot>.filter_self_from_pointcloud): bit k of keep_bits is 1 iff point k, as a sphere of
+     * radius point_radius, neither overlaps a robot sphere at configuration q nor collides with the
+     * environment. */
+    int vmv_filter_points_dev(int robot, const vmv_env *env, const float *d_q, const float *d_points_xyz, size_t n, float point_radius, uint32_t *d_keep_bits, void *stream);
+    int vmv_filter_self_from_pointcloud(int robot, const vmv_env *env, const float *q, const float *points_xyz, size_t n, float point_radius, uint32_t *keep_bits);
+
     /* Robot::fkcc_debug (robots/panda.hh:468-5224; vamp.<robot>.debug): for ONE configuration,
      * env_hits receives (fine sphere, object id) pairs -- object ids count the shapes in the
      * order they were added -- and self_hits (sphere, sphere) pairs.  Counts are returned through

@@ -315,6 +315,12 @@ class Oracle:
         self.last_states = int(states.value)
         return out.astype(bool)
 
+    def filter_points(self, env: OracleEnv, q, points, point_radius: float) -> np.ndarray:
+        p = _f32(points).reshape(-1, 3)
+        keep = np.zeros(len(p), np.uint8)
+        self.lib.or_filter_points(C.byref(self.c), env.h, _fp(_f32(q)), _fp(p), C.c_size_t(len(p)), C.c_float(point_radius), _fp(keep))
+        return keep.astype(bool)
+
     def edge_steps(self, a, b):
         return int(self.lib.or_edge_steps(C.byref(self.c), _fp(_f32(a)), _fp(_f32(b))))
 
@@ -369,6 +375,12 @@ class Ref:
             self.id, env.h, _fp(a), _fp(b), C.c_size_t(len(a)), _fp(out), C.c_int(threads)
         )
         return out.astype(bool)
+
+    def filter_points(self, env: RefEnv, q, points, point_radius: float) -> np.ndarray:
+        p = _f32(points).reshape(-1, 3)
+        keep = np.zeros(len(p), np.uint8)
+        self.lib.ref_filter_points(self.id, env.h, _fp(_f32(q)), _fp(p), C.c_size_t(len(p)), C.c_float(point_radius), _fp(keep))
+        return keep.astype(bool)
 
     def sphere_fk(self, q):
         q = _f32(q).reshape(-1, self.dof)

@@ -64,6 +64,8 @@ extern "C"
         int32_t *self_hits,
         size_t cap_self,
         size_t *n_self);
+    /* keep[k] = point k survives Helper::filter_self_from_pointcloud (bindings/robot_helper.hh:284-322) */
+    void ref_filter_points(int robot, void *env, const float *q, const float *pts, size_t n, float point_radius, uint8_t *keep);
     /* seconds for `reps` passes of ref_validate_configs / edges with `threads` threads (best pass) */
     double ref_time_configs(int robot, void *env, const float *q, size_t n, int threads, int reps);
     double

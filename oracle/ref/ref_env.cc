@@ -251,6 +251,11 @@ extern "C"
         vt(robot).eefk(q, out16);
     }
 
+    void ref_filter_points(int robot, void *env, const float *q, const float *pts, size_t n, float point_radius, uint8_t *keep)
+    {
+        vt(robot).filter_points(E(env).env, q, pts, n, point_radius, keep);
+    }
+
     void ref_debug(
         int robot,
         void *env,

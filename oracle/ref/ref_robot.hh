@@ -16,6 +16,8 @@
 #include <vector>
 
 #include <vamp/collision/environment.hh>
+#include <vamp/collision/sphere_sphere.hh>
+#include <vamp/collision/validity.hh>
 #include <vamp/planning/validate.hh>
 #include <vamp/vector.hh>
 
@@ -39,6 +41,7 @@ namespace refh
             const float *,
             std::vector<std::pair<int, int>> &,
             std::vector<std::pair<int, int>> &);
+        void (*filter_points)(const EnvF &, const float *, const float *, std::size_t, float, std::uint8_t *);
     };
 
     template <typename Fn>
@@ -196,6 +199,45 @@ namespace refh
             }
         }
 
+        // Helper::filter_self_from_pointcloud (bindings/robot_helper.hh:284-322): the binding itself
+        // needs nanobind, so its loop is composed here from the same reference functions it calls
+        // (Robot::sphere_fk<1>, sphere_sphere_sql2 with `< 0`, sphere_environment_in_collision).
+        static void filter_points(
+            const EnvF &env,
+            const float *q,
+            const float *pts,
+            std::size_t n,
+            float point_radius,
+            std::uint8_t *keep)
+        {
+            const EnvV ev(env);
+            typename Robot::template ConfigurationBlock<1> block;
+            for (std::size_t j = 0; j < Robot::dimension; ++j)
+            {
+                block[j] = q[j];
+            }
+
+            typename Robot::template Spheres<1> out;
+            Robot::template sphere_fk<1>(block, out);
+            for (std::size_t k = 0; k < n; ++k)
+            {
+                const float x = pts[3 * k], y = pts[3 * k + 1], z = pts[3 * k + 2], r = point_radius;
+                bool valid = true;
+                for (auto i = 0U; i < Robot::n_spheres; ++i)
+                {
+                    if (vamp::collision::sphere_sphere_sql2(
+                            out.x[{i, 0}], out.y[{i, 0}], out.z[{i, 0}], out.r[{i, 0}], x, y, z, r) < 0 or
+                        vamp::sphere_environment_in_collision<>(ev, x, y, z, r))
+                    {
+                        valid = false;
+                        break;
+                    }
+                }
+
+                keep[k] = valid ? 1 : 0;
+            }
+        }
+
         static constexpr RobotVTable vtable{
             static_cast<int>(Robot::dimension),
             static_cast<int>(Robot::n_spheres),
@@ -204,6 +246,7 @@ namespace refh
             &validate_edges,
             &sphere_fk,
             &eefk,
-            &debug};
+            &debug,
+            &filter_points};
     };
 }  // namespace refh

@@ -1123,6 +1123,33 @@ void or_sphere_fk(const OrModel *m, const float *q, size_t n, float *out_xyzr)
     }
 }
 
+/* Helper::filter_self_from_pointcloud (bindings/robot_helper.hh:284-322): a point survives unless its
+ * sphere (radius point_radius) overlaps a robot sphere at configuration q (`< 0`, not the sign bit) or
+ * collides with the environment */
+void or_filter_points(const OrModel *m, const OrEnv *e, const float *q, const float *pts, size_t n, float point_radius, uint8_t *keep)
+{
+    float *S = (float *)malloc((size_t)m->n_spheres * 4 * sizeof(float));
+    or_sphere_fk(m, q, 1, S);
+    for (size_t k = 0; k < n; ++k)
+    {
+        const float x = pts[3 * k], y = pts[3 * k + 1], z = pts[3 * k + 2], r = point_radius;
+        int valid = 1;
+        for (int i = 0; i < m->n_spheres && valid; ++i)
+        {
+            if (sphere_sphere_sql2(S[4 * i], S[4 * i + 1], S[4 * i + 2], S[4 * i + 3], x, y, z, r) < 0)
+            {
+                valid = 0;
+            }
+        }
+        if (valid && m->n_spheres > 0 && sphere_environment_in_collision(e, &x, &y, &z, &r, 1, NULL))
+        {
+            valid = 0;
+        }
+        keep[k] = (uint8_t)valid;
+    }
+    free(S);
+}
+
 /* EE frame, 4x4 row-major (Robot::eefk, e.g. robots/panda.hh:15447) */
 void or_eefk(const OrModel *m, const float *q, float *out16)
 {

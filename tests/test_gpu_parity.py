@@ -408,3 +408,32 @@ def test_mbm_problems_match_reference():
             a, b = scenes.random_edges("panda", 4000, seed=index + 2)
             assert (vmv.panda.validate_motion_batch(a, b, env) != O.validate_edges(oenv, a, b)).sum() <= 2, name
     assert valid_classic == 699 and len(seen) == 13
+
+
+@pytest.mark.parametrize("robot", ["panda", "fetch", "baxter"])
+def test_filter_self_from_pointcloud(robot):
+    """vamp.<robot>.filter_self_from_pointcloud (reference bindings/robot_helper.hh:284-322) against the
+    oracle, with primitives and a CAPT pointcloud in the environment."""
+    rng = np.random.default_rng(8)
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    sc = scenes.random_scene(3, keep_out=KEEP_OUT[robot])
+    env = scenes.build_product_env(sc)
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+    cloud = rng.uniform([0.4, -0.5, 0.0], [0.9, 0.5, 0.3], size=(800, 3)).astype(np.float32)
+    m = O.model
+    env.add_capt_pointcloud(cloud, m["min_radius"], m["max_radius"], vmv.POINT_RADIUS)
+    oenv.add_capt(cloud, m["min_radius"], m["max_radius"], vmv.POINT_RADIUS)
+    pts = rng.uniform([-1.0, -1.0, -0.2], [1.0, 1.0, 1.4], size=(50001, 3)).astype(np.float32)
+    for q in scenes.random_configs(robot, 2, seed=12):
+        want = O.filter_points(oenv, q, pts, 0.01)
+        got = R.filter_self_from_pointcloud(pts, 0.01, q, env)
+        assert 0.2 < want.mean() < 0.999
+        kept = np.zeros(len(pts), bool)
+        # the kept points come back in order: recover the mask by a merge walk
+        j = 0
+        for i in range(len(pts)):
+            if j < len(got) and np.array_equal(pts[i], got[j]):
+                kept[i] = True
+                j += 1
+        assert j == len(got)
+        assert (kept != want).sum() <= 2, int((kept != want).sum())

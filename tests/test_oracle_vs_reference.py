@@ -217,3 +217,18 @@ def test_rsqrt_mode_agrees_with_reference_early_out():
     assert (v1 != vr).sum() <= 1
     # exact sqrt: every disagreement is "reference skipped an object it should have tested"
     assert not np.any(v0 & ~vr & ~v1)
+
+
+@pytest.mark.parametrize("robot", ["panda", "fetch"])
+def test_filter_self_from_pointcloud(robot):
+    """Helper::filter_self_from_pointcloud (bindings/robot_helper.hh:284-322): points overlapping the
+    robot at a configuration, or colliding with the environment, are dropped."""
+    rng = np.random.default_rng(8)
+    o, r = po.Oracle(robot), po.Ref(robot)
+    sc = scenes.random_scene(3, keep_out=0.45 if robot == "fetch" else 0.0)
+    eo, er = po.add_scene(po.OracleEnv(), scenes.packed(sc)), po.add_scene(po.RefEnv(), scenes.packed(sc))
+    pts = rng.uniform([-1.0, -1.0, -0.2], [1.0, 1.0, 1.4], size=(20000, 3)).astype(np.float32)
+    for q in scenes.random_configs(robot, 3, seed=12):
+        ko, kr = o.filter_points(eo, q, pts, 0.01), r.filter_points(er, q, pts, 0.01)
+        assert 0.3 < kr.mean() < 0.999
+        assert (ko != kr).sum() <= 1, int((ko != kr).sum())

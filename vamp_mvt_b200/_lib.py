@@ -58,6 +58,8 @@ def lib():
         L.vmv_validate_edges.argtypes = [i32, vp, vp, vp, sz, i32, vp]
         L.vmv_sphere_fk_dev.argtypes = [i32, vp, sz, vp, vp]
         L.vmv_sphere_fk.argtypes = [i32, vp, sz, vp]
+        L.vmv_filter_points_dev.argtypes = [i32, vp, vp, vp, sz, f32, vp, vp]
+        L.vmv_filter_self_from_pointcloud.argtypes = [i32, vp, vp, vp, sz, f32, vp]
         L.vmv_debug.argtypes = [i32, vp, vp, vp, sz, vp, vp, sz, vp]
         L.vmv_dev_alloc.restype = vp
         L.vmv_dev_alloc.argtypes = [sz]

@@ -2297,6 +2297,99 @@ extern "C"
         return VMV_OK;
     }
 
+    extern "C++"
+    {
+    template <typename R>
+    static int launch_filter(const vmv::RobotDev &rd, const vmv::LaunchEnv &le, const float *q, const float *pts, size_t n, float r_point, uint32_t *bits, cudaStream_t s)
+    {
+        using M = typename R::Model;
+        constexpr int BLOCK = 128;
+        const uint32_t smem = ((le.blob_bytes + 15u) & ~15u) + M::kSpheres * sizeof(float4);
+        if (smem > kMaxSmem - 1024)
+        {
+            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
+        }
+        auto kernel = vmv::k_filter_points<R, BLOCK>;
+        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const size_t tiles = (n + BLOCK - 1) / BLOCK;
+        const unsigned grid = static_cast<unsigned>(std::min<size_t>(tiles, static_cast<size_t>(sm_count()) * 8));
+        kernel<<<grid, BLOCK, smem, s>>>(rd, le, q, pts, n, r_point, bits);
+        g_launches++;
+        VMV_CUDA(cudaGetLastError());
+        return VMV_OK;
+    }
+    }
+
+    int vmv_filter_points_dev(int robot, const vmv_env *env, const float *d_q, const float *d_points, size_t n, float point_radius, uint32_t *d_keep_bits, void *stream)
+    {
+        if (!valid_robot(robot) || d_q == nullptr || (n > 0 && (d_points == nullptr || d_keep_bits == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_filter_points_dev: bad argument");
+        }
+        vmv::LaunchEnv le{};
+        int rc = make_launch_env(g_robots[robot], env, le);
+        if (rc != VMV_OK || n == 0)
+        {
+            return rc;
+        }
+        vmv::RobotDev rd{};
+        rc = robot_tables(robot, rd);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        switch (robot)
+        {
+            case VMV_PANDA:
+                return launch_filter<panda_robot>(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
+            case VMV_UR5:
+                return launch_filter<ur5_robot>(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
+            case VMV_FETCH:
+                return launch_filter<fetch_robot>(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
+            default:
+                return launch_filter<baxter_robot>(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
+        }
+    }
+
+    int vmv_filter_self_from_pointcloud(int robot, const vmv_env *env, const float *q, const float *points, size_t n, float point_radius, uint32_t *keep_bits)
+    {
+        if (!valid_robot(robot) || q == nullptr || (n > 0 && (points == nullptr || keep_bits == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_filter_self_from_pointcloud: bad argument");
+        }
+        if (n == 0)
+        {
+            vmv::LaunchEnv probe{};
+            return make_launch_env(g_robots[robot], env, probe);
+        }
+        const size_t dof = g_robots[robot].dof, words = (n + 31) / 32;
+        DevBuf dq, dp, db;
+        int rc = dq.alloc(dof * sizeof(float));
+        if (rc == VMV_OK)
+        {
+            rc = dp.alloc(n * 3 * sizeof(float));
+        }
+        if (rc == VMV_OK)
+        {
+            rc = db.alloc(words * 4);
+        }
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpy(dq.p, q, dof * sizeof(float), cudaMemcpyHostToDevice));
+        VMV_CUDA(cudaMemcpy(dp.p, points, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+        rc = vmv_filter_points_dev(robot, env, static_cast<const float *>(dq.p), static_cast<const float *>(dp.p), n, point_radius,
+                                   static_cast<uint32_t *>(db.p), nullptr);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpy(keep_bits, db.p, words * 4, cudaMemcpyDeviceToHost));
+        return VMV_OK;
+    }
+
     int vmv_sphere_fk(int robot, const float *q, size_t n, float *xyzr)
     {
         if (!valid_robot(robot) || (n > 0 && (q == nullptr || xyzr == nullptr)))

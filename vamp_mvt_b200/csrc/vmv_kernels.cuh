@@ -691,6 +691,94 @@ namespace vmv
         }
     }
 
+    // Helper::filter_self_from_pointcloud (reference bindings/robot_helper.hh:284-322): point k
+    // survives unless its sphere (radius r_point) overlaps one of the robot's fine spheres at
+    // configuration q (sphere_sphere_sql2 < 0) or collides with the environment.  Streaming: 12 B in,
+    // 1 bit out per point; the robot is posed once per block into shared memory.
+    template <typename R, int BLOCK>
+    __global__ void __launch_bounds__(BLOCK) k_filter_points(
+        RobotDev robot,
+        LaunchEnv env,
+        const float *__restrict__ q,
+        const float *__restrict__ pts,
+        size_t n,
+        float r_point,
+        uint32_t *__restrict__ keep_bits)
+    {
+        using M = typename R::Model;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        float4 *spheres = reinterpret_cast<float4 *>(smem + ((env.blob_bytes + 15u) & ~15u));
+        if (threadIdx.x == 0)
+        {
+            mbar_init(&bar, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            tma_bulk_g2s(smem, env.blob, env.blob_bytes, &bar);
+        }
+        {
+            float cfg[M::kDof];
+#pragma unroll
+            for (int j = 0; j < M::kDof; ++j)
+            {
+                cfg[j] = __ldg(q + j);
+            }
+            float F[(M::kBodies - 1) * 12];
+            RegSink sink{F};
+            R::frames(cfg, sink);
+            for (int t = threadIdx.x; t < M::kTasks; t += BLOCK)
+            {
+                const SphereTask tk = robot.tasks[t];
+                if (tk.sphere < 0)
+                {
+                    continue;
+                }
+                float x = tk.cx, y = tk.cy, z = tk.cz;
+                if (tk.body > 0)
+                {
+                    const float *f = F + (tk.body - 1) * 12;
+                    x = fmaf(f[0], tk.cx, fmaf(f[1], tk.cy, fmaf(f[2], tk.cz, f[3])));
+                    y = fmaf(f[4], tk.cx, fmaf(f[5], tk.cy, fmaf(f[6], tk.cz, f[7])));
+                    z = fmaf(f[8], tk.cx, fmaf(f[9], tk.cy, fmaf(f[10], tk.cz, f[11])));
+                }
+                spheres[tk.sphere] = make_float4(x, y, z, tk.r);
+            }
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+        const float *E = reinterpret_cast<const float *>(smem);
+
+        const size_t n_tiles = (n + BLOCK - 1) / BLOCK;
+        for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        {
+            const size_t i = tile * BLOCK + threadIdx.x;
+            const bool has = i < n;
+            float x = 0.F, y = 0.F, z = 0.F;
+            if (has)
+            {
+                x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
+            }
+            bool valid = has;
+            for (int s = 0; s < M::kSpheres; ++s)
+            {
+                const float4 a = spheres[s];
+                const float dx = a.x - x, dy = a.y - y, dz = a.z - z;
+                const float rs = a.w + r_point;
+                valid = valid && !((dx * dx + dy * dy + dz * dz) - rs * rs < 0.F);
+            }
+            // every lane calls: the pointcloud scans inside are warp-cooperative
+            const bool hit = sphere_hits_env(E, x, y, z, r_point, r_point, valid);
+            valid = valid && !hit;
+            const uint32_t word = __ballot_sync(0xffffffffu, valid);
+            if ((threadIdx.x & 31) == 0 && has)
+            {
+                keep_bits[i >> 5] = word;
+            }
+        }
+    }
+
     // Robot::fkcc_debug for ONE configuration (reference robots/panda.hh:468-5224): every fine sphere
     // against every object with the early-outs of sphere_environment_get_collisions
     // (collision/validity.hh:160-257: primitives and heightfields, no pointclouds) and every allowed

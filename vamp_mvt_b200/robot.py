@@ -167,6 +167,18 @@ class Robot:
         )
         return _lib.unpack_bits(words, n)
 
+    def filter_self_from_pointcloud(self, pointcloud, point_radius: float, configuration,
+                                    environment: Optional[Environment] = None) -> np.ndarray:
+        """Points of the cloud that neither overlap the robot at `configuration` nor collide with the
+        environment, in their original order (reference bindings/robot_helper.hh:284-322, 555-561)."""
+        env = environment if environment is not None else _empty_env()
+        p = _lib.f32(pointcloud).reshape(-1, 3)
+        q = self._cfg(configuration)
+        words = np.zeros((len(p) + 31) // 32, np.uint32)
+        _lib.check(self._L.vmv_filter_self_from_pointcloud(self.id, env.handle, _lib.ptr(q), _lib.ptr(p), len(p),
+                                                           float(point_radius), _lib.ptr(words)))
+        return p[_lib.unpack_bits(words, len(p))]
+
     def fk_batch(self, configurations) -> np.ndarray:
         q = _lib.f32(configurations).reshape(-1, self._dof)
         out = np.zeros((len(q), self._n_spheres, 4), np.float32)
