@@ -199,14 +199,27 @@ def main() -> int:
     host_batches = [scenes.random_configs(ROBOT, N_CONFIGS, seed=1000 * rank + b) for b in range(N_BATCHES)]
     dev_batches = [torch.from_numpy(h).cuda() for h in host_batches]
     n_words = (N_CONFIGS + 31) // 32
-    dev_bits = torch.zeros(n_words, dtype=torch.int32, device="cuda")
-    gathered = torch.zeros(world * n_words, dtype=torch.int32, device="cuda") if world > 1 else None
+    # two verdict buffers: at N > 1 the all-gather of step i (NCCL stream) overlaps the kernel of step
+    # i + 1 (compute stream); a buffer is reused only after its gather has completed
+    bits2 = [torch.zeros(n_words, dtype=torch.int32, device="cuda") for _ in range(2)]
+    gathered2 = [torch.zeros(world * n_words, dtype=torch.int32, device="cuda") for _ in range(2)] if world > 1 else None
+    pending = [None, None]
+    dev_bits = bits2[0]
+
+    def gather_async(i: int):
+        if gathered2 is not None and not args.no_gather:
+            pending[i % 2] = dist.all_gather_into_tensor(gathered2[i % 2], bits2[i % 2], async_op=True)
+
+    def wait_slot(i: int):
+        if pending[i % 2] is not None:
+            pending[i % 2].wait()
+            pending[i % 2] = None
 
     def step(i: int):
         qd = dev_batches[i % N_BATCHES]
-        _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, dev_bits.data_ptr(), stream))
-        if gathered is not None and not args.no_gather:
-            dist.all_gather_into_tensor(gathered, dev_bits)
+        wait_slot(i)
+        _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, bits2[i % 2].data_ptr(), stream))
+        gather_async(i)
 
     def barrier():
         if world > 1:
@@ -229,11 +242,12 @@ def main() -> int:
         ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ka.record()
         qd = dev_batches[i % N_BATCHES]
-        _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, dev_bits.data_ptr(), stream))
+        wait_slot(i)
+        _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, bits2[i % 2].data_ptr(), stream))
         kb.record()
         kernel_events.append((ka, kb))
-        if gathered is not None and not args.no_gather:
-            dist.all_gather_into_tensor(gathered, dev_bits)
+        gather_async(i)
+    wait_slot(0), wait_slot(1)  # every gather has completed (the compute stream waits on them) before the end event
     e1.record()
     barrier()
     launches = int(L.vmv_launch_count() - launches0)
