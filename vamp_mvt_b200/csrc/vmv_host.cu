@@ -1379,7 +1379,11 @@ namespace
     template <>
     struct V4Tune<baxter_robot>
     {
-        static constexpr int kMaxThreads = 128, kMinBlocks = 2;  // <= 255 registers
+#if defined(VMV_V4_BAXTER_MAXT) && defined(VMV_V4_BAXTER_MINB)
+        static constexpr int kMaxThreads = VMV_V4_BAXTER_MAXT, kMinBlocks = VMV_V4_BAXTER_MINB;
+#else
+        static constexpr int kMaxThreads = 256, kMinBlocks = 1;  // <= 255 registers; measured best of (128,2) (192,2) (256,2) (256,1)
+#endif
     };
 
     template <typename R, typename MaskT>
@@ -1912,10 +1916,14 @@ extern "C"
     }
 
 #ifdef VMV_DEV_PANDA_ONLY
-    // development builds (kernel A/B timing): one robot, a quarter of the compile time
+    // development builds (kernel A/B timing): one robot (VMV_DEV_ROBOT, default panda), a quarter of
+    // the compile time; every robot id runs that robot's kernels
+#ifndef VMV_DEV_ROBOT
+#define VMV_DEV_ROBOT panda_robot
+#endif
 #define VMV_DISPATCH(robot, CALL)       \
     {                                   \
-        using R = panda_robot;          \
+        using R = VMV_DEV_ROBOT;        \
         constexpr int BLOCK = 128;      \
         (void)BLOCK;                    \
         rc = CALL;                      \
