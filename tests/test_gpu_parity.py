@@ -437,3 +437,42 @@ def test_filter_self_from_pointcloud(robot):
                 j += 1
         assert j == len(got)
         assert (kept != want).sum() <= 2, int((kept != want).sum())
+
+
+def test_baseline_sizes_cross_kernel_properties():
+    """BASELINE.json sizes (2^20 configurations, 2^18 edges): properties that need no CPU run of the
+    full batch -- the three kernel generations agree bit for bit, a zero-length edge is the
+    configuration check (validate(q) = validate_motion(q, q), planning/validate.hh:70-77), an edge with
+    an invalid end point is invalid -- plus a 2^15 sample against the oracle."""
+    L = _lib.lib()
+    R, O = vmv.panda, po.Oracle("panda")
+    sc = scenes.table_shelf_scene()
+    env = scenes.build_product_env(sc)
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+    q = scenes.random_configs("panda", 1 << 20, seed=77)
+    verdicts = {}
+    for path in (3, 2):
+        L.vmv_force_kernel_path(path)
+        try:
+            verdicts[path] = R.validate_batch(q, env)
+        finally:
+            L.vmv_force_kernel_path(0)
+    assert (verdicts[3] != verdicts[2]).sum() <= 2  # only states inside the clearance band may differ
+    sub = np.random.default_rng(1).choice(len(q), 1 << 15, replace=False)
+    assert_verdicts("panda", O, oenv, q[sub], verdicts[3][sub], O.validate_configs(oenv, q[sub]), "2^20 sample")
+    zero = R.validate_motion_batch(q[: 1 << 18], q[: 1 << 18], env)
+    assert np.array_equal(zero, verdicts[3][: 1 << 18])
+    box = scenes.build_product_env(scenes.box_scene())
+    a, b = scenes.random_edges("panda", 1 << 18, seed=78)
+    edges = {}
+    for path in (3, 2):
+        L.vmv_force_kernel_path(path)
+        try:
+            edges[path] = R.validate_motion_batch(a, b, box)
+        finally:
+            L.vmv_force_kernel_path(0)
+    assert (edges[3] != edges[2]).sum() <= 4
+    va, vb = R.validate_batch(a, box), R.validate_batch(b, box)
+    # tine 7 of the first rake block is b itself (start + vector * 8/8): an invalid b kills the edge
+    assert not (edges[3] & ~vb).any()
+    assert 0.2 < edges[3].mean() < 0.9 and va.mean() > 0.2
