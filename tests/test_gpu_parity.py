@@ -476,3 +476,36 @@ def test_baseline_sizes_cross_kernel_properties():
     # tine 7 of the first rake block is b itself (start + vector * 8/8): an invalid b kills the edge
     assert not (edges[3] & ~vb).any()
     assert 0.2 < edges[3].mean() < 0.9 and va.mean() > 0.2
+
+
+def test_concurrent_callers_share_an_environment():
+    """include/vamp_b200.h: a committed environment may be shared by concurrent calls.  Four host threads
+    (ctypes drops the GIL) validate different batches and edge sets against one environment whose voxel
+    table is built by whichever call comes first."""
+    import threading
+
+    env = scenes.build_product_env(scenes.table_shelf_scene())
+    env.commit()
+    O = po.Oracle("panda")
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.table_shelf_scene()))
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            q = scenes.random_configs("panda", 20000 + 64 * k, seed=50 + k)
+            a, b = scenes.random_edges("panda", 3000 + 32 * k, seed=60 + k)
+            for _ in range(3):
+                v, e = vmv.panda.validate_batch(q, env), vmv.panda.validate_motion_batch(a, b, env)
+            results[k] = (q, v, a, b, e)
+        except Exception as ex:  # surfaced below
+            errors.append(ex)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k, (q, v, a, b, e) in results.items():
+        assert_verdicts("panda", O, oenv, q, v, O.validate_configs(oenv, q), f"thread {k}")
+        assert (e != O.validate_edges(oenv, a, b)).sum() <= 2
