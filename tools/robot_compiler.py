@@ -832,6 +832,8 @@ def emit_cuda(model, tr, frames):
     out.append("    sink.reach_ok(" + (" & ".join(rconds) if rconds else "true") + ");")
     out.append("    // link pairs whose bounding spheres (nearly) always overlap: kinematically feasible fine pairs, ungated")
     out.append("    bool self_hit = false;")
+    out.append("    if constexpr (Sink::kInlinePairs)  // off when the two-joint verdict tables answer these pairs (vmv_pairtab.cuh)")
+    out.append("    {")
     for pa, pb, rs2 in inline_tests:
         dx = f"({operand(pa[0])} - {operand(pb[0])})"
         dy = f"({operand(pa[1])} - {operand(pb[1])})"
@@ -840,6 +842,7 @@ def emit_cuda(model, tr, frames):
             f"    {{ const float dx = {dx}, dy = {dy}, dz = {dz}; "
             f"self_hit |= vmv::sign_set(((dx * dx + dy * dy) + dz * dz) - {lit(rs2)}); }}"
         )
+    out.append("    }")
     out.append("    sink.self_inline(self_hit);")
     out.append("}")
     out.append("")

@@ -17,6 +17,7 @@
 // projection of sphere_capsule.hh:9-22.  One record type = no divergence on the object kind.
 #pragma once
 #include "vmv_kernels_v2.cuh"
+#include "vmv_pairtab.cuh"
 
 namespace vmv
 {
@@ -39,6 +40,7 @@ namespace vmv
         uint32_t n_objects;
         uint32_t max_fine;   // largest number of fine spheres of any link of the robot
         GridDev grid;
+        PairTabDev tab;      // two-joint verdict tables of the robot (n_groups = 0: none)
     };
 
     __device__ __forceinline__ float margin_obj(const float4 *__restrict__ o, float x, float y, float z, float r)

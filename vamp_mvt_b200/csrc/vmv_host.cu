@@ -27,6 +27,10 @@
 #include "gen/ur5_tables.h"
 #include "gen/fetch_tables.h"
 #include "gen/baxter_tables.h"
+#include "gen/panda_pairtab.h"
+#include "gen/ur5_pairtab.h"
+#include "gen/fetch_pairtab.h"
+#include "gen/baxter_pairtab.h"
 
 namespace
 {
@@ -61,6 +65,7 @@ namespace
     struct NAME##_robot                                                               \
     {                                                                                 \
         using Model = vmv::gen::NAME##_model;                                         \
+        using PairTab = vmv::gen::NAME##_pairtab_traits;                              \
         template <typename Sink>                                                      \
         static __device__ __forceinline__ void frames(const float (&q)[Model::kDof], Sink &s) \
         {                                                                             \
@@ -134,6 +139,12 @@ namespace
         const vmv::SpherePair *pair_lists;
         int n_pair_lists;
         float max_reach;  // farthest any link's bounding sphere extends from the world origin
+        const vmv::PairGroupHost *pair_groups;  // two-joint verdict tables (vmv_pairtab.cuh)
+        int n_pair_groups;
+        const int *pair_group_pairs;
+        const int *pair_never;
+        int n_pair_never;
+        bool inline_covered;
     };
 
 #define VMV_ROBOT_HOST(NAME)                                                                                  \
@@ -144,7 +155,9 @@ namespace
             vmv::gen::NAME##_model::kEeBody, vmv::gen::NAME##_lower, vmv::gen::NAME##_range,                  \
             vmv::gen::NAME##_tasks_host, vmv::gen::NAME##_links_host, vmv::gen::NAME##_pairs_host,            \
             vmv::gen::NAME##_attach_links_host, vmv::gen::NAME##_ee_tf_host, vmv::gen::NAME##_pair_info_host, \
-            vmv::gen::NAME##_pair_lists_host, vmv::gen::NAME##_pair_lists_count, NAME##_max_reach()           \
+            vmv::gen::NAME##_pair_lists_host, vmv::gen::NAME##_pair_lists_count, NAME##_max_reach(),          \
+            vmv::gen::NAME##_pair_groups, vmv::gen::NAME##_pair_group_count, vmv::gen::NAME##_pair_group_pairs, \
+            vmv::gen::NAME##_pair_never, vmv::gen::NAME##_pair_never_count, vmv::gen::NAME##_inline_covered   \
     }
     const RobotHost g_robots[VMV_N_ROBOTS] = {
         VMV_ROBOT_HOST(panda), VMV_ROBOT_HOST(ur5), VMV_ROBOT_HOST(fetch), VMV_ROBOT_HOST(baxter)};
@@ -1302,6 +1315,92 @@ namespace
         return VMV_OK;
     }
 
+    // Two-joint verdict tables (vmv_pairtab.cuh): built once per robot and device.
+    struct PairTabCache
+    {
+        bool ready = false;
+        vmv::PairTabDev dev{};
+        float build_ms = 0.F;
+    };
+    PairTabCache g_pair_tabs[kMaxDevices][VMV_N_ROBOTS];
+    constexpr size_t kPairTabBytes = size_t(4) << 20;  // all groups of a robot together
+
+    template <typename R>
+    int ensure_pair_tables(int robot, const vmv::RobotDev &rd, vmv::PairTabDev &out)
+    {
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        std::lock_guard<std::mutex> lock(g_mutex);
+        PairTabCache &c = g_pair_tabs[device][robot];
+        if (!c.ready)
+        {
+            const RobotHost &r = g_robots[robot];
+            vmv::PairTabDev t{};
+            for (int k = 0; k < r.n_pair_never; ++k)
+            {
+                t.never_pairs[r.pair_never[k] >> 5] |= 1u << (r.pair_never[k] & 31);
+            }
+            const int ng = std::min(r.n_pair_groups, vmv::kPairTabMaxGroups);
+            t.n_groups = ng;
+            cudaEvent_t e0, e1;
+            VMV_CUDA(cudaEventCreate(&e0));
+            VMV_CUDA(cudaEventCreate(&e1));
+            VMV_CUDA(cudaEventRecord(e0, nullptr));
+            for (int g = 0; g < ng; ++g)
+            {
+                const vmv::PairGroupHost &G = r.pair_groups[g];
+                const size_t budget = kPairTabBytes / ng;
+                int na, nb;
+                if (G.dof[1] < 0)
+                {
+                    na = static_cast<int>(std::min<size_t>(budget, 1u << 16));
+                    nb = 1;
+                }
+                else
+                {
+                    // cell widths in inverse proportion to the Lipschitz constants: equal band shares
+                    const double wa = (G.hi[0] - G.lo[0]) * std::max(G.lip[0], 1e-3F), wb = (G.hi[1] - G.lo[1]) * std::max(G.lip[1], 1e-3F);
+                    const double cells = static_cast<double>(budget);
+                    na = std::max(16, static_cast<int>(std::sqrt(cells * wa / wb)));
+                    nb = std::max(16, static_cast<int>(cells / na));
+                }
+                const float step_a = (G.hi[0] - G.lo[0]) / na, step_b = G.dof[1] < 0 ? 1.F : (G.hi[1] - G.lo[1]) / nb;
+                const float band = 0.5F * (G.lip[0] * step_a + (G.dof[1] < 0 ? 0.F : G.lip[1] * step_b)) + 2e-5F;
+                void *cells = nullptr, *d_pairs = nullptr;
+                VMV_CUDA(cudaMalloc(&cells, static_cast<size_t>(na) * nb));
+                VMV_CUDA(cudaMalloc(&d_pairs, G.count * sizeof(int)));
+                VMV_CUDA(cudaMemcpy(d_pairs, r.pair_group_pairs + G.first, G.count * sizeof(int), cudaMemcpyHostToDevice));
+                const size_t n_cells = static_cast<size_t>(na) * nb;
+                vmv::k_build_pair_table<R><<<static_cast<unsigned>((n_cells + 127) / 128), 128>>>(
+                    rd, G.dof[0], G.dof[1], G.lo[0], step_a, G.lo[1], step_b, na, nb, band, static_cast<const int *>(d_pairs), G.count,
+                    static_cast<unsigned char *>(cells));
+                g_launches++;
+                VMV_CUDA(cudaGetLastError());
+                VMV_CUDA(cudaDeviceSynchronize());
+                cudaFree(d_pairs);
+                t.dof_a[g] = G.dof[0], t.dof_b[g] = G.dof[1];
+                t.lo_a[g] = G.lo[0], t.inv_a[g] = 1.F / step_a;
+                t.lo_b[g] = G.lo[1], t.inv_b[g] = G.dof[1] < 0 ? 0.F : 1.F / step_b;
+                t.na[g] = na, t.nb[g] = nb;
+                t.cells[g] = static_cast<const unsigned char *>(cells);
+                for (int k = 0; k < G.count; ++k)
+                {
+                    const int p = r.pair_group_pairs[G.first + k];
+                    t.group_pairs[g][p >> 5] |= 1u << (p & 31);
+                }
+            }
+            VMV_CUDA(cudaEventRecord(e1, nullptr));
+            VMV_CUDA(cudaEventSynchronize(e1));
+            VMV_CUDA(cudaEventElapsedTime(&c.build_ms, e0, e1));
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            c.dev = t;
+            c.ready = true;
+        }
+        out = c.dev;
+        return VMV_OK;
+    }
+
     // Launch geometry of the warp-autonomous kernels: the number of warps per block that maximises
     // the warps resident per SM (shared memory = block-shared tables + one slice per warp), and a
     // persistent grid of that many blocks per SM.
@@ -1387,11 +1486,22 @@ namespace
     };
 
     template <typename R, typename MaskT>
-    int launch_configs_v4(const vmv::RobotDev &rd, const vmv::GridEnv &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
+    int launch_configs_v4(int robot, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
     {
         using M = typename R::Model;
+        if (R::PairTab::kUseTables && !g_robots[robot].inline_covered)
+        {
+            return fail(VMV_ERR_LIMIT, "robot's inline self-collision pairs are not covered by verdict tables");
+        }
+        {
+            int rc = ensure_pair_tables<R>(robot, rd, le.tab);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
         const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine);
-        auto kernel = vmv::k_validate_configs_v4<R, MaskT, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
+        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
@@ -1430,8 +1540,9 @@ namespace
 
     template <typename R, typename MaskT>
     int launch_edges_v4(
+        int robot,
         const vmv::RobotDev &rd,
-        const vmv::GridEnv &le,
+        vmv::GridEnv le,
         const float *a,
         const float *b,
         const uint32_t *pairs,
@@ -1441,6 +1552,17 @@ namespace
         cudaStream_t s)
     {
         using M = typename R::Model;
+        if (R::PairTab::kUseTables && !g_robots[robot].inline_covered)
+        {
+            return fail(VMV_ERR_LIMIT, "robot's inline self-collision pairs are not covered by verdict tables");
+        }
+        {
+            int rc = ensure_pair_tables<R>(robot, rd, le.tab);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
         const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine);
         int warps = 0;
         unsigned grid = 0;
@@ -1455,7 +1577,7 @@ namespace
         }
         if (pairs != nullptr)
         {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, true, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
             int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kMaxThreads, n, warps, grid, smem);
             if (rc != VMV_OK)
             {
@@ -1465,7 +1587,7 @@ namespace
         }
         else
         {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, false, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
             int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kMaxThreads, n, warps, grid, smem);
             if (rc != VMV_OK)
             {
@@ -1996,11 +2118,11 @@ extern "C"
             {
                 if (wide)
                 {
-                    VMV_DISPATCH(robot, (launch_configs_v4<R, unsigned long long>(rd, l3, d_q, n, d_bits, s)))
+                    VMV_DISPATCH(robot, (launch_configs_v4<R, unsigned long long>(robot, rd, l3, d_q, n, d_bits, s)))
                 }
                 else
                 {
-                    VMV_DISPATCH(robot, (launch_configs_v4<R, uint32_t>(rd, l3, d_q, n, d_bits, s)))
+                    VMV_DISPATCH(robot, (launch_configs_v4<R, uint32_t>(robot, rd, l3, d_q, n, d_bits, s)))
                 }
                 if (rc != VMV_ERR_LIMIT || force == 3)
                 {
@@ -2055,11 +2177,11 @@ extern "C"
             {
                 if (wide)
                 {
-                    VMV_DISPATCH(robot, (launch_edges_v4<R, unsigned long long>(rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
+                    VMV_DISPATCH(robot, (launch_edges_v4<R, unsigned long long>(robot, rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
                 }
                 else
                 {
-                    VMV_DISPATCH(robot, (launch_edges_v4<R, uint32_t>(rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
+                    VMV_DISPATCH(robot, (launch_edges_v4<R, uint32_t>(robot, rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
                 }
                 if (rc != VMV_ERR_LIMIT || force == 3)
                 {

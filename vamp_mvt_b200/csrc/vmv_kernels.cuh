@@ -85,6 +85,7 @@ namespace vmv
     template <int BLOCK>
     struct StashSink
     {
+        static constexpr bool kInlinePairs = true;
         float *base;  // already offset by threadIdx.x
 
         template <int BODY, int K>
@@ -117,6 +118,7 @@ namespace vmv
     struct RegSink
     {
         // used by k_sphere_fk: frames stay in registers/local for an immediate read-back
+        static constexpr bool kInlinePairs = false;
         float *f;
 
         template <int BODY, int K>

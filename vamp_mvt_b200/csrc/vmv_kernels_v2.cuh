@@ -112,9 +112,10 @@ namespace vmv
     }
 
     // Sink of phase A: frames -> shared stash, bounding centres -> registers.
-    template <int BLOCK, int NLINKS>
+    template <int BLOCK, int NLINKS, bool INLINE_PAIRS = true>
     struct StashBoundSink
     {
+        static constexpr bool kInlinePairs = INLINE_PAIRS;
         float *base;  // stash, already offset by threadIdx.x
         float b[NLINKS][3];
 

@@ -65,6 +65,69 @@ namespace vmv
         return fill + __shfl_sync(kFullWarp, incl, 31);
     }
 
+    // Verdict table of one pair group (vmv_pairtab.cuh): thread = cell.  The other joints stay at 0 --
+    // the relative pose of the group's links does not depend on them.
+    template <typename R>
+    __global__ void __launch_bounds__(128) k_build_pair_table(
+        RobotDev robot,
+        int dof_a,
+        int dof_b,
+        float lo_a,
+        float step_a,
+        float lo_b,
+        float step_b,
+        int na,
+        int nb,
+        float band,
+        const int *__restrict__ group_pairs,
+        int n_pairs,
+        unsigned char *__restrict__ cells)
+    {
+        using M = typename R::Model;
+        const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (v >= static_cast<size_t>(na) * nb)
+        {
+            return;
+        }
+        const int ia = static_cast<int>(v / nb), ib = static_cast<int>(v % nb);
+        float cfg[M::kDof];
+#pragma unroll
+        for (int j = 0; j < M::kDof; ++j)
+        {
+            cfg[j] = (j == dof_a) ? lo_a + (ia + 0.5F) * step_a : ((j == dof_b) ? lo_b + (ib + 0.5F) * step_b : 0.F);
+        }
+        float F[(M::kBodies - 1) * 12];
+        RegSink sink{F};
+        R::frames(cfg, sink);
+        auto pose = [&](const SphereTask &t, float &x, float &y, float &z)
+        {
+            x = t.cx, y = t.cy, z = t.cz;
+            if (t.body > 0)
+            {
+                const float *f = F + (t.body - 1) * 12;
+                x = fmaf(f[0], t.cx, fmaf(f[1], t.cy, fmaf(f[2], t.cz, f[3])));
+                y = fmaf(f[4], t.cx, fmaf(f[5], t.cy, fmaf(f[6], t.cz, f[7])));
+                z = fmaf(f[8], t.cx, fmaf(f[9], t.cy, fmaf(f[10], t.cz, f[11])));
+            }
+        };
+        float cmin = 3.0e38F;
+        for (int p = 0; p < n_pairs; ++p)
+        {
+            const PairInfo pi = robot.pair_info[group_pairs[p]];
+            for (int k = 0; k < pi.count; ++k)
+            {
+                const SpherePair sp = robot.pair_lists[pi.offset + k];
+                const SphereTask ta = robot.tasks[sp.task_a], tb = robot.tasks[sp.task_b];
+                float ax, ay, az, bx, by, bz;
+                pose(ta, ax, ay, az);
+                pose(tb, bx, by, bz);
+                const float ex = ax - bx, ey = ay - by, ez = az - bz;
+                cmin = fminf(cmin, sqrtf(ex * ex + ey * ey + ez * ez) - (ta.r + tb.r));
+            }
+        }
+        cells[v] = cmin > band ? 0 : (cmin < -band ? 1 : 2);
+    }
+
     template <typename M, typename MaskT>
     struct SmemLayoutV4
     {
@@ -337,17 +400,82 @@ namespace vmv
 
     // One pass over 32 states (lane = state in the dense phases).  Returns the warp-uniform mask of
     // invalid states (lanes without a state count as invalid).
-    template <typename R, typename MaskT>
-    __device__ __forceinline__ uint32_t v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const float (&cfg)[R::Model::kDof], const bool has)
+    template <typename R, typename MaskT, bool TAB>
+    __device__ __forceinline__ uint32_t
+    v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const PairTabDev &T, const float (&cfg)[R::Model::kDof], const bool has)
     {
         using M = typename R::Model;
         using Lay = SmemLayoutV4<M, MaskT>;
         const int lane = threadIdx.x & 31;
+        constexpr int kWords = (M::kPairs + 31) / 32 > 0 ? (M::kPairs + 31) / 32 : 1;
+        static_assert(kWords <= kPairTabWords, "pair masks of the verdict tables");
+
+        // ---- two-joint verdict tables: one byte per group, loaded ahead of the FK ------------------
+        unsigned char cell[kPairTabMaxGroups] = {2, 2, 2, 2};
+        if (TAB)
+        {
+#pragma unroll
+            for (int g = 0; g < kPairTabMaxGroups; ++g)
+            {
+                if (g < T.n_groups)
+                {
+                    float qa = 0.F, qb = 0.F;
+#pragma unroll
+                    for (int j = 0; j < M::kDof; ++j)
+                    {
+                        qa = (j == T.dof_a[g]) ? cfg[j] : qa;
+                        qb = (j == T.dof_b[g]) ? cfg[j] : qb;
+                    }
+                    // clamped: the byte is only used for states inside the joint box
+                    const int ia = min(max(__float2int_rd((qa - T.lo_a[g]) * T.inv_a[g]), 0), T.na[g] - 1);
+                    const int ib = min(max(__float2int_rd((qb - T.lo_b[g]) * T.inv_b[g]), 0), T.nb[g] - 1);
+                    cell[g] = __ldg(T.cells[g] + static_cast<size_t>(ia) * T.nb[g] + ib);
+                }
+            }
+        }
 
         // ---- A: FK ------------------------------------------------------------------------------
-        StashBoundSink<32, M::kLinks> sink;
+        StashBoundSink<32, M::kLinks, !TAB> sink;
         sink.base = X.stash + lane;
         R::frames(cfg, sink);
+        // link pairs already decided for this state (inside the joint box): by a table, or because
+        // their pruned list is empty
+        uint32_t decided[kWords];
+#pragma unroll
+        for (int w = 0; w < kWords; ++w)
+        {
+            decided[w] = 0u;
+        }
+        if (TAB && sink.inbox)
+        {
+#pragma unroll
+            for (int w = 0; w < kWords; ++w)
+            {
+                if (R::PairTab::word(w) != 0u)
+                {
+                    decided[w] = T.never_pairs[w];
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < kPairTabMaxGroups; ++g)
+            {
+                if (g < T.n_groups)
+                {
+                    sink.self_hit = sink.self_hit || cell[g] == 1;
+                    if (cell[g] != 2)
+                    {
+#pragma unroll
+                        for (int w = 0; w < kWords; ++w)
+                        {
+                            if (R::PairTab::word(w) != 0u)
+                            {
+                                decided[w] |= T.group_pairs[g][w];
+                            }
+                        }
+                    }
+                }
+            }
+        }
         const bool live = has && !(sink.inbox && sink.self_hit);
         uint32_t invalid = ~__ballot_sync(kFullWarp, live);
         const uint32_t inbox_mask = __ballot_sync(kFullWarp, sink.inbox);
@@ -376,8 +504,10 @@ namespace vmv
                     constexpr int a = decltype(la)::value, b = decltype(lb)::value, p = decltype(pi)::value;
                     const float dx = sink.b[a][0] - sink.b[b][0], dy = sink.b[a][1] - sink.b[b][1], dz = sink.b[a][2] - sink.b[b][2];
                     const float rs = brad[a] + brad[b];
-                    // pairs checked inline in phase A (inside the joint box) are skipped
-                    const bool hit = !(decltype(inl)::value != 0 && sink.inbox) && sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
+                    // skipped: pairs checked inline in phase A (inside the joint box), pairs a table decided
+                    constexpr bool tabled = ((R::PairTab::word(p >> 5) >> (p & 31)) & 1u) != 0u;
+                    const bool skip = TAB ? (tabled && ((decided[p >> 5] >> (p & 31)) & 1u) != 0u) : (decltype(inl)::value != 0 && sink.inbox);
+                    const bool hit = !skip && sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
                     word |= hit ? (1u << (p & 31)) : 0u;
                     if constexpr ((p & 31) == 31 || p + 1 == M::kPairs)
                     {
@@ -485,7 +615,7 @@ namespace vmv
     }
 
     // Persistent blocks of blockDim.x / 32 autonomous warps; tile t = states [32 t, 32 t + 32).
-    template <typename R, typename MaskT, int MAXT, int MINB>
+    template <typename R, typename MaskT, bool TAB, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB)
         k_validate_configs_v4(RobotDev robot, const __grid_constant__ GridEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
     {
@@ -508,7 +638,7 @@ namespace vmv
             }
             // (loading the next tile's configurations ahead of the pass was measured: 2 % slower, the
             // seven extra live registers cost more than the exposed load latency)
-            const uint32_t invalid = v4_pass<R, MaskT>(X, env.grid, cfg, has);
+            const uint32_t invalid = v4_pass<R, MaskT, TAB>(X, env.grid, env.tab, cfg, has);
             if (lane == 0)
             {
                 bits[tile] = ~invalid;
@@ -520,7 +650,7 @@ namespace vmv
     // and rake-step count in registers.  Every pass checks 4 rake blocks (8 tines each) of the
     // reference's schedule (planning/validate.hh:31-64), handed out round-robin over the edges still
     // alive, so an edge found invalid drops its remaining blocks -- the reference's early return.
-    template <typename R, typename MaskT, bool INDEXED, int MAXT, int MINB>
+    template <typename R, typename MaskT, bool TAB, bool INDEXED, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB) k_validate_edges_v4(
         RobotDev robot,
         const __grid_constant__ GridEnv env,
@@ -641,7 +771,7 @@ namespace vmv
                         cfg[j] = has ? c : 0.F;
                     }
                 }
-                const uint32_t invalid = v4_pass<R, MaskT>(X, env.grid, cfg, has);
+                const uint32_t invalid = v4_pass<R, MaskT, TAB>(X, env.grid, env.tab, cfg, has);
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
                 {
