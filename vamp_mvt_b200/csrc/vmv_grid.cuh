@@ -39,6 +39,7 @@ namespace vmv
         const float4 *objs;  // n_objects rounded-box records
         uint32_t n_objects;
         uint32_t max_fine;   // largest number of fine spheres of any link of the robot
+        uint32_t q2_rounds;  // fine-item queue capacity in B1 rounds (shared-memory budget of the kernel)
         GridDev grid;
         PairTabDev tab;      // two-joint verdict tables of the robot (n_groups = 0: none)
     };

@@ -1466,23 +1466,28 @@ namespace
         return VMV_OK;
     }
 
+    // Launch bounds (threads per block, blocks per SM -> register cap) and fine-item queue depth of the
+    // warp-autonomous kernels, measured per robot.  The configuration kernel needs ~90 registers
+    // (Panda) and gains from 19 resident warps (one block, one-round queue: +9 %); the edge kernel
+    // carries the edge state in registers and is best at 16 warps with the deeper queue.
     template <typename R>
     struct V4Tune
     {
 #if defined(VMV_V4_MAXT) && defined(VMV_V4_MINB)
-        static constexpr int kMaxThreads = VMV_V4_MAXT, kMinBlocks = VMV_V4_MINB;
+        static constexpr int kCfgThreads = VMV_V4_MAXT, kCfgBlocks = VMV_V4_MINB;
 #else
-        static constexpr int kMaxThreads = 256, kMinBlocks = 2;  // <= 128 registers
+        static constexpr int kCfgThreads = 640, kCfgBlocks = 1;  // <= 102 registers
 #endif
+        static constexpr int kCfgQ2Rounds = 1;
+        static constexpr int kEdgeThreads = 256, kEdgeBlocks = 2;  // <= 128 registers
+        static constexpr int kEdgeQ2Rounds = 2;
     };
     template <>
     struct V4Tune<baxter_robot>
     {
-#if defined(VMV_V4_BAXTER_MAXT) && defined(VMV_V4_BAXTER_MINB)
-        static constexpr int kMaxThreads = VMV_V4_BAXTER_MAXT, kMinBlocks = VMV_V4_BAXTER_MINB;
-#else
-        static constexpr int kMaxThreads = 256, kMinBlocks = 1;  // <= 255 registers; measured best of (128,2) (192,2) (256,2) (256,1)
-#endif
+        // <= 255 registers; measured best of (128,2) (192,2) (256,2) (256,1)
+        static constexpr int kCfgThreads = 256, kCfgBlocks = 1, kCfgQ2Rounds = 2;
+        static constexpr int kEdgeThreads = 256, kEdgeBlocks = 1, kEdgeQ2Rounds = 2;
     };
 
     template <typename R, typename MaskT>
@@ -1500,12 +1505,13 @@ namespace
                 return rc;
             }
         }
-        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine);
-        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
+        le.q2_rounds = V4Tune<R>::kCfgQ2Rounds;
+        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds);
+        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, V4Tune<R>::kCfgThreads, V4Tune<R>::kCfgBlocks>;
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
-        int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kMaxThreads, n, warps, grid, smem);
+        int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kCfgThreads, n, warps, grid, smem);
         if (rc != VMV_OK)
         {
             return rc;
@@ -1563,7 +1569,8 @@ namespace
                 return rc;
             }
         }
-        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine);
+        le.q2_rounds = V4Tune<R>::kEdgeQ2Rounds;
+        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds);
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
@@ -1577,8 +1584,8 @@ namespace
         }
         if (pairs != nullptr)
         {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
-            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kMaxThreads, n, warps, grid, smem);
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, V4Tune<R>::kEdgeThreads, V4Tune<R>::kEdgeBlocks>;
+            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kEdgeThreads, n, warps, grid, smem);
             if (rc != VMV_OK)
             {
                 return rc;
@@ -1587,8 +1594,8 @@ namespace
         }
         else
         {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, V4Tune<R>::kMaxThreads, V4Tune<R>::kMinBlocks>;
-            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kMaxThreads, n, warps, grid, smem);
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, V4Tune<R>::kEdgeThreads, V4Tune<R>::kEdgeBlocks>;
+            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kEdgeThreads, n, warps, grid, smem);
             if (rc != VMV_OK)
             {
                 return rc;

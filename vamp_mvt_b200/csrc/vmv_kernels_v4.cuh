@@ -146,7 +146,7 @@ namespace vmv
             return (v + 15u) & ~15u;
         }
 
-        __host__ __device__ SmemLayoutV4(uint32_t n_objects, uint32_t max_fine)
+        __host__ __device__ SmemLayoutV4(uint32_t n_objects, uint32_t max_fine, uint32_t q2_rounds)
         {
             uint32_t o = align16(n_objects * kObjRec * 4);
             off_tasks = o;
@@ -170,7 +170,8 @@ namespace vmv
             w_q1 = w + b;
             b += align16(M::kLinks * 32 * sizeof(uint16_t));
             w_q2 = w + b;
-            q2_cap = 2u * 32u * max_fine;  // two B1 rounds (the common case) fit without a flush in between
+            // one B1 round always fits; two (the common case) avoid a flush in between
+            q2_cap = (q2_rounds < 1u ? 1u : q2_rounds) * 32u * max_fine;
             b += align16(q2_cap * sizeof(uint16_t));
             w_pairq = w;
             const uint32_t c = align16(kPairCap * sizeof(uint16_t));
@@ -205,7 +206,7 @@ namespace vmv
     {
         using M = typename R::Model;
         using Lay = SmemLayoutV4<M, MaskT>;
-        const Lay L(env.n_objects, env.max_fine);
+        const Lay L(env.n_objects, env.max_fine, env.q2_rounds);
         const int tid = threadIdx.x, nthr = blockDim.x;
         if (tid == 0)
         {
