@@ -1112,8 +1112,8 @@ namespace
     }
 
     // ---- grid-culled path ---------------------------------------------------------------------
-    constexpr size_t kGridMinConfigs = 4096;  // smaller batches do not amortise a table build
-    constexpr size_t kGridMinEdges = 256;
+    constexpr size_t kGridMinConfigs = 1024;  // smaller batches do not amortise a table build
+    constexpr size_t kGridMinEdges = 64;  // the edge kernel cuts small batches into 8-edge chunks and wins from here
     constexpr size_t kGridMaxVoxels = 400000;
 
     struct RobotGridInfo
@@ -1574,6 +1574,8 @@ namespace
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
+        // finer chunks for batches that would otherwise leave warps idle (vmv_kernels_v4.cuh)
+        const int per_chunk = n >= (size_t(1) << 17) ? 32 : (n >= (size_t(1) << 15) ? 16 : 8);
         unsigned int *counter = nullptr;
         {
             int rc = next_counter(s, counter);
@@ -1585,22 +1587,22 @@ namespace
         if (pairs != nullptr)
         {
             auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, V4Tune<R>::kEdgeThreads, V4Tune<R>::kEdgeBlocks>;
-            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kEdgeThreads, n, warps, grid, smem);
+            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kEdgeThreads, (n + 31) / 32 * 32 * (32 / per_chunk), warps, grid, smem);
             if (rc != VMV_OK)
             {
                 return rc;
             }
-            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits, counter);
+            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits, counter, per_chunk);
         }
         else
         {
             auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, V4Tune<R>::kEdgeThreads, V4Tune<R>::kEdgeBlocks>;
-            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kEdgeThreads, n, warps, grid, smem);
+            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kEdgeThreads, (n + 31) / 32 * 32 * (32 / per_chunk), warps, grid, smem);
             if (rc != VMV_OK)
             {
                 return rc;
             }
-            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits, counter);
+            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits, counter, per_chunk);
         }
         g_launches++;
         VMV_CUDA(cudaGetLastError());

@@ -661,14 +661,18 @@ namespace vmv
         size_t n,
         float resolution,
         uint32_t *__restrict__ bits,
-        unsigned int *__restrict__ next_chunk)
+        unsigned int *__restrict__ next_chunk,
+        int edges_per_chunk)
     {
         using M = typename R::Model;
         extern __shared__ __align__(128) unsigned char smem[];
         __shared__ uint64_t bar;
         const V4Ctx<R, MaskT> X = v4_stage<R, MaskT>(smem, &bar, robot, env);
         const int lane = threadIdx.x & 31;
-        const size_t n_chunks = (n + 31) / 32;
+        // 8, 16 or 32 edges per warp: small batches are cut finer so that they still fill the GPU (a
+        // chunk is worked off serially, four rake blocks per pass)
+        // (whole verdict words are always written: chunks past the last edge store zeros)
+        const size_t n_chunks = ((n + 31) / 32) * static_cast<size_t>(32 / edges_per_chunk);
         const int my_slot = lane >> 3, tine = lane & 7;
         const float pct = static_cast<float>(tine + 1) / 8.F;
 
@@ -686,7 +690,7 @@ namespace vmv
             {
                 break;
             }
-            const size_t edge = chunk * 32 + lane;
+            const size_t edge = lane < edges_per_chunk ? min(chunk * edges_per_chunk + lane, n) : n;
             float start[M::kDof], vec[M::kDof];
             int steps = 0;
             if (edge < n)
@@ -785,7 +789,19 @@ namespace vmv
             const uint32_t word = __ballot_sync(kFullWarp, steps > 0 && !dead);
             if (lane == 0)
             {
-                bits[chunk] = word;
+                // verdict bits are little-endian in their words: a chunk of 8 / 16 edges is a byte / half word
+                if (edges_per_chunk == 32)
+                {
+                    bits[chunk] = word;
+                }
+                else if (edges_per_chunk == 16)
+                {
+                    reinterpret_cast<unsigned short *>(bits)[chunk] = static_cast<unsigned short>(word);
+                }
+                else
+                {
+                    reinterpret_cast<unsigned char *>(bits)[chunk] = static_cast<unsigned char>(word);
+                }
             }
         }
     }
