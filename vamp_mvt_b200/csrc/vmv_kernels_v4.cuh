@@ -176,7 +176,7 @@ namespace vmv
             w_pairq = w;
             const uint32_t c = align16(kPairCap * sizeof(uint16_t));
             w += b > c ? b : c;
-            warp_bytes = (w + 127u) & ~127u;
+            warp_bytes = (w + 63u) & ~63u;  // 64 B: Panda lands on 11328 B, which lets a 20th warp fit
         }
 
         __host__ __device__ uint32_t total(uint32_t warps) const
