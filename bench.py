@@ -370,7 +370,7 @@ def main() -> int:
             "traffic": captured.get("dram_bytes_per_launch"),
             "traffic_source": captured.get("capture"),
             "pipe_fma_pct_of_peak": captured.get("pipe_fma_pct"), "pipe_alu_pct_of_peak": captured.get("pipe_alu_pct"),
-            "kernel": "k_validate_configs_v4<panda, u32 masks> (vmv_kernels_v4.cuh)", "kernel_ms": kernel_ms,
+            "kernel": "k_validate_configs_v4<panda, u32 masks, verdict tables> (vmv_kernels_v4.cuh)", "kernel_ms": kernel_ms,
             "algorithmic_flops_per_config": flops_per_config,
             "peak_source": f"FP32 pipe: {n_sm} SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (clocks.max.sm); no tensor-core work on this path",
             "hbm": {"algorithmic_bytes_per_launch": bytes_per_launch,
