@@ -509,3 +509,29 @@ def test_concurrent_callers_share_an_environment():
     for k, (q, v, a, b, e) in results.items():
         assert_verdicts("panda", O, oenv, q, v, O.validate_configs(oenv, q), f"thread {k}")
         assert (e != O.validate_edges(oenv, a, b)).sum() <= 2
+
+
+def test_path_validate_matches_segmentwise_oracle():
+    """vamp.<robot>.Path.validate (reference planning/plan.hh:155-168): all consecutive segments valid."""
+    O = po.Oracle("panda")
+    sc = scenes.box_scene()
+    env = scenes.build_product_env(sc)
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+    rng = np.random.default_rng(3)
+    q = scenes.random_configs("panda", 4000, seed=91)
+    q = q[O.validate_configs(oenv, q)]
+    n_true = 0
+    for k in range(40):
+        n = int(rng.integers(2, 7))
+        start = q[rng.integers(0, len(q))]
+        steps = rng.normal(0, 0.08 if k % 2 else 0.4, size=(n - 1, 7)).astype(np.float32)
+        pts = np.vstack([start, start + np.cumsum(steps, axis=0)]).astype(np.float32)
+        path = vmv.panda.Path(pts)
+        want = bool(O.validate_edges(oenv, pts[:-1], pts[1:]).all())
+        assert path.validate(env) == want
+        n_true += want
+        assert path.cost() == pytest.approx(float(np.linalg.norm(pts[1:] - pts[:-1], axis=1).sum()), rel=1e-5)
+    assert 0 < n_true < 40
+    p2 = vmv.panda.Path([q[0], q[1]])
+    p2.subdivide()
+    assert len(p2) == 3 and np.allclose(p2[1], 0.5 * (q[0] + q[1]), atol=1e-6)

@@ -179,6 +179,12 @@ class Robot:
                                                            float(point_radius), _lib.ptr(words)))
         return p[_lib.unpack_bits(words, len(p))]
 
+    def Path(self, waypoints=()):
+        """``vamp.<robot>.Path`` (reference planning/plan.hh:10-169, bindings/robot_helper.hh:411-466)."""
+        from .path import Path
+
+        return Path(self, waypoints)
+
     def fk_batch(self, configurations) -> np.ndarray:
         q = _lib.f32(configurations).reshape(-1, self._dof)
         out = np.zeros((len(q), self._n_spheres, 4), np.float32)
