@@ -114,6 +114,7 @@ extern "C"
     /* PRM-style edge sets (prm.hh:136-146): edge i joins vertices pairs[2i], pairs[2i+1] of a
      * vertex table [n_vertices][dof]; 8 bytes per edge instead of 8*dof. */
     int vmv_validate_edges_indexed_dev(int robot, const vmv_env *env, const float *d_vertices, size_t n_vertices, const uint32_t *d_pairs, size_t n_edges, int resolution, uint32_t *d_valid_bits, void *stream);
+    int vmv_validate_edges_indexed(int robot, const vmv_env *env, const float *vertices, size_t n_vertices, const uint32_t *pairs, size_t n_edges, int resolution, uint32_t *valid_bits);
 
     /* Robot::sphere_fk (robots/panda.hh:117-462; vamp.<robot>.fk, robot_helper.hh:234-247):
      * out[i][s] = (x, y, z, r) of fine sphere s for configuration i. */

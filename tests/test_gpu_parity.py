@@ -535,3 +535,21 @@ def test_path_validate_matches_segmentwise_oracle():
     p2 = vmv.panda.Path([q[0], q[1]])
     p2.subdivide()
     assert len(p2) == 3 and np.allclose(p2[1], 0.5 * (q[0] + q[1]), atol=1e-6)
+
+
+def test_batched_prm_solves_the_sphere_cage():
+    """BASELINE config 1's problem (reference scripts/sphere_cage_example.py) through the batched PRM
+    front-end: the straight line is invalid, a roadmap grown in rounds of bulk validation connects start
+    and goal, and every edge of the returned path is one the oracle's validate_motion accepts."""
+    env = scenes.build_product_env(scenes.sphere_cage())
+    O = po.Oracle("panda")
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.sphere_cage()))
+    rm = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000, batch=4096, seed=1)
+    assert rm.path is not None and len(rm.path) > 2 and rm.rounds >= 1
+    p = np.stack(rm.path)
+    assert np.allclose(p[0], scenes.CAGE_A, atol=1e-6) and np.allclose(p[-1], scenes.CAGE_B, atol=1e-6)
+    assert O.validate_edges(oenv, p[:-1], p[1:]).all()
+    assert vmv.panda.Path(rm.path).validate(env)
+    # the roadmap's edges are all valid motions (a sample of them against the oracle)
+    e = rm.edges[np.random.default_rng(0).choice(len(rm.edges), min(2000, len(rm.edges)), replace=False)]
+    assert (~O.validate_edges(oenv, rm.vertices[e[:, 0]], rm.vertices[e[:, 1]])).sum() <= 1

@@ -54,6 +54,7 @@ def lib():
         L.vmv_validate_configs_dev.argtypes = [i32, vp, vp, sz, vp, vp]
         L.vmv_validate_edges_dev.argtypes = [i32, vp, vp, vp, sz, i32, vp, vp]
         L.vmv_validate_edges_indexed_dev.argtypes = [i32, vp, vp, sz, vp, sz, i32, vp, vp]
+        L.vmv_validate_edges_indexed.argtypes = [i32, vp, vp, sz, vp, sz, i32, vp]
         L.vmv_validate_configs.argtypes = [i32, vp, vp, sz, vp]
         L.vmv_validate_edges.argtypes = [i32, vp, vp, vp, sz, i32, vp]
         L.vmv_sphere_fk_dev.argtypes = [i32, vp, sz, vp, vp]

@@ -2436,6 +2436,60 @@ extern "C"
         return VMV_OK;
     }
 
+    int vmv_validate_edges_indexed(int robot, const vmv_env *env, const float *vertices, size_t n_vertices, const uint32_t *pairs, size_t n_edges, int resolution, uint32_t *bits)
+    {
+        if (!valid_robot(robot) || (n_edges > 0 && (vertices == nullptr || pairs == nullptr || bits == nullptr)))
+        {
+            return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed: bad argument");
+        }
+        if (n_edges == 0)
+        {
+            vmv::LaunchEnv probe{};
+            return make_launch_env(g_robots[robot], env, probe);
+        }
+        for (size_t i = 0; i < 2 * n_edges; ++i)
+        {
+            if (pairs[i] >= n_vertices)
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed: vertex index out of range");
+            }
+        }
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        HostPathPool &pool = g_pools[device % kMaxDevices];
+        std::lock_guard<std::mutex> lock(pool.mutex);
+        const size_t dof = g_robots[robot].dof;
+        int rc = pool.init();
+        if (rc == VMV_OK)
+        {
+            rc = pool.ensure(0, n_vertices * dof * sizeof(float));
+        }
+        if (rc == VMV_OK)
+        {
+            rc = pool.ensure(1, n_edges * 2 * sizeof(uint32_t));
+        }
+        if (rc == VMV_OK)
+        {
+            rc = pool.ensure(2, ((n_edges + 31) / 32) * 4);
+        }
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        cudaStream_t st = pool.streams[0];
+        VMV_CUDA(cudaMemcpyAsync(pool.buf[0], vertices, n_vertices * dof * sizeof(float), cudaMemcpyHostToDevice, st));
+        VMV_CUDA(cudaMemcpyAsync(pool.buf[1], pairs, n_edges * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        rc = vmv_validate_edges_indexed_dev(robot, env, static_cast<const float *>(pool.buf[0]), n_vertices, static_cast<const uint32_t *>(pool.buf[1]),
+                                            n_edges, resolution, static_cast<uint32_t *>(pool.buf[2]), st);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpyAsync(bits, pool.buf[2], ((n_edges + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+        VMV_CUDA(cudaStreamSynchronize(st));
+        return VMV_OK;
+    }
+
     extern "C++"
     {
     template <typename R>

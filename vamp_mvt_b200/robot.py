@@ -167,6 +167,16 @@ class Robot:
         )
         return _lib.unpack_bits(words, n)
 
+    def validate_edges_indexed(self, vertices, pairs, environment: Optional[Environment] = None, resolution: int = 0) -> np.ndarray:
+        """Edge i joins vertices pairs[i, 0] and pairs[i, 1] of the vertex table (PRM-style edge sets,
+        reference planning/prm.hh:136-146): 8 bytes per edge instead of two configurations."""
+        env = environment if environment is not None else _empty_env()
+        V = _lib.f32(vertices).reshape(-1, self._dof)
+        P = np.ascontiguousarray(np.asarray(pairs, dtype=np.uint32).reshape(-1, 2))
+        words = np.zeros((len(P) + 31) // 32, np.uint32)
+        _lib.check(self._L.vmv_validate_edges_indexed(self.id, env.handle, _lib.ptr(V), len(V), _lib.ptr(P), len(P), resolution, _lib.ptr(words)))
+        return _lib.unpack_bits(words, len(P))
+
     def filter_self_from_pointcloud(self, pointcloud, point_radius: float, configuration,
                                     environment: Optional[Environment] = None) -> np.ndarray:
         """Points of the cloud that neither overlap the robot at `configuration` nor collide with the
@@ -178,6 +188,12 @@ class Robot:
         _lib.check(self._L.vmv_filter_self_from_pointcloud(self.id, env.handle, _lib.ptr(q), _lib.ptr(p), len(p),
                                                            float(point_radius), _lib.ptr(words)))
         return p[_lib.unpack_bits(words, len(p))]
+
+    def prm(self, start, goal, environment: Optional[Environment] = None, **kwargs):
+        """Batched PRM front-end (vamp_mvt_b200/prm.py): roadmap growth in rounds of bulk validation."""
+        from .prm import prm
+
+        return prm(self, start, goal, environment, **kwargs)
 
     def Path(self, waypoints=()):
         """``vamp.<robot>.Path`` (reference planning/plan.hh:10-169, bindings/robot_helper.hh:411-466)."""
