@@ -271,14 +271,25 @@ namespace vmv
     }
 
     // C2: one lane per (state, pair) record.  Returns the states found in self collision.
-    template <typename R, typename MaskT>
+    template <typename R, typename MaskT, bool SPLIT_ALWAYS>
     __device__ __forceinline__ uint32_t
     v4_pair_records(const V4Ctx<R, MaskT> &X, uint32_t n_rec, uint32_t invalid, uint32_t inbox_mask)
     {
         using Lay = SmemLayoutV4<typename R::Model, MaskT>;
         const int lane = threadIdx.x & 31;
         uint32_t hits = 0u;
-        for (uint32_t r = lane; r < n_rec; r += 32)
+        // a round lasts as long as its longest record: two lanes share each record, taking alternate
+        // spheres of the longer link (or alternate entries of the pruned list) -- always for random
+        // configurations (measured +6 %), only up to 16 records for the bursty tiles of the edge kernel
+        // (the 8 tines of a rake block raise the same records)
+        int half = lane & 1, step = 2;
+        uint32_t first = lane >> 1, stride = 16u;
+        if constexpr (!SPLIT_ALWAYS)
+        {
+            const int sh = n_rec <= 16u ? 1 : 0;
+            half = lane & sh, step = 1 << sh, first = lane >> sh, stride = 32u >> sh;
+        }
+        for (uint32_t r = first; r < n_rec; r += stride)
         {
             const uint32_t rec = X.pairq[r];
             const int c = rec & 31u;
@@ -293,7 +304,7 @@ namespace vmv
             if (pinfo.count >= 0 && ((inbox_mask >> c) & 1u) && pinfo.offset + pinfo.count <= Lay::kMaxPairLists)
             {
                 // statically pruned list of the sphere pairs that can touch inside the joint box
-                for (int k = 0; k < pinfo.count; ++k)
+                for (int k = half; k < pinfo.count; k += step)
                 {
                     const SpherePair sp = X.plists[pinfo.offset + k];
                     const SphereTask ta = X.tasks[sp.task_a], tb = X.tasks[sp.task_b];
@@ -338,7 +349,7 @@ namespace vmv
                             ax[k] = 1e18F, ay[k] = 1e18F, az[k] = 1e18F, ar[k] = 0.F;  // never touches
                         }
                     }
-                    for (int jb = 0; jb < B.n_spheres; ++jb)
+                    for (int jb = half; jb < B.n_spheres; jb += step)
                     {
                         const float4 tb = *reinterpret_cast<const float4 *>(&X.tasks[B.bound_task + 1 + jb]);
                         float bx, by, bz;
@@ -401,7 +412,7 @@ namespace vmv
 
     // One pass over 32 states (lane = state in the dense phases).  Returns the warp-uniform mask of
     // invalid states (lanes without a state count as invalid).
-    template <typename R, typename MaskT, bool TAB>
+    template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS>
     __device__ __forceinline__ uint32_t
     v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const PairTabDev &T, const float (&cfg)[R::Model::kDof], const bool has)
     {
@@ -517,14 +528,14 @@ namespace vmv
                         if constexpr ((p + 1) % Lay::kPairChunk == 0 && p + 1 < M::kPairs)
                         {
                             __syncwarp();
-                            invalid |= v4_pair_records<R, MaskT>(X, n_rec, invalid, inbox_mask);
+                            invalid |= v4_pair_records<R, MaskT, SPLIT_ALWAYS>(X, n_rec, invalid, inbox_mask);
                             __syncwarp();
                             n_rec = 0u;
                         }
                     }
                 });
             __syncwarp();
-            invalid |= v4_pair_records<R, MaskT>(X, n_rec, invalid, inbox_mask);
+            invalid |= v4_pair_records<R, MaskT, SPLIT_ALWAYS>(X, n_rec, invalid, inbox_mask);
             __syncwarp();  // the record queue's memory is reused below
         }
 
@@ -639,7 +650,7 @@ namespace vmv
             }
             // (loading the next tile's configurations ahead of the pass was measured: 2 % slower, the
             // seven extra live registers cost more than the exposed load latency)
-            const uint32_t invalid = v4_pass<R, MaskT, TAB>(X, env.grid, env.tab, cfg, has);
+            const uint32_t invalid = v4_pass<R, MaskT, TAB, true>(X, env.grid, env.tab, cfg, has);
             if (lane == 0)
             {
                 bits[tile] = ~invalid;
@@ -776,7 +787,7 @@ namespace vmv
                         cfg[j] = has ? c : 0.F;
                     }
                 }
-                const uint32_t invalid = v4_pass<R, MaskT, TAB>(X, env.grid, env.tab, cfg, has);
+                const uint32_t invalid = v4_pass<R, MaskT, TAB, false>(X, env.grid, env.tab, cfg, has);
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
                 {
