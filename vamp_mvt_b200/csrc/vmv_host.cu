@@ -1114,7 +1114,7 @@ namespace
     // ---- grid-culled path ---------------------------------------------------------------------
     constexpr size_t kGridMinConfigs = 1024;  // smaller batches do not amortise a table build
     constexpr size_t kGridMinEdges = 64;  // the edge kernel cuts small batches into 8-edge chunks and wins from here
-    constexpr size_t kGridMaxVoxels = 400000;
+    constexpr size_t kGridMaxVoxels = 1000000;
 
     struct RobotGridInfo
     {
@@ -1252,7 +1252,7 @@ namespace
                 lo[0] = lo[1] = lo[2] = 1e6;
                 hi[0] = hi[1] = hi[2] = 1e6 + 1;
             }
-            double h = 0.04;
+            double h = 0.025;
             int nx, ny, nz;
             while (true)
             {
