@@ -735,6 +735,13 @@ namespace vmv
                     start[j] = 0.F, vec[j] = 0.F;
                 }
             }
+            // backstep = vector / (rake * n), once per edge as in validate.hh:43-48
+            float back[M::kDof];
+#pragma unroll
+            for (int j = 0; j < M::kDof; ++j)
+            {
+                back[j] = steps > 0 ? __fdiv_rn(vec[j], static_cast<float>(8 * steps)) : 0.F;
+            }
             int next = 0;
             bool dead = false;
 
@@ -772,17 +779,16 @@ namespace vmv
                 next += got;
                 float cfg[M::kDof];
                 {
-                    const float denom = static_cast<float>(8 * e_steps);
 #pragma unroll
                     for (int j = 0; j < M::kDof; ++j)
                     {
                         const float v = __shfl_sync(kFullWarp, vec[j], owner);
                         const float st = __shfl_sync(kFullWarp, start[j], owner);
-                        const float back = __fdiv_rn(v, denom);
+                        const float bk = __shfl_sync(kFullWarp, back[j], owner);
                         float c = fmaf(v, pct, st);
                         for (int k = 0; k < step; ++k)
                         {
-                            c = __fsub_rn(c, back);
+                            c = __fsub_rn(c, bk);
                         }
                         cfg[j] = has ? c : 0.F;
                     }
