@@ -139,6 +139,8 @@ def ref_lib():
         L.ref_env_dump.restype = C.c_size_t
         L.ref_time_configs.restype = C.c_double
         L.ref_time_edges.restype = C.c_double
+        if hasattr(L, "ref_simplify"):
+            L.ref_simplify.restype = C.c_size_t
         _ref_lib = L
     return _ref_lib
 
@@ -381,6 +383,24 @@ class Ref:
         keep = np.zeros(len(p), np.uint8)
         self.lib.ref_filter_points(self.id, env.h, _fp(_f32(q)), _fp(p), C.c_size_t(len(p)), C.c_float(point_radius), _fp(keep))
         return keep.astype(bool)
+
+    def simplify(self, env: RefEnv, path, operations=(2, 0), settings12=None, samples=None):
+        """The reference's own simplify<Robot, 8, resolution> (planning/simplify.hh:191-258).
+        operations: SimplifyRoutine values; settings12 as in oracle/ref/ref_robot.hh; samples: the
+        unit-cube stream behind RNG::next().  Returns (path [k][dof], iterations)."""
+        p = _f32(path).reshape(-1, self.dof)
+        ops = np.ascontiguousarray(np.asarray(operations, np.int32))
+        sf = _f32(settings12 if settings12 is not None else [5, 0, 1, 0.1, 0.5, 10, 5, 0.5, 10, 5, 5, 0.1])
+        sm = _f32(samples if samples is not None else np.zeros((1, self.dof))).reshape(-1, self.dof)
+        cap = max(4096, 64 * len(p))
+        out = np.zeros((cap, self.dof), np.float32)
+        it = C.c_size_t(0)
+        n = self.lib.ref_simplify(
+            self.id, env.h, _fp(p), C.c_size_t(len(p)), ops.ctypes.data_as(C.c_void_p), C.c_size_t(len(ops)),
+            _fp(sf), _fp(sm), C.c_size_t(len(sm)), _fp(out), C.c_size_t(cap), C.byref(it),
+        )
+        assert n <= cap
+        return out[:n].copy(), int(it.value)
 
     def sphere_fk(self, q):
         q = _f32(q).reshape(-1, self.dof)

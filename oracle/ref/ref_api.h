@@ -65,6 +65,23 @@ extern "C"
         size_t cap_self,
         size_t *n_self);
     /* keep[k] = point k survives Helper::filter_self_from_pointcloud (bindings/robot_helper.hh:284-322) */
+    /* vamp::planning::simplify<Robot, 8, Robot::resolution> (planning/simplify.hh:191-258) on a path of n
+     * waypoints.  ops: SimplifyRoutine values (0 BSPLINE, 1 REDUCE, 2 SHORTCUT, 3 PERTURB); settings12:
+     * see ref_robot.hh; samples: [n_samples][dim] unit-cube stream behind RNG::next().  Returns the
+     * number of waypoints of the result (written to `out` up to `cap`). */
+    size_t ref_simplify(
+        int robot,
+        void *env,
+        const float *path,
+        size_t n,
+        const int *ops,
+        size_t n_ops,
+        const float *settings12,
+        const float *samples,
+        size_t n_samples,
+        float *out,
+        size_t cap,
+        size_t *iterations);
     void ref_filter_points(int robot, void *env, const float *q, const float *pts, size_t n, float point_radius, uint8_t *keep);
     /* seconds for `reps` passes of ref_validate_configs / edges with `threads` threads (best pass) */
     double ref_time_configs(int robot, void *env, const float *q, size_t n, int threads, int reps);

@@ -235,6 +235,23 @@ extern "C"
         vt(robot).validate_configs(E(env).env, q, n, out, threads);
     }
 
+    size_t ref_simplify(
+        int robot,
+        void *env,
+        const float *path,
+        size_t n,
+        const int *ops,
+        size_t n_ops,
+        const float *settings12,
+        const float *samples,
+        size_t n_samples,
+        float *out,
+        size_t cap,
+        size_t *iterations)
+    {
+        return vt(robot).simplify(E(env).env, path, n, ops, n_ops, settings12, samples, n_samples, out, cap, iterations);
+    }
+
     void
     ref_validate_edges(int robot, void *env, const float *a, const float *b, size_t n, uint8_t *out, int threads)
     {

@@ -4,6 +4,7 @@
 //   Robot::sphere_fk<8>            src/impl/vamp/robots/<robot>.hh
 //   Robot::fkcc_debug<8>           src/impl/vamp/robots/<robot>.hh
 //   Robot::eefk                    src/impl/vamp/robots/<robot>.hh
+//   simplify<Robot,8,res>          src/impl/vamp/planning/simplify.hh:191 (shortcut, B-spline, reduce, perturb)
 // exactly as the nanobind layer does (src/impl/vamp/bindings/robot_helper.hh:234-267).
 #pragma once
 #include <algorithm>
@@ -19,6 +20,7 @@
 #include <vamp/collision/sphere_sphere.hh>
 #include <vamp/collision/validity.hh>
 #include <vamp/planning/validate.hh>
+#include <vamp/planning/simplify.hh>
 #include <vamp/vector.hh>
 
 namespace refh
@@ -42,6 +44,18 @@ namespace refh
             std::vector<std::pair<int, int>> &,
             std::vector<std::pair<int, int>> &);
         void (*filter_points)(const EnvF &, const float *, const float *, std::size_t, float, std::uint8_t *);
+        std::size_t (*simplify)(
+            const EnvF &,
+            const float *,
+            std::size_t,
+            const int *,
+            std::size_t,
+            const float *,
+            const float *,
+            std::size_t,
+            float *,
+            std::size_t,
+            std::size_t *);
     };
 
     template <typename Fn>
@@ -238,6 +252,91 @@ namespace refh
             }
         }
 
+        // The reference's RNG interface (random/rng.hh:9-17) fed from a caller-supplied stream of unit-cube
+        // samples, so that the product side can be driven with the same stream.  `dist` (std::mt19937
+        // seeded 0, random/distribution.hh:11) is the reference's own.
+        struct StreamRNG : public vamp::rng::RNG<Robot>
+        {
+            const float *samples{nullptr};
+            std::size_t n{0}, at{0};
+
+            inline void reset() noexcept override
+            {
+                at = 0;
+                this->dist.reset();
+            }
+
+            inline auto next() noexcept -> vamp::FloatVector<Robot::dimension> override
+            {
+                const float *s = samples + (n ? (at++ % n) : 0) * Robot::dimension;
+                return load(s);
+            }
+        };
+
+        // simplify<Robot, rake, Robot::resolution> as bindings/robot_helper.hh:269-277 calls it.
+        // ops: SimplifyRoutine values; sf = {max_iterations, interpolate, bspline.max_steps,
+        // bspline.min_change, bspline.midpoint_interpolation, reduce.max_steps, reduce.max_empty_steps,
+        // reduce.range_ratio, perturb.max_steps, perturb.max_empty_steps, perturb.perturbation_attempts,
+        // perturb.range}.  Returns the number of waypoints (written up to `cap`).
+        static std::size_t simplify(
+            const EnvF &env,
+            const float *path,
+            std::size_t n,
+            const int *ops,
+            std::size_t n_ops,
+            const float *sf,
+            const float *samples,
+            std::size_t n_samples,
+            float *out,
+            std::size_t cap,
+            std::size_t *iterations)
+        {
+            namespace vp = vamp::planning;
+            vp::Path<Robot> p;
+            for (std::size_t i = 0; i < n; ++i)
+            {
+                p.emplace_back(load(path + i * Robot::dimension));
+            }
+
+            vp::SimplifySettings st;
+            st.operations.clear();
+            for (std::size_t i = 0; i < n_ops; ++i)
+            {
+                st.operations.emplace_back(static_cast<vp::SimplifyRoutine>(ops[i]));
+            }
+
+            st.max_iterations = static_cast<std::size_t>(sf[0]);
+            st.interpolate = static_cast<std::size_t>(sf[1]);
+            st.bspline.max_steps = static_cast<std::size_t>(sf[2]);
+            st.bspline.min_change = sf[3];
+            st.bspline.midpoint_interpolation = sf[4];
+            st.reduce.max_steps = static_cast<std::size_t>(sf[5]);
+            st.reduce.max_empty_steps = static_cast<std::size_t>(sf[6]);
+            st.reduce.range_ratio = sf[7];
+            st.perturb.max_steps = static_cast<std::size_t>(sf[8]);
+            st.perturb.max_empty_steps = static_cast<std::size_t>(sf[9]);
+            st.perturb.perturbation_attempts = static_cast<std::size_t>(sf[10]);
+            st.perturb.range = sf[11];
+
+            auto rng = std::make_shared<StreamRNG>();
+            rng->samples = samples;
+            rng->n = n_samples;
+
+            const EnvV ev(env);
+            const auto result = vp::simplify<Robot, rake, Robot::resolution>(p, ev, st, rng);
+            for (std::size_t i = 0; i < result.path.size() and i < cap; ++i)
+            {
+                const auto a = result.path[i].to_array();
+                for (std::size_t j = 0; j < Robot::dimension; ++j)
+                {
+                    out[i * Robot::dimension + j] = a[j];
+                }
+            }
+
+            *iterations = result.iterations;
+            return result.path.size();
+        }
+
         static constexpr RobotVTable vtable{
             static_cast<int>(Robot::dimension),
             static_cast<int>(Robot::n_spheres),
@@ -247,6 +346,7 @@ namespace refh
             &sphere_fk,
             &eefk,
             &debug,
-            &filter_points};
+            &filter_points,
+            &simplify};
     };
 }  // namespace refh

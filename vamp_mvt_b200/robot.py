@@ -201,6 +201,13 @@ class Robot:
 
         return Path(self, waypoints)
 
+    def simplify(self, path, environment: Optional[Environment] = None, settings=None, rng=None):
+        """``vamp.<robot>.simplify(path, environment, settings, rng)`` (reference bindings/robot_helper.hh:269-277,
+        planning/simplify.hh:191-258) with the candidate edges of every routine validated as batches."""
+        from .simplify import simplify
+
+        return simplify(self, path, environment, settings, rng)
+
     def fk_batch(self, configurations) -> np.ndarray:
         q = _lib.f32(configurations).reshape(-1, self._dof)
         out = np.zeros((len(q), self._n_spheres, 4), np.float32)
