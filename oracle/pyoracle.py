@@ -402,6 +402,11 @@ class Ref:
         assert n <= cap
         return out[:n].copy(), int(it.value)
 
+    def halton(self, n: int, skip: int = 0) -> np.ndarray:
+        out = np.zeros((n, self.dof), np.float32)
+        self.lib.ref_halton(self.id, C.c_size_t(skip), C.c_size_t(n), _fp(out))
+        return out
+
     def sphere_fk(self, q):
         q = _f32(q).reshape(-1, self.dof)
         out = np.zeros((len(q), self.n_spheres, 4), np.float32)

@@ -82,6 +82,8 @@ extern "C"
         float *out,
         size_t cap,
         size_t *iterations);
+    /* vamp::rng::Halton<Robot>::next() (random/halton.hh:76-107): samples skip .. skip+n-1, [n][dim] */
+    void ref_halton(int robot, size_t skip, size_t n, float *out);
     void ref_filter_points(int robot, void *env, const float *q, const float *pts, size_t n, float point_radius, uint8_t *keep);
     /* seconds for `reps` passes of ref_validate_configs / edges with `threads` threads (best pass) */
     double ref_time_configs(int robot, void *env, const float *q, size_t n, int threads, int reps);

@@ -252,6 +252,11 @@ extern "C"
         return vt(robot).simplify(E(env).env, path, n, ops, n_ops, settings12, samples, n_samples, out, cap, iterations);
     }
 
+    void ref_halton(int robot, size_t skip, size_t n, float *out)
+    {
+        vt(robot).halton(skip, n, out);
+    }
+
     void
     ref_validate_edges(int robot, void *env, const float *a, const float *b, size_t n, uint8_t *out, int threads)
     {

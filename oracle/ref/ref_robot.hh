@@ -21,6 +21,7 @@
 #include <vamp/collision/validity.hh>
 #include <vamp/planning/validate.hh>
 #include <vamp/planning/simplify.hh>
+#include <vamp/random/halton.hh>
 #include <vamp/vector.hh>
 
 namespace refh
@@ -56,6 +57,7 @@ namespace refh
             float *,
             std::size_t,
             std::size_t *);
+        void (*halton)(std::size_t, std::size_t, float *);
     };
 
     template <typename Fn>
@@ -337,6 +339,24 @@ namespace refh
             return result.path.size();
         }
 
+        // vamp::rng::Halton<Robot> (random/halton.hh): samples skip .. skip + n - 1 of a fresh sequence,
+        // scaled to the joint ranges as next() returns them.
+        static void halton(std::size_t skip, std::size_t n, float *out)
+        {
+            vamp::rng::Halton<Robot> h;
+            for (std::size_t i = 0; i < skip + n; ++i)
+            {
+                const auto a = h.next().to_array();
+                if (i >= skip)
+                {
+                    for (std::size_t j = 0; j < Robot::dimension; ++j)
+                    {
+                        out[(i - skip) * Robot::dimension + j] = a[j];
+                    }
+                }
+            }
+        }
+
         static constexpr RobotVTable vtable{
             static_cast<int>(Robot::dimension),
             static_cast<int>(Robot::n_spheres),
@@ -347,6 +367,7 @@ namespace refh
             &eefk,
             &debug,
             &filter_points,
-            &simplify};
+            &simplify,
+            &halton};
     };
 }  // namespace refh

@@ -115,6 +115,36 @@ def test_distribution_matches_libstdcxx_stream():
     assert np.array_equal(got.path.numpy(), want)
 
 
+@pytest.mark.parametrize("robot", ["panda", "ur5", "fetch", "baxter"])
+def test_halton_sampler_matches_reference(robot):
+    ref = po.Ref(robot)
+    h = getattr(vmv, robot).halton()
+    want = ref.halton(5000)
+    assert np.array_equal(h.take(3000), want[:3000])
+    assert np.array_equal(np.stack([h.next() for _ in range(50)]), want[3000:3050])
+    assert np.array_equal(h.peek(7), want[3050:3057])
+    # across the reset / base rotation after 10^6 samples (halton.hh:78-85) and the second one
+    for skip in (999990, 2000000 - 20):
+        h.reset()
+        h.advance(skip)
+        assert np.array_equal(h.take(64), ref.halton(64, skip=skip))
+
+
+def test_perturb_with_the_halton_sampler():
+    # the reference's perturb_path scales the (already scaled) Halton sample once more (simplify.hh:171-172)
+    ref = po.Ref("panda")
+    renv = po.add_scene(po.RefEnv(), scenes.packed(scenes.box_scene()))
+    path = jagged_path("panda", ref, renv, 5)
+    ops = [S.PERTURB, S.SHORTCUT]
+    st = make_settings({}, ops)
+    # drive the compiled reference with the unit-cube stream that makes its StreamRNG return Halton's values
+    lo, rg = np.array(vmv.panda.lower_bounds(), np.float32), vmv.panda._range
+    hal = ref.halton(400)
+    want, _ = ref.simplify(renv, path, ops, settings12(st), hal)
+    got = S.simplify(vmv.panda, path, None, st, vmv.panda.halton(), validate_edges=lambda a, b: ref.validate_edges(renv, a, b))
+    assert np.array_equal(got.path.numpy(), want)
+
+
 def test_trivial_paths():
     ref = po.Ref("panda")
     renv = po.add_scene(po.RefEnv(), scenes.packed(scenes.sphere_cage()))
@@ -155,3 +185,24 @@ def test_gpu_simplify_matches_reference(case):
         exact += int(g.shape == want.shape and np.array_equal(g, want))
     # identical verdicts (outside the 1e-5 m band) give the identical path
     assert exact == 3
+
+
+@pytest.mark.gpu
+def test_gpu_plan_then_simplify_on_the_sphere_cage():
+    """BASELINE config 1's script (reference scripts/sphere_cage_example.py: plan, then simplify) on the
+    batched front-ends: PRM over Halton samples, then simplify; the simplified path must be the one the
+    reference's simplify makes of the same planned path."""
+    ref = po.Ref("panda")
+    scene = scenes.sphere_cage()
+    renv = po.add_scene(po.RefEnv(), scenes.packed(scene))
+    env = scenes.build_product_env(scene)
+    rm = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000, batch=4096, rng=vmv.panda.halton())
+    assert rm.path is not None and len(rm.path) > 2
+    planned = np.stack(rm.path)
+    assert ref.validate_edges(renv, planned[:-1], planned[1:]).all()
+    st = S.SimplifySettings()
+    got = vmv.panda.simplify(planned, env, st, vmv.panda.halton())
+    want, _ = ref.simplify(renv, planned, st.operations, settings12(st))
+    g = got.path.numpy()
+    assert np.array_equal(g, want)
+    assert got.cost <= float(np.linalg.norm(planned[1:] - planned[:-1], axis=1).sum()) + 1e-4

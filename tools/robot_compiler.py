@@ -353,7 +353,8 @@ def build_model(name, urdf_path, srdf_path):
         resolution=cfg["resolution"],
         joint_names=cfg["joints"],
         lower=[float(np.float32(v)) for v in lower],
-        range=[float(np.float32(np.float32(u) - np.float32(l))) for l, u in zip(lower, upper)],
+        # Robot::s_m of the reference's generated code is the f32 of the double difference (fetch.hh:52-60)
+        range=[float(np.float32(float(u) - float(l))) for l, u in zip(lower, upper)],
         n_spheres=sphere_index,
         min_radius=min(s[3] for c in clinks for s in c["spheres"]),
         max_radius=max(s[3] for c in clinks for s in c["spheres"]),

@@ -8,10 +8,11 @@ engine takes in bulk, so here a roadmap grows in ROUNDS: a batch of samples is v
 reference's PRM* neighbour count k = ceil((e + e/d) ln n) (planning/roadmap.hh:49-56), all candidate edges
 of the round are validated in one call as index pairs into the vertex table (``vmv_validate_edges_indexed``
 -- 8 bytes per edge), and connectivity is tracked with union-find; start and goal are the first two
-vertices and a shortest path is extracted when they meet.  Sampling is uniform in the joint box with a
-seeded generator (the reference's Halton sequence is not restated), nearest neighbours come from
-scipy's k-d tree -- so roadmaps are not the reference's, but every edge in one is an edge the reference's
-``validate_motion`` accepts.
+vertices and a shortest path is extracted when they meet.  Samples come from ``rng`` -- e.g. the
+reference's Halton sequence, ``vamp.<robot>.halton()`` (vamp_mvt_b200/halton.py), drawn a batch at a time
+-- or, without one, uniformly from a seeded generator; nearest neighbours come from scipy's k-d tree
+(the reference's nigh tree is not restated) and vertices are connected in rounds -- so roadmaps are not
+the reference's, but every edge in one is an edge the reference's ``validate_motion`` accepts.
 """
 from __future__ import annotations
 
@@ -45,13 +46,13 @@ def _find(parent, i):
 
 
 def prm(robot, start, goal, environment: Optional[Environment] = None, max_samples: int = 20000, batch: int = 4096,
-        seed: int = 0) -> Roadmap:
+        seed: int = 0, rng=None) -> Roadmap:
     from scipy.spatial import cKDTree
 
     d = robot.dimension()
     lo = np.asarray(robot.lower_bounds(), np.float32)
     hi = np.asarray(robot.upper_bounds(), np.float32)
-    rng = np.random.default_rng(seed)
+    gen = np.random.default_rng(seed)
     start = np.asarray(start, np.float32).reshape(d)
     goal = np.asarray(goal, np.float32).reshape(d)
     rm = Roadmap(vertices=np.stack([start, goal]), edges=np.zeros((0, 2), np.int64))
@@ -68,7 +69,10 @@ def prm(robot, start, goal, environment: Optional[Environment] = None, max_sampl
     parent = list(range(2))
     while len(rm.vertices) < max_samples:
         rm.rounds += 1
-        q = (lo + (hi - lo) * rng.random((batch, d), dtype=np.float32)).astype(np.float32)
+        if rng is not None:
+            q = rng.take(batch)
+        else:
+            q = (lo + (hi - lo) * gen.random((batch, d), dtype=np.float32)).astype(np.float32)
         ok = robot.validate_batch(q, environment)
         rm.configs_checked += len(q)
         new = q[ok]

@@ -208,6 +208,12 @@ class Robot:
 
         return simplify(self, path, environment, settings, rng)
 
+    def halton(self):
+        """``vamp.<robot>.halton()`` (reference random/halton.hh): the deterministic configuration sampler."""
+        from .halton import Halton
+
+        return Halton(self)
+
     def fk_batch(self, configurations) -> np.ndarray:
         q = _lib.f32(configurations).reshape(-1, self._dof)
         out = np.zeros((len(q), self._n_spheres, 4), np.float32)
