@@ -111,6 +111,21 @@ extern "C"
     int vmv_validate_configs(int robot, const vmv_env *env, const float *q, size_t n, uint32_t *valid_bits);
     int vmv_validate_edges(int robot, const vmv_env *env, const float *a, const float *b, size_t n, int resolution, uint32_t *valid_bits);
 
+    /* The reference's Halton configuration sampler (vamp::rng::Halton<Robot>::next(),
+     * src/impl/vamp/random/halton.hh:76-107) evaluated on the device: sample s (0-based) of a fresh
+     * sequence, scaled to the joint ranges exactly as next() returns it.  The planners draw every sample
+     * from it (prm.hh:109-113, rrtc.hh:79, fcit.hh:322-330), so a batched front-end can have samples
+     * first .. first+n-1 generated AND validated on the GPU and receive one bit per sample instead of
+     * uploading 4*dof bytes per sample:
+     *   vmv_halton_fill_dev   writes the configurations to device memory [n][dof];
+     *   vmv_validate_halton   = fill + vmv_validate_configs_dev + D2H of the bits (q_out, if not NULL,
+     *                           also receives the configurations, host memory [n][dof]).
+     * Exact only while the reference's f32 recurrence is (first + n <= vmv_halton_exact_limit(robot):
+     * 10^6 for up to 8 joints, 707280 for Baxter); beyond that VMV_ERR_LIMIT. */
+    int vmv_halton_fill_dev(int robot, uint64_t first, size_t n, float *d_q, void *stream);
+    int vmv_validate_halton(int robot, const vmv_env *env, uint64_t first, size_t n, uint32_t *valid_bits, float *q_out);
+    uint64_t vmv_halton_exact_limit(int robot);
+
     /* PRM-style edge sets (prm.hh:136-146): edge i joins vertices pairs[2i], pairs[2i+1] of a
      * vertex table [n_vertices][dof]; 8 bytes per edge instead of 8*dof. */
     int vmv_validate_edges_indexed_dev(int robot, const vmv_env *env, const float *d_vertices, size_t n_vertices, const uint32_t *d_pairs, size_t n_edges, int resolution, uint32_t *d_valid_bits, void *stream);

@@ -206,3 +206,49 @@ def test_gpu_plan_then_simplify_on_the_sphere_cage():
     g = got.path.numpy()
     assert np.array_equal(g, want)
     assert got.cost <= float(np.linalg.norm(planned[1:] - planned[:-1], axis=1).sum()) + 1e-4
+
+
+def test_device_halton_limits_and_errors():
+    # no GPU needed: argument checks come first, and the exact range is a host-side table
+    assert vmv.panda.halton_exact_limit() == 1000000 and vmv.fetch.halton_exact_limit() == 1000000
+    assert vmv.baxter.halton_exact_limit() == 29 ** 4 - 1
+    L = vmv._lib.lib()
+    assert L.vmv_halton_fill_dev(vmv.panda.id, 999999, 2, None, None) != 0
+    assert L.vmv_halton_fill_dev(vmv.baxter.id, 29 ** 4 - 10, 64, 16, None) != 0
+    assert b"exact range" in L.vmv_last_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot", ["panda", "ur5", "fetch", "baxter"])
+def test_gpu_halton_sampler_and_fused_validation(robot):
+    """vmv_validate_halton: the configurations the device generates are the reference's Halton samples bit
+    for bit, and the verdicts are those of the same configurations uploaded from the host."""
+    ref = po.Ref(robot)
+    R = getattr(vmv, robot)
+    scene = scene_of("table" if robot in ("panda", "ur5") else "random", robot)
+    env = scenes.build_product_env(scene)
+    limit = R.halton_exact_limit()
+    for first, n in ((0, 5000), (123457, 4096), (limit - 3000, 3000), (7, 1), (0, 33)):
+        ok, q = R.validate_halton(first, n, env, return_configs=True)
+        assert np.array_equal(q, ref.halton(n, skip=first))          # the compiled reference's sampler
+        assert np.array_equal(q, R.halton().at(first + np.arange(n)))  # the host restatement
+        assert np.array_equal(ok, R.validate_batch(q, env))
+    with pytest.raises(Exception):
+        R.validate_halton(limit - 10, 11, env)
+
+
+@pytest.mark.gpu
+def test_gpu_prm_with_device_sampling_equals_host_sampling():
+    env = scenes.build_product_env(scenes.sphere_cage())
+    a = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000, batch=4096, rng=vmv.panda.halton())
+
+    class HostOnly(S.StreamRNG):  # same samples, uploaded instead of generated on the device
+        def __init__(self, h):
+            self.h, self.dist = h, h.dist
+
+        def take(self, n):
+            return self.h.take(n)
+
+    b = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000, batch=4096, rng=HostOnly(vmv.panda.halton()))
+    assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.edges, b.edges)
+    assert a.path is not None and np.array_equal(np.stack(a.path), np.stack(b.path))

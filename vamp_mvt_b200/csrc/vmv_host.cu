@@ -18,6 +18,7 @@
 #include "../../include/vamp_b200.h"
 #include "vmv_kernels_v2.cuh"
 #include "vmv_kernels_v4.cuh"
+#include "vmv_halton.cuh"
 
 #include "gen/panda_fk.cuh"
 #include "gen/ur5_fk.cuh"
@@ -2511,6 +2512,137 @@ extern "C"
         VMV_CUDA(cudaGetLastError());
         return VMV_OK;
     }
+    }
+
+    // ---- Halton sampler on the device (vmv_halton.cuh; reference random/halton.hh) ------------------
+    extern "C++"
+    {
+    namespace
+    {
+        // largest sample count for which every joint's numerator / denominator stay below 2^24 (the regime
+        // where the reference's f32 recurrence is exactly the radical inverse) inside the first epoch
+        uint64_t halton_exact_limit(int dof)
+        {
+            uint64_t limit = 1000000;  // Halton::max_iterations (halton.hh:12): bases rotate afterwards
+            for (int j = 0; j < dof; ++j)
+            {
+                const uint64_t b = vmv::halton_prime(j);
+                uint64_t pw = 1;  // largest power of b below 2^24: indices up to pw - 1 keep den <= pw
+                while (pw * b < (1ull << 24))
+                {
+                    pw *= b;
+                }
+                limit = std::min(limit, pw - 1);
+            }
+            return limit;
+        }
+
+        template <int DOF>
+        int launch_halton(const vmv::HaltonScale &sc, uint64_t first, size_t n, float *d_q, cudaStream_t s)
+        {
+            const size_t blocks = (n + 255) / 256;
+            const unsigned grid = static_cast<unsigned>(std::min<size_t>(blocks, static_cast<size_t>(sm_count()) * 8));
+            vmv::k_halton_fill<DOF><<<grid, 256, 0, s>>>(sc, first, n, d_q);
+            g_launches++;
+            VMV_CUDA(cudaGetLastError());
+            return VMV_OK;
+        }
+    }  // namespace
+    }
+
+    int vmv_halton_fill_dev(int robot, uint64_t first, size_t n, float *d_q, void *stream)
+    {
+        if (!valid_robot(robot) || (n > 0 && d_q == nullptr))
+        {
+            return fail(VMV_ERR_ARG, "vmv_halton_fill_dev: bad argument");
+        }
+        const int dof = g_robots[robot].dof;
+        if (first + n > halton_exact_limit(dof))
+        {
+            return fail(VMV_ERR_LIMIT, "vmv_halton_fill_dev: samples beyond the exact range of the reference's f32 recurrence "
+                                       "(first epoch, base^digits < 2^24); draw those on the host");
+        }
+        if (n == 0)
+        {
+            return VMV_OK;
+        }
+        vmv::HaltonScale sc{};
+        for (int j = 0; j < dof; ++j)
+        {
+            sc.lower[j] = g_robots[robot].lower[j];
+            sc.range[j] = g_robots[robot].range[j];
+        }
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        switch (dof)
+        {
+            case 6:
+                return launch_halton<6>(sc, first, n, d_q, s);
+            case 7:
+                return launch_halton<7>(sc, first, n, d_q, s);
+            case 8:
+                return launch_halton<8>(sc, first, n, d_q, s);
+            case 14:
+                return launch_halton<14>(sc, first, n, d_q, s);
+            default:
+                return fail(VMV_ERR_ARG, "vmv_halton_fill_dev: unsupported joint count");
+        }
+    }
+
+    uint64_t vmv_halton_exact_limit(int robot)
+    {
+        return valid_robot(robot) ? halton_exact_limit(g_robots[robot].dof) : 0;
+    }
+
+    // samples first .. first+n-1 generated and validated on the device; only the verdict bits (and, if
+    // asked for, the configurations) cross PCIe
+    int vmv_validate_halton(int robot, const vmv_env *env, uint64_t first, size_t n, uint32_t *bits, float *q_out)
+    {
+        if (!valid_robot(robot) || (n > 0 && bits == nullptr))
+        {
+            return fail(VMV_ERR_ARG, "vmv_validate_halton: bad argument");
+        }
+        if (n == 0)
+        {
+            vmv::LaunchEnv probe{};
+            return make_launch_env(g_robots[robot], env, probe);
+        }
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        HostPathPool &pool = g_pools[device % kMaxDevices];
+        std::lock_guard<std::mutex> lock(pool.mutex);
+        const size_t dof = g_robots[robot].dof;
+        int rc = pool.init();
+        if (rc == VMV_OK)
+        {
+            rc = pool.ensure(0, n * dof * sizeof(float));
+        }
+        if (rc == VMV_OK)
+        {
+            rc = pool.ensure(2, ((n + 31) / 32) * 4);
+        }
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        float *dq = static_cast<float *>(pool.buf[0]);
+        uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
+        cudaStream_t st = pool.streams[0];
+        rc = vmv_halton_fill_dev(robot, first, n, dq, st);
+        if (rc == VMV_OK)
+        {
+            rc = vmv_validate_configs_dev(robot, env, dq, n, dw, st);
+        }
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        VMV_CUDA(cudaMemcpyAsync(bits, dw, ((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+        if (q_out != nullptr)
+        {
+            VMV_CUDA(cudaMemcpyAsync(q_out, dq, n * dof * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        VMV_CUDA(cudaStreamSynchronize(st));
+        return VMV_OK;
     }
 
     int vmv_filter_points_dev(int robot, const vmv_env *env, const float *d_q, const float *d_points, size_t n, float point_radius, uint32_t *d_keep_bits, void *stream)

@@ -101,6 +101,11 @@ class Halton:
         u = self._unit(idx).astype(np.float64)
         return (u * self._range + self._lower).astype(np.float32)
 
+    def at(self, index) -> np.ndarray:
+        """Samples with the given 0-based numbers (what the device generated for them)."""
+        u = self._unit(np.asarray(index, np.int64).reshape(-1)).astype(np.float64)
+        return (u * self._range + self._lower).astype(np.float32)
+
     # StreamRNG protocol of vamp_mvt_b200.simplify (peek / advance / next)
     def peek(self, k: int) -> np.ndarray:
         u = self._unit(self.count + np.arange(k, dtype=np.int64)).astype(np.float64)

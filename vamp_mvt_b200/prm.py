@@ -24,6 +24,7 @@ from typing import List, Optional
 import numpy as np
 
 from .environment import Environment
+from .halton import Halton
 
 
 @dataclass
@@ -69,13 +70,19 @@ def prm(robot, start, goal, environment: Optional[Environment] = None, max_sampl
     parent = list(range(2))
     while len(rm.vertices) < max_samples:
         rm.rounds += 1
-        if rng is not None:
-            q = rng.take(batch)
+        if isinstance(rng, Halton) and rng.count + batch <= robot.halton_exact_limit():
+            # samples generated and validated on the device; the valid ones are rebuilt here in closed form
+            ok = robot.validate_halton(rng.count, batch, environment)
+            new = rng.at(rng.count + np.nonzero(ok)[0])
+            rng.advance(batch)
         else:
-            q = (lo + (hi - lo) * gen.random((batch, d), dtype=np.float32)).astype(np.float32)
-        ok = robot.validate_batch(q, environment)
-        rm.configs_checked += len(q)
-        new = q[ok]
+            if rng is not None:
+                q = rng.take(batch)
+            else:
+                q = (lo + (hi - lo) * gen.random((batch, d), dtype=np.float32)).astype(np.float32)
+            ok = robot.validate_batch(q, environment)
+            new = q[ok]
+        rm.configs_checked += batch
         if len(new) == 0:
             continue
         base = len(rm.vertices)

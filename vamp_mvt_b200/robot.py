@@ -208,6 +208,21 @@ class Robot:
 
         return simplify(self, path, environment, settings, rng)
 
+    def validate_halton(self, first: int, n: int, environment: Optional[Environment] = None, return_configs: bool = False):
+        """Samples first .. first+n-1 of the reference's Halton sequence (random/halton.hh) generated and
+        validated on the GPU (``vmv_validate_halton``): only one bit per sample crosses PCIe.  Returns the
+        verdicts (and the configurations if asked)."""
+        env = environment if environment is not None else _empty_env()
+        words = np.zeros((n + 31) // 32, np.uint32)
+        q = np.zeros((n, self._dof), np.float32) if return_configs else None
+        _lib.check(self._L.vmv_validate_halton(self.id, env.handle, int(first), n, _lib.ptr(words),
+                                               _lib.ptr(q) if return_configs else None))
+        ok = _lib.unpack_bits(words, n)
+        return (ok, q) if return_configs else ok
+
+    def halton_exact_limit(self) -> int:
+        return int(self._L.vmv_halton_exact_limit(self.id))
+
     def halton(self):
         """``vamp.<robot>.halton()`` (reference random/halton.hh): the deterministic configuration sampler."""
         from .halton import Halton
