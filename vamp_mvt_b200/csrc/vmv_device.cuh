@@ -196,8 +196,9 @@ namespace vmv
     // Called by whichever lanes of the warp currently have a query (the converged group,
     // __activemask()).  Each lane does its own top-AABB reject, Eytzinger descent and leaf-AABB test;
     // the affordance lists of the lanes that survive are then scanned ONE LIST AT A TIME BY THE WHOLE
-    // GROUP: up to 32 lanes x 128-bit loads = 512 contiguous bytes per step, and a ballot ends the
-    // scan at the first chunk with a hit.
+    // GROUP: up to 32 lanes x four 128-bit loads per step, and a ballot ends the scan at the first chunk
+    // with a hit -- or with a point farther from the cell than the query radius (lists are ordered by
+    // that distance; a query of a small sphere reads a short prefix of a list built for r_max).
     // ------------------------------------------------------------------------------------------
     __device__ __forceinline__ bool capt_collides_warp(const CaptRec &t, float x, float y, float z, float r, bool active)
     {
@@ -247,20 +248,34 @@ namespace vmv
             const uint32_t s = __shfl_sync(group, start, src), e = __shfl_sync(group, end, src);
             const float qx = __shfl_sync(group, x, src), qy = __shfl_sync(group, y, src);
             const float qz = __shfl_sync(group, z, src), qr = __shfl_sync(group, rc_sq, src);
+            // The list is ordered by squared distance from the cell (.w, written by the host build): the
+            // centre is inside the cell, so once .w exceeds the query radius nothing further can be
+            // within it.  The slack covers the rounding of both squared distances (relative 1e-6).
+            const float qlim = qr * 1.00001F;
             bool found = false;
-            for (uint32_t base = s; base < e; base += gsize)
+            for (uint32_t base = s; base < e; base += 4u * gsize)
             {
-                const uint32_t i = base + rank;
-                bool h = false;
-                if (i < e)
+                // four independent 128-bit loads per lane and step: the scan is bound by memory latency
+                bool h = false, beyond = false;
+#pragma unroll
+                for (uint32_t u = 0; u < 4u; ++u)
                 {
-                    const float4 p = __ldg(t.points + i);
-                    const float ex = p.x - qx, ey = p.y - qy, ez = p.z - qz;
-                    h = ex * ex + ey * ey + ez * ez <= qr;
+                    const uint32_t i = base + u * gsize + rank;
+                    if (i < e)
+                    {
+                        const float4 p = __ldg(t.points + i);
+                        const float ex = p.x - qx, ey = p.y - qy, ez = p.z - qz;
+                        h = h || (ex * ex + ey * ey + ez * ez <= qr);
+                        beyond = beyond || (p.w > qlim);
+                    }
                 }
                 if (__any_sync(group, h))
                 {
                     found = true;
+                    break;
+                }
+                if (__any_sync(group, beyond))
+                {
                     break;
                 }
             }

@@ -3,6 +3,8 @@
 // CUDA device.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -255,6 +257,30 @@ namespace
         float *d_data = nullptr;
     };
 
+    // std::vector whose resize() leaves new elements uninitialised (the CAPT point array is GBs and is
+    // filled by parallel copies right after it is sized)
+    template <typename T>
+    struct NoInitAlloc : std::allocator<T>
+    {
+        template <typename U>
+        struct rebind
+        {
+            using other = NoInitAlloc<U>;
+        };
+        template <typename U, typename... A>
+        void construct(U *p, A &&...a)
+        {
+            if constexpr (sizeof...(A) == 0)
+            {
+                ::new (static_cast<void *>(p)) U;
+            }
+            else
+            {
+                ::new (static_cast<void *>(p)) U(std::forward<A>(a)...);
+            }
+        }
+    };
+
     struct HCapt
     {
         float r_min, r_max, r_point;
@@ -262,7 +288,7 @@ namespace
         std::vector<float> tests;
         std::vector<float> leaf_lo, leaf_hi;  // 3 floats per leaf
         std::vector<uint32_t> leaf_start;     // per leaf + 1, in points
-        std::vector<float> points;            // xyz0 per afforded point (representative first)
+        std::vector<float, NoInitAlloc<float>> points;  // per afforded point x, y, z, squared distance from the cell (representative first)
         float top_lo[3], top_hi[3];
         int id;
         float *d_tests = nullptr;
@@ -415,15 +441,43 @@ namespace
         }
     };
 
+    // Output of one subtree: leaves in left-to-right order.  The top levels of the tree are split on the
+    // calling thread, the subtrees below kCaptTaskDepth are independent tasks for the host's threads
+    // (disjoint ranges of `argsort` and `tests`), and their fragments are stitched in task order.
+    struct CaptFragment
+    {
+        std::vector<float> leaf_lo, leaf_hi, points;
+        std::vector<uint32_t> leaf_end;  // per leaf, in points, relative to this fragment
+        float top_lo[3], top_hi[3];
+    };
+
+    struct CaptTask
+    {
+        uint32_t begin, count, i;
+        std::vector<uint32_t> afford;
+        Vol vol;
+        int d;
+    };
+
+    constexpr int kCaptTaskDepth = 6;  // 64 subtrees
+
     struct CaptBuilder
     {
         HCapt &t;
         const std::vector<float> &pts;  // padded to 2^nlog2 points with +inf
-        std::vector<uint32_t> argsort;
+        std::vector<uint32_t> &argsort;
         float max_l2, min_l2;
+        CaptFragment *out;                              // leaves of this builder go here
+        std::vector<CaptTask> *tasks;                   // non-null: collect subtrees at kCaptTaskDepth
+        std::vector<std::pair<float, uint32_t>> near;  // scratch of the leaf step
 
-        void subdivide(uint32_t begin, uint32_t count, uint32_t i, std::vector<uint32_t> afford, Vol vol, int d)
+        void subdivide(uint32_t begin, uint32_t count, uint32_t i, std::vector<uint32_t> afford, Vol vol, int d, int depth)
         {
+            if (tasks != nullptr && depth == kCaptTaskDepth && count > 1)
+            {
+                tasks->push_back(CaptTask{begin, count, i, std::move(afford), vol, d});
+                return;
+            }
             if (count == 1)
             {
                 const float *rep = &pts[3 * argsort[begin]];
@@ -432,10 +486,10 @@ namespace
                 {
                     for (int k = 0; k < 3; ++k)
                     {
-                        t.top_lo[k] = std::min(t.top_lo[k], rep[k]);
-                        t.top_hi[k] = std::max(t.top_hi[k], rep[k]);
+                        out->top_lo[k] = std::min(out->top_lo[k], rep[k]);
+                        out->top_hi[k] = std::max(out->top_hi[k], rep[k]);
                     }
-                    t.points.insert(t.points.end(), {rep[0], rep[1], rep[2], 0.F});
+                    out->points.insert(out->points.end(), {rep[0], rep[1], rep[2], 0.F});
                     // cell entirely inside the smallest query ball around its representative:
                     // the representative alone decides (capt.hh:39-46,150)
                     const float d0 = std::max(rep[0] - vol.lo[0], vol.hi[0] - rep[0]);
@@ -443,20 +497,32 @@ namespace
                     const float d2 = std::max(rep[2] - vol.lo[2], vol.hi[2] - rep[2]);
                     if (!((d0 * d0 + d1 * d1 + d2 * d2) <= min_l2))
                     {
+                        // Same set of afforded points as the reference's list (capt.hh:150-170), but
+                        // ordered by their squared distance from the cell, which is kept in .w: a query
+                        // centre lies inside the cell it descends to, so a point farther from the cell
+                        // than the query radius cannot be within it and the device scan stops there.
+                        near.clear();
                         for (const uint32_t id : afford)
                         {
                             const float *p = &pts[3 * id];
-                            if (vol.distsq(p) <= max_l2)
+                            const float dsq = vol.distsq(p);
+                            if (dsq <= max_l2)
                             {
                                 aabb.extend(p);
-                                t.points.insert(t.points.end(), {p[0], p[1], p[2], 0.F});
+                                near.emplace_back(dsq, id);
                             }
+                        }
+                        std::stable_sort(near.begin(), near.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+                        for (const auto &[dsq, id] : near)
+                        {
+                            const float *p = &pts[3 * id];
+                            out->points.insert(out->points.end(), {p[0], p[1], p[2], dsq});
                         }
                     }
                 }
-                t.leaf_lo.insert(t.leaf_lo.end(), aabb.lo, aabb.lo + 3);
-                t.leaf_hi.insert(t.leaf_hi.end(), aabb.hi, aabb.hi + 3);
-                t.leaf_start.push_back(static_cast<uint32_t>(t.points.size() / 4));
+                out->leaf_lo.insert(out->leaf_lo.end(), aabb.lo, aabb.lo + 3);
+                out->leaf_hi.insert(out->leaf_hi.end(), aabb.hi, aabb.hi + 3);
+                out->leaf_end.push_back(static_cast<uint32_t>(out->points.size() / 4));
                 return;
             }
 
@@ -507,8 +573,8 @@ namespace
             afford.shrink_to_fit();
 
             const int nd = (d + 1) % 3;
-            subdivide(begin, half, 2 * i + 1, std::move(lo_afford), lo_vol, nd);
-            subdivide(begin + half, half, 2 * i + 2, std::move(hi_afford), hi_vol, nd);
+            subdivide(begin, half, 2 * i + 1, std::move(lo_afford), lo_vol, nd, depth + 1);
+            subdivide(begin + half, half, 2 * i + 2, std::move(hi_afford), hi_vol, nd, depth + 1);
         }
     };
 
@@ -532,10 +598,119 @@ namespace
         }
         t.tests.assign(pow2 - 1, std::numeric_limits<float>::quiet_NaN());
         t.leaf_start.assign(1, 0);
-        CaptBuilder b{t, pts, {}, max_l1 * max_l1, (r_min + r_point) * (r_min + r_point)};
-        b.argsort.resize(pow2);
-        std::iota(b.argsort.begin(), b.argsort.end(), 0u);
-        b.subdivide(0, static_cast<uint32_t>(pow2), 0, {}, Vol{{-inf, -inf, -inf}, {inf, inf, inf}}, 0);
+        t.leaf_lo.clear(), t.leaf_hi.clear(), t.points.clear();
+        std::vector<uint32_t> argsort(pow2);
+        std::iota(argsort.begin(), argsort.end(), 0u);
+        const float max_l2 = max_l1 * max_l1, min_l2 = (r_min + r_point) * (r_min + r_point);
+        auto fresh = [&](CaptFragment &f)
+        {
+            for (int k = 0; k < 3; ++k)
+            {
+                f.top_lo[k] = inf;
+                f.top_hi[k] = -inf;
+            }
+        };
+        // top levels here (a tree shallower than kCaptTaskDepth ends up entirely in `head`)
+        CaptFragment head;
+        fresh(head);
+        std::vector<CaptTask> tasks;
+        const auto tm0 = std::chrono::steady_clock::now();
+        CaptBuilder top{t, pts, argsort, max_l2, min_l2, &head, &tasks, {}};
+        top.subdivide(0, static_cast<uint32_t>(pow2), 0, {}, Vol{{-inf, -inf, -inf}, {inf, inf, inf}}, 0, 0);
+        const auto tm1 = std::chrono::steady_clock::now();
+        std::vector<CaptFragment> frags(tasks.size());
+        {
+            std::atomic<size_t> next{0};
+            auto work = [&]()
+            {
+                for (size_t k = next.fetch_add(1); k < tasks.size(); k = next.fetch_add(1))
+                {
+                    fresh(frags[k]);
+                    CaptBuilder b{t, pts, argsort, max_l2, min_l2, &frags[k], nullptr, {}};
+                    CaptTask &task = tasks[k];
+                    b.subdivide(task.begin, task.count, task.i, std::move(task.afford), task.vol, task.d, kCaptTaskDepth);
+                }
+            };
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            const size_t n_threads = std::min<size_t>({tasks.size(), hw, 32});
+            std::vector<std::thread> pool;
+            for (size_t k = 1; k < n_threads; ++k)
+            {
+                pool.emplace_back(work);
+            }
+            work();
+            for (auto &th : pool)
+            {
+                th.join();
+            }
+        }
+        const auto tm2 = std::chrono::steady_clock::now();
+        if (std::getenv("VMV_CAPT_TIMING"))
+        {
+            std::fprintf(stderr, "capt_build: top %.2f s, subtrees %.2f s\n", std::chrono::duration<double>(tm1 - tm0).count(),
+                         std::chrono::duration<double>(tm2 - tm1).count());
+        }
+        // stitch: either everything is in `head` (no tasks) or every leaf is in a task fragment
+        std::vector<CaptFragment *> order{&head};
+        for (CaptFragment &f : frags)
+        {
+            order.push_back(&f);
+        }
+        std::vector<size_t> at(order.size() + 1, 0);
+        for (size_t k = 0; k < order.size(); ++k)
+        {
+            at[k + 1] = at[k] + order[k]->points.size();
+        }
+        t.points.resize(at.back());  // uninitialised (NoInitAlloc)
+        for (size_t k = 0; k < order.size(); ++k)
+        {
+            const CaptFragment &f = *order[k];
+            const uint32_t base = static_cast<uint32_t>(at[k] / 4);
+            t.leaf_lo.insert(t.leaf_lo.end(), f.leaf_lo.begin(), f.leaf_lo.end());
+            t.leaf_hi.insert(t.leaf_hi.end(), f.leaf_hi.begin(), f.leaf_hi.end());
+            for (const uint32_t e : f.leaf_end)
+            {
+                t.leaf_start.push_back(base + e);
+            }
+            for (int c = 0; c < 3; ++c)
+            {
+                t.top_lo[c] = std::min(t.top_lo[c], f.top_lo[c]);
+                t.top_hi[c] = std::max(t.top_hi[c], f.top_hi[c]);
+            }
+        }
+        {
+            // the point lists (GBs for a wide r_max) are copied by all threads, fragments released as they go
+            std::atomic<size_t> next{0};
+            auto copy = [&]()
+            {
+                for (size_t k = next.fetch_add(1); k < order.size(); k = next.fetch_add(1))
+                {
+                    std::vector<float> &src = order[k]->points;
+                    if (!src.empty())
+                    {
+                        std::memcpy(t.points.data() + at[k], src.data(), src.size() * sizeof(float));
+                    }
+                    std::vector<float>().swap(src);
+                }
+            };
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            const size_t n_threads = std::min<size_t>({order.size(), hw, 16});
+            std::vector<std::thread> pool;
+            for (size_t k = 1; k < n_threads; ++k)
+            {
+                pool.emplace_back(copy);
+            }
+            copy();
+            for (auto &th : pool)
+            {
+                th.join();
+            }
+        }
+        if (std::getenv("VMV_CAPT_TIMING"))
+        {
+            std::fprintf(stderr, "capt_build: %zu points, %zu tasks, %zu afforded entries (%.1f MB)\n", n, tasks.size(), t.points.size() / 4,
+                         t.points.size() * 4 / 1e6);
+        }
     }
 }  // namespace
 
@@ -619,8 +794,8 @@ namespace
         return u;
     }
 
-    template <typename T>
-    int upload(vmv_env *env, const std::vector<T> &host, T *&dev)
+    template <typename T, typename A>
+    int upload(vmv_env *env, const std::vector<T, A> &host, T *&dev)
     {
         void *p = nullptr;
         const size_t bytes = std::max<size_t>(16, host.size() * sizeof(T));
@@ -851,9 +1026,12 @@ namespace
             {
                 return rc;
             }
-            std::vector<float4> pts(t.points.size() / 4);
-            std::memcpy(pts.data(), t.points.data(), t.points.size() * sizeof(float));
-            rc = upload(env, pts, t.d_points);
+            {
+                // straight from the build's array (GBs for a wide r_max: no staging copy)
+                float *dp = nullptr;
+                rc = upload(env, t.points, dp);
+                t.d_points = reinterpret_cast<float4 *>(dp);
+            }
             if (rc != VMV_OK)
             {
                 return rc;
