@@ -75,10 +75,11 @@ namespace vmv
     static_assert(sizeof(MvtRec) == kMvtRec * 4, "MvtRec layout");
 
     // Clearance grid of the pointclouds (CAPT and MVT together): per voxel a lower bound of the
-    // distance from any position inside the voxel to the nearest cloud point.  A pointcloud query can
-    // only answer "collision" on an actual point within r + r_point of the centre (capt.hh:494-509,
-    // mvt.hh:383-397), so a sphere whose clearance bound exceeds that radius skips the tree descent /
-    // voxel walk altogether -- the verdict is the one the query would have returned.
+    // distance from the voxel CENTRE to the nearest cloud point; the distance function is 1-Lipschitz, so
+    // a position at offset d from the centre is at least (that bound - d) away from every point.  A
+    // pointcloud query can only answer "collision" on an actual point within r + r_point of the centre
+    // (capt.hh:494-509, mvt.hh:383-397), so a sphere whose clearance bound exceeds that radius skips the
+    // tree descent / voxel walk altogether -- the verdict is the one the query would have returned.
     static constexpr int kCloudGridRec = 12;
     struct CloudGridRec
     {
@@ -86,16 +87,15 @@ namespace vmv
         int nx, ny, nz;
         float outside;      // clearance bound for positions outside the table
         float r_point_max;  // largest r_point of any cloud
-        float pad0;
+        float h;            // voxel edge
         const float *cells;
     };
     static_assert(sizeof(CloudGridRec) == kCloudGridRec * 4, "CloudGridRec layout");
 
     __device__ __forceinline__ float cloud_clearance(const CloudGridRec &g, float x, float y, float z)
     {
-        const int ix = __float2int_rd((x - g.x0) * g.inv_h);
-        const int iy = __float2int_rd((y - g.y0) * g.inv_h);
-        const int iz = __float2int_rd((z - g.z0) * g.inv_h);
+        const float fx = (x - g.x0) * g.inv_h, fy = (y - g.y0) * g.inv_h, fz = (z - g.z0) * g.inv_h;
+        const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
         const bool in = (static_cast<unsigned>(ix) < static_cast<unsigned>(g.nx)) & (static_cast<unsigned>(iy) < static_cast<unsigned>(g.ny)) &
                         (static_cast<unsigned>(iz) < static_cast<unsigned>(g.nz));
         if (!in)
@@ -103,7 +103,11 @@ namespace vmv
             // a centre that is not finite lands here too: no claim about it
             return (fabsf(x) < 1e30F && fabsf(y) < 1e30F && fabsf(z) < 1e30F) ? g.outside : 0.F;
         }
-        return __ldg(g.cells + (static_cast<size_t>(iz) * g.ny + iy) * g.nx + ix);
+        // offset from the voxel centre, in metres, rounded up a little (the table entry already carries
+        // the slack for its own rounding)
+        const float ox = fx - (static_cast<float>(ix) + 0.5F), oy = fy - (static_cast<float>(iy) + 0.5F), oz = fz - (static_cast<float>(iz) + 0.5F);
+        const float off = sqrtf(ox * ox + oy * oy + oz * oz) * g.h * 1.0001F;
+        return __ldg(g.cells + (static_cast<size_t>(iz) * g.ny + iy) * g.nx + ix) - off;
     }
 
     // thread = voxel; the points stream through shared memory
@@ -134,9 +138,9 @@ namespace vmv
         }
         if (v < n_vox)
         {
-            // distance from the voxel centre minus the half diagonal (and rounding slack): a lower
-            // bound for every position inside the voxel
-            out[v] = fmaxf(sqrtf(best) * 0.99999F - 0.8660255F * h - 1e-4F, 0.F);
+            // distance from the voxel centre, less the rounding slack (cloud_clearance subtracts the
+            // query's own offset from the centre)
+            out[v] = sqrtf(best) * 0.99999F - 1e-4F;
         }
     }
 
@@ -200,6 +204,11 @@ namespace vmv
     // with a hit -- or with a point farther from the cell than the query radius (lists are ordered by
     // that distance; a query of a small sphere reads a short prefix of a list built for r_max).
     // ------------------------------------------------------------------------------------------
+#ifndef VMV_CAPT_SCAN_LOADS
+#define VMV_CAPT_SCAN_LOADS 8
+#endif
+    static constexpr uint32_t kCaptScanLoads = VMV_CAPT_SCAN_LOADS;
+
     __device__ __forceinline__ bool capt_collides_warp(const CaptRec &t, float x, float y, float z, float r, bool active)
     {
         const uint32_t group = __activemask();
@@ -253,12 +262,12 @@ namespace vmv
             // within it.  The slack covers the rounding of both squared distances (relative 1e-6).
             const float qlim = qr * 1.00001F;
             bool found = false;
-            for (uint32_t base = s; base < e; base += 4u * gsize)
+            for (uint32_t base = s; base < e; base += kCaptScanLoads * gsize)
             {
-                // four independent 128-bit loads per lane and step: the scan is bound by memory latency
+                // independent 128-bit loads per lane and step: the scan is bound by memory latency
                 bool h = false, beyond = false;
 #pragma unroll
-                for (uint32_t u = 0; u < 4u; ++u)
+                for (uint32_t u = 0; u < kCaptScanLoads; ++u)
                 {
                     const uint32_t i = base + u * gsize + rank;
                     if (i < e)

@@ -912,7 +912,10 @@ namespace
     // Clearance grid of all pointcloud points (vmv_device.cuh: cloud_clearance).  The table covers the
     // points' bounding box grown by kCloudReach; outside it every cloud point is farther than that.
     constexpr float kCloudReach = 0.5F;
-    constexpr size_t kCloudMaxVoxels = 1u << 20;
+#ifndef VMV_CLOUD_MAX_VOXELS_LOG2
+#define VMV_CLOUD_MAX_VOXELS_LOG2 22
+#endif
+    constexpr size_t kCloudMaxVoxels = size_t(1) << VMV_CLOUD_MAX_VOXELS_LOG2;
 
     int build_cloud_grid(vmv_env *env, vmv::CloudGridRec &g)
     {
@@ -933,7 +936,7 @@ namespace
             }
             pts[i] = make_float4(p[0], p[1], p[2], 0.F);
         }
-        double h = 0.03;
+        double h = 0.02;
         int dim[3];
         while (true)
         {
@@ -981,6 +984,7 @@ namespace
         g.inv_h = static_cast<float>(1.0 / h);
         g.nx = dim[0], g.ny = dim[1], g.nz = dim[2];
         g.outside = kCloudReach - static_cast<float>(h) - 1e-3F;
+        g.h = static_cast<float>(h);
         g.r_point_max = env->cloud_r_point_max;
         g.cells = d_cells;
         return VMV_OK;
