@@ -60,7 +60,8 @@ def c4():
         data = (0.15 * rng.random((yd, xd)) ** 4).astype(np.float32)
         yy, xx = np.mgrid[0:yd, 0:xd]
         data[np.hypot(xx - xd / 2, yy - yd / 2) < 40] = 0.0
-        env.add_heightfield(vmv.make_heightfield([0, 0, -0.3], [0.02, 0.02, 1.0], [xd, yd], data))
+        hf = vmv.make_heightfield([0, 0, -0.3], [0.02, 0.02, 1.0], [xd, yd], data)
+        env.add_heightfield(hf)
         n = 1 << 18
         q = scenes.random_configs(robot, n, seed=0)
         dq, db = L.vmv_dev_alloc(q.nbytes), L.vmv_dev_alloc((n + 31) // 32 * 4)
@@ -70,9 +71,25 @@ def c4():
         words = np.zeros((n + 31) // 32, np.uint32)
         _lib.check(L.vmv_memcpy_d2h(_lib.ptr(words), db, words.nbytes, None))
         _lib.check(L.vmv_stream_sync(None))
-        print(json.dumps({"workload": f"C4 {robot}: 2^18 configs vs CAPT({len(pts)} pts) + 256x256 heightfield",
-                          "value": n / t, "unit": "configs/s", "ms": t * 1e3, "capt_build_ms": build_ns / 1e6,
-                          "valid_fraction": float(_lib.unpack_bits(words, n).mean())}), flush=True)
+        out = {"workload": f"C4 {robot}: 2^18 configs vs CAPT({len(pts)} pts) + 256x256 heightfield",
+               "value": n / t, "unit": "configs/s", "ms": t * 1e3, "capt_build_ms": build_ns / 1e6,
+               "valid_fraction": float(_lib.unpack_bits(words, n).mean())}
+        if "--cpu" in sys.argv:
+            # the reference's own CAPT + validate on the host cores, on a bounded sample of the same batch
+            from oracle import pyoracle as po
+            if po.ref_available():
+                renv = po.RefEnv()
+                t0 = time.perf_counter()
+                renv.add_capt(pts, rmin, rmax, vmv.POINT_RADIUS)
+                out["reference_capt_build_ms"] = (time.perf_counter() - t0) * 1e3
+                renv.add_heightfield(hf.packed(), xd, yd, data.reshape(-1))
+                ns = 1 << 15
+                thr = po.host_threads()
+                sec = po.Ref(robot).time_configs(renv, q[:ns], thr, reps=2)
+                want = po.Ref(robot).validate_configs(renv, q[:ns], threads=thr)
+                out["cpu_reference"] = {"value": ns / sec, "unit": "configs/s", "cores": thr, "sample": f"first 2^15 configs of the batch"}
+                out["mismatches_vs_reference_on_sample"] = int((want != _lib.unpack_bits(words, n)[:ns]).sum())
+        print(json.dumps(out), flush=True)
         L.vmv_dev_free(dq), L.vmv_dev_free(db)
 
 
