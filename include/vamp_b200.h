@@ -111,6 +111,20 @@ extern "C"
     int vmv_validate_configs(int robot, const vmv_env *env, const float *q, size_t n, uint32_t *valid_bits);
     int vmv_validate_edges(int robot, const vmv_env *env, const float *a, const float *b, size_t n, int resolution, uint32_t *valid_bits);
 
+    /* CenterVox pointcloud down-sampling: vamp.filter_pointcloud(..., filter_type="centervox")
+     * (bindings/environment.cc:212-239) = vamp::collision::filter_pointcloud_centervox
+     * (src/impl/vamp/collision/filter_centervox.hh:302-333): points inside the range sphere around `origin`
+     * and inside the workspace box go to a grid of at most 255^3 voxels; a voxel keeps the point closest to
+     * its centre (the earlier one on a tie); the result lists the occupied voxels in the order the
+     * reference's sparse tables created them.  points: [n][3] float32 (host; _dev: device memory on the
+     * current device).  kept_indices (host, up to `cap`; 32768 always suffices) receives the indices of the
+     * kept points in the reference's output order, *n_kept their number.  VMV_ERR_LIMIT where the reference
+     * throws "Voxel pool exhausted" (more occupied voxels than min((width/voxel_size)^3 * 0.05, 32768)). */
+    int vmv_filter_pointcloud_centervox(const float *points, size_t n, float voxel_size, float max_range, const float *origin3,
+                                        const float *workspace_min3, const float *workspace_max3, uint32_t *kept_indices, size_t cap, size_t *n_kept);
+    int vmv_filter_pointcloud_centervox_dev(const float *d_points, size_t n, float voxel_size, float max_range, const float *origin3,
+                                            const float *workspace_min3, const float *workspace_max3, uint32_t *kept_indices, size_t cap, size_t *n_kept);
+
     /* The reference's Halton configuration sampler (vamp::rng::Halton<Robot>::next(),
      * src/impl/vamp/random/halton.hh:76-107) evaluated on the device: sample s (0-based) of a fresh
      * sequence, scaled to the joint ranges exactly as next() returns it.  The planners draw every sample

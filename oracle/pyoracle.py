@@ -444,5 +444,30 @@ class Ref:
         )
 
 
+def filter_centervox(points, voxel_size, max_range, origin, ws_min, ws_max):
+    """CPU restatement (oracle/vamp_oracle.c: or_filter_centervox) of the reference's CenterVox filter
+    (collision/filter_centervox.hh): indices of the kept points in the reference's output order, or None
+    where the reference throws (voxel pool exhausted)."""
+    L = oracle_lib()
+    L.or_filter_centervox.restype = C.c_long
+    p = _f32(points).reshape(-1, 3)
+    out = np.zeros(32768, np.uint32)
+    k = L.or_filter_centervox(_fp(p), C.c_size_t(len(p)), C.c_float(voxel_size), C.c_float(max_range), _fp(_f32(origin)),
+                              _fp(_f32(ws_min)), _fp(_f32(ws_max)), out.ctypes.data_as(C.c_void_p), C.c_size_t(len(out)))
+    return None if k < 0 else out[:k].copy()
+
+
+def ref_filter_centervox(points, voxel_size, max_range, origin, ws_min, ws_max):
+    """The reference's own filter_pointcloud_centervox compiled in place (oracle/_ref): kept points [k][3],
+    or None where it throws."""
+    L = ref_lib()
+    L.ref_filter_centervox.restype = C.c_size_t
+    p = _f32(points).reshape(-1, 3)
+    out = np.zeros((max(len(p), 1), 3), np.float32)
+    k = L.ref_filter_centervox(_fp(p), C.c_size_t(len(p)), C.c_float(voxel_size), C.c_float(max_range), _fp(_f32(origin)),
+                               _fp(_f32(ws_min)), _fp(_f32(ws_max)), _fp(out), C.c_size_t(len(out)))
+    return None if k == C.c_size_t(-1).value else out[:k].copy()
+
+
 def host_threads() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)

@@ -82,6 +82,10 @@ extern "C"
         float *out,
         size_t cap,
         size_t *iterations);
+    /* vamp::collision::filter_pointcloud_centervox (collision/filter_centervox.hh:302-333); returns the number
+     * of kept points (written to out_xyz up to cap) or (size_t)-1 where the reference throws */
+    size_t ref_filter_centervox(const float *pts, size_t n, float voxel_size, float max_range, const float *origin, const float *ws_min,
+                                const float *ws_max, float *out_xyz, size_t cap);
     /* vamp::rng::Halton<Robot>::next() (random/halton.hh:76-107): samples skip .. skip+n-1, [n][dim] */
     void ref_halton(int robot, size_t skip, size_t n, float *out);
     void ref_filter_points(int robot, void *env, const float *q, const float *pts, size_t n, float point_radius, uint8_t *keep);

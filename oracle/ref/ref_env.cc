@@ -4,6 +4,7 @@
 // classification, re-sort after every insertion.  Shapes are built through the reference's own
 // constructors (collision/shapes.hh) so min_distance is the reference's value.
 #include "ref_robot.hh"
+#include <vamp/collision/filter_centervox.hh>
 #include "ref_api.h"
 
 #include <cstring>
@@ -250,6 +251,45 @@ extern "C"
         size_t *iterations)
     {
         return vt(robot).simplify(E(env).env, path, n, ops, n_ops, settings12, samples, n_samples, out, cap, iterations);
+    }
+
+    // vamp::collision::filter_pointcloud_centervox (collision/filter_centervox.hh:302-333) on [n][3] points;
+    // writes the kept points (up to cap) and returns their number, or (size_t)-1 where the reference throws
+    size_t ref_filter_centervox(
+        const float *pts,
+        size_t n,
+        float voxel_size,
+        float max_range,
+        const float *origin,
+        const float *ws_min,
+        const float *ws_max,
+        float *out_xyz,
+        size_t cap)
+    {
+        std::vector<vamp::collision::Point> pc(n);
+        for (size_t i = 0; i < n; ++i)
+        {
+            pc[i] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        }
+        try
+        {
+            const auto kept = vamp::collision::filter_pointcloud_centervox(
+                pc,
+                voxel_size,
+                max_range,
+                vamp::collision::Point{origin[0], origin[1], origin[2]},
+                vamp::collision::Point{ws_min[0], ws_min[1], ws_min[2]},
+                vamp::collision::Point{ws_max[0], ws_max[1], ws_max[2]});
+            for (size_t i = 0; i < kept.size() and i < cap; ++i)
+            {
+                out_xyz[3 * i] = kept[i][0], out_xyz[3 * i + 1] = kept[i][1], out_xyz[3 * i + 2] = kept[i][2];
+            }
+            return kept.size();
+        }
+        catch (const std::exception &)
+        {
+            return static_cast<size_t>(-1);
+        }
     }
 
     void ref_halton(int robot, size_t skip, size_t n, float *out)

@@ -1605,3 +1605,140 @@ int or_capt_query(const OrEnv *e, size_t which, const float *c, float r)
 {
     return capt_collides(&e->capts[which], c, r, NULL);
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * CenterVox pointcloud filter: filter_pointcloud_centervox / CenterSelectiveVoxelFilter
+ * (collision/filter_centervox.hh:16-45, 95-121, 139-184, 251-291, 302-333), restated as the sequential
+ * walk it is, on a dense table instead of the three-level sparse one.  The output order is the creation
+ * order of the sparse tables: x slabs by their first point, (x, y) columns by theirs, voxels by theirs.
+ * Squared distances follow the compiled reference's contraction: fma(dz, dz, fma(dx, dx, dy*dy)).
+ * Returns the number of kept points (their indices in out_idx, up to cap) or -1 where the reference throws
+ * "Voxel pool exhausted".
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct
+{
+    uint32_t vox, keep, first;
+    uint32_t first_x, first_xy;
+} OrVoxRec;
+
+static int or_voxrec_cmp(const void *a, const void *b)
+{
+    const OrVoxRec *p = (const OrVoxRec *)a, *q = (const OrVoxRec *)b;
+    if (p->first_x != q->first_x)
+    {
+        return p->first_x < q->first_x ? -1 : 1;
+    }
+    if (p->first_xy != q->first_xy)
+    {
+        return p->first_xy < q->first_xy ? -1 : 1;
+    }
+    return p->first < q->first ? -1 : (p->first > q->first ? 1 : 0);
+}
+
+static float or_sq3(float dx, float dy, float dz)
+{
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+
+static int or_vox_coord(float p, float lo, float inv)
+{
+    const float f = (p - lo) * inv;
+    /* static_cast<int> of NaN / out-of-range is what cvttss2si gives: INT_MIN, clamped to 0 */
+    const int v = (f != f || f >= 2147483648.F || f < -2147483648.F) ? INT32_MIN : (int)f;
+    return v < 0 ? 0 : (v > 254 ? 254 : v);
+}
+
+long or_filter_centervox(const float *pts, size_t n, float voxel_size, float max_range, const float *origin, const float *ws_min, const float *ws_max,
+                         uint32_t *out_idx, size_t cap)
+{
+    if (n == 0)
+    {
+        return 0;
+    }
+    float width = ws_max[0] - ws_min[0];
+    width = fmaxf(width, ws_max[1] - ws_min[1]);
+    width = fmaxf(width, ws_max[2] - ws_min[2]);
+    int grid_width = (int)ceilf(width / voxel_size);
+    grid_width = grid_width < 255 ? grid_width : 255;
+    const float inv = (float)grid_width / width;
+    const float estimate = powf(width / voxel_size, 3.0F) * 0.05F;
+    const size_t pool = estimate >= 32768.F ? 32768 : (size_t)estimate;
+    const float max_range_sq = max_range * max_range;
+    const size_t dim = 255;
+    uint32_t *keep = (uint32_t *)malloc(dim * dim * dim * sizeof(uint32_t));
+    uint32_t *first = (uint32_t *)malloc(dim * dim * dim * sizeof(uint32_t));
+    float *best = (float *)malloc(dim * dim * dim * sizeof(float));
+    memset(first, 0xff, dim * dim * dim * sizeof(uint32_t));
+    size_t allocated = 0;
+    long result = 0;
+    for (size_t i = 0; i < n && result == 0; ++i)
+    {
+        const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        if (or_sq3(x - origin[0], y - origin[1], z - origin[2]) >= max_range_sq)
+        {
+            continue;
+        }
+        if (x < ws_min[0] || x > ws_max[0] || y < ws_min[1] || y > ws_max[1] || z < ws_min[2] || z > ws_max[2])
+        {
+            continue;
+        }
+        const int vx = or_vox_coord(x, ws_min[0], inv), vy = or_vox_coord(y, ws_min[1], inv), vz = or_vox_coord(z, ws_min[2], inv);
+        const size_t id = ((size_t)vx * dim + vy) * dim + vz;
+        const float cx = fmaf((float)vx + 0.5F, voxel_size, ws_min[0]);
+        const float cy = fmaf((float)vy + 0.5F, voxel_size, ws_min[1]);
+        const float cz = fmaf((float)vz + 0.5F, voxel_size, ws_min[2]);
+        const float d = or_sq3(x - cx, y - cy, z - cz);
+        if (first[id] == 0xffffffffu)
+        {
+            if (allocated >= pool)
+            {
+                result = -1; /* allocate_voxel throws (filter_centervox.hh:130-133) */
+                break;
+            }
+            ++allocated;
+            first[id] = (uint32_t)i;
+            keep[id] = (uint32_t)i;
+            best[id] = d;
+        }
+        else if (d < best[id])
+        {
+            keep[id] = (uint32_t)i;
+            best[id] = d;
+        }
+    }
+    if (result == 0)
+    {
+        OrVoxRec *rec = (OrVoxRec *)malloc((allocated + 1) * sizeof(OrVoxRec));
+        uint32_t *fx = (uint32_t *)malloc(dim * sizeof(uint32_t));
+        uint32_t *fxy = (uint32_t *)malloc(dim * dim * sizeof(uint32_t));
+        memset(fx, 0xff, dim * sizeof(uint32_t));
+        memset(fxy, 0xff, dim * dim * sizeof(uint32_t));
+        size_t k = 0;
+        for (size_t v = 0; v < dim * dim * dim; ++v)
+        {
+            if (first[v] != 0xffffffffu)
+            {
+                const size_t vx = v / (dim * dim), vy = (v / dim) % dim;
+                rec[k].vox = (uint32_t)v, rec[k].keep = keep[v], rec[k].first = first[v];
+                fx[vx] = first[v] < fx[vx] ? first[v] : fx[vx];
+                fxy[vx * dim + vy] = first[v] < fxy[vx * dim + vy] ? first[v] : fxy[vx * dim + vy];
+                ++k;
+            }
+        }
+        for (size_t r = 0; r < k; ++r)
+        {
+            const size_t v = rec[r].vox, vx = v / (dim * dim), vy = (v / dim) % dim;
+            rec[r].first_x = fx[vx], rec[r].first_xy = fxy[vx * dim + vy];
+        }
+        qsort(rec, k, sizeof(OrVoxRec), or_voxrec_cmp);
+        for (size_t r = 0; r < k && r < cap; ++r)
+        {
+            out_idx[r] = rec[r].keep;
+        }
+        result = (long)k;
+        free(rec), free(fx), free(fxy);
+    }
+    free(keep), free(first), free(best);
+    return result;
+}

@@ -93,6 +93,57 @@ def c4():
         L.vmv_dev_free(dq), L.vmv_dev_free(db)
 
 
+def filter_bench(n=4_000_000):
+    """CenterVox filter (reference collision/filter_centervox.hh): n surface points, 2 cm voxels, the
+    reference's MBM-style arguments (src/vamp/pointcloud.py:150-174).  Points per second with the cloud
+    resident in HBM and through the host-pointer call, beside the reference's own filter on one host core
+    (it is a sequential walk)."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    a = rng.uniform([0.3, -0.8, 0.38], [1.1, 0.8, 0.40], size=(n // 2, 3))
+    b = rng.uniform([-0.4, 0.75, 0.0], [0.6, 0.78, 1.4], size=(n // 4, 3))
+    c = rng.normal([0.7, 0.2, 0.55], [0.06, 0.06, 0.1], size=(n - n // 2 - n // 4, 3))
+    p = np.concatenate([a, b, c])
+    p = np.ascontiguousarray(p[rng.permutation(len(p))].astype(np.float32))
+    vox, rad = 0.02, 1.19
+    origin = np.array([0, 0, 0.333], np.float32)
+    lo, hi = origin - np.float32(rad), origin + np.float32(rad)
+    idx = np.zeros(32768, np.uint32)
+    k = C.c_size_t(0)
+    dp = L.vmv_dev_alloc(p.nbytes)
+    _lib.check(L.vmv_memcpy_h2d(dp, _lib.ptr(p), p.nbytes, None))
+    _lib.check(L.vmv_stream_sync(None))
+    args = (len(p), vox, rad, _lib.ptr(origin), _lib.ptr(lo), _lib.ptr(hi), _lib.ptr(idx), len(idx), C.byref(k))
+
+    def wall(fn, reps=10):
+        for _ in range(2):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    t_dev = wall(lambda: _lib.check(L.vmv_filter_pointcloud_centervox_dev(dp, *args)))
+    kept_dev = idx[: k.value].copy()
+    t_host = wall(lambda: _lib.check(L.vmv_filter_pointcloud_centervox(_lib.ptr(p), *args)))
+    assert np.array_equal(kept_dev, idx[: k.value])
+    out = {"workload": f"CenterVox filter: {len(p)} surface points, 2 cm voxels, {k.value} kept",
+           "resident": {"points_per_s": len(p) / t_dev, "ms": t_dev * 1e3, "GBps_algorithmic": len(p) * 12 / t_dev / 1e9,
+                        "note": "call with device-resident points: table reset + insert + compact + D2H of the kept records + host ordering"},
+           "e2e": {"points_per_s": len(p) / t_host, "ms": t_host * 1e3, "h2d_bytes": int(p.nbytes)}}
+    from oracle import pyoracle as po
+    if po.ref_available() and hasattr(po.ref_lib(), "ref_filter_centervox"):
+        ns = min(len(p), 1_000_000)
+        t0 = time.perf_counter()
+        want = po.ref_filter_centervox(p[:ns], vox, rad, origin, lo, hi)
+        sec = time.perf_counter() - t0
+        got = vmv.filter_pointcloud_centervox(p[:ns], vox, rad, origin, lo, hi)
+        out["cpu_reference"] = {"points_per_s": ns / sec, "cores": 1, "sample": f"first {ns} points (incl. the harness's copy into std::vector<Point>)"}
+        out["identical_to_reference_on_sample"] = bool(np.array_equal(got, want))
+    print(json.dumps(out), flush=True)
+    L.vmv_dev_free(dp)
+
+
 def c5_inputs(n_edges):
     R = vmv.panda
     env = scenes.build_product_env(scenes.table_shelf_scene())
@@ -221,6 +272,8 @@ if __name__ == "__main__":
     if "robots" in what:
         robots()
     n_edges = int(sys.argv[sys.argv.index("--edges") + 1]) if "--edges" in sys.argv else 100_000_000
+    if "filter" in what:
+        filter_bench()
     if "c4" in what:
         c4()
     if "c5" in what:

@@ -12,6 +12,7 @@ from .shapes import Attachment, Cuboid, Cylinder, HeightField, Sphere, make_heig
 from .environment import Environment  # noqa: F401
 from .robot import Robot  # noqa: F401
 from .problems import problem_dict_to_vamp  # noqa: F401
+from .pointcloud import filter_pointcloud, filter_pointcloud_centervox  # noqa: F401
 from .simplify import (  # noqa: F401  (vamp.SimplifySettings / vamp.SimplifyRoutine, bindings/settings.cc)
     BSplineSettings, PerturbSettings, ReduceSettings, ShortcutSettings, SimplifySettings, StreamRNG,
 )

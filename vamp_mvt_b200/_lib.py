@@ -62,6 +62,8 @@ def lib():
         L.vmv_filter_points_dev.argtypes = [i32, vp, vp, vp, sz, f32, vp, vp]
         L.vmv_filter_self_from_pointcloud.argtypes = [i32, vp, vp, vp, sz, f32, vp]
         L.vmv_debug.argtypes = [i32, vp, vp, vp, sz, vp, vp, sz, vp]
+        L.vmv_filter_pointcloud_centervox.argtypes = [vp, sz, f32, f32, vp, vp, vp, vp, sz, vp]
+        L.vmv_filter_pointcloud_centervox_dev.argtypes = [vp, sz, f32, f32, vp, vp, vp, vp, sz, vp]
         L.vmv_halton_fill_dev.argtypes = [i32, C.c_uint64, sz, vp, vp]
         L.vmv_validate_halton.argtypes = [i32, vp, C.c_uint64, sz, vp, vp]
         L.vmv_halton_exact_limit.restype = C.c_uint64

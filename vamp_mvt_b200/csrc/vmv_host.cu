@@ -21,6 +21,7 @@
 #include "vmv_kernels_v2.cuh"
 #include "vmv_kernels_v4.cuh"
 #include "vmv_halton.cuh"
+#include "vmv_filter.cuh"
 
 #include "gen/panda_fk.cuh"
 #include "gen/ur5_fk.cuh"
@@ -2694,6 +2695,193 @@ extern "C"
         VMV_CUDA(cudaGetLastError());
         return VMV_OK;
     }
+    }
+
+    // ---- CenterVox pointcloud filter (vmv_filter.cuh; reference collision/filter_centervox.hh) -------
+    namespace
+    {
+        struct FilterPool
+        {
+            std::mutex mutex;
+            cudaStream_t stream = nullptr;
+            void *buf[4] = {nullptr, nullptr, nullptr, nullptr};  // points, keys, first indices, records + count
+            size_t cap[4] = {0, 0, 0, 0};
+
+            int ensure(int which, size_t bytes)
+            {
+                if (cap[which] < bytes)
+                {
+                    if (buf[which])
+                    {
+                        VMV_CUDA(cudaFree(buf[which]));
+                        buf[which] = nullptr;
+                        cap[which] = 0;
+                    }
+                    VMV_CUDA(cudaMalloc(&buf[which], bytes));
+                    cap[which] = bytes;
+                }
+                return VMV_OK;
+            }
+        };
+        FilterPool g_filter_pools[kMaxDevices];
+        constexpr uint32_t kCenterVoxPoolMax = 32768;  // filter_centervox.hh:118
+
+        int centervox_run(const float *pts, bool pts_on_device, size_t n, float voxel_size, float max_range, const float *origin, const float *ws_min,
+                          const float *ws_max, uint32_t *out_indices, size_t cap_out, size_t *n_out)
+        {
+            if (n_out == nullptr || origin == nullptr || ws_min == nullptr || ws_max == nullptr || (n > 0 && pts == nullptr) ||
+                (cap_out > 0 && out_indices == nullptr))
+            {
+                return fail(VMV_ERR_ARG, "vmv_filter_pointcloud_centervox: bad argument");
+            }
+            *n_out = 0;
+            if (n == 0)
+            {
+                return VMV_OK;  // filter_centervox.hh:312-314
+            }
+            if (n >= 0xffffffffull)
+            {
+                return fail(VMV_ERR_LIMIT, "vmv_filter_pointcloud_centervox: more than 2^32 - 2 points");
+            }
+            // CenterSelectiveVoxelFilter's constructor (filter_centervox.hh:95-121), in its arithmetic
+            const float width = std::max({ws_max[0] - ws_min[0], ws_max[1] - ws_min[1], ws_max[2] - ws_min[2]});
+            if (!(voxel_size > 0.F) || !(width > 0.F) || !std::isfinite(width / voxel_size))
+            {
+                return fail(VMV_ERR_ARG, "vmv_filter_pointcloud_centervox: voxel size and workspace must be positive and finite");
+            }
+            const int grid_width = std::min(255, static_cast<int>(std::ceil(width / voxel_size)));
+            vmv::CenterVoxParams P{};
+            for (int k = 0; k < 3; ++k)
+            {
+                P.origin[k] = origin[k], P.ws_min[k] = ws_min[k], P.ws_max[k] = ws_max[k];
+            }
+            P.voxel_size = voxel_size;
+            P.inv_scale = grid_width / width;
+            P.max_range_sq = max_range * max_range;
+            P.dim = std::min(grid_width + 1, 255);
+            const float per_dim = width / voxel_size;
+            const float estimate = std::pow(per_dim, 3.0F) * 0.05F;
+            const size_t pool_size = estimate >= static_cast<float>(kCenterVoxPoolMax) ? kCenterVoxPoolMax : static_cast<size_t>(estimate);
+
+            int device = 0;
+            VMV_CUDA(cudaGetDevice(&device));
+            FilterPool &pool = g_filter_pools[device % kMaxDevices];
+            std::lock_guard<std::mutex> lock(pool.mutex);
+            if (pool.stream == nullptr)
+            {
+                VMV_CUDA(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
+            }
+            cudaStream_t st = pool.stream;
+            const size_t n_vox = static_cast<size_t>(P.dim) * P.dim * P.dim;
+            const uint32_t rec_cap = kCenterVoxPoolMax;
+            int rc = VMV_OK;
+            if (!pts_on_device)
+            {
+                rc = pool.ensure(0, n * 3 * sizeof(float));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(1, n_vox * sizeof(unsigned long long));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(2, n_vox * sizeof(uint32_t));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(3, (3 * static_cast<size_t>(rec_cap) + 4) * sizeof(uint32_t));
+            }
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            const float *d_pts = pts;
+            if (!pts_on_device)
+            {
+                VMV_CUDA(cudaMemcpyAsync(pool.buf[0], pts, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+                d_pts = static_cast<const float *>(pool.buf[0]);
+            }
+            auto *d_best = static_cast<unsigned long long *>(pool.buf[1]);
+            auto *d_first = static_cast<uint32_t *>(pool.buf[2]);
+            auto *d_rec = static_cast<uint32_t *>(pool.buf[3]);
+            uint32_t *d_count = d_rec + 3 * static_cast<size_t>(rec_cap);
+            VMV_CUDA(cudaMemsetAsync(d_best, 0xff, n_vox * sizeof(unsigned long long), st));
+            VMV_CUDA(cudaMemsetAsync(d_first, 0xff, n_vox * sizeof(uint32_t), st));
+            VMV_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), st));
+            {
+                const size_t blocks = (n + 255) / 256;
+                const unsigned grid = static_cast<unsigned>(std::min<size_t>(blocks, static_cast<size_t>(sm_count()) * 8));
+                vmv::k_centervox_insert<<<grid, 256, 0, st>>>(P, d_pts, static_cast<uint32_t>(n), d_best, d_first);
+                g_launches++;
+                VMV_CUDA(cudaGetLastError());
+                vmv::k_centervox_compact<<<static_cast<unsigned>((n_vox + 255) / 256), 256, 0, st>>>(P, d_pts, d_best, d_first, n_vox, rec_cap, d_rec, d_count);
+                g_launches++;
+                VMV_CUDA(cudaGetLastError());
+            }
+            uint32_t count = 0;
+            VMV_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            VMV_CUDA(cudaStreamSynchronize(st));
+            if (count > pool_size)
+            {
+                // the reference throws std::runtime_error("Voxel pool exhausted") (filter_centervox.hh:130-133)
+                return fail(VMV_ERR_LIMIT, "vmv_filter_pointcloud_centervox: voxel pool exhausted (the reference throws here): more occupied voxels "
+                                           "than min((width / voxel_size)^3 * 0.05, 32768)");
+            }
+            std::vector<uint32_t> rec(3 * static_cast<size_t>(count));
+            if (count > 0)
+            {
+                VMV_CUDA(cudaMemcpy(rec.data(), d_rec, rec.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            }
+            // extract_points (filter_centervox.hh:167-184) walks the sparse tables in creation order: x slabs by
+            // their first point, (x, y) columns inside a slab by theirs, voxels inside a column by theirs
+            const uint32_t dim = static_cast<uint32_t>(P.dim);
+            std::vector<uint32_t> first_x(dim, 0xffffffffu), first_xy(static_cast<size_t>(dim) * dim, 0xffffffffu);
+            for (uint32_t k = 0; k < count; ++k)
+            {
+                const uint32_t v = rec[3 * k], f = rec[3 * k + 2];
+                const uint32_t vx = v / (dim * dim), vy = (v / dim) % dim;
+                first_x[vx] = std::min(first_x[vx], f);
+                first_xy[vx * dim + vy] = std::min(first_xy[vx * dim + vy], f);
+            }
+            std::vector<uint32_t> order(count);
+            std::iota(order.begin(), order.end(), 0u);
+            std::sort(
+                order.begin(),
+                order.end(),
+                [&](uint32_t a, uint32_t b)
+                {
+                    const uint32_t va = rec[3 * a], vb = rec[3 * b];
+                    const uint32_t xa = va / (dim * dim), xb = vb / (dim * dim);
+                    if (xa != xb)
+                    {
+                        return first_x[xa] < first_x[xb];
+                    }
+                    const uint32_t ya = (va / dim) % dim, yb = (vb / dim) % dim;
+                    if (ya != yb)
+                    {
+                        return first_xy[xa * dim + ya] < first_xy[xb * dim + yb];
+                    }
+                    return rec[3 * a + 2] < rec[3 * b + 2];
+                });
+            *n_out = count;
+            for (uint32_t k = 0; k < count && k < cap_out; ++k)
+            {
+                out_indices[k] = rec[3 * order[k] + 1];
+            }
+            return VMV_OK;
+        }
+    }  // namespace
+
+    int vmv_filter_pointcloud_centervox(const float *points, size_t n, float voxel_size, float max_range, const float *origin, const float *workspace_min,
+                                        const float *workspace_max, uint32_t *kept_indices, size_t cap, size_t *n_kept)
+    {
+        return centervox_run(points, false, n, voxel_size, max_range, origin, workspace_min, workspace_max, kept_indices, cap, n_kept);
+    }
+
+    int vmv_filter_pointcloud_centervox_dev(const float *d_points, size_t n, float voxel_size, float max_range, const float *origin,
+                                            const float *workspace_min, const float *workspace_max, uint32_t *kept_indices, size_t cap, size_t *n_kept)
+    {
+        return centervox_run(d_points, true, n, voxel_size, max_range, origin, workspace_min, workspace_max, kept_indices, cap, n_kept);
     }
 
     // ---- Halton sampler on the device (vmv_halton.cuh; reference random/halton.hh) ------------------
