@@ -86,8 +86,17 @@ namespace vmv
             }
             // a NaN distance never wins `new < stored`; its key is above every real distance
             const uint32_t bits = (d == d) ? __float_as_uint(d) : 0xffffffffu;
-            atomicMin(best + id, (static_cast<unsigned long long>(bits) << 32) | i);
-            atomicMin(first + id, i);
+            // most points lose against what their voxel already holds: a plain (L2) read first keeps them off
+            // the atomic units (the value only ever decreases, so a stale read is merely conservative)
+            const unsigned long long key = (static_cast<unsigned long long>(bits) << 32) | i;
+            if (key < __ldcg(best + id))
+            {
+                atomicMin(best + id, key);
+            }
+            if (i < __ldcg(first + id))
+            {
+                atomicMin(first + id, i);
+            }
         }
     }
 

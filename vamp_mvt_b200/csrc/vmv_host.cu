@@ -2819,8 +2819,10 @@ extern "C"
                 VMV_CUDA(cudaGetLastError());
             }
             uint32_t count = 0;
+            const auto tm0 = std::chrono::steady_clock::now();
             VMV_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             VMV_CUDA(cudaStreamSynchronize(st));
+            const auto tm1 = std::chrono::steady_clock::now();
             if (count > pool_size)
             {
                 // the reference throws std::runtime_error("Voxel pool exhausted") (filter_centervox.hh:130-133)
@@ -2833,40 +2835,91 @@ extern "C"
                 VMV_CUDA(cudaMemcpy(rec.data(), d_rec, rec.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
             }
             // extract_points (filter_centervox.hh:167-184) walks the sparse tables in creation order: x slabs by
-            // their first point, (x, y) columns inside a slab by theirs, voxels inside a column by theirs
+            // their first point, (x, y) columns inside a slab by theirs, voxels inside a column by theirs.
+            // Ranks of the <= 255 slabs and of the occupied columns, then one LSD radix sort of the voxels on
+            // (column rank, first point) -- comparison sorts with a decoding comparator cost milliseconds here.
             const uint32_t dim = static_cast<uint32_t>(P.dim);
-            std::vector<uint32_t> first_x(dim, 0xffffffffu), first_xy(static_cast<size_t>(dim) * dim, 0xffffffffu);
+            std::vector<uint32_t> first_x(dim, 0xffffffffu), first_xy(static_cast<size_t>(dim) * dim, 0xffffffffu), col_of(count);
             for (uint32_t k = 0; k < count; ++k)
             {
                 const uint32_t v = rec[3 * k], f = rec[3 * k + 2];
-                const uint32_t vx = v / (dim * dim), vy = (v / dim) % dim;
+                const uint32_t col = v / dim, vx = col / dim;
+                col_of[k] = col;
                 first_x[vx] = std::min(first_x[vx], f);
-                first_xy[vx * dim + vy] = std::min(first_xy[vx * dim + vy], f);
+                first_xy[col] = std::min(first_xy[col], f);
             }
-            std::vector<uint32_t> order(count);
-            std::iota(order.begin(), order.end(), 0u);
-            std::sort(
-                order.begin(),
-                order.end(),
-                [&](uint32_t a, uint32_t b)
+            std::vector<uint64_t> slabs, cols;
+            for (uint32_t vx = 0; vx < dim; ++vx)
+            {
+                if (first_x[vx] != 0xffffffffu)
                 {
-                    const uint32_t va = rec[3 * a], vb = rec[3 * b];
-                    const uint32_t xa = va / (dim * dim), xb = vb / (dim * dim);
-                    if (xa != xb)
-                    {
-                        return first_x[xa] < first_x[xb];
-                    }
-                    const uint32_t ya = (va / dim) % dim, yb = (vb / dim) % dim;
-                    if (ya != yb)
-                    {
-                        return first_xy[xa * dim + ya] < first_xy[xb * dim + yb];
-                    }
-                    return rec[3 * a + 2] < rec[3 * b + 2];
-                });
+                    slabs.push_back((static_cast<uint64_t>(first_x[vx]) << 32) | vx);
+                }
+            }
+            std::sort(slabs.begin(), slabs.end());
+            std::vector<uint32_t> rank_x(dim, 0), rank_col(static_cast<size_t>(dim) * dim, 0);
+            for (size_t r = 0; r < slabs.size(); ++r)
+            {
+                rank_x[slabs[r] & 0xffffffffu] = static_cast<uint32_t>(r);
+            }
+            std::vector<uint32_t> col_ids;
+            for (uint32_t c = 0; c < dim * dim; ++c)
+            {
+                if (first_xy[c] != 0xffffffffu)
+                {
+                    cols.push_back((static_cast<uint64_t>(rank_x[c / dim]) << 32) | first_xy[c]);
+                    col_ids.push_back(c);
+                }
+            }
+            {
+                // first points are distinct across columns: sort the keys, find each column by its first point
+                std::vector<uint64_t> sorted(cols);
+                std::sort(sorted.begin(), sorted.end());
+                for (size_t k = 0; k < cols.size(); ++k)
+                {
+                    rank_col[col_ids[k]] = static_cast<uint32_t>(std::lower_bound(sorted.begin(), sorted.end(), cols[k]) - sorted.begin());
+                }
+            }
+            struct Item
+            {
+                uint64_t key;
+                uint32_t keep;
+            };
+            std::vector<Item> items(count), scratch(count);
+            for (uint32_t k = 0; k < count; ++k)
+            {
+                items[k] = Item{(static_cast<uint64_t>(rank_col[col_of[k]]) << 32) | rec[3 * k + 2], rec[3 * k + 1]};
+            }
+            std::vector<uint32_t> hist(65537);
+            for (int pass = 0; pass < 3; ++pass)  // 48 significant bits: first point (32) + column rank (<= 16)
+            {
+                std::fill(hist.begin(), hist.end(), 0u);
+                const int shift = 16 * pass;
+                for (const Item &it : items)
+                {
+                    hist[((it.key >> shift) & 0xffffu) + 1]++;
+                }
+                for (int h = 0; h < 65536; ++h)
+                {
+                    hist[h + 1] += hist[h];
+                }
+                for (const Item &it : items)
+                {
+                    scratch[hist[(it.key >> shift) & 0xffffu]++] = it;
+                }
+                items.swap(scratch);
+            }
             *n_out = count;
             for (uint32_t k = 0; k < count && k < cap_out; ++k)
             {
-                out_indices[k] = rec[3 * order[k] + 1];
+                out_indices[k] = items[k].keep;
+            }
+            if (std::getenv("VMV_FILTER_TIMING"))
+            {
+                const auto tm2 = std::chrono::steady_clock::now();
+                std::fprintf(stderr, "centervox: device %.3f ms (wait), records + ordering %.3f ms, %u voxels, table %zu^3\n",
+                             std::chrono::duration<double, std::milli>(tm1 - tm0).count(), std::chrono::duration<double, std::milli>(tm2 - tm1).count(),
+                             count, static_cast<size_t>(P.dim));
             }
             return VMV_OK;
         }
