@@ -402,6 +402,18 @@ class Ref:
         assert n <= cap
         return out[:n].copy(), int(it.value)
 
+    def path_op(self, op: int, path, arg: int = 0):
+        """Path<Robot> members of the reference (planning/plan.hh): op 0 cost, 1 subdivide,
+        2 interpolate_to_resolution(arg), 3 interpolate_to_n_states(arg) -> (waypoints, cost)."""
+        self.lib.ref_path_op.restype = C.c_size_t
+        p = _f32(path).reshape(-1, self.dof)
+        cap = 1 << 16
+        out = np.zeros((cap, self.dof), np.float32)
+        cost = C.c_float(0)
+        n = self.lib.ref_path_op(self.id, C.c_int(op), _fp(p), C.c_size_t(len(p)), C.c_size_t(arg), _fp(out), C.c_size_t(cap), C.byref(cost))
+        assert n <= cap
+        return out[:n].copy(), float(cost.value)
+
     def halton(self, n: int, skip: int = 0) -> np.ndarray:
         out = np.zeros((n, self.dof), np.float32)
         self.lib.ref_halton(self.id, C.c_size_t(skip), C.c_size_t(n), _fp(out))

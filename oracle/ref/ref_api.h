@@ -86,6 +86,9 @@ extern "C"
      * of kept points (written to out_xyz up to cap) or (size_t)-1 where the reference throws */
     size_t ref_filter_centervox(const float *pts, size_t n, float voxel_size, float max_range, const float *origin, const float *ws_min,
                                 const float *ws_max, float *out_xyz, size_t cap);
+    /* vamp::planning::Path<Robot> (planning/plan.hh:12-153): op 0 cost, 1 subdivide, 2 interpolate_to_resolution(arg),
+     * 3 interpolate_to_n_states(arg); the resulting waypoints go to out (up to cap), its cost() to *cost */
+    size_t ref_path_op(int robot, int op, const float *path, size_t n, size_t arg, float *out, size_t cap, float *cost);
     /* vamp::rng::Halton<Robot>::next() (random/halton.hh:76-107): samples skip .. skip+n-1, [n][dim] */
     void ref_halton(int robot, size_t skip, size_t n, float *out);
     void ref_filter_points(int robot, void *env, const float *q, const float *pts, size_t n, float point_radius, uint8_t *keep);

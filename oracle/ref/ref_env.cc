@@ -292,6 +292,11 @@ extern "C"
         }
     }
 
+    size_t ref_path_op(int robot, int op, const float *path, size_t n, size_t arg, float *out, size_t cap, float *cost)
+    {
+        return vt(robot).path_op(op, path, n, arg, out, cap, cost);
+    }
+
     void ref_halton(int robot, size_t skip, size_t n, float *out)
     {
         vt(robot).halton(skip, n, out);

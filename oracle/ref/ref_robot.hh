@@ -58,6 +58,7 @@ namespace refh
             std::size_t,
             std::size_t *);
         void (*halton)(std::size_t, std::size_t, float *);
+        std::size_t (*path_op)(int, const float *, std::size_t, std::size_t, float *, std::size_t, float *);
     };
 
     template <typename Fn>
@@ -339,6 +340,43 @@ namespace refh
             return result.path.size();
         }
 
+        // vamp::planning::Path<Robot> members (planning/plan.hh:12-153): op 0 cost, 1 subdivide,
+        // 2 interpolate_to_resolution(arg), 3 interpolate_to_n_states(arg).  Returns the new size.
+        static std::size_t
+        path_op(int op, const float *path, std::size_t n, std::size_t arg, float *out, std::size_t cap, float *cost)
+        {
+            vamp::planning::Path<Robot> p;
+            for (std::size_t i = 0; i < n; ++i)
+            {
+                p.emplace_back(load(path + i * Robot::dimension));
+            }
+
+            if (op == 1)
+            {
+                p.subdivide();
+            }
+            else if (op == 2)
+            {
+                p.interpolate_to_resolution(arg);
+            }
+            else if (op == 3)
+            {
+                p.interpolate_to_n_states(arg);
+            }
+
+            *cost = p.cost();
+            for (std::size_t i = 0; i < p.size() and i < cap; ++i)
+            {
+                const auto a = p[i].to_array();
+                for (std::size_t j = 0; j < Robot::dimension; ++j)
+                {
+                    out[i * Robot::dimension + j] = a[j];
+                }
+            }
+
+            return p.size();
+        }
+
         // vamp::rng::Halton<Robot> (random/halton.hh): samples skip .. skip + n - 1 of a fresh sequence,
         // scaled to the joint ranges as next() returns them.
         static void halton(std::size_t skip, std::size_t n, float *out)
@@ -368,6 +406,7 @@ namespace refh
             &debug,
             &filter_points,
             &simplify,
-            &halton};
+            &halton,
+            &path_op};
     };
 }  // namespace refh

@@ -1312,11 +1312,19 @@ void or_validate_configs(const OrModel *m, const OrEnv *e, const float *q, size_
  * (vector/interface.hh:397-410, vector/avx.hh:441-452) */
 static float ref_l2_norm(const float *v, int dim)
 {
+    /* a second row (dim > 8: Baxter) is added as GCC contracts row0*row0 + row1*row1 in the reference build:
+     * the first product fused onto the rounded second one (read off the compiled reference) */
     float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < dim; ++i)
+    for (int k = 0; k < 8; ++k)
     {
-        const float sq = v[i] * v[i];
-        lane[i % 8] = (i < 8) ? sq : lane[i % 8] + sq;
+        if (k + 8 < dim)
+        {
+            lane[k] = fmaf(v[k], v[k], v[k + 8] * v[k + 8]);
+        }
+        else if (k < dim)
+        {
+            lane[k] = v[k] * v[k];
+        }
     }
     const float s0 = lane[4] + lane[0], s1 = lane[5] + lane[1], s2 = lane[6] + lane[2], s3 = lane[7] + lane[3];
     const float t0 = s0 + s2, t1 = s1 + s3;

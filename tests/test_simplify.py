@@ -145,6 +145,32 @@ def test_perturb_with_the_halton_sampler():
     assert np.array_equal(got.path.numpy(), want)
 
 
+@pytest.mark.parametrize("robot", ["panda", "ur5", "fetch", "baxter"])
+def test_path_members_match_reference(robot):
+    # Path::cost / subdivide / interpolate_to_resolution / interpolate_to_n_states (planning/plan.hh:12-153)
+    ref = po.Ref(robot)
+    if not hasattr(ref.lib, "ref_path_op"):
+        pytest.skip("oracle/_ref built without path_op")
+    R = getattr(vmv, robot)
+    for seed in range(4):
+        wp = scenes.random_configs(robot, 3 + 2 * seed, seed=40 + seed)
+        for op, arg in ((0, 0), (1, 0), (2, 4), (2, 32), (3, 25), (3, 3), (3, 200)):
+            want, want_cost = ref.path_op(op, wp, arg)
+            p = R.Path(wp)
+            if op == 1:
+                p.subdivide()
+            elif op == 2:
+                p.interpolate_to_resolution(arg)
+            elif op == 3:
+                p.interpolate_to_n_states(arg)
+            assert np.array_equal(p.numpy(), want), (robot, seed, op, arg)
+            assert np.float32(p.cost()) == np.float32(want_cost)
+    p = R.Path()
+    p.append(list(wp[0]))
+    p.insert(0, wp[1])
+    assert len(p) == 2 and p[0].dtype == np.float32 and np.array_equal(p[0], wp[1])
+
+
 def test_trivial_paths():
     ref = po.Ref("panda")
     renv = po.add_scene(po.RefEnv(), scenes.packed(scenes.sphere_cage()))

@@ -533,17 +533,21 @@ namespace vmv
     template <int DOF>
     __device__ __forceinline__ float ref_l2_norm(const float (&v)[DOF])
     {
+        static_assert(DOF <= 16, "two rows of 8 lanes");
+        // a second row (Baxter) is added the way GCC contracts row0*row0 + row1*row1 in the reference build:
+        // the first product fused onto the rounded second one (read off the compiled reference)
         float lane[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
         {
-            lane[k] = 0.F;
-        }
-#pragma unroll
-        for (int k = 0; k < DOF; ++k)
-        {
-            const float sq = __fmul_rn(v[k], v[k]);
-            lane[k % 8] = (k < 8) ? sq : __fadd_rn(lane[k % 8], sq);
+            if (k + 8 < DOF)
+            {
+                lane[k] = __fmaf_rn(v[k], v[k], __fmul_rn(v[k + 8 < DOF ? k + 8 : 0], v[k + 8 < DOF ? k + 8 : 0]));
+            }
+            else
+            {
+                lane[k] = (k < DOF) ? __fmul_rn(v[k < DOF ? k : 0], v[k < DOF ? k : 0]) : 0.F;
+            }
         }
         const float s0 = __fadd_rn(lane[4], lane[0]), s1 = __fadd_rn(lane[5], lane[1]);
         const float s2 = __fadd_rn(lane[6], lane[2]), s3 = __fadd_rn(lane[7], lane[3]);

@@ -101,12 +101,12 @@ def interpolate(a: np.ndarray, b: np.ndarray, alpha: float) -> np.ndarray:
 def distance(a: np.ndarray, b: np.ndarray) -> np.float32:
     """``a.distance(b)``: rows of 8 summed elementwise, then the AVX hsum tree, then sqrt."""
     d = np.asarray(b, np.float32) - np.asarray(a, np.float32)
-    sq = d * d
-    lane = np.zeros(8, np.float32)
-    for i in range(0, len(sq), 8):
-        row = np.zeros(8, np.float32)
-        row[: len(sq[i : i + 8])] = sq[i : i + 8]
-        lane = row if i == 0 else (lane + row).astype(np.float32)
+    r0, r1 = np.zeros(8, np.float32), np.zeros(8, np.float32)
+    r0[: min(len(d), 8)] = d[:8]
+    r1[: max(len(d) - 8, 0)] = d[8:16]
+    # a second row (Baxter) enters as GCC contracts row0*row0 + row1*row1 in the reference build: the first
+    # product fused onto the rounded second one
+    lane = (r0.astype(np.float64) ** 2 + (r1 * r1).astype(np.float32).astype(np.float64)).astype(np.float32)
     s = (lane[4:] + lane[:4]).astype(np.float32)
     return np.sqrt(np.float32(np.float32(s[0] + s[2]) + np.float32(s[1] + s[3])))
 
