@@ -1663,7 +1663,11 @@ namespace
         static constexpr int kCfgThreads = 640, kCfgBlocks = 1;  // <= 102 registers
 #endif
         static constexpr int kCfgQ2Rounds = 1;
+#ifdef VMV_V4_EDGE_MAXT
+        static constexpr int kEdgeThreads = VMV_V4_EDGE_MAXT, kEdgeBlocks = 2;
+#else
         static constexpr int kEdgeThreads = 256, kEdgeBlocks = 2;  // <= 128 registers
+#endif
         static constexpr int kEdgeQ2Rounds = 2;
     };
     template <>
@@ -1673,6 +1677,8 @@ namespace
         static constexpr int kCfgThreads = 256, kCfgBlocks = 1, kCfgQ2Rounds = 2;
         static constexpr int kEdgeThreads = 256, kEdgeBlocks = 1, kEdgeQ2Rounds = 2;
     };
+
+    int next_counter(cudaStream_t s, unsigned int *&out);
 
     template <typename R, typename MaskT>
     int launch_configs_v4(int robot, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
@@ -1700,7 +1706,13 @@ namespace
         {
             return rc;
         }
-        kernel<<<grid, warps * 32, smem, s>>>(rd, le, q, n, bits);
+        unsigned int *counter = nullptr;
+        rc = next_counter(s, counter);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        kernel<<<grid, warps * 32, smem, s>>>(rd, le, q, n, bits, counter);
         g_launches++;
         VMV_CUDA(cudaGetLastError());
         return VMV_OK;

@@ -629,7 +629,8 @@ namespace vmv
     // Persistent blocks of blockDim.x / 32 autonomous warps; tile t = states [32 t, 32 t + 32).
     template <typename R, typename MaskT, bool TAB, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB)
-        k_validate_configs_v4(RobotDev robot, const __grid_constant__ GridEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits)
+        k_validate_configs_v4(
+            RobotDev robot, const __grid_constant__ GridEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits, unsigned int *__restrict__ next_tile)
     {
         using M = typename R::Model;
         extern __shared__ __align__(128) unsigned char smem[];
@@ -638,7 +639,12 @@ namespace vmv
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
         const size_t n_tiles = (n + 31) / 32;
         const size_t stride = static_cast<size_t>(gridDim.x) * warps;
-        for (size_t tile = static_cast<size_t>(blockIdx.x) * warps + warp; tile < n_tiles; tile += stride)
+        // Every warp's first tile is its static one; further tiles are drawn from a device-wide counter
+        // (zeroed by the host before the launch).  With a static stride the 2^15 tiles of the headline batch
+        // are 11.07 per warp: most warps would wait for the ones that got a 12th, and tiles differ in cost
+        // (invalid states drop out early).
+        size_t tile = static_cast<size_t>(blockIdx.x) * warps + warp;
+        while (tile < n_tiles)
         {
             const size_t i = tile * 32 + lane;
             const bool has = i < n;
@@ -650,11 +656,30 @@ namespace vmv
             }
             // (loading the next tile's configurations ahead of the pass was measured: 2 % slower, the
             // seven extra live registers cost more than the exposed load latency)
+#ifndef VMV_V4_STATIC_TILES
+            // issued ahead of the pass and consumed after it, unless the kernel is at its register limit
+            // (Baxter: the ticket would be one more spilled value across the pass)
+            constexpr bool kEarly = MAXT * MINB >= 512;  // register cap <= 128
+            unsigned int ticket = 0u;
+            if (kEarly && lane == 0)
+            {
+                ticket = atomicAdd(next_tile, 1u);
+            }
+#endif
             const uint32_t invalid = v4_pass<R, MaskT, TAB, true>(X, env.grid, env.tab, cfg, has);
             if (lane == 0)
             {
                 bits[tile] = ~invalid;
             }
+#ifndef VMV_V4_STATIC_TILES
+            if (!kEarly && lane == 0)
+            {
+                ticket = atomicAdd(next_tile, 1u);
+            }
+            tile = stride + __shfl_sync(kFullWarp, ticket, 0);
+#else
+            tile += stride;
+#endif
         }
     }
 
