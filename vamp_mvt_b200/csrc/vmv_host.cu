@@ -1663,8 +1663,8 @@ namespace
         static constexpr int kCfgThreads = 640, kCfgBlocks = 1;  // <= 102 registers
 #endif
         static constexpr int kCfgQ2Rounds = 1;
-#ifdef VMV_V4_EDGE_MAXT
-        static constexpr int kEdgeThreads = VMV_V4_EDGE_MAXT, kEdgeBlocks = 2;
+#if defined(VMV_V4_EDGE_MAXT) && defined(VMV_V4_EDGE_MINB)
+        static constexpr int kEdgeThreads = VMV_V4_EDGE_MAXT, kEdgeBlocks = VMV_V4_EDGE_MINB;
 #else
         static constexpr int kEdgeThreads = 256, kEdgeBlocks = 2;  // <= 128 registers
 #endif
