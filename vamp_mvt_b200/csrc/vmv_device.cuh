@@ -110,37 +110,70 @@ namespace vmv
         return __ldg(g.cells + (static_cast<size_t>(iz) * g.ny + iy) * g.nx + ix) - off;
     }
 
-    // thread = voxel; the points stream through shared memory
+    // Table build.  Block = a brick of 8 x 8 x 4 voxels, thread = voxel.  The points arrive sorted along a
+    // Morton curve (host), in tiles of 1024 with their bounding boxes: a tile whose box is farther from every
+    // voxel of the brick than what that voxel has already found is skipped without being loaded (the first
+    // point of every tile seeds the bounds).  Without the cull this is |voxels| x |points| distance
+    // evaluations -- 1.3 s for 2^24 voxels and 10^5 points.
+    static constexpr int kCloudTile = 1024;
+
     __global__ void __launch_bounds__(256) k_build_cloud_grid(
-        const float4 *__restrict__ points, uint32_t n_points, float x0, float y0, float z0, float h, int nx, int ny, int nz, float *__restrict__ out)
+        const float4 *__restrict__ points,
+        uint32_t n_points,
+        const float4 *__restrict__ tile_boxes,  // per tile {lo.xyz, hi.x}, {hi.yz, -, -}
+        float x0,
+        float y0,
+        float z0,
+        float h,
+        int nx,
+        int ny,
+        int nz,
+        float *__restrict__ out)
     {
-        __shared__ float4 tile[1024];
-        const size_t n_vox = static_cast<size_t>(nx) * ny * nz;
-        const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-        const int ix = static_cast<int>(v % nx), iy = static_cast<int>((v / nx) % ny), iz = static_cast<int>(v / (static_cast<size_t>(nx) * ny));
+        __shared__ float4 tile[kCloudTile];
+        const int bxn = (nx + 7) / 8, byn = (ny + 7) / 8;
+        const int brick = blockIdx.x;
+        const int bx = brick % bxn, by = (brick / bxn) % byn, bz = brick / (bxn * byn);
+        const int t = threadIdx.x;
+        const int ix = bx * 8 + (t & 7), iy = by * 8 + ((t >> 3) & 7), iz = bz * 4 + (t >> 6);
         const float x = x0 + (ix + 0.5F) * h, y = y0 + (iy + 0.5F) * h, z = z0 + (iz + 0.5F) * h;
+        const uint32_t n_tiles = (n_points + kCloudTile - 1) / kCloudTile;
         float best = 3.0e38F;
-        for (uint32_t base = 0; base < n_points; base += 1024)
+        for (uint32_t k = 0; k < n_tiles; ++k)
         {
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x)
+            const float4 p = __ldg(points + static_cast<size_t>(k) * kCloudTile);
+            const float dx = p.x - x, dy = p.y - y, dz = p.z - z;
+            best = fminf(best, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        }
+        for (uint32_t k = 0; k < n_tiles; ++k)
+        {
+            const float4 b0 = __ldg(tile_boxes + 2 * k), b1 = __ldg(tile_boxes + 2 * k + 1);
+            const float ex = x - fminf(fmaxf(x, b0.x), b0.w), ey = y - fminf(fmaxf(y, b0.y), b1.x), ez = z - fminf(fmaxf(z, b0.z), b1.y);
+            // (0.999: the box distance must not exceed the distance to any point in it after rounding)
+            const bool need = (ex * ex + ey * ey + ez * ez) * 0.999F < best;
+            if (!__syncthreads_or(need))
+            {
+                continue;
+            }
+            const uint32_t base = k * kCloudTile;
+            for (uint32_t i = t; i < kCloudTile; i += blockDim.x)
             {
                 tile[i] = base + i < n_points ? __ldg(points + base + i) : make_float4(1e18F, 1e18F, 1e18F, 0.F);
             }
             __syncthreads();
 #pragma unroll 8
-            for (int i = 0; i < 1024; ++i)
+            for (int i = 0; i < kCloudTile; ++i)
             {
                 const float4 p = tile[i];
                 const float dx = p.x - x, dy = p.y - y, dz = p.z - z;
                 best = fminf(best, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
             }
         }
-        if (v < n_vox)
+        if (ix < nx && iy < ny && iz < nz)
         {
             // distance from the voxel centre, less the rounding slack (cloud_clearance subtracts the
             // query's own offset from the centre)
-            out[v] = sqrtf(best) * 0.99999F - 1e-4F;
+            out[(static_cast<size_t>(iz) * ny + iy) * nx + ix] = sqrtf(best) * 0.99999F - 1e-4F;
         }
     }
 

@@ -914,7 +914,7 @@ namespace
     // points' bounding box grown by kCloudReach; outside it every cloud point is farther than that.
     constexpr float kCloudReach = 0.5F;
 #ifndef VMV_CLOUD_MAX_VOXELS_LOG2
-#define VMV_CLOUD_MAX_VOXELS_LOG2 22
+#define VMV_CLOUD_MAX_VOXELS_LOG2 24
 #endif
     constexpr size_t kCloudMaxVoxels = size_t(1) << VMV_CLOUD_MAX_VOXELS_LOG2;
 
@@ -937,7 +937,10 @@ namespace
             }
             pts[i] = make_float4(p[0], p[1], p[2], 0.F);
         }
-        double h = 0.02;
+#ifndef VMV_CLOUD_VOXEL
+#define VMV_CLOUD_VOXEL 0.0125
+#endif
+        double h = VMV_CLOUD_VOXEL;
         int dim[3];
         while (true)
         {
@@ -954,9 +957,61 @@ namespace
             h *= 1.15;
         }
         const size_t n_vox = static_cast<size_t>(dim[0]) * dim[1] * dim[2];
-        float4 *d_pts = nullptr;
+        {
+            // Morton order over the points' bounding box (10 bits per axis), then tiles of kCloudTile points
+            // with their boxes: the build kernel skips tiles that cannot improve any voxel of a brick
+            auto spread = [](uint32_t v)
+            {
+                v &= 0x3ffu;
+                v = (v | (v << 16)) & 0x030000ffu;
+                v = (v | (v << 8)) & 0x0300f00fu;
+                v = (v | (v << 4)) & 0x030c30c3u;
+                v = (v | (v << 2)) & 0x09249249u;
+                return v;
+            };
+            std::vector<std::pair<uint32_t, uint32_t>> keys(n);
+            for (size_t i = 0; i < n; ++i)
+            {
+                uint32_t q[3];
+                for (int k = 0; k < 3; ++k)
+                {
+                    const float ext = std::max(hi[k] - lo[k], 1e-9F);
+                    q[k] = static_cast<uint32_t>(std::min(1023.F, std::max(0.F, (pts[i].x * (k == 0) + pts[i].y * (k == 1) + pts[i].z * (k == 2) - lo[k]) / ext * 1023.F)));
+                }
+                keys[i] = {spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), static_cast<uint32_t>(i)};
+            }
+            std::sort(keys.begin(), keys.end());
+            std::vector<float4> sorted(n);
+            for (size_t i = 0; i < n; ++i)
+            {
+                sorted[i] = pts[keys[i].second];
+            }
+            pts.swap(sorted);
+        }
+        const size_t n_tiles = (n + vmv::kCloudTile - 1) / vmv::kCloudTile;
+        std::vector<float4> boxes(2 * std::max<size_t>(n_tiles, 1));
+        for (size_t k = 0; k < n_tiles; ++k)
+        {
+            float blo[3] = {3e38F, 3e38F, 3e38F}, bhi[3] = {-3e38F, -3e38F, -3e38F};
+            for (size_t i = k * vmv::kCloudTile; i < std::min(n, (k + 1) * vmv::kCloudTile); ++i)
+            {
+                const float c[3] = {pts[i].x, pts[i].y, pts[i].z};
+                for (int a = 0; a < 3; ++a)
+                {
+                    blo[a] = std::min(blo[a], c[a]);
+                    bhi[a] = std::max(bhi[a], c[a]);
+                }
+            }
+            boxes[2 * k] = make_float4(blo[0], blo[1], blo[2], bhi[0]);
+            boxes[2 * k + 1] = make_float4(bhi[1], bhi[2], 0.F, 0.F);
+        }
+        float4 *d_pts = nullptr, *d_boxes = nullptr;
         float *d_cells = nullptr;
         int rc = upload(env, pts, d_pts);
+        if (rc == VMV_OK)
+        {
+            rc = upload(env, boxes, d_boxes);
+        }
         if (rc != VMV_OK)
         {
             return rc;
@@ -971,9 +1026,12 @@ namespace
         VMV_CUDA(cudaEventCreate(&e0));
         VMV_CUDA(cudaEventCreate(&e1));
         VMV_CUDA(cudaEventRecord(e0, nullptr));
-        vmv::k_build_cloud_grid<<<static_cast<unsigned>((n_vox + 255) / 256), 256>>>(
-            d_pts, static_cast<uint32_t>(n), lo[0] - kCloudReach, lo[1] - kCloudReach, lo[2] - kCloudReach, static_cast<float>(h), dim[0], dim[1],
-            dim[2], d_cells);
+        {
+            const size_t bricks = static_cast<size_t>((dim[0] + 7) / 8) * ((dim[1] + 7) / 8) * ((dim[2] + 3) / 4);
+            vmv::k_build_cloud_grid<<<static_cast<unsigned>(bricks), 256>>>(
+                d_pts, static_cast<uint32_t>(n), d_boxes, lo[0] - kCloudReach, lo[1] - kCloudReach, lo[2] - kCloudReach, static_cast<float>(h), dim[0],
+                dim[1], dim[2], d_cells);
+        }
         g_launches++;
         VMV_CUDA(cudaGetLastError());
         VMV_CUDA(cudaEventRecord(e1, nullptr));
