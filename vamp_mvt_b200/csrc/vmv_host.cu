@@ -1828,8 +1828,15 @@ namespace
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
-        // finer chunks for batches that would otherwise leave warps idle (vmv_kernels_v4.cuh)
-        const int per_chunk = n >= (size_t(1) << 17) ? 32 : (n >= (size_t(1) << 15) ? 16 : 8);
+        // finer chunks for batches that would otherwise leave warps idle (vmv_kernels_v4.cuh); measured: 2^18 edges
+        // 16 per chunk 224 M/s, 32 per chunk 217 M/s (3.5 chunks per warp leave a long tail); 9.5 M edges 4.2e8 / 4.4e8
+        static const int chunk_override = []
+        {
+            const char *e = std::getenv("VMV_EDGE_CHUNK");  // 8, 16 or 32 (tuning aid)
+            const int v = e ? std::atoi(e) : 0;
+            return (v == 8 || v == 16 || v == 32) ? v : 0;
+        }();
+        const int per_chunk = chunk_override ? chunk_override : (n >= (size_t(1) << 19) ? 32 : (n >= (size_t(1) << 15) ? 16 : 8));
         unsigned int *counter = nullptr;
         {
             int rc = next_counter(s, counter);
