@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Commit time of the C4 Fetch environment (dev tool): CAPT of ~10^5 points -- upload of the afford lists + the
+clearance grid build.  VMV_LIB selects the library build."""
 import sys, time, json
 sys.path.insert(0, ".")
 import numpy as np
