@@ -13,7 +13,21 @@ what = sys.argv[1] if len(sys.argv) > 1 else "configs"
 nlog2 = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 L = _lib.lib()
 robot = vmv.panda
-if what == "c4":
+if what == "hf":
+    # the any-environment kernel without a pointcloud: Fetch vs a 256x256 heightfield
+    R = vmv.fetch
+    rng = np.random.default_rng(1)
+    data = (0.15 * rng.random((256, 256)) ** 4).astype(np.float32)
+    env = vmv.Environment()
+    env.add_heightfield(vmv.make_heightfield([0, 0, -0.3], [0.02, 0.02, 1.0], [256, 256], data))
+    n = 1 << min(nlog2, 18)
+    q = scenes.random_configs("fetch", n, seed=0)
+    dq = L.vmv_dev_alloc(q.nbytes); db = L.vmv_dev_alloc((n + 31) // 32 * 4)
+    _lib.check(L.vmv_memcpy_h2d(dq, _lib.ptr(q), q.nbytes, None))
+    for _ in range(3):
+        _lib.check(L.vmv_validate_configs_dev(R.id, env.handle, dq, n, db, None))
+    _lib.check(L.vmv_stream_sync(None))
+elif what == "c4":
     # BASELINE config 4: Fetch vs CAPT of ~10^5 points + heightfield (the any-environment kernel)
     sys.argv = sys.argv[:1]
     from tools import bench_extra as be
