@@ -202,6 +202,11 @@ class _EnvBase:
             C.c_float(r_point),
         )
 
+    def add_raw_cloud(self, points, r_point):
+        """Oracle only: the raw points of a cloud for the clearance accounting (no tree build)."""
+        p = _f32(points).reshape(-1, 3)
+        getattr(self.lib, self.prefix + "env_add_raw_cloud")(self.h, _fp(p), C.c_size_t(len(p)), C.c_float(r_point))
+
     def attach(self, tf12, spheres):
         s = _f32(spheres).reshape(-1, 4)
         getattr(self.lib, self.prefix + "env_attach")(self.h, _fp(_f32(tf12)), _fp(s), C.c_size_t(len(s)))
@@ -342,6 +347,34 @@ class Oracle:
         return np.array(
             [self.lib.or_min_clearance(C.byref(self.c), env.h, _fp(q[i])) for i in range(len(q))]
         )
+
+    def clearance(self, env: OracleEnv, q):
+        """[n][2]: minimum signed clearance of each state (north_star's quantity) and the distance of its
+        nearest decision boundary (adds link bounding spheres vs cloud points; see or_clearance)."""
+        q = _f32(q).reshape(-1, self.dof)
+        out = np.zeros((len(q), 2), np.float64)
+        for i in range(len(q)):
+            self.lib.or_clearance(C.byref(self.c), env.h, _fp(q[i]), out[i].ctypes.data_as(C.c_void_p))
+        return out
+
+    def point_clearance(self, env: OracleEnv, q, points, point_radius: float):
+        """[n][2] for filter_self_from_pointcloud: each point's sphere vs the robot at q and the environment."""
+        p = _f32(points).reshape(-1, 3)
+        qq = _f32(q)
+        out = np.zeros((len(p), 2), np.float64)
+        for i in range(len(p)):
+            self.lib.or_point_clearance(C.byref(self.c), env.h, _fp(qq), _fp(p[i]), C.c_float(point_radius), out[i].ctypes.data_as(C.c_void_p))
+        return out
+
+    def edge_clearance(self, env: OracleEnv, a, b):
+        """[n][2] over the 8n rake states of each edge: signed clearance of the state closest to zero, and
+        the smallest nearest-decision-boundary distance."""
+        a = _f32(a).reshape(-1, self.dof)
+        b = _f32(b).reshape(-1, self.dof)
+        out = np.zeros((len(a), 2), np.float64)
+        for i in range(len(a)):
+            self.lib.or_edge_clearance(C.byref(self.c), env.h, _fp(a[i]), _fp(b[i]), out[i].ctypes.data_as(C.c_void_p))
+        return out
 
     def debug(self, env: OracleEnv, q):
         eh = np.zeros((65536, 2), np.int32)

@@ -79,6 +79,41 @@ def test_shape_factories():
     assert (hf.xs, hf.ys, hf.zs) == (2.0, 4.0, 0.5)
 
 
+def test_shape_factories_match_the_reference_factory_golden():
+    """tests/golden/factory.npz (tools/make_factory_golden.py): the fields the reference's own factory.hh stores
+    for Cuboid(center, euler, half), Cylinder(center, euler, r, length), Cylinder(p1, p2, r) and make_heightfield --
+    factory.hh compiled in place (oracle/ref/ref_factory.cc) -- plus euler_matrix(rho, theta, phi, 'sxyz') of the
+    reference's vendored transformations.py.  Conventions must agree exactly (which axis is which column, end point
+    order, inverse scales, the z-aligned predicates bindings/environment.cc:124,138 read); values to a few ulp
+    (libm vs numpy sin/cos, and the FMA contraction the reference's flags leave to the compiler)."""
+    d = np.load(REPO / "tests" / "golden" / "factory.npz")
+    ulp1 = float(np.spacing(np.float32(1)))
+    for i in range(len(d["centre"])):
+        c, e = d["centre"][i], d["euler"][i]
+        box = vmv.Cuboid(c, e, d["half"][i]).packed()
+        want = d["cuboid"][i]
+        assert np.array_equal(box[:3], want[:3]) and np.array_equal(box[12:], want[12:])
+        assert np.abs(box[3:12] - want[3:12]).max() <= 4 * ulp1, i
+        assert (box[11] == 1.0) == (want[11] == 1.0)  # z-aligned classification of the cuboid
+        axes = np.stack([box[3:6], box[6:9], box[9:12]], axis=1)  # columns
+        assert np.abs(axes - d["euler_matrix"][i]).max() < 1e-6, i
+        cyl, want = vmv.Cylinder(c, e, d["radius"][i], d["length"][i]).packed(), d["cylinder_center"][i]
+        assert np.abs(cyl[:6] - want[:6]).max() <= 8 * ulp1 * max(1.0, float(np.abs(want[:6]).max())), i
+        assert cyl[6] == want[6]
+        assert ((cyl[3] == 0) and (cyl[4] == 0)) == ((want[3] == 0) and (want[4] == 0))  # z-aligned capsule
+        # rdv is float(1.0 / |v|^2) of the stored v on both sides (factory.hh:113-124)
+        for k in (cyl, want):
+            v = k[3:6].astype(np.float64)
+            assert k[7] == pytest.approx(1.0 / float(v @ v), rel=1e-6)
+        # end point order: p1 = centre + R (0, 0, +length/2)
+        assert np.abs((cyl[:3] + 0.5 * cyl[3:6]) - c).max() < 1e-6
+        assert float(cyl[3:6] @ d["euler_matrix"][i][:, 2]) == pytest.approx(-float(d["length"][i]), rel=1e-5)
+        cyl, want = vmv.Cylinder(c, d["p2"][i], d["radius"][i]).packed(), d["cylinder_endpoints"][i]
+        assert np.array_equal(cyl[:7], want[:7]) and cyl[7] == pytest.approx(want[7], rel=4 * ulp1), i
+        hf = vmv.make_heightfield(c, d["scale"][i], [2, 2], np.zeros(4)).packed()
+        assert np.array_equal(hf, d["heightfield"][i])
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_environment_packing_matches_oracle(seed):
     sc = scenes.random_scene(seed, n_spheres=6, n_cuboids=9, n_capsules=7)

@@ -50,6 +50,26 @@ def _quat_rotate(q, v):
     )
 
 
+def _quat_matrix(q):
+    """Eigen QuaternionBase::toRotationMatrix in float32 (the linear part of ``Translation3f * q``,
+    factory.hh:170-174)."""
+    w, x, y, z = q
+    two = F(2)
+    tx, ty, tz = F(two * x), F(two * y), F(two * z)
+    twx, twy, twz = F(tx * w), F(ty * w), F(tz * w)
+    txx, txy, txz = F(tx * x), F(ty * x), F(tz * x)
+    tyy, tyz, tzz = F(ty * y), F(tz * y), F(tz * z)
+    one = F(1)
+    return np.array(
+        [
+            [F(one - F(tyy + tzz)), F(txy - twz), F(txz + twy)],
+            [F(txy + twz), F(one - F(txx + tzz)), F(tyz - twx)],
+            [F(txz - twy), F(tyz + twx), F(one - F(txx + tyy))],
+        ],
+        dtype=F,
+    )
+
+
 def euler_xyz_quaternion(rho, theta, phi):
     """AngleAxis(phi,Z) * AngleAxis(theta,Y) * AngleAxis(rho,X) as a float32 quaternion (w,x,y,z)."""
     rho, theta, phi = F(rho), F(theta), F(phi)
@@ -127,11 +147,13 @@ class Cylinder:
             p2 = np.array(b, dtype=F)
             radius = c
         else:
-            q = euler_xyz_quaternion(*b)
+            # factory.hh:166-177: tf = Translation(center) * (AngleAxis products), an isometry whose linear part
+            # is the quaternion's rotation MATRIX; the end points are tf * (0, 0, +-length/2)
+            R = _quat_matrix(euler_xyz_quaternion(*b))
             centre = np.array(a, dtype=F)
             half = F(F(length) / F(2))
-            p1 = (_quat_rotate(q, (0, 0, half)) + centre).astype(F)
-            p2 = (_quat_rotate(q, (0, 0, -half)) + centre).astype(F)
+            p1 = np.array([F(F(R[i, 2] * half) + centre[i]) for i in range(3)], dtype=F)
+            p2 = np.array([F(F(R[i, 2] * F(-half)) + centre[i]) for i in range(3)], dtype=F)
             radius = c
         v = (p2 - p1).astype(F)
         dot = F(F(v[0] * v[0]) + F(v[1] * v[1]) + F(v[2] * v[2]))
