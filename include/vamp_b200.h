@@ -87,7 +87,9 @@ extern "C"
     int vmv_env_attach(vmv_env *env, const float *tf12, const float *spheres_xyzr, size_t n);
     int vmv_env_detach(vmv_env *env);
     /* sort + classify + pack + upload.  Adders may be called again afterwards; the next commit
-     * re-packs.  Compute calls require a committed environment. */
+     * re-packs.  Compute calls require a committed environment.  A commit after attach / detach alone
+     * rewrites a few hundred bytes and keeps every device table (attach / detach are O(1) in the
+     * reference: std::optional<Attachment>, collision/environment.hh:28). */
     int vmv_env_commit(vmv_env *env);
     /* introspection used by the tests: kind 0 spheres, 1 capsules, 2 z-capsules, 3 cuboids,
      * 4 z-cuboids; writes the stored fields followed by min_distance, in sorted order; returns count */
@@ -162,6 +164,46 @@ extern "C"
      * order they were added -- and self_hits (sphere, sphere) pairs.  Counts are returned through
      * n_env / n_self even when they exceed the capacities. */
     int vmv_debug(int robot, const vmv_env *env, const float *q, int32_t *env_hits, size_t cap_env, size_t *n_env, int32_t *self_hits, size_t cap_self, size_t *n_self);
+
+    /* --- multi-GPU: one process per GPU of one node --------------------------------------------------
+     * The reference is single-process and has no counterpart: a batch shards by unit, every rank
+     * validates the contiguous word-aligned range it owns against its replica of the environment, and the verdict
+     * words are gathered only where the planner needs the global mask (prm.hh:136-146 consumes one bit per
+     * candidate edge).  NCCL (loaded at run time; never needed on one GPU) carries the plain collectives; the
+     * gather itself can be fused into the validation kernels over CUDA-IPC windows (below).
+     *
+     * vmv_comm_unique_id   rank 0: 128 bytes to hand to every rank by any out-of-band means (ncclGetUniqueId)
+     * vmv_comm_create      collective: rank `rank` of `world` (<= 8) on the CURRENT device
+     * vmv_env_broadcast    collective: `root`'s environment (everything added so far, built CAPT / MVT tables
+     *                      included -- no rank rebuilds them) replaces `env` on the other ranks; committed on return
+     * vmv_allgather_bits   plain ncclAllGather of words_per_rank verdict words per rank into d_global
+     *                      [world][words_per_rank], asynchronous on `stream` */
+    typedef struct vmv_comm vmv_comm;
+    int vmv_comm_unique_id(unsigned char *id128);
+    int vmv_comm_create(vmv_comm **comm, const unsigned char *id128, int rank, int world);
+    void vmv_comm_destroy(vmv_comm *comm);
+    int vmv_comm_rank(const vmv_comm *comm);
+    int vmv_comm_world(const vmv_comm *comm);
+    int vmv_env_broadcast(vmv_comm *comm, vmv_env *env, int root);
+    int vmv_allgather_bits(vmv_comm *comm, const uint32_t *d_local_words, size_t words_per_rank, uint32_t *d_global_words, void *stream);
+
+    /* Gather fused into the validation kernels.  vmv_comm_window (collective, once) gives every rank a window
+     * of `slots` (<= 4) global masks [world][stride] words (stride = words_per_rank rounded up to 4, see
+     * vmv_comm_window_stride) and maps all windows into every process (CUDA IPC over NVLink / NVSwitch).
+     * vmv_validate_*_gather_dev (collective per slot: every rank calls it for the same slot the same number of
+     * times) validates this rank's shard and stores each verdict word, as it is produced, into row `rank` of
+     * slot `slot` of EVERY rank's window -- one predicated store instruction per 32 units, no collective
+     * kernel, no SM taken from the validation blocks; the last block publishes a sequence number behind a
+     * system-scope fence.  vmv_comm_wait enqueues, on `stream`, a wait until the latest gather into `slot` has
+     * landed from every rank; work enqueued behind it on that stream may read vmv_comm_window_ptr(comm, slot).
+     * A slot may be written again once every rank is done reading its previous contents (the caller's
+     * protocol; with two slots used alternately and a wait per step that holds by construction). */
+    int vmv_comm_window(vmv_comm *comm, size_t words_per_rank, int slots);
+    uint32_t *vmv_comm_window_ptr(vmv_comm *comm, int slot);
+    size_t vmv_comm_window_stride(const vmv_comm *comm);
+    int vmv_validate_configs_gather_dev(int robot, const vmv_env *env, vmv_comm *comm, int slot, const float *d_q, size_t n, void *stream);
+    int vmv_validate_edges_indexed_gather_dev(int robot, const vmv_env *env, vmv_comm *comm, int slot, const float *d_vertices, size_t n_vertices, const uint32_t *d_pairs, size_t n_edges, int resolution, void *stream);
+    int vmv_comm_wait(vmv_comm *comm, int slot, void *stream);
 
     /* --- device buffers for callers that do not bring their own allocator ---------------------- */
     void *vmv_dev_alloc(size_t bytes);

@@ -1,0 +1,134 @@
+"""The multi-GPU communicator of the C ABI (vmv_comm_*): world 1 on any GPU box, world 2 where the box has
+two GPUs.  Checked: the fused gather leaves in every rank's window exactly the verdict words a plain local
+launch produces (configs and indexed edges, every kernel generation), the plain ncclAllGather path agrees,
+and vmv_env_broadcast replicates an environment (primitives + CAPT + heightfield + attachment)."""
+import os
+import socket
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REPO = Path(__file__).resolve().parents[1]
+pytestmark = pytest.mark.gpu
+
+
+def _scene_env(vmv, scenes, with_cloud: bool):
+    env = scenes.build_product_env(scenes.table_shelf_scene())
+    if with_cloud:
+        rng = np.random.default_rng(3)
+        pts = rng.uniform([0.3, -0.6, 0.0], [0.9, 0.6, 0.4], size=(3000, 3)).astype(np.float32)
+        env.add_capt_pointcloud(pts, 0.012, 0.08, vmv.POINT_RADIUS)
+        data = (0.05 * rng.random((32, 32))).astype(np.float32)
+        env.add_heightfield(vmv.make_heightfield([0, 0, -0.3], [0.1, 0.1, 1.0], [32, 32], data))
+        att = vmv.Attachment(np.eye(4, dtype=np.float32))
+        att.add_spheres([vmv.Sphere([0, 0, 0.05], 0.03)])
+        env.attach(att)
+    return env
+
+
+def _rank_main(rank: int, world: int, uid_path: str, out_dir: str):
+    sys.path.insert(0, str(REPO))
+    import vamp_mvt_b200 as vmv
+    from tests import scenes
+    from vamp_mvt_b200 import _lib, comm, sharding
+
+    L = _lib.lib()
+    _lib.check(L.vmv_set_device(rank))
+    if rank == 0:
+        Path(uid_path + ".tmp").write_bytes(comm.unique_id())
+        os.replace(uid_path + ".tmp", uid_path)
+    else:
+        for _ in range(600):
+            if os.path.exists(uid_path):
+                break
+            time.sleep(0.05)
+    C = comm.Communicator(Path(uid_path).read_bytes(), rank, world)
+    results = {}
+    for with_cloud in (False, True):
+        # rank 0 owns the environment; the others receive it through the library
+        env = _scene_env(vmv, scenes, with_cloud) if rank == 0 else vmv.Environment()
+        C.broadcast_environment(env, root=0)
+        n = 50_000 + 37
+        q = scenes.random_configs("panda", n, seed=11)  # every rank generates the same global batch
+        lo, hi = sharding.shard_bounds(n, rank, world)
+        if with_cloud is False:
+            C.window(sharding.words_per_rank(n, world), slots=2)
+        dq = L.vmv_dev_alloc(q.nbytes)
+        _lib.check(L.vmv_memcpy_h2d(dq, _lib.ptr(q), q.nbytes, None))
+        _lib.check(L.vmv_stream_sync(None))
+        shard_ptr = dq + lo * 7 * 4
+        for path in ((0, 1, 2, 3) if not with_cloud else (0,)):
+            L.vmv_force_kernel_path(path)
+            try:
+                C.validate_configs_gather(vmv.panda.id, env.handle, path % 2, shard_ptr, hi - lo)
+                C.wait(path % 2)
+            finally:
+                L.vmv_force_kernel_path(0)
+            sizes = [sharding.shard_bounds(n, r, world)[1] - sharding.shard_bounds(n, r, world)[0] for r in range(world)]
+            results[f"configs_cloud{int(with_cloud)}_path{path}"] = C.read_window(path % 2, sizes)
+        results[f"configs_cloud{int(with_cloud)}_local"] = vmv.panda.validate_batch(q, env)
+        if not with_cloud:
+            # indexed edges through the fused gather and through the plain NCCL all-gather
+            V = scenes.random_configs("panda", 3000, seed=12)
+            rng = np.random.default_rng(12)
+            ne = 20_000 + 5
+            pairs = rng.integers(0, len(V), size=(ne, 2)).astype(np.uint32)
+            elo, ehi = sharding.shard_bounds(ne, rank, world)
+            dV, dP = L.vmv_dev_alloc(V.nbytes), L.vmv_dev_alloc(pairs.nbytes)
+            _lib.check(L.vmv_memcpy_h2d(dV, _lib.ptr(V), V.nbytes, None))
+            _lib.check(L.vmv_memcpy_h2d(dP, _lib.ptr(pairs), pairs.nbytes, None))
+            _lib.check(L.vmv_stream_sync(None))
+            C.validate_edges_indexed_gather(vmv.panda.id, env.handle, 0, dV, len(V), dP + elo * 8, ehi - elo)
+            C.wait(0)
+            esizes = [sharding.shard_bounds(ne, r, world)[1] - sharding.shard_bounds(ne, r, world)[0] for r in range(world)]
+            results["edges_fused"] = C.read_window(0, esizes)
+            per = sharding.words_per_rank(ne, world)
+            dl, dg = L.vmv_dev_alloc(per * 4), L.vmv_dev_alloc(per * 4 * world)
+            _lib.check(L.vmv_validate_edges_indexed_dev(vmv.panda.id, env.handle, dV, len(V), dP + elo * 8, ehi - elo, 0, dl, None))
+            C.allgather_words(dl, per, dg)
+            words = np.zeros(per * world, np.uint32)
+            _lib.check(L.vmv_memcpy_d2h(_lib.ptr(words), dg, words.nbytes, None))
+            _lib.check(L.vmv_stream_sync(None))
+            results["edges_nccl"] = np.concatenate([_lib.unpack_bits(words[r * per : (r + 1) * per], esizes[r]) for r in range(world)])
+            results["edges_local"] = vmv.panda.validate_motion_batch(V[pairs[:, 0]], V[pairs[:, 1]], env)
+    np.savez(Path(out_dir) / f"rank{rank}.npz", **results)
+    C.close()
+
+
+def _check(out_dir, world):
+    for rank in range(world):
+        d = np.load(Path(out_dir) / f"rank{rank}.npz")
+        for cloud in (0, 1):
+            local = d[f"configs_cloud{cloud}_local"]
+            assert 0.05 < local.mean() < 0.95
+            for path in ((0, 1, 2, 3) if cloud == 0 else (0,)):
+                got = d[f"configs_cloud{cloud}_path{path}"]
+                # (kernel generations may differ from the automatic choice only inside the clearance band)
+                assert (got != local).sum() <= (0 if path in (0, 3) else 2), (rank, cloud, path)
+        assert np.array_equal(d["edges_fused"], d["edges_local"])
+        assert np.array_equal(d["edges_nccl"], d["edges_local"])
+
+
+def test_single_rank_communicator(tmp_path):
+    _rank_main(0, 1, str(tmp_path / "uid"), str(tmp_path))
+    _check(tmp_path, 1)
+
+
+def test_two_rank_fused_gather(tmp_path):
+    from vamp_mvt_b200 import _lib
+
+    if _lib.lib().vmv_device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, str(tmp_path / "uid"), str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    _check(tmp_path, 2)

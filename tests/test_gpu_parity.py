@@ -264,6 +264,36 @@ def test_capt_pointcloud_and_heightfield(robot):
     assert_edge_verdicts(O, oenv, a, b, R.validate_motion_batch(a, b, env), O.validate_edges(oenv, a, b), "capt+heightfield edges", has_cloud=True)
 
 
+@pytest.mark.parametrize("robot", ["fetch", "ur5"])
+def test_c4_baseline_size(robot):
+    """BASELINE config 4 at its full size: a CAPT over 100 k synthetic surface points plus a 256 x 256 heightfield
+    (tests/workloads.py), 2^18 configurations on the GPU; a 2^15 sample against the reference's own CAPT +
+    validate compiled in place (oracle/_ref), every mismatch classified by the oracle's clearance accounting on
+    the raw cloud; without oracle/_ref a 2^11 sample against the C oracle."""
+    from tests import workloads
+
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    env, pts, hf, _ = workloads.c4_environment(robot)
+    assert len(pts) > 90_000
+    n = 1 << 18
+    q = scenes.random_configs(robot, n, seed=0)
+    got = R.validate_batch(q, env)
+    assert 0.05 < got.mean() < 0.95
+    assert np.array_equal(got, R.validate_batch(q, env))  # idempotent
+    if po.ref_available():
+        ns = 1 << 15
+        renv = workloads.c4_checker_env(po.RefEnv, robot, pts, hf)
+        want = po.Ref(robot).validate_configs(renv, q[:ns], threads=po.host_threads())
+        raw = workloads.c4_checker_env(po.OracleEnv, robot, pts, hf, raw_only=True)
+        assert_verdicts(robot, O, raw, q[:ns], got[:ns], want, "C4 full size vs reference", has_cloud=True)
+    else:
+        ns = 1 << 11
+        oenv = workloads.c4_checker_env(po.OracleEnv, robot, pts, hf)
+        assert_verdicts(robot, O, oenv, q[:ns], got[:ns], O.validate_configs(oenv, q[:ns]), "C4 full size vs oracle", has_cloud=True)
+    # monotone: the heightfield and the cloud can only remove valid configurations
+    assert not np.any(got & ~R.validate_batch(q, vmv.Environment()))
+
+
 @pytest.mark.parametrize("robot", ["panda", "fetch", "ur5"])
 def test_mvt_pointcloud(robot):
     """Multi-level Voxel Table pointcloud (reference collision/mvt.hh) next to primitives: configs and
@@ -367,20 +397,34 @@ def test_uncommitted_environment_is_an_error():
     L.vmv_env_destroy(h)
 
 
-def test_debug_attribution():
-    env = scenes.build_product_env(scenes.table_shelf_scene())
-    O = po.Oracle("panda")
-    oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.table_shelf_scene()))
-    names = [shape.name for _, shape in scenes.table_shelf_scene()["order"]]
-    q = scenes.random_configs("panda", 60, seed=61)
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_debug_attribution(robot):
+    """Robot::fkcc_debug (robots/panda.hh:468-5224 and the other three): per-sphere object names and
+    self-colliding sphere pairs, against the oracle and -- where it travelled -- the compiled reference."""
+    sc = scenes.table_shelf_scene() if robot == "panda" else scenes.random_scene(4, keep_out=KEEP_OUT[robot])
+    env = scenes.build_product_env(sc)
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+    ref = po.Ref(robot) if po.ref_available() else None
+    renv = po.add_scene(po.RefEnv(), scenes.packed(sc)) if ref else None
+    names = [shape.name for _, shape in sc["order"]]
+    q = scenes.random_configs(robot, 40, seed=61)
+    n_env = n_self = 0
     for i in range(len(q)):
-        per_sphere, self_pairs = vmv.panda.debug(q[i], env)
-        eh, sh = O.debug(oenv, q[i])
-        want = [[] for _ in range(59)]
-        for s, obj in eh:
-            want[s].append(names[obj])
-        assert [sorted(x) for x in per_sphere] == [sorted(x) for x in want]
-        assert sorted(self_pairs) == sorted(map(tuple, sh.tolist()))
+        per_sphere, self_pairs = R.debug(q[i], env)
+        assert len(per_sphere) == R.n_spheres()
+        for checker, cenv in ((O, oenv), (ref, renv)):
+            if checker is None:
+                continue
+            eh, sh = checker.debug(cenv, q[i])
+            want = [[] for _ in range(R.n_spheres())]
+            for s, obj in eh:
+                want[s].append(names[obj])
+            assert [sorted(x) for x in per_sphere] == [sorted(x) for x in want], (robot, i)
+            assert sorted(self_pairs) == sorted(map(tuple, sh.tolist())), (robot, i)
+        n_env += sum(len(x) for x in per_sphere)
+        n_self += len(self_pairs)
+    assert n_env > 0 and (n_self > 0 or robot == "ur5")
 
 
 def _product_env_from_packed(scene):

@@ -79,6 +79,22 @@ def lib():
         L.vmv_stream_sync.argtypes = [vp]
         L.vmv_launch_count.restype = C.c_uint64
         L.vmv_force_kernel_path.argtypes = [i32]
+        L.vmv_comm_unique_id.argtypes = [vp]
+        L.vmv_comm_create.argtypes = [vp, vp, i32, i32]
+        L.vmv_comm_destroy.argtypes = [vp]
+        L.vmv_comm_destroy.restype = None
+        L.vmv_comm_rank.argtypes = [vp]
+        L.vmv_comm_world.argtypes = [vp]
+        L.vmv_env_broadcast.argtypes = [vp, vp, i32]
+        L.vmv_allgather_bits.argtypes = [vp, vp, sz, vp, vp]
+        L.vmv_comm_window.argtypes = [vp, sz, i32]
+        L.vmv_comm_window_ptr.restype = vp
+        L.vmv_comm_window_ptr.argtypes = [vp, i32]
+        L.vmv_comm_window_stride.restype = sz
+        L.vmv_comm_window_stride.argtypes = [vp]
+        L.vmv_validate_configs_gather_dev.argtypes = [i32, vp, vp, i32, vp, sz, vp]
+        L.vmv_validate_edges_indexed_gather_dev.argtypes = [i32, vp, vp, i32, vp, sz, vp, sz, i32, vp]
+        L.vmv_comm_wait.argtypes = [vp, i32, vp]
         _lib = L
     return _lib
 

@@ -117,7 +117,7 @@ namespace vmv
     // evaluations -- 1.3 s for 2^24 voxels and 10^5 points.
     static constexpr int kCloudTile = 1024;
 
-    __global__ void __launch_bounds__(256) k_build_cloud_grid(
+    static __global__ void __launch_bounds__(256) k_build_cloud_grid(
         const float4 *__restrict__ points,
         uint32_t n_points,
         const float4 *__restrict__ tile_boxes,  // per tile {lo.xyz, hi.x}, {hi.yz, -, -}
@@ -218,7 +218,7 @@ namespace vmv
 #ifdef VMV_SINCOS_INLINE
     __device__ __forceinline__ void sincos_f32(float x, float &s, float &c)
 #else
-    __device__ __noinline__ void sincos_f32(float x, float &s, float &c)
+    static __device__ __noinline__ void sincos_f32(float x, float &s, float &c)
 #endif
     {
         s = ref_sin(x);

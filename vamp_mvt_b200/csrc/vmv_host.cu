@@ -1,6 +1,7 @@
-// Host side of the C ABI (include/vamp_b200.h): environment construction, packing and upload,
-// robot registry, kernel launches.  No torch, no CPU fallback: every compute entry point needs a
-// CUDA device.
+// Host side of the C ABI (include/vamp_b200.h): environment construction, packing and upload, the
+// robot-independent kernels (voxel tables, clearance grid, Halton, CenterVox, gather), the multi-GPU
+// communicator, and the entry points, which dispatch to the per-robot launchers (vmv_robot_<name>.cu)
+// through vmvh::RobotOps.  No torch, no CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -11,35 +12,26 @@
 #include <cstring>
 #include <limits>
 #include <mutex>
+#include <new>
 #include <numeric>
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include <cuda_runtime.h>
 
-#include "../../include/vamp_b200.h"
-#include "vmv_kernels_v2.cuh"
-#include "vmv_kernels_v4.cuh"
+#include "vmv_internal.h"
+#include "vmv_comm.cuh"
 #include "vmv_halton.cuh"
 #include "vmv_filter.cuh"
 
-#include "gen/panda_fk.cuh"
-#include "gen/ur5_fk.cuh"
-#include "gen/fetch_fk.cuh"
-#include "gen/baxter_fk.cuh"
-#include "gen/panda_tables.h"
-#include "gen/ur5_tables.h"
-#include "gen/fetch_tables.h"
-#include "gen/baxter_tables.h"
-#include "gen/panda_pairtab.h"
-#include "gen/ur5_pairtab.h"
-#include "gen/fetch_pairtab.h"
-#include "gen/baxter_pairtab.h"
-
-namespace
+namespace vmvh
 {
     thread_local std::string g_error;
     std::atomic<uint64_t> g_launches{0};
+    std::mutex g_mutex;
+    std::atomic<int> g_force_path{0};
 
     int fail(int code, const std::string &msg)
     {
@@ -52,122 +44,31 @@ namespace
         return fail(VMV_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     }
 
-#define VMV_CUDA(call)                        \
-    do                                        \
-    {                                         \
-        cudaError_t e_ = (call);              \
-        if (e_ != cudaSuccess)                \
-        {                                     \
-            return cuda_fail(e_, #call);      \
-        }                                     \
-    } while (0)
-
-    // ---------------------------------------------------------------------------------------
-    // robots
-    // ---------------------------------------------------------------------------------------
-#define VMV_ROBOT(NAME)                                                               \
-    struct NAME##_robot                                                               \
-    {                                                                                 \
-        using Model = vmv::gen::NAME##_model;                                         \
-        using PairTab = vmv::gen::NAME##_pairtab_traits;                              \
-        template <typename Sink>                                                      \
-        static __device__ __forceinline__ void frames(const float (&q)[Model::kDof], Sink &s) \
-        {                                                                             \
-            vmv::gen::NAME##_frames(q, s);                                            \
-        }                                                                             \
-        template <typename F>                                                         \
-        static __device__ __forceinline__ void for_each_link(F &&f)                   \
-        {                                                                             \
-            VMV_##NAME##_LINKS_DISPATCH                                               \
-        }                                                                             \
-        template <typename F>                                                         \
-        static __device__ __forceinline__ void for_each_pair(F &&f)                   \
-        {                                                                             \
-            VMV_##NAME##_PAIRS_DISPATCH                                               \
-        }                                                                             \
-    };
-#define VMV_X_LINK(l, r, n, t, reach) f(vmv::IC<l>{}, r, n, t, reach);
-#define VMV_X_PAIR(p, a, b, inl) f(vmv::IC<p>{}, vmv::IC<a>{}, vmv::IC<b>{}, vmv::IC<inl>{});
-#define VMV_panda_LINKS_DISPATCH VMV_PANDA_LINKS(VMV_X_LINK)
-#define VMV_panda_PAIRS_DISPATCH VMV_PANDA_PAIRS(VMV_X_PAIR)
-#define VMV_ur5_LINKS_DISPATCH VMV_UR5_LINKS(VMV_X_LINK)
-#define VMV_ur5_PAIRS_DISPATCH VMV_UR5_PAIRS(VMV_X_PAIR)
-#define VMV_fetch_LINKS_DISPATCH VMV_FETCH_LINKS(VMV_X_LINK)
-#define VMV_fetch_PAIRS_DISPATCH VMV_FETCH_PAIRS(VMV_X_PAIR)
-#define VMV_baxter_LINKS_DISPATCH VMV_BAXTER_LINKS(VMV_X_LINK)
-#define VMV_baxter_PAIRS_DISPATCH VMV_BAXTER_PAIRS(VMV_X_PAIR)
-    VMV_ROBOT(panda)
-    VMV_ROBOT(ur5)
-    VMV_ROBOT(fetch)
-    VMV_ROBOT(baxter)
-#undef VMV_ROBOT
-
-#define VMV_X_MAXREACH(l, r, n, t, reach) m = (reach) > m ? (reach) : m;
-    float panda_max_reach()
+    const RobotOps &ops(int robot)
     {
-        float m = 0.F;
-        VMV_PANDA_LINKS(VMV_X_MAXREACH)
-        return m;
+        switch (robot)
+        {
+            case VMV_PANDA:
+                return ops_panda;
+            case VMV_UR5:
+                return ops_ur5;
+            case VMV_FETCH:
+                return ops_fetch;
+            default:
+                return ops_baxter;
+        }
     }
-    float ur5_max_reach()
-    {
-        float m = 0.F;
-        VMV_UR5_LINKS(VMV_X_MAXREACH)
-        return m;
-    }
-    float fetch_max_reach()
-    {
-        float m = 0.F;
-        VMV_FETCH_LINKS(VMV_X_MAXREACH)
-        return m;
-    }
-    float baxter_max_reach()
-    {
-        float m = 0.F;
-        VMV_BAXTER_LINKS(VMV_X_MAXREACH)
-        return m;
-    }
-#undef VMV_X_MAXREACH
+}  // namespace vmvh
 
-    struct RobotHost
+using namespace vmvh;
+
+namespace
+{
+    const RobotHost &robot_host(int robot)
     {
-        const char *name;
-        int dof, n_spheres, n_links, n_pairs, n_tasks, resolution, n_attach_links, ee_body;
-        const float *lower, *range;
-        const vmv::SphereTask *tasks;
-        const vmv::LinkInfo *links;
-        const vmv::LinkPair *pairs;
-        const int *attach_links;
-        const float *ee_tf;
-        const vmv::PairInfo *pair_info;
-        const vmv::SpherePair *pair_lists;
-        int n_pair_lists;
-        float max_reach;  // farthest any link's bounding sphere extends from the world origin
-        const vmv::PairGroupHost *pair_groups;  // two-joint verdict tables (vmv_pairtab.cuh)
-        int n_pair_groups;
-        const int *pair_group_pairs;
-        const int *pair_never;
-        int n_pair_never;
-        bool inline_covered;
-    };
-
-#define VMV_ROBOT_HOST(NAME)                                                                                  \
-    {                                                                                                         \
-        vmv::gen::NAME##_model::kName, vmv::gen::NAME##_model::kDof, vmv::gen::NAME##_model::kSpheres,        \
-            vmv::gen::NAME##_model::kLinks, vmv::gen::NAME##_model::kPairs, vmv::gen::NAME##_model::kTasks,   \
-            vmv::gen::NAME##_model::kResolution, vmv::gen::NAME##_model::kAttachLinks,                        \
-            vmv::gen::NAME##_model::kEeBody, vmv::gen::NAME##_lower, vmv::gen::NAME##_range,                  \
-            vmv::gen::NAME##_tasks_host, vmv::gen::NAME##_links_host, vmv::gen::NAME##_pairs_host,            \
-            vmv::gen::NAME##_attach_links_host, vmv::gen::NAME##_ee_tf_host, vmv::gen::NAME##_pair_info_host, \
-            vmv::gen::NAME##_pair_lists_host, vmv::gen::NAME##_pair_lists_count, NAME##_max_reach(),          \
-            vmv::gen::NAME##_pair_groups, vmv::gen::NAME##_pair_group_count, vmv::gen::NAME##_pair_group_pairs, \
-            vmv::gen::NAME##_pair_never, vmv::gen::NAME##_pair_never_count, vmv::gen::NAME##_inline_covered   \
+        return *ops(robot).host;
     }
-    const RobotHost g_robots[VMV_N_ROBOTS] = {
-        VMV_ROBOT_HOST(panda), VMV_ROBOT_HOST(ur5), VMV_ROBOT_HOST(fetch), VMV_ROBOT_HOST(baxter)};
-#undef VMV_ROBOT_HOST
 
-    constexpr int kMaxDevices = 16;
     struct RobotDevTables
     {
         bool ready = false;
@@ -188,7 +89,7 @@ namespace
         RobotDevTables &t = g_dev_tables[device][robot];
         if (!t.ready)
         {
-            const RobotHost &r = g_robots[robot];
+            const RobotHost &r = robot_host(robot);
             void *p = nullptr;
             VMV_CUDA(cudaMalloc(&p, r.n_tasks * sizeof(vmv::SphereTask)));
             VMV_CUDA(cudaMemcpy(p, r.tasks, r.n_tasks * sizeof(vmv::SphereTask), cudaMemcpyHostToDevice));
@@ -622,14 +523,22 @@ namespace
         std::vector<CaptFragment> frags(tasks.size());
         {
             std::atomic<size_t> next{0};
+            std::atomic<bool> failed{false};  // an exception must not leave a worker thread (std::terminate)
             auto work = [&]()
             {
-                for (size_t k = next.fetch_add(1); k < tasks.size(); k = next.fetch_add(1))
+                try
                 {
-                    fresh(frags[k]);
-                    CaptBuilder b{t, pts, argsort, max_l2, min_l2, &frags[k], nullptr, {}};
-                    CaptTask &task = tasks[k];
-                    b.subdivide(task.begin, task.count, task.i, std::move(task.afford), task.vol, task.d, kCaptTaskDepth);
+                    for (size_t k = next.fetch_add(1); k < tasks.size() && !failed.load(); k = next.fetch_add(1))
+                    {
+                        fresh(frags[k]);
+                        CaptBuilder b{t, pts, argsort, max_l2, min_l2, &frags[k], nullptr, {}};
+                        CaptTask &task = tasks[k];
+                        b.subdivide(task.begin, task.count, task.i, std::move(task.afford), task.vol, task.d, kCaptTaskDepth);
+                    }
+                }
+                catch (...)
+                {
+                    failed.store(true);
                 }
             };
             const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -643,6 +552,10 @@ namespace
             for (auto &th : pool)
             {
                 th.join();
+            }
+            if (failed.load())
+            {
+                throw std::bad_alloc();  // becomes an error code at the ABI (guarded)
             }
         }
         const auto tm2 = std::chrono::steady_clock::now();
@@ -732,9 +645,16 @@ struct vmv_env
     int next_id = 0;
 
     bool committed = false;
+    // shapes_dirty: a primitive, heightfield or pointcloud changed since the last commit (full re-pack); an
+    // attach / detach alone only rewrites the attachment tail of the blob (a few hundred bytes) and keeps every
+    // device array, voxel table and the clearance grid -- attach / detach are O(1) in the reference too
+    // (std::optional<Attachment>, collision/environment.hh:28)
+    bool shapes_dirty = true;
     int device = -1;
     std::vector<uint32_t> blob;
     float *d_blob = nullptr;
+    size_t d_blob_cap = 0;   // bytes
+    uint32_t attach_off = 0; // word offset of the attachment tail in the blob
     int *d_object_ids = nullptr;  // packed object index -> insertion id (vmv_debug)
     std::vector<void *> owned;  // device allocations referenced from the blob
 
@@ -776,6 +696,8 @@ struct vmv_env
             cudaFree(d_blob);
             d_blob = nullptr;
         }
+        d_blob_cap = 0;
+        shapes_dirty = true;
         committed = false;
     }
 };
@@ -1049,6 +971,30 @@ namespace
         return VMV_OK;
     }
 
+    // the attachment tail of the blob: {n 0 0 0} then n x {x y z r}; everything before attach_off stays
+    void append_attachment(vmv_env *env)
+    {
+        std::vector<uint32_t> &B = env->blob;
+        B.resize(env->attach_off);
+        const uint32_t n_attach = env->has_attachment ? static_cast<uint32_t>(env->attach_spheres.size() / 4) : 0u;
+        B.push_back(n_attach), B.push_back(0), B.push_back(0), B.push_back(0);
+        if (env->has_attachment)
+        {
+            for (float v : env->attach_spheres)
+            {
+                B.push_back(f2u(v));
+            }
+        }
+        while (B.size() % 4)
+        {
+            B.push_back(0u);
+        }
+        vmv::EnvHeader H;
+        std::memcpy(&H, B.data(), sizeof(H));
+        H.n_attach = n_attach;
+        std::memcpy(B.data(), &H, sizeof(H));
+    }
+
     int pack_and_upload(vmv_env *env)
     {
         env->release_device();
@@ -1236,19 +1182,11 @@ namespace
                 B.insert(B.end(), w, w + vmv::kCloudGridRec);
             }
         }
-        H.n_attach = env->has_attachment ? static_cast<uint32_t>(env->attach_spheres.size() / 4) : 0u;
         align4();
         H.off_attach = static_cast<uint32_t>(B.size());
-        B.push_back(H.n_attach), B.push_back(0), B.push_back(0), B.push_back(0);
-        if (env->has_attachment)
-        {
-            for (float v : env->attach_spheres)
-            {
-                pf(v);
-            }
-        }
-        align4();
+        env->attach_off = H.off_attach;
         std::memcpy(B.data(), &H, sizeof(H));
+        append_attachment(env);
 
         {
             std::vector<int> ids;
@@ -1264,7 +1202,8 @@ namespace
                 return rc;
             }
         }
-        VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&env->d_blob), B.size() * 4));
+        env->d_blob_cap = B.size() * 4 + 4096;  // room for an attachment to come and go without reallocating
+        VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&env->d_blob), env->d_blob_cap));
         VMV_CUDA(cudaMemcpy(env->d_blob, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
         {
             build_rounded_boxes(env);
@@ -1276,13 +1215,32 @@ namespace
                 return rc;
             }
         }
+        env->shapes_dirty = false;
         env->committed = true;
         return VMV_OK;
     }
 
-    // ---------------------------------------------------------------------------------------
-    // launches
-    // ---------------------------------------------------------------------------------------
+    // attach / detach on an otherwise unchanged, committed environment: rewrite the blob's tail only
+    int repack_attachment(vmv_env *env)
+    {
+        append_attachment(env);
+        const size_t bytes = env->blob.size() * 4;
+        if (bytes > env->d_blob_cap)
+        {
+            VMV_CUDA(cudaFree(env->d_blob));
+            env->d_blob = nullptr;
+            env->d_blob_cap = bytes + 4096;
+            VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&env->d_blob), env->d_blob_cap));
+        }
+        VMV_CUDA(cudaMemcpy(env->d_blob, env->blob.data(), bytes, cudaMemcpyHostToDevice));
+        env->committed = true;
+        return VMV_OK;
+    }
+
+}  // namespace
+
+namespace vmvh
+{
     int sm_count()
     {
         static int cached[kMaxDevices] = {0};
@@ -1295,6 +1253,109 @@ namespace
         return device < kMaxDevices ? std::max(1, cached[device]) : 148;
     }
 
+    // Work counters of the persistent kernels: a ring of slots per device, two words per slot (tile ticket,
+    // finished-block count), zeroed on the launch's stream.  A slot carries the event recorded behind its last
+    // launch and is handed out again only once that event has completed: however many streams and host threads
+    // launch concurrently, no two live kernels share a counter.
+    namespace
+    {
+        constexpr int kCounterSlots = 256;
+        struct CounterRing
+        {
+            unsigned int *mem = nullptr;
+            cudaEvent_t events[kCounterSlots] = {};
+            bool used[kCounterSlots] = {};
+            bool busy[kCounterSlots] = {};  // acquired, not yet released (the launch is being issued)
+            unsigned next = 0;
+        };
+        CounterRing g_rings[kMaxDevices];
+        std::mutex g_ring_mutex;
+    }  // namespace
+
+    int counter_acquire(cudaStream_t s, unsigned int *&counter, int &slot)
+    {
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        if (device >= kMaxDevices)
+        {
+            return fail(VMV_ERR_ARG, "device index too large");
+        }
+        {
+            std::lock_guard<std::mutex> lock(g_ring_mutex);
+            CounterRing &r = g_rings[device];
+            if (r.mem == nullptr)
+            {
+                VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&r.mem), kCounterSlots * 2 * sizeof(unsigned int)));
+            }
+            slot = -1;
+            for (int tries = 0; tries < kCounterSlots && slot < 0; ++tries)
+            {
+                const int k = static_cast<int>(r.next++ % kCounterSlots);
+                if (r.busy[k])
+                {
+                    continue;
+                }
+                if (r.used[k])
+                {
+                    const cudaError_t q = cudaEventQuery(r.events[k]);
+                    if (q == cudaErrorNotReady)
+                    {
+                        continue;
+                    }
+                    if (q != cudaSuccess)
+                    {
+                        return cuda_fail(q, "cudaEventQuery(counter slot)");
+                    }
+                }
+                slot = k;
+            }
+            if (slot < 0)
+            {
+                // every slot belongs to a kernel still in flight: wait for the oldest one that is not being issued
+                for (int tries = 0; tries < kCounterSlots && slot < 0; ++tries)
+                {
+                    const int k = static_cast<int>(r.next++ % kCounterSlots);
+                    if (!r.busy[k])
+                    {
+                        VMV_CUDA(cudaEventSynchronize(r.events[k]));
+                        slot = k;
+                    }
+                }
+                if (slot < 0)
+                {
+                    return fail(VMV_ERR_LIMIT, "more than 256 launches being issued concurrently");
+                }
+            }
+            r.busy[slot] = true;
+            if (!r.used[slot])
+            {
+                VMV_CUDA(cudaEventCreateWithFlags(&r.events[slot], cudaEventDisableTiming));
+                r.used[slot] = true;
+            }
+            counter = r.mem + 2 * slot;
+        }
+        VMV_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), s));
+        return VMV_OK;
+    }
+
+    int counter_release(cudaStream_t s, int slot)
+    {
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        std::lock_guard<std::mutex> lock(g_ring_mutex);
+        CounterRing &r = g_rings[device % kMaxDevices];
+        const cudaError_t e = cudaEventRecord(r.events[slot], s);
+        r.busy[slot] = false;
+        if (e != cudaSuccess)
+        {
+            return cuda_fail(e, "cudaEventRecord(counter slot)");
+        }
+        return VMV_OK;
+    }
+}  // namespace vmvh
+
+namespace
+{
     int make_launch_env(const RobotHost &r, const vmv_env *env, vmv::LaunchEnv &le)
     {
         if (env == nullptr || !env->committed)
@@ -1330,29 +1391,6 @@ namespace
         return VMV_OK;
     }
 
-    constexpr uint32_t kMaxSmem = 227 * 1024;
-
-    // 0: pick automatically; 1: generic per-thread kernel; 2: block-cooperative kernel
-    std::atomic<int> g_force_path{0};
-
-    template <typename R, int BLOCK>
-    int launch_configs_v2(const vmv::RobotDev &rd, const vmv::LaunchEnv &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
-    {
-        using M = typename R::Model;
-        const vmv::SmemLayoutV2<M, BLOCK> L(le.blob_bytes);
-        if (L.total > kMaxSmem)
-        {
-            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
-        }
-        auto kernel = vmv::k_validate_configs_v2<R, BLOCK>;
-        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
-        const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
-        kernel<<<grid, BLOCK, L.total, s>>>(rd, le, q, n, bits);
-        g_launches++;
-        VMV_CUDA(cudaGetLastError());
-        return VMV_OK;
-    }
-
     // ---- grid-culled path ---------------------------------------------------------------------
     constexpr size_t kGridMinConfigs = 1024;  // smaller batches do not amortise a table build
     constexpr size_t kGridMinEdges = 64;  // the edge kernel cuts small batches into 8-edge chunks and wins from here
@@ -1378,7 +1416,7 @@ namespace
         {
             return gi;
         }
-        const RobotHost &r = g_robots[robot];
+        const RobotHost &r = robot_host(robot);
         const int n = r.n_links;
         std::vector<int> order(n);
         std::iota(order.begin(), order.end(), 0);
@@ -1556,431 +1594,6 @@ namespace
         ok = true;
         return VMV_OK;
     }
-
-    // Two-joint verdict tables (vmv_pairtab.cuh): built once per robot and device.
-    struct PairTabCache
-    {
-        bool ready = false;
-        vmv::PairTabDev dev{};
-        float build_ms = 0.F;
-    };
-    PairTabCache g_pair_tabs[kMaxDevices][VMV_N_ROBOTS];
-    constexpr size_t kPairTabBytes = size_t(4) << 20;  // all groups of a robot together
-
-    template <typename R>
-    int ensure_pair_tables(int robot, const vmv::RobotDev &rd, vmv::PairTabDev &out)
-    {
-        int device = 0;
-        VMV_CUDA(cudaGetDevice(&device));
-        std::lock_guard<std::mutex> lock(g_mutex);
-        PairTabCache &c = g_pair_tabs[device][robot];
-        if (!c.ready)
-        {
-            const RobotHost &r = g_robots[robot];
-            vmv::PairTabDev t{};
-            for (int k = 0; k < r.n_pair_never; ++k)
-            {
-                t.never_pairs[r.pair_never[k] >> 5] |= 1u << (r.pair_never[k] & 31);
-            }
-            const int ng = std::min(r.n_pair_groups, vmv::kPairTabMaxGroups);
-            t.n_groups = ng;
-            cudaEvent_t e0, e1;
-            VMV_CUDA(cudaEventCreate(&e0));
-            VMV_CUDA(cudaEventCreate(&e1));
-            VMV_CUDA(cudaEventRecord(e0, nullptr));
-            for (int g = 0; g < ng; ++g)
-            {
-                const vmv::PairGroupHost &G = r.pair_groups[g];
-                const size_t budget = kPairTabBytes / ng;
-                int na, nb;
-                if (G.dof[1] < 0)
-                {
-                    na = static_cast<int>(std::min<size_t>(budget, 1u << 16));
-                    nb = 1;
-                }
-                else
-                {
-                    // cell widths in inverse proportion to the Lipschitz constants: equal band shares
-                    const double wa = (G.hi[0] - G.lo[0]) * std::max(G.lip[0], 1e-3F), wb = (G.hi[1] - G.lo[1]) * std::max(G.lip[1], 1e-3F);
-                    const double cells = static_cast<double>(budget);
-                    na = std::max(16, static_cast<int>(std::sqrt(cells * wa / wb)));
-                    nb = std::max(16, static_cast<int>(cells / na));
-                }
-                const float step_a = (G.hi[0] - G.lo[0]) / na, step_b = G.dof[1] < 0 ? 1.F : (G.hi[1] - G.lo[1]) / nb;
-                const float band = 0.5F * (G.lip[0] * step_a + (G.dof[1] < 0 ? 0.F : G.lip[1] * step_b)) + 2e-5F;
-                void *cells = nullptr, *d_pairs = nullptr;
-                VMV_CUDA(cudaMalloc(&cells, static_cast<size_t>(na) * nb));
-                VMV_CUDA(cudaMalloc(&d_pairs, G.count * sizeof(int)));
-                VMV_CUDA(cudaMemcpy(d_pairs, r.pair_group_pairs + G.first, G.count * sizeof(int), cudaMemcpyHostToDevice));
-                const size_t n_cells = static_cast<size_t>(na) * nb;
-                vmv::k_build_pair_table<R><<<static_cast<unsigned>((n_cells + 127) / 128), 128>>>(
-                    rd, G.dof[0], G.dof[1], G.lo[0], step_a, G.lo[1], step_b, na, nb, band, static_cast<const int *>(d_pairs), G.count,
-                    static_cast<unsigned char *>(cells));
-                g_launches++;
-                VMV_CUDA(cudaGetLastError());
-                VMV_CUDA(cudaDeviceSynchronize());
-                cudaFree(d_pairs);
-                t.dof_a[g] = G.dof[0], t.dof_b[g] = G.dof[1];
-                t.lo_a[g] = G.lo[0], t.inv_a[g] = 1.F / step_a;
-                t.lo_b[g] = G.lo[1], t.inv_b[g] = G.dof[1] < 0 ? 0.F : 1.F / step_b;
-                t.na[g] = na, t.nb[g] = nb;
-                t.cells[g] = static_cast<const unsigned char *>(cells);
-                for (int k = 0; k < G.count; ++k)
-                {
-                    const int p = r.pair_group_pairs[G.first + k];
-                    t.group_pairs[g][p >> 5] |= 1u << (p & 31);
-                }
-            }
-            VMV_CUDA(cudaEventRecord(e1, nullptr));
-            VMV_CUDA(cudaEventSynchronize(e1));
-            VMV_CUDA(cudaEventElapsedTime(&c.build_ms, e0, e1));
-            cudaEventDestroy(e0);
-            cudaEventDestroy(e1);
-            c.dev = t;
-            c.ready = true;
-        }
-        out = c.dev;
-        return VMV_OK;
-    }
-
-    // Launch geometry of the warp-autonomous kernels: the number of warps per block that maximises
-    // the warps resident per SM (shared memory = block-shared tables + one slice per warp), and a
-    // persistent grid of that many blocks per SM.
-    // The search runs once per (kernel, shared-memory shape, device) and is cached: the occupancy
-    // queries cost more host time than a launch.
-    struct V4Geometry
-    {
-        const void *kernel;
-        uint32_t shared_bytes, warp_bytes;
-        int device, warps, blocks_per_sm;
-    };
-    std::vector<V4Geometry> g_v4_geometry;
-
-    template <typename K>
-    int v4_geometry(K kernel, uint32_t shared_bytes, uint32_t warp_bytes, int max_threads, size_t units, int &warps, unsigned &grid, uint32_t &smem)
-    {
-        int device = 0;
-        VMV_CUDA(cudaGetDevice(&device));
-        const void *key = reinterpret_cast<const void *>(kernel);
-        int best_w = 0, best_blocks = 0;
-        {
-            std::lock_guard<std::mutex> lock(g_mutex);
-            for (const auto &g : g_v4_geometry)
-            {
-                if (g.kernel == key && g.shared_bytes == shared_bytes && g.warp_bytes == warp_bytes && g.device == device)
-                {
-                    best_w = g.warps, best_blocks = g.blocks_per_sm;
-                    break;
-                }
-            }
-        }
-        if (best_w == 0)
-        {
-            constexpr uint32_t kMaxDynamic = kMaxSmem - 1024;  // the opt-in limit counts static shared memory too
-            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynamic)));
-            for (int w = 1; w <= max_threads / 32; ++w)
-            {
-                const size_t bytes = static_cast<size_t>(shared_bytes) + static_cast<size_t>(w) * warp_bytes;
-                if (bytes > kMaxDynamic)
-                {
-                    break;
-                }
-                int blocks = 0;
-                VMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, w * 32, bytes));
-                if (blocks * w > best_blocks * best_w || (blocks * w == best_blocks * best_w && blocks > 0))
-                {
-                    best_w = w;
-                    best_blocks = blocks;
-                }
-            }
-            if (best_w == 0 || best_blocks == 0)
-            {
-                return fail(VMV_ERR_LIMIT, "robot tables too large for the grid-culled kernel");
-            }
-            std::lock_guard<std::mutex> lock(g_mutex);
-            g_v4_geometry.push_back({key, shared_bytes, warp_bytes, device, best_w, best_blocks});
-        }
-        warps = best_w;
-        smem = shared_bytes + static_cast<uint32_t>(best_w) * warp_bytes;
-        const size_t tiles = (units + 31) / 32;
-        const size_t blocks_needed = (tiles + best_w - 1) / best_w;
-        grid = static_cast<unsigned>(std::min<size_t>(blocks_needed, static_cast<size_t>(sm_count()) * best_blocks));
-        return VMV_OK;
-    }
-
-    // Launch bounds (threads per block, blocks per SM -> register cap) and fine-item queue depth of the
-    // warp-autonomous kernels, measured per robot.  The configuration kernel needs ~90 registers
-    // (Panda) and gains from 19 resident warps (one block, one-round queue: +9 %); the edge kernel
-    // carries the edge state in registers and is best at 16 warps with the deeper queue.
-    template <typename R>
-    struct V4Tune
-    {
-#if defined(VMV_V4_MAXT) && defined(VMV_V4_MINB)
-        static constexpr int kCfgThreads = VMV_V4_MAXT, kCfgBlocks = VMV_V4_MINB;
-#else
-        static constexpr int kCfgThreads = 640, kCfgBlocks = 1;  // <= 102 registers
-#endif
-        static constexpr int kCfgQ2Rounds = 1;
-#if defined(VMV_V4_EDGE_MAXT) && defined(VMV_V4_EDGE_MINB)
-        static constexpr int kEdgeThreads = VMV_V4_EDGE_MAXT, kEdgeBlocks = VMV_V4_EDGE_MINB;
-#else
-        static constexpr int kEdgeThreads = 256, kEdgeBlocks = 2;  // <= 128 registers
-#endif
-        static constexpr int kEdgeQ2Rounds = 2;
-    };
-    template <>
-    struct V4Tune<baxter_robot>
-    {
-        // <= 255 registers; measured best of (128,2) (192,2) (256,2) (256,1)
-        static constexpr int kCfgThreads = 256, kCfgBlocks = 1, kCfgQ2Rounds = 2;
-        static constexpr int kEdgeThreads = 256, kEdgeBlocks = 1, kEdgeQ2Rounds = 2;
-    };
-
-    int next_counter(cudaStream_t s, unsigned int *&out);
-
-    template <typename R, typename MaskT>
-    int launch_configs_v4(int robot, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
-    {
-        using M = typename R::Model;
-        if (R::PairTab::kUseTables && !g_robots[robot].inline_covered)
-        {
-            return fail(VMV_ERR_LIMIT, "robot's inline self-collision pairs are not covered by verdict tables");
-        }
-        {
-            int rc = ensure_pair_tables<R>(robot, rd, le.tab);
-            if (rc != VMV_OK)
-            {
-                return rc;
-            }
-        }
-        le.q2_rounds = V4Tune<R>::kCfgQ2Rounds;
-        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds);
-        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, V4Tune<R>::kCfgThreads, V4Tune<R>::kCfgBlocks>;
-        int warps = 0;
-        unsigned grid = 0;
-        uint32_t smem = 0;
-        int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kCfgThreads, n, warps, grid, smem);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        unsigned int *counter = nullptr;
-        rc = next_counter(s, counter);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        kernel<<<grid, warps * 32, smem, s>>>(rd, le, q, n, bits, counter);
-        g_launches++;
-        VMV_CUDA(cudaGetLastError());
-        return VMV_OK;
-    }
-
-    // work counters of the persistent edge kernels: a ring per device, one slot per launch, zeroed
-    // on the launch's stream
-    constexpr int kCounterSlots = 256;
-    unsigned int *g_counters[kMaxDevices] = {nullptr};
-    std::atomic<unsigned> g_counter_next{0};
-
-    int next_counter(cudaStream_t s, unsigned int *&out)
-    {
-        int device = 0;
-        VMV_CUDA(cudaGetDevice(&device));
-        {
-            std::lock_guard<std::mutex> lock(g_mutex);
-            if (g_counters[device] == nullptr)
-            {
-                VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&g_counters[device]), kCounterSlots * sizeof(unsigned int)));
-            }
-        }
-        out = g_counters[device] + (g_counter_next++ % kCounterSlots);
-        VMV_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned int), s));
-        return VMV_OK;
-    }
-
-    template <typename R, typename MaskT>
-    int launch_edges_v4(
-        int robot,
-        const vmv::RobotDev &rd,
-        vmv::GridEnv le,
-        const float *a,
-        const float *b,
-        const uint32_t *pairs,
-        size_t n,
-        float resolution,
-        uint32_t *bits,
-        cudaStream_t s)
-    {
-        using M = typename R::Model;
-        if (R::PairTab::kUseTables && !g_robots[robot].inline_covered)
-        {
-            return fail(VMV_ERR_LIMIT, "robot's inline self-collision pairs are not covered by verdict tables");
-        }
-        {
-            int rc = ensure_pair_tables<R>(robot, rd, le.tab);
-            if (rc != VMV_OK)
-            {
-                return rc;
-            }
-        }
-        le.q2_rounds = V4Tune<R>::kEdgeQ2Rounds;
-        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds);
-        int warps = 0;
-        unsigned grid = 0;
-        uint32_t smem = 0;
-        // finer chunks for batches that would otherwise leave warps idle (vmv_kernels_v4.cuh); measured: 2^18 edges
-        // 16 per chunk 224 M/s, 32 per chunk 217 M/s (3.5 chunks per warp leave a long tail); 9.5 M edges 4.2e8 / 4.4e8
-        static const int chunk_override = []
-        {
-            const char *e = std::getenv("VMV_EDGE_CHUNK");  // 8, 16 or 32 (tuning aid)
-            const int v = e ? std::atoi(e) : 0;
-            return (v == 8 || v == 16 || v == 32) ? v : 0;
-        }();
-        const int per_chunk = chunk_override ? chunk_override : (n >= (size_t(1) << 19) ? 32 : (n >= (size_t(1) << 15) ? 16 : 8));
-        unsigned int *counter = nullptr;
-        {
-            int rc = next_counter(s, counter);
-            if (rc != VMV_OK)
-            {
-                return rc;
-            }
-        }
-        if (pairs != nullptr)
-        {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, V4Tune<R>::kEdgeThreads, V4Tune<R>::kEdgeBlocks>;
-            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kEdgeThreads, (n + 31) / 32 * 32 * (32 / per_chunk), warps, grid, smem);
-            if (rc != VMV_OK)
-            {
-                return rc;
-            }
-            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits, counter, per_chunk);
-        }
-        else
-        {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, V4Tune<R>::kEdgeThreads, V4Tune<R>::kEdgeBlocks>;
-            int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, V4Tune<R>::kEdgeThreads, (n + 31) / 32 * 32 * (32 / per_chunk), warps, grid, smem);
-            if (rc != VMV_OK)
-            {
-                return rc;
-            }
-            kernel<<<grid, warps * 32, smem, s>>>(rd, le, a, b, pairs, n, resolution, bits, counter, per_chunk);
-        }
-        g_launches++;
-        VMV_CUDA(cudaGetLastError());
-        return VMV_OK;
-    }
-
-    template <typename R, int BLOCK>
-    int launch_configs(const vmv::RobotDev &rd, const vmv::LaunchEnv &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
-    {
-        using M = typename R::Model;
-        const int force = g_force_path.load();
-        if (force != 1 && le.primitives_only && le.n_objects <= 64)
-        {
-            const vmv::SmemLayoutV2<M, BLOCK> L2(le.blob_bytes);
-            if (L2.total <= kMaxSmem)
-            {
-                return launch_configs_v2<R, BLOCK>(rd, le, q, n, bits, s);
-            }
-        }
-        if (force == 2)
-        {
-            return fail(VMV_ERR_LIMIT, "block-cooperative kernel not applicable to this environment");
-        }
-        const vmv::SmemLayout<M, BLOCK> L(le.blob_bytes);
-        if (L.total > kMaxSmem)
-        {
-            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
-        }
-        auto kernel = vmv::k_validate_configs<R, BLOCK>;
-        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
-        const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
-        kernel<<<grid, BLOCK, L.total, s>>>(rd, le, q, n, bits);
-        g_launches++;
-        VMV_CUDA(cudaGetLastError());
-        return VMV_OK;
-    }
-
-    template <typename R, int BLOCK>
-    int launch_edges(
-        const vmv::RobotDev &rd,
-        const vmv::LaunchEnv &le,
-        const float *a,
-        const float *b,
-        const uint32_t *pairs,
-        size_t n,
-        float resolution,
-        uint32_t *bits,
-        cudaStream_t s)
-    {
-        using M = typename R::Model;
-        const vmv::SmemLayout<M, BLOCK> L(le.blob_bytes);
-        if (L.total > kMaxSmem)
-        {
-            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
-        }
-        const int force = g_force_path.load();
-        if (BLOCK == 128 && force != 1 && le.primitives_only && le.n_objects <= 64)
-        {
-            const vmv::SmemLayoutV2<M, 128> L2(le.blob_bytes);
-            if (L2.total <= kMaxSmem)
-            {
-                const size_t chunks = (n + 31) / 32;
-                const int per_sm2 = std::max<int>(1, static_cast<int>(kMaxSmem / std::max<uint32_t>(L2.total + 4096, 1)));
-                const unsigned grid2 = static_cast<unsigned>(std::min<size_t>(chunks, static_cast<size_t>(sm_count()) * per_sm2 * 8));
-                if (pairs != nullptr)
-                {
-                    auto kernel = vmv::k_validate_edges_v2<R, 128, true>;
-                    VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L2.total)));
-                    kernel<<<grid2, 128, L2.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
-                }
-                else
-                {
-                    auto kernel = vmv::k_validate_edges_v2<R, 128, false>;
-                    VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L2.total)));
-                    kernel<<<grid2, 128, L2.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
-                }
-                g_launches++;
-                VMV_CUDA(cudaGetLastError());
-                return VMV_OK;
-            }
-        }
-        if (force == 2)
-        {
-            return fail(VMV_ERR_LIMIT, "block-cooperative kernel not applicable to this environment");
-        }
-        const size_t rounds = (n + 31) / 32;  // one warp-round per verdict word
-        const size_t blocks_needed = (rounds + BLOCK / 32 - 1) / (BLOCK / 32);
-        const int per_sm = std::max<int>(1, static_cast<int>(kMaxSmem / std::max<uint32_t>(L.total, 1)));
-        const unsigned grid = static_cast<unsigned>(std::min<size_t>(blocks_needed, static_cast<size_t>(sm_count()) * per_sm * 4));
-        if (pairs != nullptr)
-        {
-            auto kernel = vmv::k_validate_edges<R, BLOCK, true>;
-            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
-            kernel<<<grid, BLOCK, L.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
-        }
-        else
-        {
-            auto kernel = vmv::k_validate_edges<R, BLOCK, false>;
-            VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
-            kernel<<<grid, BLOCK, L.total, s>>>(rd, le, a, b, pairs, n, resolution, bits);
-        }
-        g_launches++;
-        VMV_CUDA(cudaGetLastError());
-        return VMV_OK;
-    }
-
-    template <typename R>
-    int launch_fk(const vmv::RobotDev &rd, const float *q, size_t n, float *out, cudaStream_t s)
-    {
-        constexpr int BLOCK = 128;
-        const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
-        vmv::k_sphere_fk<R, BLOCK><<<grid, BLOCK, 0, s>>>(rd, q, n, out);
-        g_launches++;
-        VMV_CUDA(cudaGetLastError());
-        return VMV_OK;
-    }
-
     bool valid_robot(int robot)
     {
         return robot >= 0 && robot < VMV_N_ROBOTS;
@@ -1990,6 +1603,32 @@ namespace
 // =============================================================================================
 // C ABI
 // =============================================================================================
+namespace
+{
+    // No exception crosses the C ABI (include/vamp_b200.h): allocation failures and anything else thrown by the
+    // host-side builds (CAPT / MVT construction, vectors, std::thread) become error codes.
+    template <typename F>
+    auto guarded(const char *what, F &&f) noexcept -> decltype(f())
+    {
+        try
+        {
+            return f();
+        }
+        catch (const std::bad_alloc &)
+        {
+            return fail(VMV_ERR_LIMIT, std::string(what) + ": out of host memory");
+        }
+        catch (const std::exception &e)
+        {
+            return fail(VMV_ERR_STATE, std::string(what) + ": " + e.what());
+        }
+        catch (...)
+        {
+            return fail(VMV_ERR_STATE, std::string(what) + ": unknown exception");
+        }
+    }
+}  // namespace
+
 extern "C"
 {
     const char *vmv_last_error(void)
@@ -2023,7 +1662,7 @@ extern "C"
     {
         for (int i = 0; i < VMV_N_ROBOTS; ++i)
         {
-            if (name != nullptr && std::strcmp(name, g_robots[i].name) == 0)
+            if (name != nullptr && std::strcmp(name, robot_host(i).name) == 0)
             {
                 return i;
             }
@@ -2033,33 +1672,36 @@ extern "C"
 
     const char *vmv_robot_name(int robot)
     {
-        return valid_robot(robot) ? g_robots[robot].name : nullptr;
+        return valid_robot(robot) ? robot_host(robot).name : nullptr;
     }
 
     int vmv_robot_dof(int robot)
     {
-        return valid_robot(robot) ? g_robots[robot].dof : fail(VMV_ERR_ARG, "unknown robot");
+        return valid_robot(robot) ? robot_host(robot).dof : fail(VMV_ERR_ARG, "unknown robot");
     }
 
     int vmv_robot_n_spheres(int robot)
     {
-        return valid_robot(robot) ? g_robots[robot].n_spheres : fail(VMV_ERR_ARG, "unknown robot");
+        return valid_robot(robot) ? robot_host(robot).n_spheres : fail(VMV_ERR_ARG, "unknown robot");
     }
 
     int vmv_robot_resolution(int robot)
     {
-        return valid_robot(robot) ? g_robots[robot].resolution : fail(VMV_ERR_ARG, "unknown robot");
+        return valid_robot(robot) ? robot_host(robot).resolution : fail(VMV_ERR_ARG, "unknown robot");
     }
 
     int vmv_robot_bounds(int robot, float *lower, float *range)
     {
-        if (!valid_robot(robot) || lower == nullptr || range == nullptr)
+        return guarded("vmv_robot_bounds", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_robot_bounds: bad argument");
-        }
-        std::memcpy(lower, g_robots[robot].lower, g_robots[robot].dof * sizeof(float));
-        std::memcpy(range, g_robots[robot].range, g_robots[robot].dof * sizeof(float));
-        return VMV_OK;
+            if (!valid_robot(robot) || lower == nullptr || range == nullptr)
+            {
+                return fail(VMV_ERR_ARG, "vmv_robot_bounds: bad argument");
+            }
+            std::memcpy(lower, robot_host(robot).lower, robot_host(robot).dof * sizeof(float));
+            std::memcpy(range, robot_host(robot).range, robot_host(robot).dof * sizeof(float));
+            return VMV_OK;
+        });
     }
 
     vmv_env *vmv_env_create(void)
@@ -2078,291 +1720,309 @@ extern "C"
 
     int vmv_env_add_spheres(vmv_env *env, const float *f, size_t n)
     {
-        if (env == nullptr || (f == nullptr && n > 0))
+        return guarded("vmv_env_add_spheres", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_add_spheres: null argument");
-        }
-        for (size_t i = 0; i < n; ++i, f += 4)
-        {
-            HSphere s{f[0], f[1], f[2], f[3], 0.F, env->next_id++};
-            s.min_d = std::sqrt(s.x * s.x + s.y * s.y + s.z * s.z) - s.r;  // shapes.hh:238
-            env->spheres.push_back(s);
-        }
-        env->committed = false;
-        return VMV_OK;
+            if (env == nullptr || (f == nullptr && n > 0))
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_add_spheres: null argument");
+            }
+            for (size_t i = 0; i < n; ++i, f += 4)
+            {
+                HSphere s{f[0], f[1], f[2], f[3], 0.F, env->next_id++};
+                s.min_d = std::sqrt(s.x * s.x + s.y * s.y + s.z * s.z) - s.r;  // shapes.hh:238
+                env->spheres.push_back(s);
+            }
+            env->shapes_dirty = true;
+            env->committed = false;
+            return VMV_OK;
+        });
     }
 
     int vmv_env_add_cuboids(vmv_env *env, const float *f, size_t n)
     {
-        if (env == nullptr || (f == nullptr && n > 0))
+        return guarded("vmv_env_add_cuboids", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_add_cuboids: null argument");
-        }
-        for (size_t i = 0; i < n; ++i, f += 15)
-        {
-            HCuboid c{};
-            std::memcpy(c.f, f, sizeof(c.f));
-            c.id = env->next_id++;
-            // Cuboid::compute_min_distance, shapes.hh:52-67
-            const float x = f[0], y = f[1], z = f[2];
-            const float d1 = dot3(-x, -y, -z, f[3], f[4], f[5]);
-            const float d2 = dot3(-x, -y, -z, f[6], f[7], f[8]);
-            const float d3 = dot3(-x, -y, -z, f[9], f[10], f[11]);
-            const float v1 = clamp_ref(d1, -f[12], f[12]);
-            const float v2 = clamp_ref(d2, -f[13], f[13]);
-            const float v3 = clamp_ref(d3, -f[14], f[14]);
-            const float xn = x + f[3] * v1 + f[6] * v2 + f[9] * v3;
-            const float yn = y + f[4] * v1 + f[7] * v2 + f[10] * v3;
-            const float zn = z + f[5] * v1 + f[8] * v2 + f[11] * v3;
-            c.min_d = finite_or_neg_inf(std::sqrt(xn * xn + yn * yn + zn * zn));
-            // z-aligned iff axis_3_z == 1 (bindings/environment.cc:124)
-            (f[11] == 1.F ? env->z_cuboids : env->cuboids).push_back(c);
-        }
-        env->committed = false;
-        return VMV_OK;
+            if (env == nullptr || (f == nullptr && n > 0))
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_add_cuboids: null argument");
+            }
+            for (size_t i = 0; i < n; ++i, f += 15)
+            {
+                HCuboid c{};
+                std::memcpy(c.f, f, sizeof(c.f));
+                c.id = env->next_id++;
+                // Cuboid::compute_min_distance, shapes.hh:52-67
+                const float x = f[0], y = f[1], z = f[2];
+                const float d1 = dot3(-x, -y, -z, f[3], f[4], f[5]);
+                const float d2 = dot3(-x, -y, -z, f[6], f[7], f[8]);
+                const float d3 = dot3(-x, -y, -z, f[9], f[10], f[11]);
+                const float v1 = clamp_ref(d1, -f[12], f[12]);
+                const float v2 = clamp_ref(d2, -f[13], f[13]);
+                const float v3 = clamp_ref(d3, -f[14], f[14]);
+                const float xn = x + f[3] * v1 + f[6] * v2 + f[9] * v3;
+                const float yn = y + f[4] * v1 + f[7] * v2 + f[10] * v3;
+                const float zn = z + f[5] * v1 + f[8] * v2 + f[11] * v3;
+                c.min_d = finite_or_neg_inf(std::sqrt(xn * xn + yn * yn + zn * zn));
+                // z-aligned iff axis_3_z == 1 (bindings/environment.cc:124)
+                (f[11] == 1.F ? env->z_cuboids : env->cuboids).push_back(c);
+            }
+            env->shapes_dirty = true;
+            env->committed = false;
+            return VMV_OK;
+        });
     }
 
     int vmv_env_add_capsules(vmv_env *env, const float *f, size_t n)
     {
-        if (env == nullptr || (f == nullptr && n > 0))
+        return guarded("vmv_env_add_capsules", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_add_capsules: null argument");
-        }
-        for (size_t i = 0; i < n; ++i, f += 8)
-        {
-            HCapsule c{f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], 0.F, env->next_id++};
-            // Cylinder::compute_min_distance, shapes.hh:165-189
-            const float dot = clamp_ref(dot3(-c.x1, -c.y1, -c.z1, c.xv, c.yv, c.zv) * c.rdv, 0.F, 1.F);
-            const float xp = c.x1 + c.xv * dot, yp = c.y1 + c.yv * dot, zp = c.z1 + c.zv * dot;
-            float xo = -xp, yo = -yp, zo = -zp;
-            const float ol = std::sqrt(dot3(xo, yo, zo, xo, yo, zo));
-            xo = xo / ol, yo = yo / ol, zo = zo / ol;
-            const float ro = clamp_ref(ol, 0.F, c.r);
-            const float xn = xp + ro * xo, yn = yp + ro * yo, zn = zp + ro * zo;
-            c.min_d = finite_or_neg_inf(std::sqrt(xn * xn + yn * yn + zn * zn));
-            // z-aligned iff xv == 0 and yv == 0 (bindings/environment.cc:138)
-            ((c.xv == 0.F && c.yv == 0.F) ? env->z_capsules : env->capsules).push_back(c);
-        }
-        env->committed = false;
-        return VMV_OK;
+            if (env == nullptr || (f == nullptr && n > 0))
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_add_capsules: null argument");
+            }
+            for (size_t i = 0; i < n; ++i, f += 8)
+            {
+                HCapsule c{f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], 0.F, env->next_id++};
+                // Cylinder::compute_min_distance, shapes.hh:165-189
+                const float dot = clamp_ref(dot3(-c.x1, -c.y1, -c.z1, c.xv, c.yv, c.zv) * c.rdv, 0.F, 1.F);
+                const float xp = c.x1 + c.xv * dot, yp = c.y1 + c.yv * dot, zp = c.z1 + c.zv * dot;
+                float xo = -xp, yo = -yp, zo = -zp;
+                const float ol = std::sqrt(dot3(xo, yo, zo, xo, yo, zo));
+                xo = xo / ol, yo = yo / ol, zo = zo / ol;
+                const float ro = clamp_ref(ol, 0.F, c.r);
+                const float xn = xp + ro * xo, yn = yp + ro * yo, zn = zp + ro * zo;
+                c.min_d = finite_or_neg_inf(std::sqrt(xn * xn + yn * yn + zn * zn));
+                // z-aligned iff xv == 0 and yv == 0 (bindings/environment.cc:138)
+                ((c.xv == 0.F && c.yv == 0.F) ? env->z_capsules : env->capsules).push_back(c);
+            }
+            env->shapes_dirty = true;
+            env->committed = false;
+            return VMV_OK;
+        });
     }
 
     int vmv_env_add_heightfield(vmv_env *env, const float *f6, size_t xd, size_t yd, const float *data)
     {
-        if (env == nullptr || f6 == nullptr || data == nullptr || xd == 0 || yd == 0)
+        return guarded("vmv_env_add_heightfield", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_add_heightfield: bad argument");
-        }
-        HHeight h;
-        std::memcpy(h.f, f6, sizeof(h.f));
-        h.xd = xd, h.yd = yd;
-        h.data.assign(data, data + xd * yd);
-        h.id = env->next_id++;
-        env->heightfields.push_back(std::move(h));
-        env->committed = false;
-        return VMV_OK;
+            if (env == nullptr || f6 == nullptr || data == nullptr || xd == 0 || yd == 0)
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_add_heightfield: bad argument");
+            }
+            HHeight h;
+            std::memcpy(h.f, f6, sizeof(h.f));
+            h.xd = xd, h.yd = yd;
+            h.data.assign(data, data + xd * yd);
+            h.id = env->next_id++;
+            env->heightfields.push_back(std::move(h));
+            env->shapes_dirty = true;
+            env->committed = false;
+            return VMV_OK;
+        });
     }
 
     int vmv_env_add_capt(vmv_env *env, const float *pts, size_t n, float r_min, float r_max, float r_point)
     {
-        if (env == nullptr || (pts == nullptr && n > 0))
+        return guarded("vmv_env_add_capt", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_add_capt: null argument");
-        }
-        HCapt t;
-        capt_build(t, pts, n, r_min, r_max, r_point);
-        t.id = env->next_id++;
-        env->capts.push_back(std::move(t));
-        env->cloud_xyz.insert(env->cloud_xyz.end(), pts, pts + 3 * n);
-        env->cloud_r_point_max = std::max(env->cloud_r_point_max, r_point);
-        env->committed = false;
-        return VMV_OK;
+            if (env == nullptr || (pts == nullptr && n > 0))
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_add_capt: null argument");
+            }
+            HCapt t;
+            capt_build(t, pts, n, r_min, r_max, r_point);
+            t.id = env->next_id++;
+            env->capts.push_back(std::move(t));
+            env->cloud_xyz.insert(env->cloud_xyz.end(), pts, pts + 3 * n);
+            env->cloud_r_point_max = std::max(env->cloud_r_point_max, r_point);
+            env->shapes_dirty = true;
+            env->committed = false;
+            return VMV_OK;
+        });
     }
 
     int vmv_env_add_mvt(vmv_env *env, const float *pts, size_t n, float r_min, float r_max, const float *aabb_min, const float *aabb_max, float r_point)
     {
-        if (env == nullptr || (n > 0 && pts == nullptr) || aabb_min == nullptr || aabb_max == nullptr || !(r_max > 0.F))
+        return guarded("vmv_env_add_mvt", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_add_mvt: bad argument");
-        }
-        HMvt t;
-        const int rc = mvt_build(t, pts, n, r_min, r_max, aabb_min, aabb_max, r_point);
-        if (rc == -1)
-        {
-            return fail(VMV_ERR_ARG, "vmv_env_add_mvt: workspace narrower than r_max");
-        }
-        if (rc == -2)
-        {
-            return fail(VMV_ERR_LIMIT, "vmv_env_add_mvt: more than 2^26 grid cells");
-        }
-        t.id = env->next_id++;
-        env->mvts.push_back(std::move(t));
-        env->cloud_xyz.insert(env->cloud_xyz.end(), pts, pts + 3 * n);
-        env->cloud_r_point_max = std::max(env->cloud_r_point_max, r_point);
-        env->committed = false;
-        return VMV_OK;
+            if (env == nullptr || (n > 0 && pts == nullptr) || aabb_min == nullptr || aabb_max == nullptr || !(r_max > 0.F))
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_add_mvt: bad argument");
+            }
+            HMvt t;
+            const int rc = mvt_build(t, pts, n, r_min, r_max, aabb_min, aabb_max, r_point);
+            if (rc == -1)
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_add_mvt: workspace narrower than r_max");
+            }
+            if (rc == -2)
+            {
+                return fail(VMV_ERR_LIMIT, "vmv_env_add_mvt: more than 2^26 grid cells");
+            }
+            t.id = env->next_id++;
+            env->mvts.push_back(std::move(t));
+            env->cloud_xyz.insert(env->cloud_xyz.end(), pts, pts + 3 * n);
+            env->cloud_r_point_max = std::max(env->cloud_r_point_max, r_point);
+            env->shapes_dirty = true;
+            env->committed = false;
+            return VMV_OK;
+        });
     }
 
     int vmv_env_attach(vmv_env *env, const float *tf12, const float *spheres, size_t n)
     {
-        if (env == nullptr || tf12 == nullptr || (spheres == nullptr && n > 0))
+        return guarded("vmv_env_attach", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_attach: null argument");
-        }
-        for (int r = 0; r < 3; ++r)
-        {
-            for (int c = 0; c < 3; ++c)
+            if (env == nullptr || tf12 == nullptr || (spheres == nullptr && n > 0))
             {
-                env->attach_tf[4 * r + c] = tf12[3 + 3 * c + r];
+                return fail(VMV_ERR_ARG, "vmv_env_attach: null argument");
             }
-            env->attach_tf[4 * r + 3] = tf12[r];
-        }
-        env->attach_spheres.assign(spheres, spheres + 4 * n);
-        env->has_attachment = true;
-        env->committed = false;
-        return VMV_OK;
+            for (int r = 0; r < 3; ++r)
+            {
+                for (int c = 0; c < 3; ++c)
+                {
+                    env->attach_tf[4 * r + c] = tf12[3 + 3 * c + r];
+                }
+                env->attach_tf[4 * r + 3] = tf12[r];
+            }
+            env->attach_spheres.assign(spheres, spheres + 4 * n);
+            env->has_attachment = true;
+            env->committed = false;
+            return VMV_OK;
+        });
     }
 
     int vmv_env_detach(vmv_env *env)
     {
-        if (env == nullptr)
+        return guarded("vmv_env_detach", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_detach: null argument");
-        }
-        env->has_attachment = false;
-        env->attach_spheres.clear();
-        env->committed = false;
-        return VMV_OK;
+            if (env == nullptr)
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_detach: null argument");
+            }
+            env->has_attachment = false;
+            env->attach_spheres.clear();
+            env->committed = false;
+            return VMV_OK;
+        });
     }
 
     int vmv_env_commit(vmv_env *env)
     {
-        if (env == nullptr)
+        return guarded("vmv_env_commit", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_env_commit: null argument");
-        }
-        sort_by_min_distance(env->spheres);
-        sort_by_min_distance(env->capsules);
-        sort_by_min_distance(env->z_capsules);
-        sort_by_min_distance(env->cuboids);
-        sort_by_min_distance(env->z_cuboids);
-        return pack_and_upload(env);
+            if (env == nullptr)
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_commit: null argument");
+            }
+            if (!env->shapes_dirty && env->d_blob != nullptr)
+            {
+                int device = 0;
+                VMV_CUDA(cudaGetDevice(&device));
+                if (device == env->device)
+                {
+                    return env->committed ? VMV_OK : repack_attachment(env);
+                }
+            }
+            sort_by_min_distance(env->spheres);
+            sort_by_min_distance(env->capsules);
+            sort_by_min_distance(env->z_capsules);
+            sort_by_min_distance(env->cuboids);
+            sort_by_min_distance(env->z_cuboids);
+            return pack_and_upload(env);
+        });
     }
 
     long vmv_env_dump(const vmv_env *env, int kind, float *out, size_t cap)
     {
-        if (env == nullptr)
+        return guarded("vmv_env_dump", [&]() -> long
         {
-            return fail(VMV_ERR_ARG, "vmv_env_dump: null argument");
-        }
-        // dump reflects the order a commit would produce
-        vmv_env tmp;
-        tmp.spheres = env->spheres, tmp.capsules = env->capsules, tmp.z_capsules = env->z_capsules;
-        tmp.cuboids = env->cuboids, tmp.z_cuboids = env->z_cuboids;
-        sort_by_min_distance(tmp.spheres), sort_by_min_distance(tmp.capsules), sort_by_min_distance(tmp.z_capsules);
-        sort_by_min_distance(tmp.cuboids), sort_by_min_distance(tmp.z_cuboids);
-        size_t k = 0;
-        auto put = [&](float v)
-        {
-            if (k < cap && out != nullptr)
+            if (env == nullptr)
             {
-                out[k] = v;
+                return fail(VMV_ERR_ARG, "vmv_env_dump: null argument");
             }
-            ++k;
-        };
-        switch (kind)
-        {
-            case 0:
-                for (const auto &s : tmp.spheres)
-                {
-                    put(s.x), put(s.y), put(s.z), put(s.r), put(s.min_d);
-                }
-                return static_cast<long>(tmp.spheres.size());
-            case 1:
-            case 2:
+            // dump reflects the order a commit would produce
+            vmv_env tmp;
+            tmp.spheres = env->spheres, tmp.capsules = env->capsules, tmp.z_capsules = env->z_capsules;
+            tmp.cuboids = env->cuboids, tmp.z_cuboids = env->z_cuboids;
+            sort_by_min_distance(tmp.spheres), sort_by_min_distance(tmp.capsules), sort_by_min_distance(tmp.z_capsules);
+            sort_by_min_distance(tmp.cuboids), sort_by_min_distance(tmp.z_cuboids);
+            size_t k = 0;
+            auto put = [&](float v)
             {
-                const auto &v = kind == 1 ? tmp.capsules : tmp.z_capsules;
-                for (const auto &c : v)
+                if (k < cap && out != nullptr)
                 {
-                    put(c.x1), put(c.y1), put(c.z1), put(c.xv), put(c.yv), put(c.zv), put(c.r), put(c.rdv), put(c.min_d);
+                    out[k] = v;
                 }
-                return static_cast<long>(v.size());
-            }
-            case 3:
-            case 4:
+                ++k;
+            };
+            switch (kind)
             {
-                const auto &v = kind == 3 ? tmp.cuboids : tmp.z_cuboids;
-                for (const auto &c : v)
-                {
-                    for (float f : c.f)
+                case 0:
+                    for (const auto &s : tmp.spheres)
                     {
-                        put(f);
+                        put(s.x), put(s.y), put(s.z), put(s.r), put(s.min_d);
                     }
-                    put(c.min_d);
+                    return static_cast<long>(tmp.spheres.size());
+                case 1:
+                case 2:
+                {
+                    const auto &v = kind == 1 ? tmp.capsules : tmp.z_capsules;
+                    for (const auto &c : v)
+                    {
+                        put(c.x1), put(c.y1), put(c.z1), put(c.xv), put(c.yv), put(c.zv), put(c.r), put(c.rdv), put(c.min_d);
+                    }
+                    return static_cast<long>(v.size());
                 }
-                return static_cast<long>(v.size());
+                case 3:
+                case 4:
+                {
+                    const auto &v = kind == 3 ? tmp.cuboids : tmp.z_cuboids;
+                    for (const auto &c : v)
+                    {
+                        for (float f : c.f)
+                        {
+                            put(f);
+                        }
+                        put(c.min_d);
+                    }
+                    return static_cast<long>(v.size());
+                }
+                default:
+                    return fail(VMV_ERR_ARG, "vmv_env_dump: unknown kind");
             }
-            default:
-                return fail(VMV_ERR_ARG, "vmv_env_dump: unknown kind");
-        }
+        });
     }
 
-#ifdef VMV_DEV_PANDA_ONLY
-    // development builds (kernel A/B timing): one robot (VMV_DEV_ROBOT, default panda), a quarter of
-    // the compile time; every robot id runs that robot's kernels
-#ifndef VMV_DEV_ROBOT
-#define VMV_DEV_ROBOT panda_robot
-#endif
-#define VMV_DISPATCH(robot, CALL)       \
-    {                                   \
-        using R = VMV_DEV_ROBOT;        \
-        constexpr int BLOCK = 128;      \
-        (void)BLOCK;                    \
-        rc = CALL;                      \
-    }
-#else
-#define VMV_DISPATCH(robot, CALL)            \
-    switch (robot)                           \
-    {                                        \
-        case VMV_PANDA:                      \
-        {                                    \
-            using R = panda_robot;           \
-            constexpr int BLOCK = 128;       \
-            rc = CALL;                       \
-            break;                           \
-        }                                    \
-        case VMV_UR5:                        \
-        {                                    \
-            using R = ur5_robot;             \
-            constexpr int BLOCK = 128;       \
-            rc = CALL;                       \
-            break;                           \
-        }                                    \
-        case VMV_FETCH:                      \
-        {                                    \
-            using R = fetch_robot;           \
-            constexpr int BLOCK = 128;       \
-            rc = CALL;                       \
-            break;                           \
-        }                                    \
-        default:                             \
-        {                                    \
-            using R = baxter_robot;          \
-            constexpr int BLOCK = 64;        \
-            rc = CALL;                       \
-            break;                           \
-        }                                    \
-    }
-#endif
 
-    int vmv_validate_configs_dev(int robot, const vmv_env *env, const float *d_q, size_t n, uint32_t *d_bits, void *stream)
+    // gathers for the kernel generations without fused peer stores: local words -> every window, then the flags
+    static int push_gather(const GatherDev &gather, const uint32_t *d_bits, size_t n_words, cudaStream_t s)
     {
-        if (!valid_robot(robot) || (n > 0 && (d_q == nullptr || d_bits == nullptr)))
+        if (gather.world == 0)
         {
-            return fail(VMV_ERR_ARG, "vmv_validate_configs_dev: bad argument");
+            return VMV_OK;
         }
+        GatherDev g = gather;
+        unsigned int *counter = nullptr;
+        int slot = -1;
+        int rc = counter_acquire(s, counter, slot);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        g.done = counter + 1;
+        const unsigned grid = static_cast<unsigned>(std::min<size_t>((n_words + 255) / 256, static_cast<size_t>(sm_count())));
+        vmv::k_comm_push<<<std::max(1u, grid), 256, 0, s>>>(d_bits, n_words, g);
+        g_launches++;
+        const cudaError_t e = cudaGetLastError();
+        rc = counter_release(s, slot);
+        return e != cudaSuccess ? cuda_fail(e, "k_comm_push launch") : rc;
+    }
+
+    static int configs_common(int robot, const vmv_env *env, const float *d_q, size_t n, uint32_t *d_bits, const GatherDev &gather, void *stream)
+    {
         vmv::LaunchEnv le{};
-        int rc = make_launch_env(g_robots[robot], env, le);
+        int rc = make_launch_env(robot_host(robot), env, le);
         if (rc != VMV_OK || n == 0)
         {
             return rc;
@@ -2386,14 +2046,7 @@ extern "C"
             }
             if (ok)
             {
-                if (wide)
-                {
-                    VMV_DISPATCH(robot, (launch_configs_v4<R, unsigned long long>(robot, rd, l3, d_q, n, d_bits, s)))
-                }
-                else
-                {
-                    VMV_DISPATCH(robot, (launch_configs_v4<R, uint32_t>(robot, rd, l3, d_q, n, d_bits, s)))
-                }
+                rc = ops(robot).configs_v4(robot, wide, rd, l3, d_q, n, d_bits, gather, s);
                 if (rc != VMV_ERR_LIMIT || force == 3)
                 {
                     return rc;
@@ -2404,8 +2057,20 @@ extern "C"
                 return fail(VMV_ERR_LIMIT, "grid-culled kernel not applicable to this environment");
             }
         }
-        VMV_DISPATCH(robot, (launch_configs<R, BLOCK>(rd, le, d_q, n, d_bits, s)))
-        return rc;
+        rc = ops(robot).configs(rd, le, d_q, n, d_bits, s);
+        return rc == VMV_OK ? push_gather(gather, d_bits, (n + 31) / 32, s) : rc;
+    }
+
+    int vmv_validate_configs_dev(int robot, const vmv_env *env, const float *d_q, size_t n, uint32_t *d_bits, void *stream)
+    {
+        return guarded("vmv_validate_configs_dev", [&]() -> int
+        {
+            if (!valid_robot(robot) || (n > 0 && (d_q == nullptr || d_bits == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_configs_dev: bad argument");
+            }
+            return configs_common(robot, env, d_q, n, d_bits, GatherDev{}, stream);
+        });
     }
 
     static int edges_common(
@@ -2417,10 +2082,11 @@ extern "C"
         size_t n,
         int resolution,
         uint32_t *d_bits,
+        const GatherDev &gather,
         void *stream)
     {
         vmv::LaunchEnv le{};
-        int rc = make_launch_env(g_robots[robot], env, le);
+        int rc = make_launch_env(robot_host(robot), env, le);
         if (rc != VMV_OK || n == 0)
         {
             return rc;
@@ -2431,7 +2097,7 @@ extern "C"
         {
             return rc;
         }
-        const float res = static_cast<float>(resolution > 0 ? resolution : g_robots[robot].resolution);
+        const float res = static_cast<float>(resolution > 0 ? resolution : robot_host(robot).resolution);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         const int force = g_force_path.load();
         if ((force == 0 && n >= kGridMinEdges) || force == 3)
@@ -2445,14 +2111,7 @@ extern "C"
             }
             if (ok)
             {
-                if (wide)
-                {
-                    VMV_DISPATCH(robot, (launch_edges_v4<R, unsigned long long>(robot, rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
-                }
-                else
-                {
-                    VMV_DISPATCH(robot, (launch_edges_v4<R, uint32_t>(robot, rd, l3, d_a, d_b, d_pairs, n, res, d_bits, s)))
-                }
+                rc = ops(robot).edges_v4(robot, wide, rd, l3, d_a, d_b, d_pairs, n, res, d_bits, gather, s);
                 if (rc != VMV_ERR_LIMIT || force == 3)
                 {
                     return rc;
@@ -2463,57 +2122,56 @@ extern "C"
                 return fail(VMV_ERR_LIMIT, "grid-culled kernel not applicable to this environment");
             }
         }
-        VMV_DISPATCH(robot, (launch_edges<R, BLOCK>(rd, le, d_a, d_b, d_pairs, n, res, d_bits, s)))
-        return rc;
+        rc = ops(robot).edges(rd, le, d_a, d_b, d_pairs, n, res, d_bits, s);
+        return rc == VMV_OK ? push_gather(gather, d_bits, (n + 31) / 32, s) : rc;
     }
 
     int vmv_validate_edges_dev(int robot, const vmv_env *env, const float *d_a, const float *d_b, size_t n, int resolution, uint32_t *d_bits, void *stream)
     {
-        if (!valid_robot(robot) || (n > 0 && (d_a == nullptr || d_b == nullptr || d_bits == nullptr)))
+        return guarded("vmv_validate_edges_dev", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_validate_edges_dev: bad argument");
-        }
-        return edges_common(robot, env, d_a, d_b, nullptr, n, resolution, d_bits, stream);
+            if (!valid_robot(robot) || (n > 0 && (d_a == nullptr || d_b == nullptr || d_bits == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_edges_dev: bad argument");
+            }
+            return edges_common(robot, env, d_a, d_b, nullptr, n, resolution, d_bits, GatherDev{}, stream);
+        });
     }
 
     int vmv_validate_edges_indexed_dev(int robot, const vmv_env *env, const float *d_vertices, size_t n_vertices, const uint32_t *d_pairs, size_t n_edges, int resolution, uint32_t *d_bits, void *stream)
     {
-        (void)n_vertices;
-        if (!valid_robot(robot) || (n_edges > 0 && (d_vertices == nullptr || d_pairs == nullptr || d_bits == nullptr)))
+        return guarded("vmv_validate_edges_indexed_dev", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed_dev: bad argument");
-        }
-        return edges_common(robot, env, d_vertices, nullptr, d_pairs, n_edges, resolution, d_bits, stream);
+            (void)n_vertices;
+            if (!valid_robot(robot) || (n_edges > 0 && (d_vertices == nullptr || d_pairs == nullptr || d_bits == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed_dev: bad argument");
+            }
+            return edges_common(robot, env, d_vertices, nullptr, d_pairs, n_edges, resolution, d_bits, GatherDev{}, stream);
+        });
     }
 
     int vmv_sphere_fk_dev(int robot, const float *d_q, size_t n, float *d_xyzr, void *stream)
     {
-        if (!valid_robot(robot) || (n > 0 && (d_q == nullptr || d_xyzr == nullptr)))
+        return guarded("vmv_sphere_fk_dev", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_sphere_fk_dev: bad argument");
-        }
-        if (n == 0)
-        {
-            return VMV_OK;
-        }
-        vmv::RobotDev rd{};
-        int rc = robot_tables(robot, rd);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        cudaStream_t s = static_cast<cudaStream_t>(stream);
-        switch (robot)
-        {
-            case VMV_PANDA:
-                return launch_fk<panda_robot>(rd, d_q, n, d_xyzr, s);
-            case VMV_UR5:
-                return launch_fk<ur5_robot>(rd, d_q, n, d_xyzr, s);
-            case VMV_FETCH:
-                return launch_fk<fetch_robot>(rd, d_q, n, d_xyzr, s);
-            default:
-                return launch_fk<baxter_robot>(rd, d_q, n, d_xyzr, s);
-        }
+            if (!valid_robot(robot) || (n > 0 && (d_q == nullptr || d_xyzr == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_sphere_fk_dev: bad argument");
+            }
+            if (n == 0)
+            {
+                return VMV_OK;
+            }
+            vmv::RobotDev rd{};
+            int rc = robot_tables(robot, rd);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            cudaStream_t s = static_cast<cudaStream_t>(stream);
+            return ops(robot).fk(rd, d_q, n, d_xyzr, s);
+        });
     }
 
     // ---- host-buffer versions: H2D + kernel + D2H + sync ------------------------------------
@@ -2578,6 +2236,23 @@ extern "C"
         };
         HostPathPool g_pools[kMaxDevices];
 
+        // No return -- error or not -- leaves a copy in flight on the pool's streams: the caller may free or
+        // reuse q / a / b / bits as soon as the call is back.
+        struct PoolDrain
+        {
+            HostPathPool &pool;
+            ~PoolDrain()
+            {
+                for (cudaStream_t st : pool.streams)
+                {
+                    if (st != nullptr)
+                    {
+                        cudaStreamSynchronize(st);
+                    }
+                }
+            }
+        };
+
         // multiple of 32: chunks own whole verdict words.  VMV_CHUNK_LOG2 overrides (tuning aid).
         size_t chunk_units()
         {
@@ -2593,185 +2268,174 @@ extern "C"
 
     int vmv_validate_configs(int robot, const vmv_env *env, const float *q, size_t n, uint32_t *bits)
     {
-        if (!valid_robot(robot) || (n > 0 && (q == nullptr || bits == nullptr)))
+        return guarded("vmv_validate_configs", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_validate_configs: bad argument");
-        }
-        if (n == 0)
-        {
-            vmv::LaunchEnv probe{};
-            return make_launch_env(g_robots[robot], env, probe);
-        }
-        int device = 0;
-        VMV_CUDA(cudaGetDevice(&device));
-        HostPathPool &pool = g_pools[device % kMaxDevices];
-        std::lock_guard<std::mutex> lock(pool.mutex);
-        const size_t dof = g_robots[robot].dof;
-        int rc = pool.init();
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(0, n * dof * sizeof(float));
-        }
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(2, ((n + 31) / 32) * 4);
-        }
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        float *dq = static_cast<float *>(pool.buf[0]);
-        uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
-        int k = 0;
-        const size_t chunk_cfg = chunk_units();
-        for (size_t off = 0; off < n; off += chunk_cfg, ++k)
-        {
-            const size_t cnt = std::min(chunk_cfg, n - off);
-            cudaStream_t st = pool.streams[k & 1];
-            VMV_CUDA(cudaMemcpyAsync(dq + off * dof, q + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
-            rc = vmv_validate_configs_dev(robot, env, dq + off * dof, cnt, dw + off / 32, st);
+            if (!valid_robot(robot) || (n > 0 && (q == nullptr || bits == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_configs: bad argument");
+            }
+            if (n == 0)
+            {
+                vmv::LaunchEnv probe{};
+                return make_launch_env(robot_host(robot), env, probe);
+            }
+            int device = 0;
+            VMV_CUDA(cudaGetDevice(&device));
+            HostPathPool &pool = g_pools[device % kMaxDevices];
+            std::lock_guard<std::mutex> lock(pool.mutex);
+            const PoolDrain drain{pool};
+            const size_t dof = robot_host(robot).dof;
+            int rc = pool.init();
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(0, n * dof * sizeof(float));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(2, ((n + 31) / 32) * 4);
+            }
             if (rc != VMV_OK)
             {
                 return rc;
             }
-            VMV_CUDA(cudaMemcpyAsync(bits + off / 32, dw + off / 32, ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
-        }
-        VMV_CUDA(cudaStreamSynchronize(pool.streams[0]));
-        VMV_CUDA(cudaStreamSynchronize(pool.streams[1]));
-        return VMV_OK;
+            float *dq = static_cast<float *>(pool.buf[0]);
+            uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
+            int k = 0;
+            const size_t chunk_cfg = chunk_units();
+            for (size_t off = 0; off < n; off += chunk_cfg, ++k)
+            {
+                const size_t cnt = std::min(chunk_cfg, n - off);
+                cudaStream_t st = pool.streams[k & 1];
+                VMV_CUDA(cudaMemcpyAsync(dq + off * dof, q + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
+                rc = vmv_validate_configs_dev(robot, env, dq + off * dof, cnt, dw + off / 32, st);
+                if (rc != VMV_OK)
+                {
+                    return rc;
+                }
+                VMV_CUDA(cudaMemcpyAsync(bits + off / 32, dw + off / 32, ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+            }
+            VMV_CUDA(cudaStreamSynchronize(pool.streams[0]));
+            VMV_CUDA(cudaStreamSynchronize(pool.streams[1]));
+            return VMV_OK;
+        });
     }
 
     int vmv_validate_edges(int robot, const vmv_env *env, const float *a, const float *b, size_t n, int resolution, uint32_t *bits)
     {
-        if (!valid_robot(robot) || (n > 0 && (a == nullptr || b == nullptr || bits == nullptr)))
+        return guarded("vmv_validate_edges", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_validate_edges: bad argument");
-        }
-        if (n == 0)
-        {
-            vmv::LaunchEnv probe{};
-            return make_launch_env(g_robots[robot], env, probe);
-        }
-        int device = 0;
-        VMV_CUDA(cudaGetDevice(&device));
-        HostPathPool &pool = g_pools[device % kMaxDevices];
-        std::lock_guard<std::mutex> lock(pool.mutex);
-        const size_t dof = g_robots[robot].dof;
-        int rc = pool.init();
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(0, n * dof * sizeof(float));
-        }
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(1, n * dof * sizeof(float));
-        }
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(2, ((n + 31) / 32) * 4);
-        }
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        float *da = static_cast<float *>(pool.buf[0]);
-        float *db = static_cast<float *>(pool.buf[1]);
-        uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
-        const size_t chunk = chunk_units() / 4;
-        int k = 0;
-        for (size_t off = 0; off < n; off += chunk, ++k)
-        {
-            const size_t cnt = std::min(chunk, n - off);
-            cudaStream_t st = pool.streams[k & 1];
-            VMV_CUDA(cudaMemcpyAsync(da + off * dof, a + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
-            VMV_CUDA(cudaMemcpyAsync(db + off * dof, b + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
-            rc = vmv_validate_edges_dev(robot, env, da + off * dof, db + off * dof, cnt, resolution, dw + off / 32, st);
+            if (!valid_robot(robot) || (n > 0 && (a == nullptr || b == nullptr || bits == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_edges: bad argument");
+            }
+            if (n == 0)
+            {
+                vmv::LaunchEnv probe{};
+                return make_launch_env(robot_host(robot), env, probe);
+            }
+            int device = 0;
+            VMV_CUDA(cudaGetDevice(&device));
+            HostPathPool &pool = g_pools[device % kMaxDevices];
+            std::lock_guard<std::mutex> lock(pool.mutex);
+            const PoolDrain drain{pool};
+            const size_t dof = robot_host(robot).dof;
+            int rc = pool.init();
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(0, n * dof * sizeof(float));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(1, n * dof * sizeof(float));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(2, ((n + 31) / 32) * 4);
+            }
             if (rc != VMV_OK)
             {
                 return rc;
             }
-            VMV_CUDA(cudaMemcpyAsync(bits + off / 32, dw + off / 32, ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
-        }
-        VMV_CUDA(cudaStreamSynchronize(pool.streams[0]));
-        VMV_CUDA(cudaStreamSynchronize(pool.streams[1]));
-        return VMV_OK;
+            float *da = static_cast<float *>(pool.buf[0]);
+            float *db = static_cast<float *>(pool.buf[1]);
+            uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
+            const size_t chunk = chunk_units() / 4;
+            int k = 0;
+            for (size_t off = 0; off < n; off += chunk, ++k)
+            {
+                const size_t cnt = std::min(chunk, n - off);
+                cudaStream_t st = pool.streams[k & 1];
+                VMV_CUDA(cudaMemcpyAsync(da + off * dof, a + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
+                VMV_CUDA(cudaMemcpyAsync(db + off * dof, b + off * dof, cnt * dof * sizeof(float), cudaMemcpyHostToDevice, st));
+                rc = vmv_validate_edges_dev(robot, env, da + off * dof, db + off * dof, cnt, resolution, dw + off / 32, st);
+                if (rc != VMV_OK)
+                {
+                    return rc;
+                }
+                VMV_CUDA(cudaMemcpyAsync(bits + off / 32, dw + off / 32, ((cnt + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+            }
+            VMV_CUDA(cudaStreamSynchronize(pool.streams[0]));
+            VMV_CUDA(cudaStreamSynchronize(pool.streams[1]));
+            return VMV_OK;
+        });
     }
 
     int vmv_validate_edges_indexed(int robot, const vmv_env *env, const float *vertices, size_t n_vertices, const uint32_t *pairs, size_t n_edges, int resolution, uint32_t *bits)
     {
-        if (!valid_robot(robot) || (n_edges > 0 && (vertices == nullptr || pairs == nullptr || bits == nullptr)))
+        return guarded("vmv_validate_edges_indexed", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed: bad argument");
-        }
-        if (n_edges == 0)
-        {
-            vmv::LaunchEnv probe{};
-            return make_launch_env(g_robots[robot], env, probe);
-        }
-        for (size_t i = 0; i < 2 * n_edges; ++i)
-        {
-            if (pairs[i] >= n_vertices)
+            if (!valid_robot(robot) || (n_edges > 0 && (vertices == nullptr || pairs == nullptr || bits == nullptr)))
             {
-                return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed: vertex index out of range");
+                return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed: bad argument");
             }
-        }
-        int device = 0;
-        VMV_CUDA(cudaGetDevice(&device));
-        HostPathPool &pool = g_pools[device % kMaxDevices];
-        std::lock_guard<std::mutex> lock(pool.mutex);
-        const size_t dof = g_robots[robot].dof;
-        int rc = pool.init();
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(0, n_vertices * dof * sizeof(float));
-        }
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(1, n_edges * 2 * sizeof(uint32_t));
-        }
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(2, ((n_edges + 31) / 32) * 4);
-        }
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        cudaStream_t st = pool.streams[0];
-        VMV_CUDA(cudaMemcpyAsync(pool.buf[0], vertices, n_vertices * dof * sizeof(float), cudaMemcpyHostToDevice, st));
-        VMV_CUDA(cudaMemcpyAsync(pool.buf[1], pairs, n_edges * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        rc = vmv_validate_edges_indexed_dev(robot, env, static_cast<const float *>(pool.buf[0]), n_vertices, static_cast<const uint32_t *>(pool.buf[1]),
-                                            n_edges, resolution, static_cast<uint32_t *>(pool.buf[2]), st);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        VMV_CUDA(cudaMemcpyAsync(bits, pool.buf[2], ((n_edges + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
-        VMV_CUDA(cudaStreamSynchronize(st));
-        return VMV_OK;
-    }
-
-    extern "C++"
-    {
-    template <typename R>
-    static int launch_filter(const vmv::RobotDev &rd, const vmv::LaunchEnv &le, const float *q, const float *pts, size_t n, float r_point, uint32_t *bits, cudaStream_t s)
-    {
-        using M = typename R::Model;
-        constexpr int BLOCK = 128;
-        const uint32_t smem = ((le.blob_bytes + 15u) & ~15u) + M::kSpheres * sizeof(float4);
-        if (smem > kMaxSmem - 1024)
-        {
-            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");
-        }
-        auto kernel = vmv::k_filter_points<R, BLOCK>;
-        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        const size_t tiles = (n + BLOCK - 1) / BLOCK;
-        const unsigned grid = static_cast<unsigned>(std::min<size_t>(tiles, static_cast<size_t>(sm_count()) * 8));
-        kernel<<<grid, BLOCK, smem, s>>>(rd, le, q, pts, n, r_point, bits);
-        g_launches++;
-        VMV_CUDA(cudaGetLastError());
-        return VMV_OK;
-    }
+            if (n_edges == 0)
+            {
+                vmv::LaunchEnv probe{};
+                return make_launch_env(robot_host(robot), env, probe);
+            }
+            for (size_t i = 0; i < 2 * n_edges; ++i)
+            {
+                if (pairs[i] >= n_vertices)
+                {
+                    return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed: vertex index out of range");
+                }
+            }
+            int device = 0;
+            VMV_CUDA(cudaGetDevice(&device));
+            HostPathPool &pool = g_pools[device % kMaxDevices];
+            std::lock_guard<std::mutex> lock(pool.mutex);
+            const PoolDrain drain{pool};
+            const size_t dof = robot_host(robot).dof;
+            int rc = pool.init();
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(0, n_vertices * dof * sizeof(float));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(1, n_edges * 2 * sizeof(uint32_t));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(2, ((n_edges + 31) / 32) * 4);
+            }
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            cudaStream_t st = pool.streams[0];
+            VMV_CUDA(cudaMemcpyAsync(pool.buf[0], vertices, n_vertices * dof * sizeof(float), cudaMemcpyHostToDevice, st));
+            VMV_CUDA(cudaMemcpyAsync(pool.buf[1], pairs, n_edges * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            rc = vmv_validate_edges_indexed_dev(robot, env, static_cast<const float *>(pool.buf[0]), n_vertices, static_cast<const uint32_t *>(pool.buf[1]),
+                                                n_edges, resolution, static_cast<uint32_t *>(pool.buf[2]), st);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpyAsync(bits, pool.buf[2], ((n_edges + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+            VMV_CUDA(cudaStreamSynchronize(st));
+            return VMV_OK;
+        });
     }
 
     // ---- CenterVox pointcloud filter (vmv_filter.cuh; reference collision/filter_centervox.hh) -------
@@ -3005,13 +2669,19 @@ extern "C"
     int vmv_filter_pointcloud_centervox(const float *points, size_t n, float voxel_size, float max_range, const float *origin, const float *workspace_min,
                                         const float *workspace_max, uint32_t *kept_indices, size_t cap, size_t *n_kept)
     {
-        return centervox_run(points, false, n, voxel_size, max_range, origin, workspace_min, workspace_max, kept_indices, cap, n_kept);
+        return guarded("vmv_filter_pointcloud_centervox", [&]() -> int
+        {
+            return centervox_run(points, false, n, voxel_size, max_range, origin, workspace_min, workspace_max, kept_indices, cap, n_kept);
+        });
     }
 
     int vmv_filter_pointcloud_centervox_dev(const float *d_points, size_t n, float voxel_size, float max_range, const float *origin,
                                             const float *workspace_min, const float *workspace_max, uint32_t *kept_indices, size_t cap, size_t *n_kept)
     {
-        return centervox_run(d_points, true, n, voxel_size, max_range, origin, workspace_min, workspace_max, kept_indices, cap, n_kept);
+        return guarded("vmv_filter_pointcloud_centervox_dev", [&]() -> int
+        {
+            return centervox_run(d_points, true, n, voxel_size, max_range, origin, workspace_min, workspace_max, kept_indices, cap, n_kept);
+        });
     }
 
     // ---- Halton sampler on the device (vmv_halton.cuh; reference random/halton.hh) ------------------
@@ -3052,275 +2722,261 @@ extern "C"
 
     int vmv_halton_fill_dev(int robot, uint64_t first, size_t n, float *d_q, void *stream)
     {
-        if (!valid_robot(robot) || (n > 0 && d_q == nullptr))
+        return guarded("vmv_halton_fill_dev", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_halton_fill_dev: bad argument");
-        }
-        const int dof = g_robots[robot].dof;
-        if (first + n > halton_exact_limit(dof))
-        {
-            return fail(VMV_ERR_LIMIT, "vmv_halton_fill_dev: samples beyond the exact range of the reference's f32 recurrence "
-                                       "(first epoch, base^digits < 2^24); draw those on the host");
-        }
-        if (n == 0)
-        {
-            return VMV_OK;
-        }
-        vmv::HaltonScale sc{};
-        for (int j = 0; j < dof; ++j)
-        {
-            sc.lower[j] = g_robots[robot].lower[j];
-            sc.range[j] = g_robots[robot].range[j];
-        }
-        cudaStream_t s = static_cast<cudaStream_t>(stream);
-        switch (dof)
-        {
-            case 6:
-                return launch_halton<6>(sc, first, n, d_q, s);
-            case 7:
-                return launch_halton<7>(sc, first, n, d_q, s);
-            case 8:
-                return launch_halton<8>(sc, first, n, d_q, s);
-            case 14:
-                return launch_halton<14>(sc, first, n, d_q, s);
-            default:
-                return fail(VMV_ERR_ARG, "vmv_halton_fill_dev: unsupported joint count");
-        }
+            if (!valid_robot(robot) || (n > 0 && d_q == nullptr))
+            {
+                return fail(VMV_ERR_ARG, "vmv_halton_fill_dev: bad argument");
+            }
+            const int dof = robot_host(robot).dof;
+            if (first + n > halton_exact_limit(dof))
+            {
+                return fail(VMV_ERR_LIMIT, "vmv_halton_fill_dev: samples beyond the exact range of the reference's f32 recurrence "
+                                           "(first epoch, base^digits < 2^24); draw those on the host");
+            }
+            if (n == 0)
+            {
+                return VMV_OK;
+            }
+            vmv::HaltonScale sc{};
+            for (int j = 0; j < dof; ++j)
+            {
+                sc.lower[j] = robot_host(robot).lower[j];
+                sc.range[j] = robot_host(robot).range[j];
+            }
+            cudaStream_t s = static_cast<cudaStream_t>(stream);
+            switch (dof)
+            {
+                case 6:
+                    return launch_halton<6>(sc, first, n, d_q, s);
+                case 7:
+                    return launch_halton<7>(sc, first, n, d_q, s);
+                case 8:
+                    return launch_halton<8>(sc, first, n, d_q, s);
+                case 14:
+                    return launch_halton<14>(sc, first, n, d_q, s);
+                default:
+                    return fail(VMV_ERR_ARG, "vmv_halton_fill_dev: unsupported joint count");
+            }
+        });
     }
 
     uint64_t vmv_halton_exact_limit(int robot)
     {
-        return valid_robot(robot) ? halton_exact_limit(g_robots[robot].dof) : 0;
+        return valid_robot(robot) ? halton_exact_limit(robot_host(robot).dof) : 0;
     }
 
     // samples first .. first+n-1 generated and validated on the device; only the verdict bits (and, if
     // asked for, the configurations) cross PCIe
     int vmv_validate_halton(int robot, const vmv_env *env, uint64_t first, size_t n, uint32_t *bits, float *q_out)
     {
-        if (!valid_robot(robot) || (n > 0 && bits == nullptr))
+        return guarded("vmv_validate_halton", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_validate_halton: bad argument");
-        }
-        if (n == 0)
-        {
-            vmv::LaunchEnv probe{};
-            return make_launch_env(g_robots[robot], env, probe);
-        }
-        int device = 0;
-        VMV_CUDA(cudaGetDevice(&device));
-        HostPathPool &pool = g_pools[device % kMaxDevices];
-        std::lock_guard<std::mutex> lock(pool.mutex);
-        const size_t dof = g_robots[robot].dof;
-        int rc = pool.init();
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(0, n * dof * sizeof(float));
-        }
-        if (rc == VMV_OK)
-        {
-            rc = pool.ensure(2, ((n + 31) / 32) * 4);
-        }
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        float *dq = static_cast<float *>(pool.buf[0]);
-        uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
-        cudaStream_t st = pool.streams[0];
-        rc = vmv_halton_fill_dev(robot, first, n, dq, st);
-        if (rc == VMV_OK)
-        {
-            rc = vmv_validate_configs_dev(robot, env, dq, n, dw, st);
-        }
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        VMV_CUDA(cudaMemcpyAsync(bits, dw, ((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
-        if (q_out != nullptr)
-        {
-            VMV_CUDA(cudaMemcpyAsync(q_out, dq, n * dof * sizeof(float), cudaMemcpyDeviceToHost, st));
-        }
-        VMV_CUDA(cudaStreamSynchronize(st));
-        return VMV_OK;
+            if (!valid_robot(robot) || (n > 0 && bits == nullptr))
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_halton: bad argument");
+            }
+            if (n == 0)
+            {
+                vmv::LaunchEnv probe{};
+                return make_launch_env(robot_host(robot), env, probe);
+            }
+            int device = 0;
+            VMV_CUDA(cudaGetDevice(&device));
+            HostPathPool &pool = g_pools[device % kMaxDevices];
+            std::lock_guard<std::mutex> lock(pool.mutex);
+            const PoolDrain drain{pool};
+            const size_t dof = robot_host(robot).dof;
+            int rc = pool.init();
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(0, n * dof * sizeof(float));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = pool.ensure(2, ((n + 31) / 32) * 4);
+            }
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            float *dq = static_cast<float *>(pool.buf[0]);
+            uint32_t *dw = static_cast<uint32_t *>(pool.buf[2]);
+            cudaStream_t st = pool.streams[0];
+            rc = vmv_halton_fill_dev(robot, first, n, dq, st);
+            if (rc == VMV_OK)
+            {
+                rc = vmv_validate_configs_dev(robot, env, dq, n, dw, st);
+            }
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpyAsync(bits, dw, ((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+            if (q_out != nullptr)
+            {
+                VMV_CUDA(cudaMemcpyAsync(q_out, dq, n * dof * sizeof(float), cudaMemcpyDeviceToHost, st));
+            }
+            VMV_CUDA(cudaStreamSynchronize(st));
+            return VMV_OK;
+        });
     }
 
     int vmv_filter_points_dev(int robot, const vmv_env *env, const float *d_q, const float *d_points, size_t n, float point_radius, uint32_t *d_keep_bits, void *stream)
     {
-        if (!valid_robot(robot) || d_q == nullptr || (n > 0 && (d_points == nullptr || d_keep_bits == nullptr)))
+        return guarded("vmv_filter_points_dev", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_filter_points_dev: bad argument");
-        }
-        vmv::LaunchEnv le{};
-        int rc = make_launch_env(g_robots[robot], env, le);
-        if (rc != VMV_OK || n == 0)
-        {
-            return rc;
-        }
-        vmv::RobotDev rd{};
-        rc = robot_tables(robot, rd);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        cudaStream_t s = static_cast<cudaStream_t>(stream);
-        switch (robot)
-        {
-            case VMV_PANDA:
-                return launch_filter<panda_robot>(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
-            case VMV_UR5:
-                return launch_filter<ur5_robot>(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
-            case VMV_FETCH:
-                return launch_filter<fetch_robot>(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
-            default:
-                return launch_filter<baxter_robot>(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
-        }
+            if (!valid_robot(robot) || d_q == nullptr || (n > 0 && (d_points == nullptr || d_keep_bits == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_filter_points_dev: bad argument");
+            }
+            vmv::LaunchEnv le{};
+            int rc = make_launch_env(robot_host(robot), env, le);
+            if (rc != VMV_OK || n == 0)
+            {
+                return rc;
+            }
+            vmv::RobotDev rd{};
+            rc = robot_tables(robot, rd);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            cudaStream_t s = static_cast<cudaStream_t>(stream);
+            return ops(robot).filter(rd, le, d_q, d_points, n, point_radius, d_keep_bits, s);
+        });
     }
 
     int vmv_filter_self_from_pointcloud(int robot, const vmv_env *env, const float *q, const float *points, size_t n, float point_radius, uint32_t *keep_bits)
     {
-        if (!valid_robot(robot) || q == nullptr || (n > 0 && (points == nullptr || keep_bits == nullptr)))
+        return guarded("vmv_filter_self_from_pointcloud", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_filter_self_from_pointcloud: bad argument");
-        }
-        if (n == 0)
-        {
-            vmv::LaunchEnv probe{};
-            return make_launch_env(g_robots[robot], env, probe);
-        }
-        const size_t dof = g_robots[robot].dof, words = (n + 31) / 32;
-        DevBuf dq, dp, db;
-        int rc = dq.alloc(dof * sizeof(float));
-        if (rc == VMV_OK)
-        {
-            rc = dp.alloc(n * 3 * sizeof(float));
-        }
-        if (rc == VMV_OK)
-        {
-            rc = db.alloc(words * 4);
-        }
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        VMV_CUDA(cudaMemcpy(dq.p, q, dof * sizeof(float), cudaMemcpyHostToDevice));
-        VMV_CUDA(cudaMemcpy(dp.p, points, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
-        rc = vmv_filter_points_dev(robot, env, static_cast<const float *>(dq.p), static_cast<const float *>(dp.p), n, point_radius,
-                                   static_cast<uint32_t *>(db.p), nullptr);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        VMV_CUDA(cudaMemcpy(keep_bits, db.p, words * 4, cudaMemcpyDeviceToHost));
-        return VMV_OK;
+            if (!valid_robot(robot) || q == nullptr || (n > 0 && (points == nullptr || keep_bits == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_filter_self_from_pointcloud: bad argument");
+            }
+            if (n == 0)
+            {
+                vmv::LaunchEnv probe{};
+                return make_launch_env(robot_host(robot), env, probe);
+            }
+            const size_t dof = robot_host(robot).dof, words = (n + 31) / 32;
+            DevBuf dq, dp, db;
+            int rc = dq.alloc(dof * sizeof(float));
+            if (rc == VMV_OK)
+            {
+                rc = dp.alloc(n * 3 * sizeof(float));
+            }
+            if (rc == VMV_OK)
+            {
+                rc = db.alloc(words * 4);
+            }
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpy(dq.p, q, dof * sizeof(float), cudaMemcpyHostToDevice));
+            VMV_CUDA(cudaMemcpy(dp.p, points, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+            rc = vmv_filter_points_dev(robot, env, static_cast<const float *>(dq.p), static_cast<const float *>(dp.p), n, point_radius,
+                                       static_cast<uint32_t *>(db.p), nullptr);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpy(keep_bits, db.p, words * 4, cudaMemcpyDeviceToHost));
+            return VMV_OK;
+        });
     }
 
     int vmv_sphere_fk(int robot, const float *q, size_t n, float *xyzr)
     {
-        if (!valid_robot(robot) || (n > 0 && (q == nullptr || xyzr == nullptr)))
+        return guarded("vmv_sphere_fk", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_sphere_fk: bad argument");
-        }
-        if (n == 0)
-        {
+            if (!valid_robot(robot) || (n > 0 && (q == nullptr || xyzr == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_sphere_fk: bad argument");
+            }
+            if (n == 0)
+            {
+                return VMV_OK;
+            }
+            const size_t qbytes = n * robot_host(robot).dof * sizeof(float);
+            const size_t obytes = n * robot_host(robot).n_spheres * 4 * sizeof(float);
+            DevBuf dq, dout;
+            int rc = dq.alloc(qbytes);
+            if (rc == VMV_OK)
+            {
+                rc = dout.alloc(obytes);
+            }
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, nullptr));
+            rc = vmv_sphere_fk_dev(robot, static_cast<const float *>(dq.p), n, static_cast<float *>(dout.p), nullptr);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpyAsync(xyzr, dout.p, obytes, cudaMemcpyDeviceToHost, nullptr));
+            VMV_CUDA(cudaStreamSynchronize(nullptr));
             return VMV_OK;
-        }
-        const size_t qbytes = n * g_robots[robot].dof * sizeof(float);
-        const size_t obytes = n * g_robots[robot].n_spheres * 4 * sizeof(float);
-        DevBuf dq, dout;
-        int rc = dq.alloc(qbytes);
-        if (rc == VMV_OK)
-        {
-            rc = dout.alloc(obytes);
-        }
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        VMV_CUDA(cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, nullptr));
-        rc = vmv_sphere_fk_dev(robot, static_cast<const float *>(dq.p), n, static_cast<float *>(dout.p), nullptr);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        VMV_CUDA(cudaMemcpyAsync(xyzr, dout.p, obytes, cudaMemcpyDeviceToHost, nullptr));
-        VMV_CUDA(cudaStreamSynchronize(nullptr));
-        return VMV_OK;
+        });
     }
 
     int vmv_debug(int robot, const vmv_env *env, const float *q, int32_t *env_hits, size_t cap_env, size_t *n_env, int32_t *self_hits, size_t cap_self, size_t *n_self)
     {
-        if (!valid_robot(robot) || q == nullptr || n_env == nullptr || n_self == nullptr || (cap_env > 0 && env_hits == nullptr) ||
-            (cap_self > 0 && self_hits == nullptr))
+        return guarded("vmv_debug", [&]() -> int
         {
-            return fail(VMV_ERR_ARG, "vmv_debug: bad argument");
-        }
-        vmv::LaunchEnv le{};
-        int rc = make_launch_env(g_robots[robot], env, le);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        vmv::RobotDev rd{};
-        rc = robot_tables(robot, rd);
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        const size_t dof = g_robots[robot].dof;
-        DevBuf dq, de, ds, dc;
-        rc = dq.alloc(dof * sizeof(float));
-        rc = rc == VMV_OK ? de.alloc(2 * cap_env * sizeof(int32_t)) : rc;
-        rc = rc == VMV_OK ? ds.alloc(2 * cap_self * sizeof(int32_t)) : rc;
-        rc = rc == VMV_OK ? dc.alloc(2 * sizeof(uint32_t)) : rc;
-        if (rc != VMV_OK)
-        {
-            return rc;
-        }
-        VMV_CUDA(cudaMemcpy(dq.p, q, dof * sizeof(float), cudaMemcpyHostToDevice));
-        VMV_CUDA(cudaMemset(dc.p, 0, 2 * sizeof(uint32_t)));
-        constexpr int BLOCK = 64;
-#define VMV_DEBUG_LAUNCH(RT)                                                                                                  \
-    {                                                                                                                         \
-        const vmv::SmemLayout<RT::Model, BLOCK> L(le.blob_bytes);                                                             \
-        if (L.total > kMaxSmem)                                                                                               \
-        {                                                                                                                     \
-            return fail(VMV_ERR_LIMIT, "environment too large for shared-memory staging");                                    \
-        }                                                                                                                     \
-        auto kernel = vmv::k_debug<RT, BLOCK>;                                                                                \
-        VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));       \
-        kernel<<<1, BLOCK, L.total, nullptr>>>(                                                                               \
-            rd, le, static_cast<const float *>(dq.p), env->d_object_ids, static_cast<int32_t *>(de.p),                        \
-            static_cast<uint32_t>(cap_env), static_cast<int32_t *>(ds.p), static_cast<uint32_t>(cap_self),                    \
-            static_cast<uint32_t *>(dc.p));                                                                                   \
-    }
-        switch (robot)
-        {
-            case VMV_PANDA:
-                VMV_DEBUG_LAUNCH(panda_robot) break;
-            case VMV_UR5:
-                VMV_DEBUG_LAUNCH(ur5_robot) break;
-            case VMV_FETCH:
-                VMV_DEBUG_LAUNCH(fetch_robot) break;
-            default:
-                VMV_DEBUG_LAUNCH(baxter_robot) break;
-        }
-#undef VMV_DEBUG_LAUNCH
-        g_launches++;
-        VMV_CUDA(cudaGetLastError());
-        uint32_t counts[2] = {0, 0};
-        VMV_CUDA(cudaMemcpy(counts, dc.p, sizeof(counts), cudaMemcpyDeviceToHost));
-        *n_env = counts[0];
-        *n_self = counts[1];
-        if (cap_env > 0)
-        {
-            VMV_CUDA(cudaMemcpy(env_hits, de.p, 2 * std::min<size_t>(cap_env, counts[0]) * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        }
-        if (cap_self > 0)
-        {
-            VMV_CUDA(cudaMemcpy(self_hits, ds.p, 2 * std::min<size_t>(cap_self, counts[1]) * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        }
-        return VMV_OK;
+            if (!valid_robot(robot) || q == nullptr || n_env == nullptr || n_self == nullptr || (cap_env > 0 && env_hits == nullptr) ||
+                (cap_self > 0 && self_hits == nullptr))
+            {
+                return fail(VMV_ERR_ARG, "vmv_debug: bad argument");
+            }
+            vmv::LaunchEnv le{};
+            int rc = make_launch_env(robot_host(robot), env, le);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            vmv::RobotDev rd{};
+            rc = robot_tables(robot, rd);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            const size_t dof = robot_host(robot).dof;
+            DevBuf dq, de, ds, dc;
+            rc = dq.alloc(dof * sizeof(float));
+            rc = rc == VMV_OK ? de.alloc(2 * cap_env * sizeof(int32_t)) : rc;
+            rc = rc == VMV_OK ? ds.alloc(2 * cap_self * sizeof(int32_t)) : rc;
+            rc = rc == VMV_OK ? dc.alloc(2 * sizeof(uint32_t)) : rc;
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_CUDA(cudaMemcpy(dq.p, q, dof * sizeof(float), cudaMemcpyHostToDevice));
+            VMV_CUDA(cudaMemset(dc.p, 0, 2 * sizeof(uint32_t)));
+            rc = ops(robot).debug(rd, le, static_cast<const float *>(dq.p), env->d_object_ids, static_cast<int32_t *>(de.p), static_cast<uint32_t>(cap_env),
+                                  static_cast<int32_t *>(ds.p), static_cast<uint32_t>(cap_self), static_cast<uint32_t *>(dc.p));
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            uint32_t counts[2] = {0, 0};
+            VMV_CUDA(cudaMemcpy(counts, dc.p, sizeof(counts), cudaMemcpyDeviceToHost));
+            *n_env = counts[0];
+            *n_self = counts[1];
+            if (cap_env > 0)
+            {
+                VMV_CUDA(cudaMemcpy(env_hits, de.p, 2 * std::min<size_t>(cap_env, counts[0]) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            }
+            if (cap_self > 0)
+            {
+                VMV_CUDA(cudaMemcpy(self_hits, ds.p, 2 * std::min<size_t>(cap_self, counts[1]) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            }
+            return VMV_OK;
+        });
     }
 
     void *vmv_dev_alloc(size_t bytes)
@@ -3391,4 +3047,559 @@ extern "C"
         g_force_path.store(path);
         return VMV_OK;
     }
+    // =========================================================================================
+    // multi-GPU: one process per GPU of one node; NCCL for the plain collectives (loaded at run time, so
+    // single-GPU users need no NCCL), CUDA IPC windows for the gather fused into the validation kernels
+    // =========================================================================================
+    extern "C++"
+    {
+    namespace
+    {
+        struct NcclId
+        {
+            char internal[128];
+        };
+        struct NcclApi
+        {
+            void *lib = nullptr;
+            int (*GetUniqueId)(NcclId *) = nullptr;
+            int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+            int (*CommDestroy)(void *) = nullptr;
+            int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+            int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+            const char *(*GetErrorString)(int) = nullptr;
+        };
+        constexpr int kNcclUint8 = 1, kNcclUint32 = 3;  // ncclDataType_t (nccl.h)
+
+        int nccl_api(const NcclApi *&out)
+        {
+            static NcclApi api;
+            static bool tried = false;
+            std::lock_guard<std::mutex> lock(g_mutex);
+            if (!tried)
+            {
+                tried = true;
+                // a process that already holds an NCCL (torch's bundled copy) gets that one: same soname
+                void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+                if (lib == nullptr)
+                {
+                    lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+                }
+                if (lib != nullptr)
+                {
+                    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+                    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+                    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+                    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
+                    api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(lib, "ncclBroadcast"));
+                    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+                    if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GetErrorString)
+                    {
+                        api.lib = lib;
+                    }
+                }
+            }
+            if (api.lib == nullptr)
+            {
+                return fail(VMV_ERR_STATE, "NCCL is not available (libnccl.so.2 could not be loaded)");
+            }
+            out = &api;
+            return VMV_OK;
+        }
+
+        int nccl_fail(const NcclApi &api, int code, const char *what)
+        {
+            return fail(VMV_ERR_CUDA, std::string(what) + ": " + api.GetErrorString(code));
+        }
+
+#define VMV_NCCL(api, call)                          \
+    do                                               \
+    {                                                \
+        const int c_ = (call);                       \
+        if (c_ != 0)                                 \
+        {                                            \
+            return nccl_fail(api, c_, #call);        \
+        }                                            \
+    } while (0)
+
+        constexpr int kMaxSlots = 4;
+
+        // byte stream of an environment's host-side description (vmv_env_broadcast)
+        struct Writer
+        {
+            std::vector<unsigned char> b;
+            template <typename T>
+            void pod(const T &v)
+            {
+                const unsigned char *p = reinterpret_cast<const unsigned char *>(&v);
+                b.insert(b.end(), p, p + sizeof(T));
+            }
+            template <typename T, typename A>
+            void vec(const std::vector<T, A> &v)
+            {
+                pod<uint64_t>(v.size());
+                const unsigned char *p = reinterpret_cast<const unsigned char *>(v.data());
+                b.insert(b.end(), p, p + v.size() * sizeof(T));
+            }
+        };
+        struct Reader
+        {
+            const unsigned char *p, *end;
+            bool ok = true;
+            template <typename T>
+            void pod(T &v)
+            {
+                if (static_cast<size_t>(end - p) < sizeof(T))
+                {
+                    ok = false;
+                    return;
+                }
+                std::memcpy(&v, p, sizeof(T));
+                p += sizeof(T);
+            }
+            template <typename T, typename A>
+            void vec(std::vector<T, A> &v)
+            {
+                uint64_t n = 0;
+                pod(n);
+                if (!ok || static_cast<uint64_t>(end - p) < n * sizeof(T))
+                {
+                    ok = false;
+                    return;
+                }
+                v.resize(n);
+                std::memcpy(v.data(), p, n * sizeof(T));
+                p += n * sizeof(T);
+            }
+        };
+    }  // namespace
+    }
+
+}
+
+struct vmv_comm
+{
+    int rank = 0, world = 1, device = 0;
+    void *nccl = nullptr;
+    size_t words_per_rank = 0;
+    int slots = 0;
+    size_t flags_off = 0, window_words = 0;  // in words from the window base
+    uint32_t *window = nullptr;
+    uint32_t *peer_window[vmv::kMaxPeers] = {};
+    uint32_t seq[4] = {0, 0, 0, 0};
+};
+
+namespace
+{
+    GatherDev gather_for(vmv_comm *c, int slot)
+    {
+        GatherDev g{};
+        g.world = c->world;
+        g.rank = c->rank;
+        g.seq = ++c->seq[slot];
+        const size_t row = static_cast<size_t>(slot) * c->world * c->words_per_rank + static_cast<size_t>(c->rank) * c->words_per_rank;
+        for (int p = 0; p < c->world; ++p)
+        {
+            g.peer_bits[p] = c->peer_window[p] + row;
+            g.peer_flag[p] = c->peer_window[p] + c->flags_off + static_cast<size_t>(slot) * vmv::kMaxPeers + c->rank;
+        }
+        return g;
+    }
+
+    int check_gather_call(const vmv_comm *c, int slot, size_t n_units)
+    {
+        if (c == nullptr || c->window == nullptr)
+        {
+            return fail(VMV_ERR_STATE, "no gather window (call vmv_comm_window)");
+        }
+        if (slot < 0 || slot >= c->slots)
+        {
+            return fail(VMV_ERR_ARG, "gather slot out of range");
+        }
+        if ((n_units + 31) / 32 > c->words_per_rank)
+        {
+            return fail(VMV_ERR_ARG, "batch larger than the window's words_per_rank * 32 units");
+        }
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        if (device != c->device)
+        {
+            return fail(VMV_ERR_STATE, "communicator belongs to another device");
+        }
+        return VMV_OK;
+    }
+}  // namespace
+
+extern "C"
+{
+    int vmv_comm_unique_id(unsigned char *id128)
+    {
+        return guarded("vmv_comm_unique_id", [&]() -> int
+        {
+            if (id128 == nullptr)
+            {
+                return fail(VMV_ERR_ARG, "vmv_comm_unique_id: null argument");
+            }
+            const NcclApi *api = nullptr;
+            int rc = nccl_api(api);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            NcclId id{};
+            VMV_NCCL(*api, api->GetUniqueId(&id));
+            std::memcpy(id128, id.internal, sizeof(id.internal));
+            return VMV_OK;
+        });
+    }
+
+    int vmv_comm_create(vmv_comm **out, const unsigned char *id128, int rank, int world)
+    {
+        return guarded("vmv_comm_create", [&]() -> int
+        {
+            if (out == nullptr || id128 == nullptr || world < 1 || world > vmv::kMaxPeers || rank < 0 || rank >= world)
+            {
+                return fail(VMV_ERR_ARG, "vmv_comm_create: bad argument (1 <= world <= 8, 0 <= rank < world)");
+            }
+            const NcclApi *api = nullptr;
+            int rc = nccl_api(api);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            vmv_comm *c = new vmv_comm();
+            c->rank = rank, c->world = world;
+            VMV_CUDA(cudaGetDevice(&c->device));
+            NcclId id{};
+            std::memcpy(id.internal, id128, sizeof(id.internal));
+            const int code = api->CommInitRank(&c->nccl, world, id, rank);
+            if (code != 0)
+            {
+                delete c;
+                return nccl_fail(*api, code, "ncclCommInitRank");
+            }
+            *out = c;
+            return VMV_OK;
+        });
+    }
+
+    void vmv_comm_destroy(vmv_comm *c)
+    {
+        if (c == nullptr)
+        {
+            return;
+        }
+        for (int p = 0; p < c->world; ++p)
+        {
+            if (p != c->rank && c->peer_window[p] != nullptr)
+            {
+                cudaIpcCloseMemHandle(c->peer_window[p]);
+            }
+        }
+        if (c->window != nullptr)
+        {
+            cudaFree(c->window);
+        }
+        const NcclApi *api = nullptr;
+        if (c->nccl != nullptr && nccl_api(api) == VMV_OK)
+        {
+            api->CommDestroy(c->nccl);
+        }
+        delete c;
+    }
+
+    int vmv_comm_rank(const vmv_comm *c)
+    {
+        return c ? c->rank : fail(VMV_ERR_ARG, "vmv_comm_rank: null argument");
+    }
+
+    int vmv_comm_world(const vmv_comm *c)
+    {
+        return c ? c->world : fail(VMV_ERR_ARG, "vmv_comm_world: null argument");
+    }
+
+    int vmv_allgather_bits(vmv_comm *c, const uint32_t *d_local, size_t words_per_rank, uint32_t *d_global, void *stream)
+    {
+        return guarded("vmv_allgather_bits", [&]() -> int
+        {
+            if (c == nullptr || (words_per_rank > 0 && (d_local == nullptr || d_global == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_allgather_bits: bad argument");
+            }
+            const NcclApi *api = nullptr;
+            int rc = nccl_api(api);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            VMV_NCCL(*api, api->AllGather(d_local, d_global, words_per_rank, kNcclUint32, c->nccl, static_cast<cudaStream_t>(stream)));
+            return VMV_OK;
+        });
+    }
+
+    int vmv_comm_window(vmv_comm *c, size_t words_per_rank, int slots)
+    {
+        return guarded("vmv_comm_window", [&]() -> int
+        {
+            if (c == nullptr || words_per_rank == 0 || slots < 1 || slots > kMaxSlots)
+            {
+                return fail(VMV_ERR_ARG, "vmv_comm_window: bad argument (1 <= slots <= 4)");
+            }
+            if (c->window != nullptr)
+            {
+                return fail(VMV_ERR_STATE, "vmv_comm_window: the communicator already has a window");
+            }
+            const NcclApi *api = nullptr;
+            int rc = nccl_api(api);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            // rows are 16-byte aligned so that the push kernel and consumers may use wide accesses
+            c->words_per_rank = (words_per_rank + 3) & ~size_t(3);
+            c->slots = slots;
+            c->flags_off = static_cast<size_t>(slots) * c->world * c->words_per_rank;
+            c->window_words = c->flags_off + static_cast<size_t>(slots) * vmv::kMaxPeers;
+            VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->window), c->window_words * sizeof(uint32_t)));
+            VMV_CUDA(cudaMemset(c->window, 0, c->window_words * sizeof(uint32_t)));
+            c->peer_window[c->rank] = c->window;
+            if (c->world > 1)
+            {
+                // exchange the IPC handles of the windows through the communicator, then map every peer's window
+                cudaIpcMemHandle_t mine;
+                VMV_CUDA(cudaIpcGetMemHandle(&mine, c->window));
+                unsigned char *d_handles = nullptr;
+                VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_handles), sizeof(mine) * c->world));
+                VMV_CUDA(cudaMemcpy(d_handles + sizeof(mine) * c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+                const int code = api->AllGather(d_handles + sizeof(mine) * c->rank, d_handles, sizeof(mine), kNcclUint8, c->nccl, nullptr);
+                if (code != 0)
+                {
+                    cudaFree(d_handles);
+                    return nccl_fail(*api, code, "ncclAllGather(ipc handles)");
+                }
+                std::vector<cudaIpcMemHandle_t> all(c->world);
+                VMV_CUDA(cudaMemcpy(all.data(), d_handles, sizeof(mine) * c->world, cudaMemcpyDeviceToHost));
+                cudaFree(d_handles);
+                for (int p = 0; p < c->world; ++p)
+                {
+                    if (p != c->rank)
+                    {
+                        void *ptr = nullptr;
+                        VMV_CUDA(cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess));
+                        c->peer_window[p] = static_cast<uint32_t *>(ptr);
+                    }
+                }
+                // nobody writes into a window before every rank has mapped (and zeroed) its own: one more collective
+                uint32_t *d_tok = nullptr;
+                VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_tok), sizeof(uint32_t) * c->world));
+                const int code2 = api->AllGather(d_tok + c->rank, d_tok, 1, kNcclUint32, c->nccl, nullptr);
+                VMV_CUDA(cudaStreamSynchronize(nullptr));
+                cudaFree(d_tok);
+                if (code2 != 0)
+                {
+                    return nccl_fail(*api, code2, "ncclAllGather(window barrier)");
+                }
+            }
+            return VMV_OK;
+        });
+    }
+
+    uint32_t *vmv_comm_window_ptr(vmv_comm *c, int slot)
+    {
+        if (c == nullptr || c->window == nullptr || slot < 0 || slot >= c->slots)
+        {
+            fail(VMV_ERR_ARG, "vmv_comm_window_ptr: bad argument");
+            return nullptr;
+        }
+        return c->window + static_cast<size_t>(slot) * c->world * c->words_per_rank;
+    }
+
+    size_t vmv_comm_window_stride(const vmv_comm *c)
+    {
+        return c ? c->words_per_rank : 0;
+    }
+
+    int vmv_validate_configs_gather_dev(int robot, const vmv_env *env, vmv_comm *c, int slot, const float *d_q, size_t n, void *stream)
+    {
+        return guarded("vmv_validate_configs_gather_dev", [&]() -> int
+        {
+            if (!valid_robot(robot) || (n > 0 && d_q == nullptr))
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_configs_gather_dev: bad argument");
+            }
+            int rc = check_gather_call(c, slot, n);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            const GatherDev g = gather_for(c, slot);
+            if (n == 0)
+            {
+                return push_gather(g, g.peer_bits[c->rank], 0, static_cast<cudaStream_t>(stream));
+            }
+            return configs_common(robot, env, d_q, n, g.peer_bits[c->rank], g, stream);
+        });
+    }
+
+    int vmv_validate_edges_indexed_gather_dev(int robot, const vmv_env *env, vmv_comm *c, int slot, const float *d_vertices, size_t n_vertices,
+                                              const uint32_t *d_pairs, size_t n_edges, int resolution, void *stream)
+    {
+        return guarded("vmv_validate_edges_indexed_gather_dev", [&]() -> int
+        {
+            (void)n_vertices;
+            if (!valid_robot(robot) || (n_edges > 0 && (d_vertices == nullptr || d_pairs == nullptr)))
+            {
+                return fail(VMV_ERR_ARG, "vmv_validate_edges_indexed_gather_dev: bad argument");
+            }
+            int rc = check_gather_call(c, slot, n_edges);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            const GatherDev g = gather_for(c, slot);
+            if (n_edges == 0)
+            {
+                return push_gather(g, g.peer_bits[c->rank], 0, static_cast<cudaStream_t>(stream));
+            }
+            return edges_common(robot, env, d_vertices, nullptr, d_pairs, n_edges, resolution, g.peer_bits[c->rank], g, stream);
+        });
+    }
+
+    int vmv_comm_wait(vmv_comm *c, int slot, void *stream)
+    {
+        return guarded("vmv_comm_wait", [&]() -> int
+        {
+            if (c == nullptr || c->window == nullptr || slot < 0 || slot >= c->slots)
+            {
+                return fail(VMV_ERR_ARG, "vmv_comm_wait: bad argument");
+            }
+            if (c->seq[slot] == 0)
+            {
+                return VMV_OK;  // nothing was gathered into this slot yet
+            }
+            vmv::k_comm_wait<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(c->window + c->flags_off + static_cast<size_t>(slot) * vmv::kMaxPeers, c->world,
+                                                                                 c->seq[slot]);
+            g_launches++;
+            VMV_CUDA(cudaGetLastError());
+            return VMV_OK;
+        });
+    }
+
+    int vmv_env_broadcast(vmv_comm *c, vmv_env *env, int root)
+    {
+        return guarded("vmv_env_broadcast", [&]() -> int
+        {
+            if (c == nullptr || env == nullptr || root < 0 || root >= c->world)
+            {
+                return fail(VMV_ERR_ARG, "vmv_env_broadcast: bad argument");
+            }
+            const NcclApi *api = nullptr;
+            int rc = nccl_api(api);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            Writer w;
+            if (c->rank == root)
+            {
+                w.vec(env->spheres), w.vec(env->capsules), w.vec(env->z_capsules), w.vec(env->cuboids), w.vec(env->z_cuboids);
+                w.pod<uint64_t>(env->heightfields.size());
+                for (const auto &h : env->heightfields)
+                {
+                    w.pod(h.f), w.pod<uint64_t>(h.xd), w.pod<uint64_t>(h.yd), w.pod(h.id), w.vec(h.data);
+                }
+                w.pod<uint64_t>(env->capts.size());
+                for (const auto &t : env->capts)
+                {
+                    w.pod(t.r_min), w.pod(t.r_max), w.pod(t.r_point), w.pod(t.nlog2), w.pod(t.top_lo), w.pod(t.top_hi), w.pod(t.id);
+                    w.vec(t.tests), w.vec(t.leaf_lo), w.vec(t.leaf_hi), w.vec(t.leaf_start), w.vec(t.points);
+                }
+                w.pod<uint64_t>(env->mvts.size());
+                for (const auto &t : env->mvts)
+                {
+                    w.pod(t.r_min), w.pod(t.r_max), w.pod(t.r_point), w.pod(t.ws_min), w.pod(t.ws_max), w.pod(t.g_min), w.pod(t.g_max);
+                    w.pod(t.inv_scale), w.pod(t.grid_width), w.pod(t.id);
+                    w.vec(t.cells), w.vec(t.voxels), w.vec(t.points);
+                }
+                w.vec(env->cloud_xyz), w.pod(env->cloud_r_point_max);
+                w.pod<int>(env->has_attachment ? 1 : 0), w.pod(env->attach_tf), w.vec(env->attach_spheres), w.pod(env->next_id);
+            }
+            unsigned long long size = w.b.size();
+            unsigned long long *d_size = nullptr;
+            VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_size), sizeof(size)));
+            VMV_CUDA(cudaMemcpy(d_size, &size, sizeof(size), cudaMemcpyHostToDevice));
+            int code = api->Broadcast(d_size, d_size, sizeof(size), kNcclUint8, root, c->nccl, nullptr);
+            if (code == 0)
+            {
+                VMV_CUDA(cudaMemcpy(&size, d_size, sizeof(size), cudaMemcpyDeviceToHost));
+            }
+            cudaFree(d_size);
+            if (code != 0)
+            {
+                return nccl_fail(*api, code, "ncclBroadcast(size)");
+            }
+            unsigned char *d_buf = nullptr;
+            VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_buf), std::max<size_t>(size, 16)));
+            if (c->rank == root)
+            {
+                VMV_CUDA(cudaMemcpy(d_buf, w.b.data(), size, cudaMemcpyHostToDevice));
+            }
+            code = api->Broadcast(d_buf, d_buf, size, kNcclUint8, root, c->nccl, nullptr);
+            if (code != 0)
+            {
+                cudaFree(d_buf);
+                return nccl_fail(*api, code, "ncclBroadcast(environment)");
+            }
+            if (c->rank != root)
+            {
+                std::vector<unsigned char> b(size);
+                VMV_CUDA(cudaMemcpy(b.data(), d_buf, size, cudaMemcpyDeviceToHost));
+                cudaFree(d_buf);
+                Reader r{b.data(), b.data() + b.size()};
+                env->release_device();
+                env->shapes_dirty = true;
+                r.vec(env->spheres), r.vec(env->capsules), r.vec(env->z_capsules), r.vec(env->cuboids), r.vec(env->z_cuboids);
+                uint64_t k = 0;
+                r.pod(k);
+                env->heightfields.assign(r.ok ? k : 0, HHeight{});
+                for (auto &h : env->heightfields)
+                {
+                    uint64_t xd = 0, yd = 0;
+                    r.pod(h.f), r.pod(xd), r.pod(yd), r.pod(h.id), r.vec(h.data);
+                    h.xd = xd, h.yd = yd;
+                }
+                r.pod(k);
+                env->capts.clear();
+                env->capts.resize(r.ok ? k : 0);
+                for (auto &t : env->capts)
+                {
+                    r.pod(t.r_min), r.pod(t.r_max), r.pod(t.r_point), r.pod(t.nlog2), r.pod(t.top_lo), r.pod(t.top_hi), r.pod(t.id);
+                    r.vec(t.tests), r.vec(t.leaf_lo), r.vec(t.leaf_hi), r.vec(t.leaf_start), r.vec(t.points);
+                }
+                r.pod(k);
+                env->mvts.clear();
+                env->mvts.resize(r.ok ? k : 0);
+                for (auto &t : env->mvts)
+                {
+                    r.pod(t.r_min), r.pod(t.r_max), r.pod(t.r_point), r.pod(t.ws_min), r.pod(t.ws_max), r.pod(t.g_min), r.pod(t.g_max);
+                    r.pod(t.inv_scale), r.pod(t.grid_width), r.pod(t.id);
+                    r.vec(t.cells), r.vec(t.voxels), r.vec(t.points);
+                }
+                int att = 0;
+                r.vec(env->cloud_xyz), r.pod(env->cloud_r_point_max);
+                r.pod(att), r.pod(env->attach_tf), r.vec(env->attach_spheres), r.pod(env->next_id);
+                env->has_attachment = att != 0;
+                if (!r.ok)
+                {
+                    return fail(VMV_ERR_STATE, "vmv_env_broadcast: truncated environment stream");
+                }
+            }
+            else
+            {
+                cudaFree(d_buf);
+            }
+            return vmv_env_commit(env);
+        });
+    }
+
 }

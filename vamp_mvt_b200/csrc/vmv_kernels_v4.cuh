@@ -23,6 +23,82 @@ namespace vmv
 {
     static constexpr uint32_t kFullWarp = 0xffffffffu;
 
+    // Multi-GPU verdict gather fused into the validation kernels (include/vamp_b200.h: vmv_comm_*).  Every rank
+    // owns a window [world][words_per_rank] of verdict words; the windows of all ranks are mapped into every
+    // process (CUDA IPC over NVLink / NVSwitch).  A kernel launched with world > 0 stores each verdict word it
+    // produces into the launching rank's row of EVERY rank's window -- lane p of the warp stores to peer p, one
+    // predicated 4-byte store instruction per 32 units -- so the all-gather costs no kernel of its own and no SM
+    // is taken from the persistent validation blocks.  The last block to finish publishes `seq` in the flag
+    // word (slot, rank) of every window, after a system-scope fence; consumers wait on their own flags.
+    static constexpr int kMaxPeers = 8;
+    struct GatherDev
+    {
+        int world;                      // 0: local launch, nothing below is read
+        int rank;
+        uint32_t seq;                   // value published when this launch's words have landed everywhere
+        unsigned int *done;             // zeroed counter of finished blocks (local memory)
+        uint32_t *peer_bits[kMaxPeers]; // this rank's row in peer p's window, for the slot being written
+        uint32_t *peer_flag[kMaxPeers]; // flag word (slot, this rank) in peer p's window
+    };
+
+    // width = 4, 2 or 1 bytes (32, 16 or 8 units per verdict item)
+    __device__ __forceinline__ void store_verdict(uint32_t *base, size_t index, uint32_t word, int width)
+    {
+        if (width == 4)
+        {
+            base[index] = word;
+        }
+        else if (width == 2)
+        {
+            reinterpret_cast<unsigned short *>(base)[index] = static_cast<unsigned short>(word);
+        }
+        else
+        {
+            reinterpret_cast<unsigned char *>(base)[index] = static_cast<unsigned char>(word);
+        }
+    }
+
+    // called by every lane of a warp with the warp-uniform verdict item
+    __device__ __forceinline__ void publish_verdict(uint32_t *bits, const GatherDev &g, size_t index, uint32_t word, int width)
+    {
+        const int lane = threadIdx.x & 31;
+        if (g.world == 0)
+        {
+            if (lane == 0)
+            {
+                store_verdict(bits, index, word, width);
+            }
+        }
+        else if (lane < g.world)
+        {
+            // lane == rank writes the local window row (peer_bits[rank] is the local mapping)
+            store_verdict(g.peer_bits[lane], index, word, width);
+        }
+    }
+
+    // end of a gathering kernel: called by every thread of the block after its last verdict store
+    __device__ __forceinline__ void gather_finish(const GatherDev &g)
+    {
+        if (g.world == 0)
+        {
+            return;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            __threadfence_system();  // this block's remote stores are performed before the ticket below is visible
+            const unsigned int t = atomicAdd(g.done, 1u);
+            if (t == gridDim.x - 1)
+            {
+                __threadfence_system();
+                for (int p = 0; p < g.world; ++p)
+                {
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.peer_flag[p]), "r"(g.seq) : "memory");
+                }
+            }
+        }
+    }
+
     template <typename MaskT>
     __device__ __forceinline__ int mask_pop_lowest(MaskT &m);
 
@@ -630,7 +706,13 @@ namespace vmv
     template <typename R, typename MaskT, bool TAB, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB)
         k_validate_configs_v4(
-            RobotDev robot, const __grid_constant__ GridEnv env, const float *__restrict__ q, size_t n, uint32_t *__restrict__ bits, unsigned int *__restrict__ next_tile)
+            RobotDev robot,
+            const __grid_constant__ GridEnv env,
+            const float *__restrict__ q,
+            size_t n,
+            uint32_t *__restrict__ bits,
+            unsigned int *__restrict__ next_tile,
+            const __grid_constant__ GatherDev gather)
     {
         using M = typename R::Model;
         extern __shared__ __align__(128) unsigned char smem[];
@@ -667,10 +749,7 @@ namespace vmv
             }
 #endif
             const uint32_t invalid = v4_pass<R, MaskT, TAB, true>(X, env.grid, env.tab, cfg, has);
-            if (lane == 0)
-            {
-                bits[tile] = ~invalid;
-            }
+            publish_verdict(bits, gather, tile, ~invalid, 4);
 #ifndef VMV_V4_STATIC_TILES
             if (!kEarly && lane == 0)
             {
@@ -681,6 +760,7 @@ namespace vmv
             tile += stride;
 #endif
         }
+        gather_finish(gather);
     }
 
     // Edges.  A warp owns a chunk of 32 edges (one verdict word): lane e keeps edge e's start, vector
@@ -698,7 +778,8 @@ namespace vmv
         float resolution,
         uint32_t *__restrict__ bits,
         unsigned int *__restrict__ next_chunk,
-        int edges_per_chunk)
+        int edges_per_chunk,
+        const __grid_constant__ GatherDev gather)
     {
         using M = typename R::Model;
         extern __shared__ __align__(128) unsigned char smem[];
@@ -829,22 +910,9 @@ namespace vmv
             }
 
             const uint32_t word = __ballot_sync(kFullWarp, steps > 0 && !dead);
-            if (lane == 0)
-            {
-                // verdict bits are little-endian in their words: a chunk of 8 / 16 edges is a byte / half word
-                if (edges_per_chunk == 32)
-                {
-                    bits[chunk] = word;
-                }
-                else if (edges_per_chunk == 16)
-                {
-                    reinterpret_cast<unsigned short *>(bits)[chunk] = static_cast<unsigned short>(word);
-                }
-                else
-                {
-                    reinterpret_cast<unsigned char *>(bits)[chunk] = static_cast<unsigned char>(word);
-                }
-            }
+            // verdict bits are little-endian in their words: a chunk of 8 / 16 edges is a byte / half word
+            publish_verdict(bits, gather, chunk, word, edges_per_chunk >> 3);
         }
+        gather_finish(gather);
     }
 }  // namespace vmv
