@@ -189,8 +189,9 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl", "none"],
-                    help="N > 1: verdict gather by the validation kernel's peer stores (default), by ncclAllGather, or not at all")
+    ap.add_argument("--gather", default="fused", choices=["fused", "ce", "nccl", "none"],
+                    help="N > 1: verdict gather by the validation kernel's peer stores (fused), by copy-engine publication of the "
+                         "rank's window row (ce), by ncclAllGather (nccl), or not at all")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
     ap.add_argument("--no-edges", action="store_true", help="skip the C3 block")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 block")
@@ -254,7 +255,7 @@ def main() -> int:
     bits2 = [torch.zeros(n_words, dtype=torch.int32, device="cuda") for _ in range(2)]
     gather_mode = args.gather if world > 1 else "none"
     gathered2 = None
-    if gather_mode == "fused":
+    if gather_mode in ("fused", "ce"):
         C.window(max(n_words, sharding.words_per_rank(args.c5_edges, world)), slots=2)
     elif gather_mode == "nccl":
         gathered2 = [torch.zeros(world * n_words, dtype=torch.int32, device="cuda") for _ in range(2)]
@@ -265,6 +266,13 @@ def main() -> int:
             # verdict words go straight into slot i % 2 of every rank's window; the wait for the PREVIOUS step's
             # slot rides behind this kernel, so it never stalls and bounds the ranks' skew to one step
             C.validate_configs_gather(robot.id, h_env, i % 2, qd.data_ptr(), N_CONFIGS, stream)
+            if i > 0:
+                C.wait((i - 1) % 2, stream)
+        elif gather_mode == "ce":
+            # the kernel writes this rank's row of its own window; the copy engines carry it to the peers on a side
+            # stream while the next step's kernel runs
+            _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, C.local_row(i % 2), stream))
+            C.publish(i % 2, n_words, stream)
             if i > 0:
                 C.wait((i - 1) % 2, stream)
         else:
@@ -292,13 +300,19 @@ def main() -> int:
             kb.record()
             if i > 0:
                 C.wait((i - 1) % 2, stream)
+        elif gather_mode == "ce":
+            _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, C.local_row(i % 2), stream))
+            kb.record()
+            C.publish(i % 2, n_words, stream)
+            if i > 0:
+                C.wait((i - 1) % 2, stream)
         else:
             _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, bits2[i % 2].data_ptr(), stream))
             kb.record()
             if gather_mode == "nccl":
                 C.allgather_words(bits2[i % 2].data_ptr(), n_words, gathered2[i % 2].data_ptr(), stream)
         kernel_events.append((ka, kb))
-    if gather_mode == "fused":
+    if gather_mode in ("fused", "ce"):
         C.wait((args.steps - 1) % 2, stream)  # the last gather has landed from every rank before the end event
     e1.record()
     barrier()
@@ -311,7 +325,7 @@ def main() -> int:
 
     # verdict words of the last step (batch index (steps - 1) % N_BATCHES), for the parity block
     last = args.steps - 1
-    if gather_mode == "fused":
+    if gather_mode in ("fused", "ce"):
         last_valid = C.read_window(last % 2, [N_CONFIGS] * world)
         gather_ok = None
         if rank == 0:
@@ -401,6 +415,10 @@ def main() -> int:
             if gather_mode == "fused":
                 C.validate_edges_indexed_gather(robot.id, h_env, i % 2, dV.data_ptr(), len(V), dP.data_ptr(), hi5 - lo5, 0, stream)
                 C.wait(i % 2, stream)  # the planner consumes the global mask of THIS step
+            elif gather_mode == "ce":
+                _lib.check(L.vmv_validate_edges_indexed_dev(robot.id, h_env, dV.data_ptr(), len(V), dP.data_ptr(), hi5 - lo5, 0, C.local_row(i % 2), stream))
+                C.publish(i % 2, (hi5 - lo5 + 31) // 32, stream)
+                C.wait(i % 2, stream)
             else:
                 _lib.check(L.vmv_validate_edges_indexed_dev(robot.id, h_env, dV.data_ptr(), len(V), dP.data_ptr(), hi5 - lo5, 0, local5.data_ptr(), stream))
                 if gather_mode == "nccl":
@@ -417,7 +435,7 @@ def main() -> int:
         s1.record()
         barrier()
         ms5 = max_over_ranks(s0.elapsed_time(s1) / reps5)
-        if gather_mode == "fused":
+        if gather_mode in ("fused", "ce"):
             allv = C.read_window((reps5 - 1) % 2, [sharding.shard_bounds(n5, r, world)[1] - sharding.shard_bounds(n5, r, world)[0] for r in range(world)])
             c5_valid_fraction = float(allv.mean())
             mine5 = allv[lo5:hi5]
@@ -427,6 +445,7 @@ def main() -> int:
         c5 = {"workload": f"C5: {n5} PRM-style Panda edges as (u32,u32) index pairs into 2^20 vertices (clusters of 64, sigma 0.12 rad), table/shelf scene",
               "value": n5 / (ms5 * 1e-3), "unit": "edges/s", "ms_per_step": ms5, "n_gpus": world, "scaling": "strong",
               "collective": {"fused": f"verdict words stored by the kernel into every rank's window ({per5 * 4} B per rank per step), then a flag wait",
+                             "ce": f"this rank's window row ({per5 * 4} B) copied to every peer by the copy engines, then a flag wait",
                              "nccl": f"one ncclAllGather of {per5 * 4} B per rank per step", "none": "none"}[gather_mode],
               "valid_fraction": c5_valid_fraction, "bytes_per_edge_in": 8}
 

@@ -204,6 +204,12 @@ extern "C"
     int vmv_validate_configs_gather_dev(int robot, const vmv_env *env, vmv_comm *comm, int slot, const float *d_q, size_t n, void *stream);
     int vmv_validate_edges_indexed_gather_dev(int robot, const vmv_env *env, vmv_comm *comm, int slot, const float *d_vertices, size_t n_vertices, const uint32_t *d_pairs, size_t n_edges, int resolution, void *stream);
     int vmv_comm_wait(vmv_comm *comm, int slot, void *stream);
+    /* The same gather without touching the kernels: a launch on `stream` writes this rank's verdict words into
+     * its OWN window row (vmv_comm_local_row), then vmv_comm_publish (collective per slot, like the fused calls)
+     * hands the row and its flag to the copy engines on a side stream that waits for `stream` -- no SM is used
+     * and the copies overlap the next launch.  At most 4095 publications per slot. */
+    uint32_t *vmv_comm_local_row(vmv_comm *comm, int slot);
+    int vmv_comm_publish(vmv_comm *comm, int slot, size_t n_words, void *stream);
 
     /* --- device buffers for callers that do not bring their own allocator ---------------------- */
     void *vmv_dev_alloc(size_t bytes);
@@ -217,6 +223,8 @@ extern "C"
     /* --- measurement helpers -------------------------------------------------------------------
      * number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
     uint64_t vmv_launch_count(void);
+    /* development aid: 64 counters filled by builds compiled with -DVMV_C4_STATS (zeros otherwise) */
+    int vmv_dev_stats(uint64_t *out64, int reset);
     /* testing aid: 0 = automatic choice (default), 1 = force the generic per-thread kernel,
      * 2 = force the block-cooperative kernel, 3 = force the grid-culled kernel (2 and 3 fail with
      * VMV_ERR_LIMIT when they do not apply to the environment) */

@@ -85,6 +85,11 @@ def _rank_main(rank: int, world: int, uid_path: str, out_dir: str):
             C.wait(0)
             esizes = [sharding.shard_bounds(ne, r, world)[1] - sharding.shard_bounds(ne, r, world)[0] for r in range(world)]
             results["edges_fused"] = C.read_window(0, esizes)
+            # the same through the copy-engine publication of the rank's own row
+            _lib.check(L.vmv_validate_edges_indexed_dev(vmv.panda.id, env.handle, dV, len(V), dP + elo * 8, ehi - elo, 0, C.local_row(1), None))
+            C.publish(1, (ehi - elo + 31) // 32)
+            C.wait(1)
+            results["edges_ce"] = C.read_window(1, esizes)
             per = sharding.words_per_rank(ne, world)
             dl, dg = L.vmv_dev_alloc(per * 4), L.vmv_dev_alloc(per * 4 * world)
             _lib.check(L.vmv_validate_edges_indexed_dev(vmv.panda.id, env.handle, dV, len(V), dP + elo * 8, ehi - elo, 0, dl, None))
@@ -110,6 +115,7 @@ def _check(out_dir, world):
                 assert (got != local).sum() <= (0 if path in (0, 3) else 2), (rank, cloud, path)
         assert np.array_equal(d["edges_fused"], d["edges_local"])
         assert np.array_equal(d["edges_nccl"], d["edges_local"])
+        assert np.array_equal(d["edges_ce"], d["edges_local"])
 
 
 def test_single_rank_communicator(tmp_path):

@@ -1,0 +1,28 @@
+#!/usr/bin/env python3
+"""dev tool: query statistics of the any-environment kernel on BASELINE config 4 (needs a -DVMV_C4_STATS build:
+tools/build_variant.py stats --units vmv_robot_fetch,vmv_robot_ur5 -DVMV_C4_STATS; VMV_LIB=variants/lib_stats.so)."""
+import ctypes as C, json, sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+import vamp_mvt_b200 as vmv
+from vamp_mvt_b200 import _lib
+from tests import scenes, workloads
+
+L = _lib.lib()
+L.vmv_dev_stats.argtypes = [C.c_void_p, C.c_int]
+NAMES = ["sphere_queries", "hit_primitives", "grid_lookups", "undecided_after_grid", "capt_active_calls", "need_scan", "lists_scanned",
+         "scan_steps", "points_loaded", "scan_hits", "group_size_sum", "warp_calls", "bounding_queries", "fine_queries", "bounding_hits", "fine_hits"]
+for robot in sys.argv[1:] or ["fetch", "ur5"]:
+    R = getattr(vmv, robot)
+    env, pts, hf, _ = workloads.c4_environment(robot)
+    n = 1 << 16
+    q = scenes.random_configs(robot, n, seed=0)
+    out = np.zeros(64, np.uint64)
+    R.validate_batch(q[:64], env)
+    L.vmv_dev_stats(None, 1)
+    v = R.validate_batch(q, env)
+    L.vmv_dev_stats(_lib.ptr(out), 1)
+    d = {k: float(out[i]) / n for i, k in enumerate(NAMES)}
+    d["valid"] = float(v.mean())
+    print(robot, json.dumps(d, indent=1))

@@ -95,6 +95,9 @@ def lib():
         L.vmv_validate_configs_gather_dev.argtypes = [i32, vp, vp, i32, vp, sz, vp]
         L.vmv_validate_edges_indexed_gather_dev.argtypes = [i32, vp, vp, i32, vp, sz, vp, sz, i32, vp]
         L.vmv_comm_wait.argtypes = [vp, i32, vp]
+        L.vmv_comm_local_row.restype = vp
+        L.vmv_comm_local_row.argtypes = [vp, i32]
+        L.vmv_comm_publish.argtypes = [vp, i32, sz, vp]
         _lib = L
     return _lib
 

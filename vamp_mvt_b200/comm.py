@@ -61,6 +61,14 @@ class Communicator:
         _lib.check(self._L.vmv_validate_edges_indexed_gather_dev(robot_id, env_handle, self.handle, slot, d_vertices, n_vertices, d_pairs, n_edges,
                                                                  resolution, stream))
 
+    def local_row(self, slot: int) -> int:
+        """Device pointer of this rank's row in its own window (the target of a launch followed by publish)."""
+        return int(self._L.vmv_comm_local_row(self.handle, slot))
+
+    def publish(self, slot: int, n_words: int, stream=None):
+        """Copy-engine publication of the local row of `slot` to every peer, ordered behind `stream`."""
+        _lib.check(self._L.vmv_comm_publish(self.handle, slot, n_words, stream))
+
     def wait(self, slot: int, stream=None):
         _lib.check(self._L.vmv_comm_wait(self.handle, slot, stream))
 

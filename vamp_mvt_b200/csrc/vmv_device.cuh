@@ -177,6 +177,14 @@ namespace vmv
         }
     }
 
+    // development counters (tools/c4_stats.py builds with -DVMV_C4_STATS): where the any-environment kernel spends its queries
+#ifdef VMV_C4_STATS
+    static __device__ unsigned long long *g_stats = nullptr;
+#define VMV_STAT(i, v) atomicAdd(g_stats + (i), static_cast<unsigned long long>(v))
+#else
+#define VMV_STAT(i, v) ((void)0)
+#endif
+
     __device__ __forceinline__ bool sign_set(float v)
     {
         return __float_as_int(v) < 0;
@@ -283,6 +291,17 @@ namespace vmv
 
         bool hit = false;
         uint32_t pending = __ballot_sync(group, need);
+        if (active)
+        {
+            VMV_STAT(4, 1);
+            VMV_STAT(5, need ? 1 : 0);
+        }
+        if (rank == 0)
+        {
+            VMV_STAT(11, 1);
+            VMV_STAT(10, gsize);
+            VMV_STAT(6, __popc(pending));
+        }
         while (pending != 0u)
         {
             const int src = __ffs(pending) - 1;
@@ -311,9 +330,18 @@ namespace vmv
                         beyond = beyond || (p.w > qlim);
                     }
                 }
+                if (rank == 0)
+                {
+                    VMV_STAT(7, 1);
+                    VMV_STAT(8, min(e - base, kCaptScanLoads * gsize));
+                }
                 if (__any_sync(group, h))
                 {
                     found = true;
+                    if (rank == 0)
+                    {
+                        VMV_STAT(9, 1);
+                    }
                     break;
                 }
                 if (__any_sync(group, beyond))
@@ -544,10 +572,17 @@ namespace vmv
         }
         // no cloud point within reach: every pointcloud query would answer "no"
         bool query = active && !hit;
+        if (active)
+        {
+            VMV_STAT(0, 1);
+            VMV_STAT(1, hit ? 1 : 0);
+        }
         if (H.off_cloud_grid != 0 && query)
         {
             const CloudGridRec &g = *reinterpret_cast<const CloudGridRec *>(E + H.off_cloud_grid);
             query = !(cloud_clearance(g, x, y, z) > r_pc + g.r_point_max);
+            VMV_STAT(2, 1);
+            VMV_STAT(3, query ? 1 : 0);
         }
         for (uint32_t i = 0; i < H.n_capts; ++i)
         {

@@ -1253,6 +1253,20 @@ namespace vmvh
         return device < kMaxDevices ? std::max(1, cached[device]) : 148;
     }
 
+    unsigned long long *stats_buffer()
+    {
+        static unsigned long long *buf[kMaxDevices] = {};
+        int device = 0;
+        cudaGetDevice(&device);
+        device %= kMaxDevices;
+        if (buf[device] == nullptr)
+        {
+            cudaMalloc(reinterpret_cast<void **>(&buf[device]), 64 * sizeof(unsigned long long));
+            cudaMemset(buf[device], 0, 64 * sizeof(unsigned long long));
+        }
+        return buf[device];
+    }
+
     // Work counters of the persistent kernels: a ring of slots per device, two words per slot (tile ticket,
     // finished-block count), zeroed on the launch's stream.  A slot carries the event recorded behind its last
     // launch and is handed out again only once that event has completed: however many streams and host threads
@@ -3037,6 +3051,21 @@ extern "C"
         return VMV_OK;
     }
 
+    int vmv_dev_stats(uint64_t *out64, int reset)
+    {
+        unsigned long long *b = stats_buffer();
+        VMV_CUDA(cudaDeviceSynchronize());
+        if (out64 != nullptr)
+        {
+            VMV_CUDA(cudaMemcpy(out64, b, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        }
+        if (reset)
+        {
+            VMV_CUDA(cudaMemset(b, 0, 64 * sizeof(unsigned long long)));
+        }
+        return VMV_OK;
+    }
+
     uint64_t vmv_launch_count(void)
     {
         return g_launches.load();
@@ -3187,7 +3216,13 @@ struct vmv_comm
     uint32_t *window = nullptr;
     uint32_t *peer_window[vmv::kMaxPeers] = {};
     uint32_t seq[4] = {0, 0, 0, 0};
+    // copy-engine publication (vmv_comm_publish): a side stream, an event per slot, and a device table of
+    // sequence numbers the flag copies read from
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ready[4] = {};
+    uint32_t *d_seq = nullptr;
 };
+constexpr uint32_t kSeqTable = 4096;
 
 namespace
 {
@@ -3299,6 +3334,21 @@ extern "C"
         if (c->window != nullptr)
         {
             cudaFree(c->window);
+        }
+        if (c->copy_stream != nullptr)
+        {
+            cudaStreamDestroy(c->copy_stream);
+        }
+        for (cudaEvent_t e : c->ready)
+        {
+            if (e != nullptr)
+            {
+                cudaEventDestroy(e);
+            }
+        }
+        if (c->d_seq != nullptr)
+        {
+            cudaFree(c->d_seq);
         }
         const NcclApi *api = nullptr;
         if (c->nccl != nullptr && nccl_api(api) == VMV_OK)
@@ -3414,6 +3464,12 @@ extern "C"
         return c->window + static_cast<size_t>(slot) * c->world * c->words_per_rank;
     }
 
+    uint32_t *vmv_comm_local_row(vmv_comm *c, int slot)
+    {
+        uint32_t *base = vmv_comm_window_ptr(c, slot);
+        return base ? base + static_cast<size_t>(c->rank) * c->words_per_rank : nullptr;
+    }
+
     size_t vmv_comm_window_stride(const vmv_comm *c)
     {
         return c ? c->words_per_rank : 0;
@@ -3462,6 +3518,53 @@ extern "C"
                 return push_gather(g, g.peer_bits[c->rank], 0, static_cast<cudaStream_t>(stream));
             }
             return edges_common(robot, env, d_vertices, nullptr, d_pairs, n_edges, resolution, g.peer_bits[c->rank], g, stream);
+        });
+    }
+
+    // Publication of this rank's row of `slot` -- already written into the LOCAL window by any kernel enqueued on
+    // `stream` -- to every peer by the copy engines: a side stream waits for `stream`, then per peer one copy of
+    // the row followed by one copy of the flag word (in-stream order: the data lands before the flag).  No SM
+    // is involved, and the copies overlap whatever `stream` runs next.
+    int vmv_comm_publish(vmv_comm *c, int slot, size_t n_words, void *stream)
+    {
+        return guarded("vmv_comm_publish", [&]() -> int
+        {
+            int rc = check_gather_call(c, slot, n_words * 32);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            if (c->copy_stream == nullptr)
+            {
+                VMV_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+                for (cudaEvent_t &e : c->ready)
+                {
+                    VMV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                }
+                std::vector<uint32_t> table(kSeqTable);
+                std::iota(table.begin(), table.end(), 0u);
+                VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_seq), kSeqTable * sizeof(uint32_t)));
+                VMV_CUDA(cudaMemcpy(c->d_seq, table.data(), kSeqTable * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            }
+            const uint32_t seq = ++c->seq[slot];
+            if (seq >= kSeqTable)
+            {
+                return fail(VMV_ERR_LIMIT, "vmv_comm_publish: more than 4095 publications into one slot (recreate the window)");
+            }
+            VMV_CUDA(cudaEventRecord(c->ready[slot], static_cast<cudaStream_t>(stream)));
+            VMV_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ready[slot], 0));
+            const size_t row = static_cast<size_t>(slot) * c->world * c->words_per_rank + static_cast<size_t>(c->rank) * c->words_per_rank;
+            const size_t flag = c->flags_off + static_cast<size_t>(slot) * vmv::kMaxPeers + c->rank;
+            for (int k = 1; k <= c->world; ++k)
+            {
+                const int p = (c->rank + k) % c->world;  // the local flag last; peers in a rotated order (no hot receiver)
+                if (p != c->rank && n_words > 0)
+                {
+                    VMV_CUDA(cudaMemcpyAsync(c->peer_window[p] + row, c->window + row, n_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->copy_stream));
+                }
+                VMV_CUDA(cudaMemcpyAsync(c->peer_window[p] + flag, c->d_seq + seq, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->copy_stream));
+            }
+            return VMV_OK;
         });
     }
 

@@ -37,6 +37,7 @@ namespace vmvh
     extern std::atomic<int> g_force_path;
 
     int sm_count();
+    unsigned long long *stats_buffer();  // 64 zero-initialised counters on the current device (development builds)
 
     // A zeroed work counter for one launch of a persistent kernel on stream s.  Slots come from a ring per
     // device; a slot is handed out again only after the event recorded behind its previous launch has

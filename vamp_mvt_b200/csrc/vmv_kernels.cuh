@@ -262,6 +262,31 @@ namespace vmv
             return v;
         }
         static constexpr bool kWarp = false;
+        static constexpr bool kTogether = false;
+    };
+
+    // Configurations, one per lane: every lane is its own unit (no early stop on a neighbour's collision), but the
+    // lanes of a warp stay in the loops TOGETHER until the last one is done, and a lane without work keeps calling
+    // sphere_hits_env as a helper.  The pointcloud scans inside are cooperative over the lanes that arrive together:
+    // with per-lane loops the late lanes -- the ones that went on to fine spheres -- scanned their affordance lists
+    // in ever smaller groups, a lone lane reading 8 points per step from a list of thousands (measured on BASELINE
+    // config 4: the stragglers were 2.3x the average SM time).
+    struct LaneVote
+    {
+        __device__ __forceinline__ bool stop(bool) const
+        {
+            return false;
+        }
+        __device__ __forceinline__ bool any(bool v) const
+        {
+            return __any_sync(0xffffffffu, v);
+        }
+        __device__ __forceinline__ bool rake_any(bool v) const
+        {
+            return v;
+        }
+        static constexpr bool kWarp = false;
+        static constexpr bool kTogether = true;
     };
 
     struct WarpVote
@@ -282,6 +307,7 @@ namespace vmv
             return ((b >> ((threadIdx.x & 31) & 24)) & 0xffu) != 0u;
         }
         static constexpr bool kWarp = true;
+        static constexpr bool kTogether = true;
     };
 
     template <typename M, int BLOCK, typename Vote>
@@ -296,21 +322,28 @@ namespace vmv
         // pointcloud in the environment the hierarchy is part of the verdict and is reproduced as
         // the reference runs it: the un-inflated bounding radius, and "any lane of the rake block
         // hits" decides whether the block's fine spheres are swept (robots/panda.hh:5634-5645).
-        const bool collective = Vote::kWarp && (reinterpret_cast<const EnvHeader *>(c.env)->n_capts > 0 ||
-                                                reinterpret_cast<const EnvHeader *>(c.env)->n_mvts > 0);
+        const bool has_cloud = reinterpret_cast<const EnvHeader *>(c.env)->n_capts > 0 || reinterpret_cast<const EnvHeader *>(c.env)->n_mvts > 0;
+        const bool collective = Vote::kWarp && has_cloud;
         {
             int ti = 0;
             bool active = has_state;
             while (vote.any(active))
             {
+                // every lane reads a valid task (a lane without work re-reads its first one and contributes nothing):
+                // no load in this loop depends on a condition, whichever lanes are still at work
+                const SphereTask t = c.tasks[active ? ti : 0];
+                float x, y, z;
+                task_centre<BLOCK>(t, c.stash, x, y, z);
                 bool hit = false;
-                SphereTask t{};
-                float x = 0.F, y = 0.F, z = 0.F;
+                if ((Vote::kTogether && has_cloud) || active)
+                {
+                    // (with a pointcloud in the environment every lane of the warp calls: one without a sphere helps the scans)
+                    hit = sphere_hits_env(c.env, x, y, z, t.r, t.skip >= 0 ? t.r - 1e-6f : t.r, active);
+                }
                 if (active)
                 {
-                    t = c.tasks[ti];
-                    task_centre<BLOCK>(t, c.stash, x, y, z);
-                    hit = sphere_hits_env(c.env, x, y, z, t.r, t.skip >= 0 ? t.r - 1e-6f : t.r, true);
+                    VMV_STAT(t.skip >= 0 ? 12 : 13, 1);
+                    VMV_STAT(t.skip >= 0 ? 14 : 15, hit ? 1 : 0);
                 }
                 if (collective)
                 {
@@ -339,7 +372,7 @@ namespace vmv
                 }
             }
         }
-        if (!Vote::kWarp && bad)
+        if (!Vote::kTogether && bad)
         {
             return false;
         }
@@ -400,7 +433,7 @@ namespace vmv
                 }
             }
         }
-        if (!Vote::kWarp && bad)
+        if (!Vote::kTogether && bad)
         {
             return false;
         }
@@ -446,13 +479,19 @@ namespace vmv
             }
             const float4 *S = reinterpret_cast<const float4 *>(c.env + H.off_attach + kAttachHdr);
             // attachment vs environment (validity.hh:259-276)
-            for (uint32_t i = 0; i < H.n_attach && has_state && !bad; ++i)
+            for (uint32_t i = 0; i < H.n_attach && ((Vote::kTogether && has_cloud) ? vote.any(has_state && !bad) : (has_state && !bad)); ++i)
             {
                 const float4 s = S[i];
                 const float x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
                 const float y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
                 const float z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
-                bad = sphere_hits_env(c.env, x, y, z, s.w, s.w, true);
+                const bool live = has_state && !bad;
+                bool h = false;
+                if (has_cloud || live)
+                {
+                    h = sphere_hits_env(c.env, x, y, z, s.w, s.w, live);
+                }
+                bad = bad || (live && h);
             }
             // attachment vs links, bounding sphere first (validity.hh:278-301); per lane
             for (int k = 0; k < M::kAttachLinks && has_state && !bad; ++k)
@@ -530,7 +569,13 @@ namespace vmv
         R::frames(cfg, sink);
 
         ctx_wait(&bar);
-        const bool valid = has && check_state<M, BLOCK>(c, env, has, NoVote{});
+        // (every thread calls: the lanes of a warp move through check_state together)
+#ifdef VMV_LANEVOTE_OFF  // development A/B
+        const bool clear = check_state<M, BLOCK>(c, env, has, NoVote{});
+#else
+        const bool clear = check_state<M, BLOCK>(c, env, has, LaneVote{});
+#endif
+        const bool valid = has && clear;
         const uint32_t word = __ballot_sync(0xffffffffu, valid);
         if ((threadIdx.x & 31) == 0 && has)
         {

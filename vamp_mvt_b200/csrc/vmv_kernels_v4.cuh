@@ -58,11 +58,14 @@ namespace vmv
         }
     }
 
-    // called by every lane of a warp with the warp-uniform verdict item
+    // called by every lane of a warp with the warp-uniform verdict item.  GATHER is a template parameter of the
+    // kernels: carrying the peer table through a local launch costs registers (measured 3 % on the configuration
+    // kernel), so local launches run an instantiation without it.
+    template <bool GATHER>
     __device__ __forceinline__ void publish_verdict(uint32_t *bits, const GatherDev &g, size_t index, uint32_t word, int width)
     {
         const int lane = threadIdx.x & 31;
-        if (g.world == 0)
+        if (!GATHER || g.world == 0)
         {
             if (lane == 0)
             {
@@ -77,9 +80,10 @@ namespace vmv
     }
 
     // end of a gathering kernel: called by every thread of the block after its last verdict store
+    template <bool GATHER = true>
     __device__ __forceinline__ void gather_finish(const GatherDev &g)
     {
-        if (g.world == 0)
+        if (!GATHER || g.world == 0)
         {
             return;
         }
@@ -354,17 +358,15 @@ namespace vmv
         using Lay = SmemLayoutV4<typename R::Model, MaskT>;
         const int lane = threadIdx.x & 31;
         uint32_t hits = 0u;
-        // a round lasts as long as its longest record: two lanes share each record, taking alternate
-        // spheres of the longer link (or alternate entries of the pruned list) -- always for random
-        // configurations (measured +6 %), only up to 16 records for the bursty tiles of the edge kernel
-        // (the 8 tines of a rake block raise the same records)
-        int half = lane & 1, step = 2;
-        uint32_t first = lane >> 1, stride = 16u;
-        if constexpr (!SPLIT_ALWAYS)
-        {
-            const int sh = n_rec <= 16u ? 1 : 0;
-            half = lane & sh, step = 1 << sh, first = lane >> sh, stride = 32u >> sh;
-        }
+        // A round lasts as long as its longest record (the hand's 18 spheres): lanes share records, each taking every
+        // step-th sphere of the longer link (or entry of the pruned list).  Configuration kernel: two lanes per
+        // record (measured +6 % over one; 4 and 8 lanes for rounds of few records: -0.7 % -- the kernel is bound
+        // by the latency of its dependent steps, not by the instructions of this loop).  Edge kernel: its tiles are
+        // bursty (the 8 tines of a rake block raise the same records), so the lanes are dealt out by the number of
+        // records -- 8 per record up to 4, 4 up to 8, 2 up to 16, one above (measured +1.3 %).
+        const int sh = SPLIT_ALWAYS ? 1 : (n_rec <= 4u ? 3 : (n_rec <= 8u ? 2 : (n_rec <= 16u ? 1 : 0)));
+        const int half = lane & ((1 << sh) - 1), step = 1 << sh;
+        const uint32_t first = lane >> sh, stride = 32u >> sh;
         for (uint32_t r = first; r < n_rec; r += stride)
         {
             const uint32_t rec = X.pairq[r];
@@ -703,7 +705,7 @@ namespace vmv
     }
 
     // Persistent blocks of blockDim.x / 32 autonomous warps; tile t = states [32 t, 32 t + 32).
-    template <typename R, typename MaskT, bool TAB, int MAXT, int MINB>
+    template <typename R, typename MaskT, bool TAB, bool GATHER, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB)
         k_validate_configs_v4(
             RobotDev robot,
@@ -749,7 +751,7 @@ namespace vmv
             }
 #endif
             const uint32_t invalid = v4_pass<R, MaskT, TAB, true>(X, env.grid, env.tab, cfg, has);
-            publish_verdict(bits, gather, tile, ~invalid, 4);
+            publish_verdict<GATHER>(bits, gather, tile, ~invalid, 4);
 #ifndef VMV_V4_STATIC_TILES
             if (!kEarly && lane == 0)
             {
@@ -760,14 +762,14 @@ namespace vmv
             tile += stride;
 #endif
         }
-        gather_finish(gather);
+        gather_finish<GATHER>(gather);
     }
 
     // Edges.  A warp owns a chunk of 32 edges (one verdict word): lane e keeps edge e's start, vector
     // and rake-step count in registers.  Every pass checks 4 rake blocks (8 tines each) of the
     // reference's schedule (planning/validate.hh:31-64), handed out round-robin over the edges still
     // alive, so an edge found invalid drops its remaining blocks -- the reference's early return.
-    template <typename R, typename MaskT, bool TAB, bool INDEXED, int MAXT, int MINB>
+    template <typename R, typename MaskT, bool TAB, bool INDEXED, bool GATHER, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB) k_validate_edges_v4(
         RobotDev robot,
         const __grid_constant__ GridEnv env,
@@ -911,8 +913,8 @@ namespace vmv
 
             const uint32_t word = __ballot_sync(kFullWarp, steps > 0 && !dead);
             // verdict bits are little-endian in their words: a chunk of 8 / 16 edges is a byte / half word
-            publish_verdict(bits, gather, chunk, word, edges_per_chunk >> 3);
+            publish_verdict<GATHER>(bits, gather, chunk, word, edges_per_chunk >> 3);
         }
-        gather_finish(gather);
+        gather_finish<GATHER>(gather);
     }
 }  // namespace vmv

@@ -216,7 +216,7 @@ namespace vmvh
         static constexpr int kEdgeThreads = 256, kEdgeBlocks = 1, kEdgeQ2Rounds = 2;
     };
 
-    template <typename R, typename MaskT>
+    template <typename R, typename MaskT, bool GATHER>
     int launch_configs_v4(const RobotHost &rh, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits,
                           GatherDev gather, cudaStream_t s)
     {
@@ -235,7 +235,7 @@ namespace vmvh
         }
         le.q2_rounds = Tune::kCfgQ2Rounds;
         const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds);
-        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, Tune::kCfgThreads, Tune::kCfgBlocks>;
+        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, GATHER, Tune::kCfgThreads, Tune::kCfgBlocks>;
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
@@ -263,7 +263,7 @@ namespace vmvh
         return rc;
     }
 
-    template <typename R, typename MaskT>
+    template <typename R, typename MaskT, bool GATHER>
     int launch_edges_v4(const RobotHost &rh, const vmv::RobotDev &rd, vmv::GridEnv le, const float *a, const float *b, const uint32_t *pairs, size_t n,
                         float resolution, uint32_t *bits, GatherDev gather, cudaStream_t s)
     {
@@ -300,7 +300,7 @@ namespace vmvh
         cudaError_t e = cudaSuccess;
         if (pairs != nullptr)
         {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, Tune::kEdgeThreads, Tune::kEdgeBlocks>;
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, GATHER, Tune::kEdgeThreads, Tune::kEdgeBlocks>;
             int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, Tune::kEdgeThreads, units, warps, grid, smem);
             rc = rc == VMV_OK ? counter_acquire(s, counter, slot) : rc;
             if (rc != VMV_OK)
@@ -313,7 +313,7 @@ namespace vmvh
         }
         else
         {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, Tune::kEdgeThreads, Tune::kEdgeBlocks>;
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, GATHER, Tune::kEdgeThreads, Tune::kEdgeBlocks>;
             int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, Tune::kEdgeThreads, units, warps, grid, smem);
             rc = rc == VMV_OK ? counter_acquire(s, counter, slot) : rc;
             if (rc != VMV_OK)
@@ -357,6 +357,12 @@ namespace vmvh
         }
         auto kernel = vmv::k_validate_configs<R, BLOCK>;
         VMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
+#ifdef VMV_C4_STATS
+        {
+            unsigned long long *sp = stats_buffer();
+            VMV_CUDA(cudaMemcpyToSymbol(vmv::g_stats, &sp, sizeof(sp)));
+        }
+#endif
         const unsigned grid = static_cast<unsigned>((n + BLOCK - 1) / BLOCK);
         kernel<<<grid, BLOCK, L.total, s>>>(rd, le, q, n, bits);
         g_launches++;
@@ -491,15 +497,25 @@ namespace vmvh
         static int configs_v4(int, bool wide, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits, const GatherDev &g,
                               cudaStream_t s)
         {
-            return wide ? launch_configs_v4<R, unsigned long long>(host(), rd, le, q, n, bits, g, s)
-                        : launch_configs_v4<R, uint32_t>(host(), rd, le, q, n, bits, g, s);
+            if (g.world > 0)
+            {
+                return wide ? launch_configs_v4<R, unsigned long long, true>(host(), rd, le, q, n, bits, g, s)
+                            : launch_configs_v4<R, uint32_t, true>(host(), rd, le, q, n, bits, g, s);
+            }
+            return wide ? launch_configs_v4<R, unsigned long long, false>(host(), rd, le, q, n, bits, g, s)
+                        : launch_configs_v4<R, uint32_t, false>(host(), rd, le, q, n, bits, g, s);
         }
 
         static int edges_v4(int, bool wide, const vmv::RobotDev &rd, vmv::GridEnv le, const float *a, const float *b, const uint32_t *pairs, size_t n,
                             float resolution, uint32_t *bits, const GatherDev &g, cudaStream_t s)
         {
-            return wide ? launch_edges_v4<R, unsigned long long>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s)
-                        : launch_edges_v4<R, uint32_t>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s);
+            if (g.world > 0)
+            {
+                return wide ? launch_edges_v4<R, unsigned long long, true>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s)
+                            : launch_edges_v4<R, uint32_t, true>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s);
+            }
+            return wide ? launch_edges_v4<R, unsigned long long, false>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s)
+                        : launch_edges_v4<R, uint32_t, false>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s);
         }
 
         static int configs(const vmv::RobotDev &rd, const vmv::LaunchEnv &le, const float *q, size_t n, uint32_t *bits, cudaStream_t s)
