@@ -189,7 +189,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gather", default="fused", choices=["fused", "ce", "nccl", "none"],
+    ap.add_argument("--gather", default="ce", choices=["fused", "ce", "nccl", "none"],
                     help="N > 1: verdict gather by the validation kernel's peer stores (fused), by copy-engine publication of the "
                          "rank's window row (ce), by ncclAllGather (nccl), or not at all")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")

@@ -165,6 +165,27 @@ extern "C"
      * n_env / n_self even when they exceed the capacities. */
     int vmv_debug(int robot, const vmv_env *env, const float *q, int32_t *env_hits, size_t cap_env, size_t *n_env, int32_t *self_hits, size_t cap_self, size_t *n_self);
 
+    /* --- batched roadmap planner front-end: PRM<Robot, rake, resolution> (planning/prm.hh:43-300) -----------------
+     * The reference's loop -- sample, fkcc, k nearest roadmap vertices within the PRM* radius (roadmap.hh:42-67),
+     * validate_motion per neighbour, union-find, A* -- restated as bulk steps (csrc/vmv_planner.cu): Halton samples
+     * generated and validated on the device, every vertex's exact neighbours among the earlier vertices by one
+     * kernel, all candidate edges as one indexed edge batch, and the sequential bookkeeping replayed on the host
+     * from the verdict bits.  The result is the reference's: same vertices, adjacency, iteration count and (solve) path.
+     *   solve = 0: PRM::build_roadmap(start, goal, env, settings, rng)        (prm.hh:198-300)
+     *   solve = 1: PRM::solve(start, goal, env, settings, rng)                (prm.hh:43-196): stops at the iteration that
+     *              connects start and goal; vmv_roadmap_path then gives the waypoints start .. goal (utils::recover_path,
+     *              planning/utils.hh:144-162), vmv_roadmap_iterations the reference's `iterations`.
+     * Sampler: the reference's default, Halton (random/halton.hh); settings: max_iterations, max_samples and
+     * PRMStarNeighborParams(dof, space_measure) -- space_measure = Robot::space_measure() (robots/panda.hh:111-114). */
+    typedef struct vmv_roadmap vmv_roadmap;
+    int vmv_prm(int robot, const vmv_env *env, const float *start, const float *goal, size_t max_iterations, size_t max_samples, double space_measure, int solve, vmv_roadmap **out);
+    void vmv_roadmap_destroy(vmv_roadmap *roadmap);
+    size_t vmv_roadmap_vertices(const vmv_roadmap *roadmap, const float **q);                         /* count; [n][dof] */
+    size_t vmv_roadmap_edges(const vmv_roadmap *roadmap, const uint32_t **pairs, const float **cost); /* adjacency entries (from, to), Roadmap::edges order */
+    size_t vmv_roadmap_path(const vmv_roadmap *roadmap, const float **q, float *cost);                /* waypoints (0: no solution) */
+    size_t vmv_roadmap_iterations(const vmv_roadmap *roadmap);
+    size_t vmv_roadmap_work(const vmv_roadmap *roadmap, size_t *edges_checked);                       /* samples drawn */
+
     /* --- multi-GPU: one process per GPU of one node --------------------------------------------------
      * The reference is single-process and has no counterpart: a batch shards by unit, every rank
      * validates the contiguous word-aligned range it owns against its replica of the environment, and the verdict

@@ -447,6 +447,24 @@ class Ref:
         assert n <= cap
         return out[:n].copy(), float(cost.value)
 
+    def planner(self, which: int, env: RefEnv, start, goal, max_iterations=100000, max_samples=100000, batch_size=1000):
+        """The reference's own planners compiled in place over an exact brute-force NN stand-in and its Halton sampler:
+        which = 0 PRM::build_roadmap -> (vertices, edges [(from, to)] per adjacency entry, iterations);
+        1 PRM::solve, 2 FCIT::solve -> (path waypoints as the reference returns them, cost, iterations)."""
+        self.lib.ref_planner.restype = C.c_size_t
+        cap_v = max_samples + 8
+        verts = np.zeros((cap_v, self.dof), np.float32)
+        cap_e = 1 << 22
+        edges = np.zeros((cap_e, 2), np.uint32)
+        ne, it, cost = C.c_size_t(0), C.c_size_t(0), C.c_float(0)
+        nv = self.lib.ref_planner(self.id, C.c_int(which), env.h, _fp(_f32(start)), _fp(_f32(goal)), C.c_size_t(max_iterations), C.c_size_t(max_samples),
+                                  C.c_size_t(batch_size), _fp(verts), C.c_size_t(cap_v), edges.ctypes.data_as(C.c_void_p), C.c_size_t(cap_e),
+                                  C.byref(ne), C.byref(it), C.byref(cost))
+        assert nv <= cap_v and ne.value <= cap_e
+        if which == 0:
+            return verts[:nv].copy(), edges[: ne.value].copy(), int(it.value)
+        return verts[:nv].copy(), float(cost.value), int(it.value)
+
     def halton(self, n: int, skip: int = 0) -> np.ndarray:
         out = np.zeros((n, self.dof), np.float32)
         self.lib.ref_halton(self.id, C.c_size_t(skip), C.c_size_t(n), _fp(out))

@@ -90,6 +90,9 @@ extern "C"
      * 3 interpolate_to_n_states(arg); the resulting waypoints go to out (up to cap), its cost() to *cost */
     size_t ref_path_op(int robot, int op, const float *path, size_t n, size_t arg, float *out, size_t cap, float *cost);
     /* vamp::rng::Halton<Robot>::next() (random/halton.hh:76-107): samples skip .. skip+n-1, [n][dim] */
+    /* the reference's planners over an exact brute-force NN stand-in: which = 0 PRM::build_roadmap, 1 PRM::solve, 2 FCIT::solve */
+    size_t ref_planner(int robot, int which, void *env, const float *start, const float *goal, size_t max_iterations, size_t max_samples,
+                       size_t batch_size, float *verts, size_t cap_v, uint32_t *edges, size_t cap_e, size_t *n_edges, size_t *iterations, float *cost);
     void ref_halton(int robot, size_t skip, size_t n, float *out);
     void ref_filter_points(int robot, void *env, const float *q, const float *pts, size_t n, float point_radius, uint8_t *keep);
     /* seconds for `reps` passes of ref_validate_configs / edges with `threads` threads (best pass) */

@@ -297,6 +297,13 @@ extern "C"
         return vt(robot).path_op(op, path, n, arg, out, cap, cost);
     }
 
+    size_t ref_planner(int robot, int which, void *env, const float *start, const float *goal, size_t max_iterations, size_t max_samples,
+                       size_t batch_size, float *verts, size_t cap_v, uint32_t *edges, size_t cap_e, size_t *n_edges, size_t *iterations, float *cost)
+    {
+        return vt(robot).planner(which, E(env).env, start, goal, max_iterations, max_samples, batch_size, verts, cap_v, edges, cap_e, n_edges, iterations,
+                                 cost);
+    }
+
     void ref_halton(int robot, size_t skip, size_t n, float *out)
     {
         vt(robot).halton(skip, n, out);

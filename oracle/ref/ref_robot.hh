@@ -22,6 +22,8 @@
 #include <vamp/planning/validate.hh>
 #include <vamp/planning/simplify.hh>
 #include <vamp/random/halton.hh>
+#include <vamp/planning/prm.hh>
+#include <vamp/planning/fcit.hh>
 #include <vamp/vector.hh>
 
 namespace refh
@@ -59,6 +61,10 @@ namespace refh
             std::size_t *);
         void (*halton)(std::size_t, std::size_t, float *);
         std::size_t (*path_op)(int, const float *, std::size_t, std::size_t, float *, std::size_t, float *);
+        // planner: 0 PRM::build_roadmap, 1 PRM::solve, 2 FCIT::solve (planning/prm.hh, fcit.hh) with the Halton sampler.
+        // out: vertices [n][dim] (roadmap) or the path's waypoints (solve); edges as (from, to) pairs per adjacency entry
+        std::size_t (*planner)(int, const EnvF &, const float *, const float *, std::size_t, std::size_t, std::size_t, float *, std::size_t,
+                               std::uint32_t *, std::size_t, std::size_t *, std::size_t *, float *);
     };
 
     template <typename Fn>
@@ -395,6 +401,93 @@ namespace refh
             }
         }
 
+        // The reference's own roadmap planners (planning/prm.hh:43-300, fcit.hh:82-360), unmodified, over the exact
+        // brute-force NN stand-in (shim/vamp/planning/nn.hh) and the reference's Halton sampler.
+        static std::size_t planner(
+            int which,
+            const EnvF &env_f,
+            const float *start_f,
+            const float *goal_f,
+            std::size_t max_iterations,
+            std::size_t max_samples,
+            std::size_t batch_size,
+            float *verts,
+            std::size_t cap_v,
+            std::uint32_t *edges,
+            std::size_t cap_e,
+            std::size_t *n_edges,
+            std::size_t *iterations,
+            float *cost)
+        {
+            namespace vp = vamp::planning;
+            const EnvV env(env_f);
+            const Configuration start(load(start_f)), goal(load(goal_f));
+            typename vamp::rng::RNG<Robot>::Ptr rng = std::make_shared<vamp::rng::Halton<Robot>>();
+            std::size_t nv = 0;
+            *n_edges = 0;
+            auto put = [&](const Configuration &c)
+            {
+                if (nv < cap_v)
+                {
+                    const auto a = c.to_array();
+                    for (std::size_t j = 0; j < Robot::dimension; ++j)
+                    {
+                        verts[nv * Robot::dimension + j] = a[j];
+                    }
+                }
+                ++nv;
+            };
+            if (which == 0)
+            {
+                vp::RoadmapSettings<vp::PRMStarNeighborParams> settings(vp::PRMStarNeighborParams(Robot::dimension, Robot::space_measure()));
+                settings.max_iterations = max_iterations, settings.max_samples = max_samples;
+                const auto rm = vp::PRM<Robot, rake, Robot::resolution>::build_roadmap(start, goal, env, settings, rng);
+                for (const auto &v : rm.vertices)
+                {
+                    put(v);
+                }
+                for (std::size_t i = 0; i < rm.edges.size(); ++i)
+                {
+                    for (const auto j : rm.edges[i])
+                    {
+                        if (*n_edges < cap_e)
+                        {
+                            edges[2 * *n_edges] = static_cast<std::uint32_t>(i);
+                            edges[2 * *n_edges + 1] = static_cast<std::uint32_t>(j);
+                        }
+                        ++*n_edges;
+                    }
+                }
+                *iterations = rm.iterations;
+                *cost = 0.F;
+            }
+            else if (which == 1)
+            {
+                vp::RoadmapSettings<vp::PRMStarNeighborParams> settings(vp::PRMStarNeighborParams(Robot::dimension, Robot::space_measure()));
+                settings.max_iterations = max_iterations, settings.max_samples = max_samples;
+                const auto res = vp::PRM<Robot, rake, Robot::resolution>::solve(start, goal, env, settings, rng);
+                for (const auto &v : res.path)
+                {
+                    put(v);
+                }
+                *iterations = res.iterations;
+                *cost = res.cost;
+            }
+            else
+            {
+                vp::RoadmapSettings<vp::FCITStarNeighborParams> settings(vp::FCITStarNeighborParams(Robot::dimension, Robot::space_measure()));
+                settings.max_iterations = max_iterations, settings.max_samples = max_samples, settings.batch_size = batch_size;
+                const auto res = vp::FCIT<Robot, rake, Robot::resolution>::solve(start, goal, env, settings, rng);
+                for (const auto &v : res.path)
+                {
+                    put(v);
+                }
+                *iterations = res.iterations;
+                *cost = res.cost;
+            }
+            return nv;
+        }
+
         static constexpr RobotVTable vtable{
             static_cast<int>(Robot::dimension),
             static_cast<int>(Robot::n_spheres),
@@ -407,6 +500,7 @@ namespace refh
             &filter_points,
             &simplify,
             &halton,
-            &path_op};
+            &path_op,
+            &planner};
     };
 }  // namespace refh

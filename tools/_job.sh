@@ -1,3 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r2_t7_tests.log
-python bench.py --no-c5 --steps 20 > gpurun_out/r2_t7_bench.json 2> gpurun_out/r2_t7_bench.err
-python tools/time_generic.py > gpurun_out/r2_t7_generic.txt 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_validate_configs -c 1 -s 2 -o gpurun_out/r2_c4_fetch_v1 python tools/prof_configs.py c4 18 fetch > gpurun_out/r2_ncu2.log 2>&1

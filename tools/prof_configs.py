@@ -29,20 +29,12 @@ if what == "hf":
     _lib.check(L.vmv_stream_sync(None))
 elif what == "c4":
     # BASELINE config 4: Fetch vs CAPT of ~10^5 points + heightfield (the any-environment kernel)
-    sys.argv = sys.argv[:1]
-    from tools import bench_extra as be
-    R = vmv.fetch
-    rmin, rmax = R.min_max_radii()
-    pts = be.synth_pointcloud(100_000, 0.55)
-    env = vmv.Environment()
-    env.add_capt_pointcloud(pts, rmin, rmax, vmv.POINT_RADIUS)
-    rng = np.random.default_rng(1)
-    data = (0.15 * rng.random((256, 256)) ** 4).astype(np.float32)
-    yy, xx = np.mgrid[0:256, 0:256]
-    data[np.hypot(xx - 128, yy - 128) < 40] = 0.0
-    env.add_heightfield(vmv.make_heightfield([0, 0, -0.3], [0.02, 0.02, 1.0], [256, 256], data))
+    from tests import workloads
+    rb = sys.argv[3] if len(sys.argv) > 3 else "fetch"
+    R = getattr(vmv, rb)
+    env, pts, hf, _ = workloads.c4_environment(rb)
     n = 1 << min(nlog2, 18)
-    q = scenes.random_configs("fetch", n, seed=0)
+    q = scenes.random_configs(rb, n, seed=0)
     dq = L.vmv_dev_alloc(q.nbytes); db = L.vmv_dev_alloc((n + 31) // 32 * 4)
     _lib.check(L.vmv_memcpy_h2d(dq, _lib.ptr(q), q.nbytes, None))
     for _ in range(3):

@@ -79,6 +79,16 @@ def lib():
         L.vmv_stream_sync.argtypes = [vp]
         L.vmv_launch_count.restype = C.c_uint64
         L.vmv_force_kernel_path.argtypes = [i32]
+        L.vmv_prm.argtypes = [i32, vp, vp, vp, sz, sz, C.c_double, i32, vp]
+        L.vmv_roadmap_destroy.argtypes = [vp]
+        L.vmv_roadmap_destroy.restype = None
+        for fn in ("vmv_roadmap_vertices", "vmv_roadmap_edges", "vmv_roadmap_path", "vmv_roadmap_iterations", "vmv_roadmap_work"):
+            getattr(L, fn).restype = sz
+        L.vmv_roadmap_vertices.argtypes = [vp, vp]
+        L.vmv_roadmap_edges.argtypes = [vp, vp, vp]
+        L.vmv_roadmap_path.argtypes = [vp, vp, vp]
+        L.vmv_roadmap_iterations.argtypes = [vp]
+        L.vmv_roadmap_work.argtypes = [vp, vp]
         L.vmv_comm_unique_id.argtypes = [vp]
         L.vmv_comm_create.argtypes = [vp, vp, i32, i32]
         L.vmv_comm_destroy.argtypes = [vp]

@@ -249,6 +249,10 @@ namespace vmv
 #define VMV_CAPT_SCAN_LOADS 8
 #endif
     static constexpr uint32_t kCaptScanLoads = VMV_CAPT_SCAN_LOADS;
+#ifndef VMV_CAPT_HEAD
+#define VMV_CAPT_HEAD 4
+#endif
+    static constexpr uint32_t kCaptHead = VMV_CAPT_HEAD;  // list entries a lane tests by itself before the cooperative scan
 
     __device__ __forceinline__ bool capt_collides_warp(const CaptRec &t, float x, float y, float z, float r, bool active)
     {
@@ -256,7 +260,7 @@ namespace vmv
         const int lane = threadIdx.x & 31;
         const int rank = __popc(group & ((1u << lane) - 1u));  // position of this lane inside the group
         const int gsize = __popc(group);
-        bool need = false;
+        bool need = false, head_hit = false;
         uint32_t start = 0, end = 0;
         float rc_sq = 0.F;
         if (active)
@@ -286,10 +290,34 @@ namespace vmv
                 need = d0 * d0 + d1 * d1 + d2 * d2 <= rc_sq;
                 start = __float_as_uint(b1.z);
                 end = __float_as_uint(b1.w);
+                if (need)
+                {
+                    // The head of the list by the lane itself: the representative of the cell comes first and the rest
+                    // in order of distance from the cell, so a query that hits at all usually hits within the first
+                    // few entries (measured on BASELINE config 4: 80 % of the scans end with a hit).  Four independent
+                    // loads, one latency period for all lanes of the warp together; only what is still undecided
+                    // afterwards goes to the cooperative scan below.
+                    const float qlim0 = rc_sq * 1.00001F;
+                    bool h = false, beyond = false;
+#pragma unroll
+                    for (uint32_t u = 0; u < kCaptHead; ++u)
+                    {
+                        if (start + u < end)
+                        {
+                            const float4 p = __ldg(t.points + start + u);
+                            const float ex = p.x - x, ey = p.y - y, ez = p.z - z;
+                            h = h || (ex * ex + ey * ey + ez * ez <= rc_sq);
+                            beyond = beyond || (p.w > qlim0);
+                        }
+                    }
+                    head_hit = h;
+                    start = min(start + kCaptHead, end);
+                    need = !h && !beyond && start < end;
+                }
             }
         }
 
-        bool hit = false;
+        bool hit = head_hit;
         uint32_t pending = __ballot_sync(group, need);
         if (active)
         {

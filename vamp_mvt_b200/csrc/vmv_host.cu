@@ -3153,6 +3153,41 @@ extern "C"
 
         constexpr int kMaxSlots = 4;
 
+        // cuStreamBatchMemOp of the driver API (libcuda, loaded at run time): the flag waits of vmv_comm_wait as stream
+        // memory operations -- executed by the front end, no kernel launch and no SM -- where the driver offers them
+        using BatchMemOpFn = int (*)(cudaStream_t, unsigned int, void *, unsigned int);
+        BatchMemOpFn batch_mem_op()
+        {
+            static BatchMemOpFn fn = []() -> BatchMemOpFn
+            {
+                if (std::getenv("VMV_COMM_WAIT_KERNEL") != nullptr)
+                {
+                    return nullptr;  // tuning aid: force the kernel
+                }
+                void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+                if (lib == nullptr)
+                {
+                    return nullptr;
+                }
+                void *f = dlsym(lib, "cuStreamBatchMemOp_v2");
+                return reinterpret_cast<BatchMemOpFn>(f);
+            }();
+            return fn;
+        }
+        // CUstreamBatchMemOpParams (cuda.h): a union padded to 6 x 8 bytes; the wait-value member
+        struct WaitValueOp
+        {
+            unsigned int operation;  // CU_STREAM_MEM_OP_WAIT_VALUE_32 = 1
+            unsigned int pad0;
+            unsigned long long address;
+            unsigned long long value;  // low 32 bits
+            unsigned int flags;        // CU_STREAM_WAIT_VALUE_GEQ = 0: (int32_t)(*addr - value) >= 0
+            unsigned int pad1;
+            unsigned long long alias;
+            unsigned long long pad2;
+        };
+        static_assert(sizeof(WaitValueOp) == 48, "CUstreamBatchMemOpParams is 6 x 8 bytes");
+
         // byte stream of an environment's host-side description (vmv_env_broadcast)
         struct Writer
         {
@@ -3580,8 +3615,24 @@ extern "C"
             {
                 return VMV_OK;  // nothing was gathered into this slot yet
             }
-            vmv::k_comm_wait<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(c->window + c->flags_off + static_cast<size_t>(slot) * vmv::kMaxPeers, c->world,
-                                                                                 c->seq[slot]);
+            const uint32_t *flags = c->window + c->flags_off + static_cast<size_t>(slot) * vmv::kMaxPeers;
+            if (BatchMemOpFn op = batch_mem_op())
+            {
+                WaitValueOp ops[vmv::kMaxPeers] = {};
+                for (int p = 0; p < c->world; ++p)
+                {
+                    ops[p].operation = 1;
+                    ops[p].address = reinterpret_cast<unsigned long long>(flags + p);
+                    ops[p].value = c->seq[slot];
+                    ops[p].flags = 0;
+                }
+                if (op(static_cast<cudaStream_t>(stream), static_cast<unsigned int>(c->world), ops, 0) == 0)
+                {
+                    return VMV_OK;
+                }
+                // (not supported on this driver / device: fall through to the kernel)
+            }
+            vmv::k_comm_wait<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, c->world, c->seq[slot]);
             g_launches++;
             VMV_CUDA(cudaGetLastError());
             return VMV_OK;

@@ -1,138 +1,80 @@
-"""Batched PRM front-end over the validation engine -- a first slice of SURVEY.md 8(f) rank 1, not a
-port of the reference planner.
+"""Batched PRM front-end: ``vamp.<robot>.prm`` / ``vamp.<robot>.roadmap`` of the reference
+(bindings/robot_helper.hh:177-221, planning/prm.hh:43-300) over the C ABI's ``vmv_prm`` (csrc/vmv_planner.cu).
 
-The reference's PRM (planning/prm.hh:43-196) is strictly serial: one sample, one ``fkcc``, its k nearest
-roadmap vertices, one ``validate_motion`` per neighbour.  The work it generates is exactly what the
-engine takes in bulk, so here a roadmap grows in ROUNDS: a batch of samples is validated in one call
-(``vmv_validate_configs``), every valid sample proposes edges to its k nearest earlier vertices with the
-reference's PRM* neighbour count k = ceil((e + e/d) ln n) (planning/roadmap.hh:49-56), all candidate edges
-of the round are validated in one call as index pairs into the vertex table (``vmv_validate_edges_indexed``
--- 8 bytes per edge), and connectivity is tracked with union-find; start and goal are the first two
-vertices and a shortest path is extracted when they meet.  Samples come from ``rng`` -- e.g. the
-reference's Halton sequence, ``vamp.<robot>.halton()`` (vamp_mvt_b200/halton.py), drawn a batch at a time
--- or, without one, uniformly from a seeded generator; nearest neighbours come from scipy's k-d tree
-(the reference's nigh tree is not restated) and vertices are connected in rounds -- so roadmaps are not
-the reference's, but every edge in one is an edge the reference's ``validate_motion`` accepts.
+The reference draws one Halton sample at a time, checks it, asks its k-d tree for the PRM* neighbours and validates one
+edge per neighbour.  Here the same roadmap comes out of three bulk steps on the GPU -- samples generated and validated
+on the device, exact causal k-nearest neighbours by one kernel, all candidate edges as one indexed edge batch -- and a
+host replay of union-find / A*.  Vertices, adjacency, iteration count and path are the reference's
+(tests/test_planner.py compares them with the reference's own prm.hh compiled in place).
 """
 from __future__ import annotations
 
-import heapq
-import math
+import ctypes as C
 from dataclasses import dataclass, field
 from typing import List, Optional
 
 import numpy as np
 
+from . import _lib
 from .environment import Environment
-from .halton import Halton
+
+# Robot::space_measure() of the reference (robots/panda.hh:111-114, ur5.hh:105-108, fetch.hh:117-120, baxter.hh:153-156):
+# a float-returning function, so the literal is narrowed to float before PRMStarNeighborParams takes it as a double
+SPACE_MEASURE = {"panda": 57376.4026747593, "ur5": 61528.90796697732, "fetch": 16384.87636281249, "baxter": 590532810.7756369}
 
 
 @dataclass
 class Roadmap:
-    vertices: np.ndarray
-    edges: np.ndarray  # [m, 2] vertex indices of validated edges
-    path: Optional[List[np.ndarray]] = None
+    vertices: np.ndarray          # [n][dof]: start, goal, then the valid samples in stream order
+    edges: np.ndarray             # [m][2] adjacency entries (from, to) in the reference's Roadmap::edges enumeration
+    edge_cost: np.ndarray         # [m] the neighbour distance stored with each entry
+    path: Optional[List[np.ndarray]] = None  # solve: start ... goal
     cost: float = float("inf")
-    rounds: int = 0
-    configs_checked: int = 0
+    iterations: int = 0
+    samples_drawn: int = 0
     edges_checked: int = 0
     stats: dict = field(default_factory=dict)
 
-
-def _find(parent, i):
-    while parent[i] != i:
-        parent[i] = parent[parent[i]]
-        i = parent[i]
-    return i
+    def undirected_edges(self) -> np.ndarray:
+        e = np.sort(self.edges.astype(np.int64), axis=1)
+        return np.unique(e, axis=0)
 
 
-def prm(robot, start, goal, environment: Optional[Environment] = None, max_samples: int = 20000, batch: int = 4096,
-        seed: int = 0, rng=None) -> Roadmap:
-    from scipy.spatial import cKDTree
-
+def _run(robot, start, goal, environment: Optional[Environment], max_iterations: int, max_samples: int, solve: bool) -> Roadmap:
+    L = _lib.lib()
+    env = environment if environment is not None else Environment()
     d = robot.dimension()
-    lo = np.asarray(robot.lower_bounds(), np.float32)
-    hi = np.asarray(robot.upper_bounds(), np.float32)
-    gen = np.random.default_rng(seed)
-    start = np.asarray(start, np.float32).reshape(d)
-    goal = np.asarray(goal, np.float32).reshape(d)
-    rm = Roadmap(vertices=np.stack([start, goal]), edges=np.zeros((0, 2), np.int64))
-    ends_ok = robot.validate_batch(rm.vertices, environment)
-    rm.configs_checked += 2
-    if not ends_ok.all():
-        return rm
-    # straight line first, as the reference does (prm.hh:57-70)
-    rm.edges_checked += 1
-    if robot.validate_motion(start, goal, environment):
-        rm.edges = np.array([[0, 1]])
-        rm.path, rm.cost = [start, goal], float(np.linalg.norm(goal - start))
-        return rm
-    parent = list(range(2))
-    while len(rm.vertices) < max_samples:
-        rm.rounds += 1
-        if isinstance(rng, Halton) and rng.count + batch <= robot.halton_exact_limit():
-            # samples generated and validated on the device; the valid ones are rebuilt here in closed form
-            ok = robot.validate_halton(rng.count, batch, environment)
-            new = rng.at(rng.count + np.nonzero(ok)[0])
-            rng.advance(batch)
-        else:
-            if rng is not None:
-                q = rng.take(batch)
-            else:
-                q = (lo + (hi - lo) * gen.random((batch, d), dtype=np.float32)).astype(np.float32)
-            ok = robot.validate_batch(q, environment)
-            new = q[ok]
-        rm.configs_checked += batch
-        if len(new) == 0:
-            continue
-        base = len(rm.vertices)
-        V = np.vstack([rm.vertices, new]).astype(np.float32)
-        n = len(V)
-        k = int(math.ceil((math.e + math.e / d) * math.log(n)))
-        tree = cKDTree(V)
-        _, nbr = tree.query(new, k=min(k + 1, n))
-        src = np.repeat(np.arange(base, n), nbr.shape[1])
-        dst = nbr.reshape(-1)
-        keep = dst < src  # an edge is proposed once, by its later vertex
-        pairs = np.stack([src[keep], dst[keep]], axis=1).astype(np.uint32)
-        valid = robot.validate_edges_indexed(V, pairs, environment)
-        rm.edges_checked += len(pairs)
-        good = pairs[valid].astype(np.int64)
-        rm.vertices = V
-        rm.edges = np.vstack([rm.edges, good])
-        parent.extend(range(base, n))
-        for a, b in good:
-            ra, rb = _find(parent, int(a)), _find(parent, int(b))
-            if ra != rb:
-                parent[ra] = rb
-        if _find(parent, 0) == _find(parent, 1):
-            break
-    if _find(parent, 0) != _find(parent, 1):
-        return rm
-    # Dijkstra on the validated edges
-    adj = [[] for _ in range(len(rm.vertices))]
-    w = np.linalg.norm(rm.vertices[rm.edges[:, 0]] - rm.vertices[rm.edges[:, 1]], axis=1)
-    for (a, b), c in zip(rm.edges, w):
-        adj[a].append((b, float(c)))
-        adj[b].append((a, float(c)))
-    dist = {0: 0.0}
-    prev = {}
-    heap = [(0.0, 0)]
-    while heap:
-        du, u = heapq.heappop(heap)
-        if u == 1:
-            break
-        if du > dist.get(u, float("inf")):
-            continue
-        for v, c in adj[u]:
-            if du + c < dist.get(v, float("inf")):
-                dist[v] = du + c
-                prev[v] = u
-                heapq.heappush(heap, (du + c, v))
-    node, idx = 1, [1]
-    while node != 0:
-        node = prev[node]
-        idx.append(node)
-    rm.path = [rm.vertices[i] for i in reversed(idx)]
-    rm.cost = dist[1]
-    return rm
+    s = _lib.f32(start).reshape(d)
+    g = _lib.f32(goal).reshape(d)
+    h = C.c_void_p()
+    measure = float(np.float32(SPACE_MEASURE[robot.name]))
+    _lib.check(L.vmv_prm(robot.id, env.handle, _lib.ptr(s), _lib.ptr(g), max_iterations, max_samples, measure, 1 if solve else 0, C.byref(h)))
+    try:
+        p = C.c_void_p()
+        n = L.vmv_roadmap_vertices(h, C.byref(p))
+        V = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n * d,)).reshape(n, d).copy() if n else np.zeros((0, d), np.float32)
+        pe, pc = C.c_void_p(), C.c_void_p()
+        m = L.vmv_roadmap_edges(h, C.byref(pe), C.byref(pc))
+        E = np.ctypeslib.as_array(C.cast(pe, C.POINTER(C.c_uint32)), shape=(2 * m,)).reshape(m, 2).copy() if m else np.zeros((0, 2), np.uint32)
+        W = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_float)), shape=(m,)).copy() if m else np.zeros(0, np.float32)
+        pp, cost = C.c_void_p(), C.c_float(0)
+        k = L.vmv_roadmap_path(h, C.byref(pp), C.byref(cost))
+        path = None
+        if k:
+            P = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), shape=(k * d,)).reshape(k, d).copy()
+            path = [P[i] for i in range(k)]
+        ec = C.c_size_t(0)
+        drawn = L.vmv_roadmap_work(h, C.byref(ec))
+        return Roadmap(V, E, W, path, float(cost.value), int(L.vmv_roadmap_iterations(h)), int(drawn), int(ec.value))
+    finally:
+        L.vmv_roadmap_destroy(h)
+
+
+def prm(robot, start, goal, environment: Optional[Environment] = None, max_iterations: int = 100000, max_samples: int = 100000) -> Roadmap:
+    """vamp.<robot>.prm: PRM::solve with the Halton sampler and PRM* neighbour parameters."""
+    return _run(robot, start, goal, environment, max_iterations, max_samples, True)
+
+
+def roadmap(robot, start, goal, environment: Optional[Environment] = None, max_iterations: int = 100000, max_samples: int = 100000) -> Roadmap:
+    """vamp.<robot>.roadmap: PRM::build_roadmap."""
+    return _run(robot, start, goal, environment, max_iterations, max_samples, False)

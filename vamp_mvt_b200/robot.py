@@ -190,10 +190,16 @@ class Robot:
         return p[_lib.unpack_bits(words, len(p))]
 
     def prm(self, start, goal, environment: Optional[Environment] = None, **kwargs):
-        """Batched PRM front-end (vamp_mvt_b200/prm.py): roadmap growth in rounds of bulk validation."""
+        """``vamp.<robot>.prm`` (PRM::solve, reference planning/prm.hh:43-196) as bulk GPU steps: vamp_mvt_b200/prm.py."""
         from .prm import prm
 
         return prm(self, start, goal, environment, **kwargs)
+
+    def roadmap(self, start, goal, environment: Optional[Environment] = None, **kwargs):
+        """``vamp.<robot>.roadmap`` (PRM::build_roadmap, reference planning/prm.hh:198-300): vamp_mvt_b200/prm.py."""
+        from .prm import roadmap
+
+        return roadmap(self, start, goal, environment, **kwargs)
 
     def Path(self, waypoints=()):
         """``vamp.<robot>.Path`` (reference planning/plan.hh:10-169, bindings/robot_helper.hh:411-466)."""
