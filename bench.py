@@ -260,6 +260,8 @@ def main() -> int:
     elif gather_mode == "nccl":
         gathered2 = [torch.zeros(world * n_words, dtype=torch.int32, device="cuda") for _ in range(2)]
 
+    consumer = torch.cuda.Stream() if gather_mode == "ce" else None
+
     def step(i: int):
         qd = dev_batches[i % N_BATCHES]
         if gather_mode == "fused":
@@ -270,11 +272,13 @@ def main() -> int:
                 C.wait((i - 1) % 2, stream)
         elif gather_mode == "ce":
             # the kernel writes this rank's row of its own window; the copy engines carry it to the peers on a side
-            # stream while the next step's kernel runs
+            # stream while the next step's kernel runs; the global mask of the previous step is awaited on the CONSUMER's
+            # stream (where a planner would read it), so the compute stream carries nothing but the kernels
+            C.acquire(i % 2, stream)
             _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, C.local_row(i % 2), stream))
             C.publish(i % 2, n_words, stream)
             if i > 0:
-                C.wait((i - 1) % 2, stream)
+                C.wait((i - 1) % 2, consumer.cuda_stream)
         else:
             _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, bits2[i % 2].data_ptr(), stream))
             if gather_mode == "nccl":
@@ -301,19 +305,23 @@ def main() -> int:
             if i > 0:
                 C.wait((i - 1) % 2, stream)
         elif gather_mode == "ce":
+            C.acquire(i % 2, stream)
             _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, C.local_row(i % 2), stream))
             kb.record()
             C.publish(i % 2, n_words, stream)
             if i > 0:
-                C.wait((i - 1) % 2, stream)
+                C.wait((i - 1) % 2, consumer.cuda_stream)
         else:
             _lib.check(L.vmv_validate_configs_dev(robot.id, h_env, qd.data_ptr(), N_CONFIGS, bits2[i % 2].data_ptr(), stream))
             kb.record()
             if gather_mode == "nccl":
                 C.allgather_words(bits2[i % 2].data_ptr(), n_words, gathered2[i % 2].data_ptr(), stream)
         kernel_events.append((ka, kb))
-    if gather_mode in ("fused", "ce"):
+    if gather_mode == "fused":
         C.wait((args.steps - 1) % 2, stream)  # the last gather has landed from every rank before the end event
+    elif gather_mode == "ce":
+        C.wait((args.steps - 1) % 2, consumer.cuda_stream)
+        torch.cuda.current_stream().wait_stream(consumer)  # ... and every mask has been seen complete by the consumer
     e1.record()
     barrier()
     launches = int(L.vmv_launch_count() - launches0)
@@ -416,6 +424,7 @@ def main() -> int:
                 C.validate_edges_indexed_gather(robot.id, h_env, i % 2, dV.data_ptr(), len(V), dP.data_ptr(), hi5 - lo5, 0, stream)
                 C.wait(i % 2, stream)  # the planner consumes the global mask of THIS step
             elif gather_mode == "ce":
+                C.acquire(i % 2, stream)
                 _lib.check(L.vmv_validate_edges_indexed_dev(robot.id, h_env, dV.data_ptr(), len(V), dP.data_ptr(), hi5 - lo5, 0, C.local_row(i % 2), stream))
                 C.publish(i % 2, (hi5 - lo5 + 31) // 32, stream)
                 C.wait(i % 2, stream)

@@ -179,6 +179,14 @@ extern "C"
      * PRMStarNeighborParams(dof, space_measure) -- space_measure = Robot::space_measure() (robots/panda.hh:111-114). */
     typedef struct vmv_roadmap vmv_roadmap;
     int vmv_prm(int robot, const vmv_env *env, const float *start, const float *goal, size_t max_iterations, size_t max_samples, double space_measure, int solve, vmv_roadmap **out);
+    /* FCIT<Robot, rake, resolution>::solve (planning/fcit.hh:82-360): a lazy best-first search over the complete graph
+     * of the samples, fed by batches.  The search itself is sequential and runs on the host (csrc/vmv_fcit.hpp, the
+     * reference's control flow restated); what it consumes comes from the GPU in bulk: each batch of batch_size valid
+     * samples from chunks of the Halton stream generated and validated on the device (fcit.hh:322-348), and each edge
+     * verdict (fcit.hh:230-260) from a row cache -- the first question about a parent validates its edges to every
+     * node in one indexed batch.  Path, cost and iteration count are the reference's.  vmv_roadmap_vertices then
+     * lists start, goal and the samples; vmv_roadmap_path the solution (just the start when there is none). */
+    int vmv_fcit(int robot, const vmv_env *env, const float *start, const float *goal, size_t max_iterations, size_t max_samples, size_t batch_size, int optimize, vmv_roadmap **out);
     void vmv_roadmap_destroy(vmv_roadmap *roadmap);
     size_t vmv_roadmap_vertices(const vmv_roadmap *roadmap, const float **q);                         /* count; [n][dof] */
     size_t vmv_roadmap_edges(const vmv_roadmap *roadmap, const uint32_t **pairs, const float **cost); /* adjacency entries (from, to), Roadmap::edges order */
@@ -231,6 +239,9 @@ extern "C"
      * and the copies overlap the next launch.  At most 4095 publications per slot. */
     uint32_t *vmv_comm_local_row(vmv_comm *comm, int slot);
     int vmv_comm_publish(vmv_comm *comm, int slot, size_t n_words, void *stream);
+    /* before a launch on `stream` overwrites the local row of `slot`: a device-side wait until the copy engines
+     * have sent its previous contents (no-op for a slot never published) */
+    int vmv_comm_acquire(vmv_comm *comm, int slot, void *stream);
 
     /* --- device buffers for callers that do not bring their own allocator ---------------------- */
     void *vmv_dev_alloc(size_t bytes);

@@ -24,6 +24,9 @@
 #include <vamp/random/halton.hh>
 #include <vamp/planning/prm.hh>
 #include <vamp/planning/fcit.hh>
+
+// the product's host-side FCIT* restatement, driven here by the reference's own checks (CPU pin of its control flow)
+#include "../../vamp_mvt_b200/csrc/vmv_fcit.hpp"
 #include <vamp/vector.hh>
 
 namespace refh
@@ -469,6 +472,46 @@ namespace refh
                 for (const auto &v : res.path)
                 {
                     put(v);
+                }
+                *iterations = res.iterations;
+                *cost = res.cost;
+            }
+            else if (which == 3)
+            {
+                // vmvfcit::solve (the product's restatement) with the reference's fkcc / validate_motion / Halton as providers
+                std::vector<float> states(start_f, start_f + Robot::dimension);
+                states.insert(states.end(), goal_f, goal_f + Robot::dimension);
+                auto dist = [](const float *a, const float *b) { return load(a).distance(load(b)); };
+                auto samples = [&](std::size_t n, std::vector<float> &st)
+                {
+                    std::size_t got = 0;
+                    typename Robot::template ConfigurationBlock<rake> block;
+                    while (got < n)
+                    {
+                        auto c = rng->next();
+                        for (auto i = 0U; i < Robot::dimension; ++i)
+                        {
+                            block[i] = c.broadcast(i);
+                        }
+                        if (not Robot::template fkcc<rake>(env, block))
+                        {
+                            continue;
+                        }
+                        const auto a = c.to_array();
+                        st.insert(st.end(), a.begin(), a.begin() + Robot::dimension);
+                        ++got;
+                    }
+                    return got;
+                };
+                auto edges = [&](std::uint32_t p, std::uint32_t c)
+                {
+                    return vp::validate_motion<Robot, rake, Robot::resolution>(
+                        load(states.data() + p * Robot::dimension), load(states.data() + c * Robot::dimension), env);
+                };
+                const auto res = vmvfcit::solve(states, Robot::dimension, max_iterations, max_samples, batch_size, false, dist, samples, edges);
+                for (const auto i : res.path)
+                {
+                    put(load(states.data() + i * Robot::dimension));
                 }
                 *iterations = res.iterations;
                 *cost = res.cost;

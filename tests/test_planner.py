@@ -66,12 +66,32 @@ def test_prm_solve_is_the_references(key):
 
 @pytest.mark.gpu
 def test_prm_straight_line_and_limits():
+    from tests import scenes
+
     env = vmv.Environment()
-    a = np.zeros(7, np.float32)
-    a[3] = -1.5
+    a = np.array(scenes.CAGE_A, np.float32)
     b = a.copy()
-    b[0] = 0.4
+    b[0] += 0.4
+    assert vmv.panda.validate_motion(a, b, env)
     res = vmv.panda.prm(a, b, env)  # empty environment: the straight line is valid (prm.hh:57-70)
-    assert res.iterations == 0 and len(res.path) == 2
+    assert res.iterations == 0 and len(res.path) == 2 and np.array_equal(res.path[0], a) and np.array_equal(res.path[1], b)
     with pytest.raises(_lib.VmvError):
         vmv.panda.roadmap(a, b, env, max_iterations=10**7)  # beyond the exact range of the device Halton sampler
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [1000, 100, 20])
+@pytest.mark.parametrize("key", ["cage", "mbm_bookshelf_small"])
+def test_fcit_solve_is_the_references(key, batch):
+    """FCIT* (planning/fcit.hh): host search over GPU sample batches and GPU edge rows -- the reference's path, cost
+    and iteration count."""
+    d = np.load(GOLDEN)
+    env = _env(d, key)
+    tag = "fcit" if batch == 1000 else f"fcit{batch}"
+    res = vmv.panda.fcit(d[f"{key}_start"], d[f"{key}_goal"], env, batch_size=batch, max_samples=100000 if batch == 1000 else 4000)
+    P = d[f"{key}_{tag}_path"]
+    assert res.iterations == int(d[f"{key}_{tag}_iterations"])
+    assert res.path is not None and len(res.path) == len(P) and np.array_equal(np.stack(res.path), P)
+    assert res.cost == pytest.approx(float(d[f"{key}_{tag}_cost"]), rel=1e-6)
+    assert vmv.panda.Path(res.path).validate(env)
+    assert res.edges_checked > 0

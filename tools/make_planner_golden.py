@@ -28,6 +28,9 @@ def main():
         V, E, it = r.planner(0, env, a, b, max_iterations=4000, max_samples=4000)
         P, cost, it_s = r.planner(1, env, a, b)
         F, fcost, it_f = r.planner(2, env, a, b)
+        for bs in (100, 20):
+            Fb, cb, ib = r.planner(2, env, a, b, batch_size=bs, max_samples=4000)
+            out.update({f"{key}_fcit{bs}_path": Fb, f"{key}_fcit{bs}_cost": cb, f"{key}_fcit{bs}_iterations": ib})
         out.update({f"{key}_start": a, f"{key}_goal": b, f"{key}_vertices": V, f"{key}_edges": E, f"{key}_iterations": it,
                     f"{key}_path": P, f"{key}_cost": cost, f"{key}_solve_iterations": it_s,
                     f"{key}_fcit_path": F, f"{key}_fcit_cost": fcost, f"{key}_fcit_iterations": it_f})

@@ -80,6 +80,7 @@ def lib():
         L.vmv_launch_count.restype = C.c_uint64
         L.vmv_force_kernel_path.argtypes = [i32]
         L.vmv_prm.argtypes = [i32, vp, vp, vp, sz, sz, C.c_double, i32, vp]
+        L.vmv_fcit.argtypes = [i32, vp, vp, vp, sz, sz, sz, i32, vp]
         L.vmv_roadmap_destroy.argtypes = [vp]
         L.vmv_roadmap_destroy.restype = None
         for fn in ("vmv_roadmap_vertices", "vmv_roadmap_edges", "vmv_roadmap_path", "vmv_roadmap_iterations", "vmv_roadmap_work"):
@@ -108,6 +109,7 @@ def lib():
         L.vmv_comm_local_row.restype = vp
         L.vmv_comm_local_row.argtypes = [vp, i32]
         L.vmv_comm_publish.argtypes = [vp, i32, sz, vp]
+        L.vmv_comm_acquire.argtypes = [vp, i32, vp]
         _lib = L
     return _lib
 

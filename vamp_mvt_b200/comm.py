@@ -69,6 +69,10 @@ class Communicator:
         """Copy-engine publication of the local row of `slot` to every peer, ordered behind `stream`."""
         _lib.check(self._L.vmv_comm_publish(self.handle, slot, n_words, stream))
 
+    def acquire(self, slot: int, stream=None):
+        """Order `stream` behind the copy engines' send of the slot's previous row (call before overwriting it)."""
+        _lib.check(self._L.vmv_comm_acquire(self.handle, slot, stream))
+
     def wait(self, slot: int, stream=None):
         _lib.check(self._L.vmv_comm_wait(self.handle, slot, stream))
 

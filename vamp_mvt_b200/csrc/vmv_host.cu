@@ -3255,6 +3255,8 @@ struct vmv_comm
     // sequence numbers the flag copies read from
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ready[4] = {};
+    cudaEvent_t copied[4] = {};  // recorded on the copy stream behind a slot's publication
+    bool published[4] = {false, false, false, false};
     uint32_t *d_seq = nullptr;
 };
 constexpr uint32_t kSeqTable = 4096;
@@ -3375,6 +3377,13 @@ extern "C"
             cudaStreamDestroy(c->copy_stream);
         }
         for (cudaEvent_t e : c->ready)
+        {
+            if (e != nullptr)
+            {
+                cudaEventDestroy(e);
+            }
+        }
+        for (cudaEvent_t e : c->copied)
         {
             if (e != nullptr)
             {
@@ -3576,6 +3585,10 @@ extern "C"
                 {
                     VMV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 }
+                for (cudaEvent_t &e : c->copied)
+                {
+                    VMV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                }
                 std::vector<uint32_t> table(kSeqTable);
                 std::iota(table.begin(), table.end(), 0u);
                 VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&c->d_seq), kSeqTable * sizeof(uint32_t)));
@@ -3598,6 +3611,26 @@ extern "C"
                     VMV_CUDA(cudaMemcpyAsync(c->peer_window[p] + row, c->window + row, n_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->copy_stream));
                 }
                 VMV_CUDA(cudaMemcpyAsync(c->peer_window[p] + flag, c->d_seq + seq, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->copy_stream));
+            }
+            VMV_CUDA(cudaEventRecord(c->copied[slot], c->copy_stream));
+            c->published[slot] = true;
+            return VMV_OK;
+        });
+    }
+
+    // Before a launch on `stream` overwrites this rank's row of `slot`: wait (on the device, no host block) until the
+    // copy engines have finished sending the row's previous contents.
+    int vmv_comm_acquire(vmv_comm *c, int slot, void *stream)
+    {
+        return guarded("vmv_comm_acquire", [&]() -> int
+        {
+            if (c == nullptr || c->window == nullptr || slot < 0 || slot >= c->slots)
+            {
+                return fail(VMV_ERR_ARG, "vmv_comm_acquire: bad argument");
+            }
+            if (c->published[slot])
+            {
+                VMV_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->copied[slot], 0));
             }
             return VMV_OK;
         });

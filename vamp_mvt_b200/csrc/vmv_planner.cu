@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "vmv_internal.h"
+#include "vmv_fcit.hpp"
 
 using namespace vmvh;
 
@@ -567,6 +568,111 @@ namespace
         return VMV_OK;
     }
 
+    // FCIT* (fcit.hh) with the GPU behind both providers of vmvfcit::solve
+    int fcit_run(int robot, const vmv_env *env, const float *start, const float *goal, size_t max_iterations, size_t max_samples, size_t batch_size,
+                 bool optimize, vmv_roadmap &R)
+    {
+        const RobotHost &rh = *ops(robot).host;
+        const int dof = rh.dof;
+        R.dof = dof;
+        std::vector<float> &states = R.vertices;
+        states.assign(start, start + dof);
+        states.insert(states.end(), goal, goal + dof);
+        int err = VMV_OK;
+
+        // samples: the Halton stream generated and validated on the device a chunk at a time; what a batch does not
+        // use stays in the look-ahead buffer for the next one
+        const uint64_t limit = vmv_halton_exact_limit(robot);
+        uint64_t pos = 0;  // next sample of the stream not yet fetched
+        std::vector<uint32_t> bits;
+        std::vector<float> q;
+        size_t have = 0, at = 0;  // samples in the buffer / next one to look at
+        auto samples = [&](size_t n, std::vector<float> &st) -> size_t
+        {
+            size_t got = 0;
+            while (got < n && err == VMV_OK)
+            {
+                if (at == have)
+                {
+                    const size_t chunk = std::min<uint64_t>(std::max<size_t>(4096, 2 * (n - got)), limit > pos ? limit - pos : 0);
+                    if (chunk == 0)
+                    {
+                        break;  // beyond the exact range of the device sampler
+                    }
+                    bits.assign((chunk + 31) / 32, 0u);
+                    q.resize(chunk * dof);
+                    err = vmv_validate_halton(robot, env, pos, chunk, bits.data(), q.data());
+                    if (err != VMV_OK)
+                    {
+                        break;
+                    }
+                    pos += chunk;
+                    have = chunk, at = 0;
+                }
+                for (; at < have && got < n; ++at)
+                {
+                    if ((bits[at >> 5] >> (at & 31)) & 1u)
+                    {
+                        st.insert(st.end(), q.begin() + at * dof, q.begin() + (at + 1) * dof);
+                        ++got;
+                    }
+                }
+            }
+            R.samples_drawn = static_cast<size_t>(pos - (have - at));
+            return got;
+        };
+
+        // edges: the first question about a parent validates its edges to EVERY node known so far in one indexed batch
+        std::vector<std::vector<uint32_t>> rows;
+        std::vector<uint32_t> rows_len;
+        std::vector<uint32_t> pairs, words;
+        auto edges = [&](uint32_t p, uint32_t c) -> bool
+        {
+            const uint32_t n_nodes = static_cast<uint32_t>(states.size() / dof);
+            if (rows.size() < n_nodes)
+            {
+                rows.resize(n_nodes);
+                rows_len.resize(n_nodes, 0);
+            }
+            if (c >= rows_len[p] && err == VMV_OK)
+            {
+                const uint32_t lo = rows_len[p];
+                pairs.clear();
+                for (uint32_t j = lo; j < n_nodes; ++j)
+                {
+                    pairs.push_back(p);
+                    pairs.push_back(j);
+                }
+                words.assign((n_nodes - lo + 31) / 32, 0u);
+                err = vmv_validate_edges_indexed(robot, env, states.data(), n_nodes, pairs.data(), n_nodes - lo, rh.resolution, words.data());
+                R.edges_checked += n_nodes - lo;
+                rows[p].resize((n_nodes + 31) / 32, 0u);
+                for (uint32_t j = lo; j < n_nodes; ++j)
+                {
+                    if ((words[(j - lo) >> 5] >> ((j - lo) & 31)) & 1u)
+                    {
+                        rows[p][j >> 5] |= 1u << (j & 31);
+                    }
+                }
+                rows_len[p] = n_nodes;
+            }
+            return err == VMV_OK && ((rows[p][c >> 5] >> (c & 31)) & 1u) != 0u;
+        };
+        auto dist = [dof](const float *a, const float *b) { return ref_distance(a, b, dof); };
+        const vmvfcit::Result res = vmvfcit::solve(states, dof, max_iterations, max_samples, batch_size, optimize, dist, samples, edges);
+        if (err != VMV_OK)
+        {
+            return err;
+        }
+        for (const uint32_t i : res.path)
+        {
+            R.path.insert(R.path.end(), states.begin() + static_cast<size_t>(i) * dof, states.begin() + static_cast<size_t>(i + 1) * dof);
+        }
+        R.cost = res.cost;
+        R.iterations = res.iterations;
+        return VMV_OK;
+    }
+
     template <typename F>
     int guarded_planner(const char *what, F &&f) noexcept
     {
@@ -602,6 +708,27 @@ extern "C"
             }
             vmv_roadmap *R = new vmv_roadmap();
             const int rc = prm_run(robot, env, start, goal, max_iterations, max_samples, space_measure, solve ? 1 : 0, *R);
+            if (rc != VMV_OK)
+            {
+                delete R;
+                return rc;
+            }
+            *out = R;
+            return VMV_OK;
+        });
+    }
+
+    int vmv_fcit(int robot, const vmv_env *env, const float *start, const float *goal, size_t max_iterations, size_t max_samples, size_t batch_size,
+                 int optimize, vmv_roadmap **out)
+    {
+        return guarded_planner("vmv_fcit", [&]() -> int
+        {
+            if (robot < 0 || robot >= VMV_N_ROBOTS || env == nullptr || start == nullptr || goal == nullptr || out == nullptr || max_samples < 2)
+            {
+                return fail(VMV_ERR_ARG, "vmv_fcit: bad argument");
+            }
+            vmv_roadmap *R = new vmv_roadmap();
+            const int rc = fcit_run(robot, env, start, goal, max_iterations, max_samples, batch_size, optimize != 0, *R);
             if (rc != VMV_OK)
             {
                 delete R;

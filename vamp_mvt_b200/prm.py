@@ -40,7 +40,8 @@ class Roadmap:
         return np.unique(e, axis=0)
 
 
-def _run(robot, start, goal, environment: Optional[Environment], max_iterations: int, max_samples: int, solve: bool) -> Roadmap:
+def _run(robot, start, goal, environment: Optional[Environment], max_iterations: int, max_samples: int, solve: bool, fcit_batch: int = 0,
+         optimize: bool = False) -> Roadmap:
     L = _lib.lib()
     env = environment if environment is not None else Environment()
     d = robot.dimension()
@@ -48,7 +49,10 @@ def _run(robot, start, goal, environment: Optional[Environment], max_iterations:
     g = _lib.f32(goal).reshape(d)
     h = C.c_void_p()
     measure = float(np.float32(SPACE_MEASURE[robot.name]))
-    _lib.check(L.vmv_prm(robot.id, env.handle, _lib.ptr(s), _lib.ptr(g), max_iterations, max_samples, measure, 1 if solve else 0, C.byref(h)))
+    if fcit_batch > 0:
+        _lib.check(L.vmv_fcit(robot.id, env.handle, _lib.ptr(s), _lib.ptr(g), max_iterations, max_samples, fcit_batch, 1 if optimize else 0, C.byref(h)))
+    else:
+        _lib.check(L.vmv_prm(robot.id, env.handle, _lib.ptr(s), _lib.ptr(g), max_iterations, max_samples, measure, 1 if solve else 0, C.byref(h)))
     try:
         p = C.c_void_p()
         n = L.vmv_roadmap_vertices(h, C.byref(p))
@@ -73,6 +77,12 @@ def _run(robot, start, goal, environment: Optional[Environment], max_iterations:
 def prm(robot, start, goal, environment: Optional[Environment] = None, max_iterations: int = 100000, max_samples: int = 100000) -> Roadmap:
     """vamp.<robot>.prm: PRM::solve with the Halton sampler and PRM* neighbour parameters."""
     return _run(robot, start, goal, environment, max_iterations, max_samples, True)
+
+
+def fcit(robot, start, goal, environment: Optional[Environment] = None, max_iterations: int = 100000, max_samples: int = 100000,
+         batch_size: int = 1000, optimize: bool = False) -> Roadmap:
+    """vamp.<robot>.fcit: FCIT*::solve (planning/fcit.hh) -- host search, GPU sample batches and edge rows."""
+    return _run(robot, start, goal, environment, max_iterations, max_samples, True, fcit_batch=batch_size, optimize=optimize)
 
 
 def roadmap(robot, start, goal, environment: Optional[Environment] = None, max_iterations: int = 100000, max_samples: int = 100000) -> Roadmap:

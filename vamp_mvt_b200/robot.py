@@ -195,6 +195,12 @@ class Robot:
 
         return prm(self, start, goal, environment, **kwargs)
 
+    def fcit(self, start, goal, environment: Optional[Environment] = None, **kwargs):
+        """``vamp.<robot>.fcit`` (FCIT*::solve, reference planning/fcit.hh:82-360): vamp_mvt_b200/prm.py."""
+        from .prm import fcit
+
+        return fcit(self, start, goal, environment, **kwargs)
+
     def roadmap(self, start, goal, environment: Optional[Environment] = None, **kwargs):
         """``vamp.<robot>.roadmap`` (PRM::build_roadmap, reference planning/prm.hh:198-300): vamp_mvt_b200/prm.py."""
         from .prm import roadmap
