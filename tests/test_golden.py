@@ -53,7 +53,8 @@ def mbm_problems():
     """Yields (set name, index, packed scene dict, start, goal, ref valid_start, ref valid_goal, classic)
     from tests/golden/mbm_panda.npz (tools/make_mbm_golden.py: the reference's converter rules and the
     reference's own verdicts)."""
-    d = np.load(GOLDEN / "mbm_panda.npz")
+    z = np.load(GOLDEN / "mbm_panda.npz")
+    d = {k: z[k] for k in z.files}  # (an NpzFile decompresses a member on every access)
     kinds = {0: "spheres", 1: "cuboids", 2: "capsules"}
     for k in range(len(d["start"])):
         lo, hi = d["offsets"][k], d["offsets"][k + 1]

@@ -12,15 +12,22 @@ from tests import scenes
 pytestmark = pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built")
 
 
+_CASES = []
+
+
 def _cases(limit=5):
     from tests.test_golden import mbm_problems
 
-    yield "cage", scenes.packed(scenes.sphere_cage()), scenes.CAGE_A, scenes.CAGE_B
-    seen = set()
-    for name, index, scene, start, goal, vs, vg, classic in mbm_problems():
-        if vs and vg and name not in seen and len(seen) < limit:
-            seen.add(name)
-            yield name, scene, start, goal
+    if not _CASES:
+        _CASES.append(("cage", scenes.packed(scenes.sphere_cage()), scenes.CAGE_A, scenes.CAGE_B))
+        seen = set()
+        for name, index, scene, start, goal, vs, vg, classic in mbm_problems():
+            if vs and vg and name not in seen:
+                seen.add(name)
+                _CASES.append((name, scene, start, goal))
+                if len(seen) >= limit:
+                    break
+    return _CASES
 
 
 @pytest.mark.parametrize("batch", [1000, 100, 20, 5])
