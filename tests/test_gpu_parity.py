@@ -597,19 +597,21 @@ def test_path_validate_matches_segmentwise_oracle():
 
 
 def test_batched_prm_solves_the_sphere_cage():
-    """BASELINE config 1's problem (reference scripts/sphere_cage_example.py) through the batched PRM
-    front-end: the straight line is invalid, a roadmap grown in rounds of bulk validation connects start
-    and goal, and every edge of the returned path is one the oracle's validate_motion accepts."""
+    """BASELINE config 1's problem (reference scripts/sphere_cage_example.py) through the batched PRM front-end
+    (vmv_prm): the straight line is invalid, the roadmap connects start and goal, and every edge of the returned path
+    -- and a sample of the roadmap's edges -- is one the oracle's validate_motion accepts.  (tests/test_planner.py
+    pins the same call against the reference's own planner, vertex for vertex.)"""
     env = scenes.build_product_env(scenes.sphere_cage())
     O = po.Oracle("panda")
     oenv = po.add_scene(po.OracleEnv(), scenes.packed(scenes.sphere_cage()))
-    rm = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000, batch=4096, seed=1)
-    assert rm.path is not None and len(rm.path) > 2 and rm.rounds >= 1
-    p = np.stack(rm.path)
+    res = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env)
+    assert res.path is not None and len(res.path) > 2 and res.iterations > 0
+    p = np.stack(res.path)
     assert np.allclose(p[0], scenes.CAGE_A, atol=1e-6) and np.allclose(p[-1], scenes.CAGE_B, atol=1e-6)
     assert O.validate_edges(oenv, p[:-1], p[1:]).all()
-    assert vmv.panda.Path(rm.path).validate(env)
-    # the roadmap's edges are all valid motions (a sample of them against the oracle)
-    e = rm.edges[np.random.default_rng(0).choice(len(rm.edges), min(2000, len(rm.edges)), replace=False)]
-    ea, eb = rm.vertices[e[:, 0]], rm.vertices[e[:, 1]]
+    assert vmv.panda.Path(res.path).validate(env)
+    rm = vmv.panda.roadmap(scenes.CAGE_A, scenes.CAGE_B, env, max_iterations=3000, max_samples=3000)
+    e = rm.edges[np.random.default_rng(0).choice(len(rm.edges), min(2000, len(rm.edges)), replace=False)].astype(np.int64)
+    lo, hi = e.min(axis=1), e.max(axis=1)  # the reference validated every edge as (earlier vertex -> later vertex)
+    ea, eb = rm.vertices[lo], rm.vertices[hi]
     assert_edge_verdicts(O, oenv, ea, eb, np.ones(len(e), bool), O.validate_edges(oenv, ea, eb), "roadmap edges")

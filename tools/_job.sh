@@ -1,3 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29530 bench.py --gpus 8 --steps 40 --warmup 5 > gpurun_out/r2_n8_bench.json 2> gpurun_out/r2_n8_bench.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 40 --warmup 5 --gather none --no-c5 --no-edges --no-cpu 2>> gpurun_out/r2_n8_bench.err | tail -1 > gpurun_out/r2_n8_none.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 8 --steps 40 --warmup 5 --gather nccl --no-c5 --no-edges --no-cpu 2>> gpurun_out/r2_n8_bench.err | tail -1 > gpurun_out/r2_n8_nccl.json
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r2_t10_tests.log
+python bench.py --no-c5 --no-edges --steps 10 > gpurun_out/r2_t10_bench.json 2> gpurun_out/r2_t10_bench.err

@@ -674,6 +674,9 @@ struct vmv_env
     };
     mutable std::mutex grid_mutex;
     mutable GridCache grids[VMV_N_ROBOTS];
+    // verdict of the robot's world-fixed links against this environment (any-environment kernels): 0 not checked yet,
+    // 1 clear, 2 in collision (then every configuration is invalid)
+    mutable int static_state[VMV_N_ROBOTS] = {0, 0, 0, 0};
 
     void release_device()
     {
@@ -684,6 +687,10 @@ struct vmv_env
                 cudaFree(g.mem);
             }
             g = GridCache{};
+        }
+        for (int &st : static_state)
+        {
+            st = 0;
         }
         d_uobjs = nullptr;  // freed through `owned`
         for (void *p : owned)
@@ -1387,6 +1394,7 @@ namespace
         le.n_objects = static_cast<uint32_t>(
             env->spheres.size() + env->capsules.size() + env->z_capsules.size() + env->cuboids.size() + env->z_cuboids.size());
         le.primitives_only = env->heightfields.empty() && env->capts.empty() && env->mvts.empty() && !env->has_attachment;
+        le.static_mode = 0;
         // attach_tf = ee_tf(robot) * attachment offset
         const float *E = r.ee_tf;
         float A[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -2033,6 +2041,53 @@ extern "C"
         return e != cudaSuccess ? cuda_fail(e, "k_comm_push launch") : rc;
     }
 
+    // The robot's world-fixed links against the environment, once per environment (any-environment kernels; the
+    // grid-culled kernels answer them with one table load).  state: 1 clear, 2 in collision.
+    static int static_links_state(int robot, const vmv_env *env, const vmv::RobotDev &rd, vmv::LaunchEnv le, int &state)
+    {
+        const RobotHost &rh = robot_host(robot);
+        bool any = false;
+        for (int t = 0; t < rh.n_tasks; ++t)
+        {
+            any = any || rh.tasks[t].body == 0;
+        }
+        if (!any || le.primitives_only)
+        {
+            state = 0;  // nothing to gain: leave the launch as it is
+            return VMV_OK;
+        }
+        std::lock_guard<std::mutex> lock(env->grid_mutex);
+        if (env->static_state[robot] == 0)
+        {
+            std::vector<float> q(rh.dof);
+            for (int j = 0; j < rh.dof; ++j)
+            {
+                q[j] = rh.lower[j] + 0.5F * rh.range[j];
+            }
+            void *dq = nullptr, *dw = nullptr;
+            VMV_CUDA(cudaMalloc(&dq, rh.dof * sizeof(float)));
+            VMV_CUDA(cudaMalloc(&dw, sizeof(uint32_t)));
+            VMV_CUDA(cudaMemcpy(dq, q.data(), rh.dof * sizeof(float), cudaMemcpyHostToDevice));
+            le.static_mode = 2;
+            int rc = ops(robot).configs(rd, le, static_cast<const float *>(dq), 1, static_cast<uint32_t *>(dw), nullptr);
+            uint32_t w = 0;
+            if (rc == VMV_OK)
+            {
+                const cudaError_t e = cudaMemcpy(&w, dw, sizeof(w), cudaMemcpyDeviceToHost);
+                rc = e == cudaSuccess ? VMV_OK : cuda_fail(e, "cudaMemcpy(static links verdict)");
+            }
+            cudaFree(dq);
+            cudaFree(dw);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            env->static_state[robot] = (w & 1u) ? 1 : 2;
+        }
+        state = env->static_state[robot];
+        return VMV_OK;
+    }
+
     static int configs_common(int robot, const vmv_env *env, const float *d_q, size_t n, uint32_t *d_bits, const GatherDev &gather, void *stream)
     {
         vmv::LaunchEnv le{};
@@ -2070,6 +2125,22 @@ extern "C"
             {
                 return fail(VMV_ERR_LIMIT, "grid-culled kernel not applicable to this environment");
             }
+        }
+        if (force != 2)
+        {
+            int st = 0;
+            rc = static_links_state(robot, env, rd, le, st);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            if (st == 2)
+            {
+                // a world-fixed link is in collision: no configuration is valid
+                VMV_CUDA(cudaMemsetAsync(d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), s));
+                return push_gather(gather, d_bits, (n + 31) / 32, s);
+            }
+            le.static_mode = st == 1 ? 1u : 0u;
         }
         rc = ops(robot).configs(rd, le, d_q, n, d_bits, s);
         return rc == VMV_OK ? push_gather(gather, d_bits, (n + 31) / 32, s) : rc;
@@ -2135,6 +2206,21 @@ extern "C"
             {
                 return fail(VMV_ERR_LIMIT, "grid-culled kernel not applicable to this environment");
             }
+        }
+        if (force != 2)
+        {
+            int st = 0;
+            rc = static_links_state(robot, env, rd, le, st);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+            if (st == 2)
+            {
+                VMV_CUDA(cudaMemsetAsync(d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), s));
+                return push_gather(gather, d_bits, (n + 31) / 32, s);
+            }
+            le.static_mode = st == 1 ? 1u : 0u;
         }
         rc = ops(robot).edges(rd, le, d_a, d_b, d_pairs, n, res, d_bits, s);
         return rc == VMV_OK ? push_gather(gather, d_bits, (n + 31) / 32, s) : rc;

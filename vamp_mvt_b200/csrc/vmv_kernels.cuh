@@ -40,6 +40,10 @@ namespace vmv
         float attach_tf[12];  // end-effector frame (in its body) * attachment offset, row-major 3x4
         uint32_t n_objects;   // spheres + capsules + cuboids
         bool primitives_only; // no heightfield / pointcloud / attachment
+        // World-fixed links (rigid body 0: Fetch's base and torso column, Baxter's torso, head and pedestal) meet the
+        // environment the same way in every configuration: the host checks them ONCE per environment and robot
+        // (mode 2, one launch of one state) and every later launch skips them (mode 1).  0 = check everything.
+        uint32_t static_mode;
     };
 
     // A body frame is a rigid transform [R | t] (row-major 3x4, K = 4*row + col).  The stash keeps the
@@ -335,10 +339,12 @@ namespace vmv
                 float x, y, z;
                 task_centre<BLOCK>(t, c.stash, x, y, z);
                 bool hit = false;
-                if ((Vote::kTogether && has_cloud) || active)
+                // static_mode 1: world-fixed links were checked when the environment was first used; 2: only they are
+                const bool skip_task = (env.static_mode == 1u && t.body == 0) || (env.static_mode == 2u && t.body != 0);
+                if ((Vote::kTogether && has_cloud) || (active && !skip_task))
                 {
                     // (with a pointcloud in the environment every lane of the warp calls: one without a sphere helps the scans)
-                    hit = sphere_hits_env(c.env, x, y, z, t.r, t.skip >= 0 ? t.r - 1e-6f : t.r, active);
+                    hit = sphere_hits_env(c.env, x, y, z, t.r, t.skip >= 0 ? t.r - 1e-6f : t.r, active && !skip_task);
                 }
                 if (active)
                 {
@@ -375,6 +381,10 @@ namespace vmv
         if (!Vote::kTogether && bad)
         {
             return false;
+        }
+        if (env.static_mode == 2u)
+        {
+            return !bad;  // the one-off check of the world-fixed links: environment only
         }
 
         // ---- C: self collision --------------------------------------------------------------
