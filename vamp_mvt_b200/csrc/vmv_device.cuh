@@ -342,15 +342,19 @@ namespace vmv
             // within it.  The slack covers the rounding of both squared distances (relative 1e-6).
             const float qlim = qr * 1.00001F;
             bool found = false;
-            for (uint32_t base = s; base < e; base += kCaptScanLoads * gsize)
+            // The step widens as the scan goes on -- 1, 2, 4, then kCaptScanLoads independent 128-bit loads per lane: most
+            // scans need a short prefix of a list built for r_max (a step of 8 x 32 lanes fetched 256 points for the few
+            // dozen a small sphere can reach), while the long no-hit scans of big spheres reach the full width after three
+            // steps and are bound by memory latency from there.
+            uint32_t per = 1u;
+            for (uint32_t base = s; base < e; base += per * gsize, per = min(per * 2u, kCaptScanLoads))
             {
-                // independent 128-bit loads per lane and step: the scan is bound by memory latency
                 bool h = false, beyond = false;
 #pragma unroll
                 for (uint32_t u = 0; u < kCaptScanLoads; ++u)
                 {
                     const uint32_t i = base + u * gsize + rank;
-                    if (i < e)
+                    if (u < per && i < e)
                     {
                         const float4 p = __ldg(t.points + i);
                         const float ex = p.x - qx, ey = p.y - qy, ez = p.z - qz;
@@ -361,7 +365,7 @@ namespace vmv
                 if (rank == 0)
                 {
                     VMV_STAT(7, 1);
-                    VMV_STAT(8, min(e - base, kCaptScanLoads * gsize));
+                    VMV_STAT(8, min(e - base, per * gsize));
                 }
                 if (__any_sync(group, h))
                 {
@@ -453,6 +457,29 @@ namespace vmv
     // objects we test is a superset of every object that can actually touch the sphere.
     // r_pc is the radius used for pointcloud queries (see check_state: a link's bounding sphere is
     // queried with its exact, un-inflated radius there).
+    // heightfields for one sphere (reference collision/sphere_heightfield.hh:9-30); no warp-level operations
+    __device__ __forceinline__ bool sphere_hits_heightfields(const float *__restrict__ E, float x, float y, float z, float r)
+    {
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
+        for (uint32_t i = 0; i < H.n_heightfields; ++i)
+        {
+            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_heightfields + kHeightRec * i);
+            const float4 a = p[0], b = p[1], c = p[2];
+            const float xo = a.x - x, yo = a.y - y;
+            const float xi = floorf(fminf(fmaxf(fmaf(a.w, xo, c.x), 0.F), b.z));
+            const float yi = floorf(fminf(fmaxf(fmaf(b.x, yo, c.y), 0.F), b.w));
+            const int index = __float2int_rn(fmaf(yi, b.z, xi));
+            const float *data = reinterpret_cast<const float *>(
+                (static_cast<unsigned long long>(__float_as_uint(c.w)) << 32) | __float_as_uint(c.z));
+            const float zh = __ldg(data + index);
+            if (sign_set(z - r - fmaf(b.y, zh, a.z)))
+            {
+                return true;
+            }
+        }
+        return false;
+    }
+
     // spheres, capsules, cuboids and heightfields for one sphere (no warp-level operations)
     __device__ __forceinline__ bool sphere_hits_primitives(const float *__restrict__ E, float x, float y, float z, float r)
     {
@@ -562,49 +589,16 @@ namespace vmv
             }
         }
 
-        for (uint32_t i = 0; i < H.n_heightfields; ++i)
-        {
-            // reference collision/sphere_heightfield.hh:9-30
-            const float4 *p = reinterpret_cast<const float4 *>(E + H.off_heightfields + kHeightRec * i);
-            const float4 a = p[0], b = p[1], c = p[2];
-            const float xo = a.x - x, yo = a.y - y;
-            const float xi = floorf(fminf(fmaxf(fmaf(a.w, xo, c.x), 0.F), b.z));
-            const float yi = floorf(fminf(fmaxf(fmaf(b.x, yo, c.y), 0.F), b.w));
-            const int index = __float2int_rn(fmaf(yi, b.z, xi));
-            const float *data = reinterpret_cast<const float *>(
-                (static_cast<unsigned long long>(__float_as_uint(c.w)) << 32) | __float_as_uint(c.z));
-            const float zh = __ldg(data + index);
-            if (sign_set(z - r - fmaf(b.y, zh, a.z)))
-            {
-                return true;
-            }
-        }
-
-        return false;
+        return sphere_hits_heightfields(E, x, y, z, r);
     }
 
-    // May be called by any subset of a warp's lanes; lanes that arrive together cooperate on the
-    // pointcloud scans (`active` false = lane has no sphere but helps scanning).
-    __device__ __forceinline__ bool
-    sphere_hits_env(const float *__restrict__ E, float x, float y, float z, float r, float r_pc, bool active)
+    // The pointclouds (CAPT and MVT) for one sphere, warp-cooperative: every lane of the converged group calls,
+    // `query` false = the lane has nothing to ask but helps scanning.  The clearance grid answers first.
+    __device__ __forceinline__ bool sphere_hits_clouds(const float *__restrict__ E, float x, float y, float z, float r_pc, bool query)
     {
-        bool hit = false;
-        if (active)
-        {
-            hit = sphere_hits_primitives(E, x, y, z, r);
-        }
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
-        if (H.n_capts + H.n_mvts == 0)
-        {
-            return hit;
-        }
+        bool hit = false;
         // no cloud point within reach: every pointcloud query would answer "no"
-        bool query = active && !hit;
-        if (active)
-        {
-            VMV_STAT(0, 1);
-            VMV_STAT(1, hit ? 1 : 0);
-        }
         if (H.off_cloud_grid != 0 && query)
         {
             const CloudGridRec &g = *reinterpret_cast<const CloudGridRec *>(E + H.off_cloud_grid);
@@ -630,6 +624,29 @@ namespace vmv
             }
         }
         return hit;
+    }
+
+    // One sphere against everything.  May be called by any subset of a warp's lanes; lanes that arrive together
+    // cooperate on the pointcloud scans (`active` false = lane has no sphere but helps scanning).
+    __device__ __forceinline__ bool
+    sphere_hits_env(const float *__restrict__ E, float x, float y, float z, float r, float r_pc, bool active)
+    {
+        bool hit = false;
+        if (active)
+        {
+            hit = sphere_hits_primitives(E, x, y, z, r);
+        }
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
+        if (H.n_capts + H.n_mvts == 0)
+        {
+            return hit;
+        }
+        if (active)
+        {
+            VMV_STAT(0, 1);
+            VMV_STAT(1, hit ? 1 : 0);
+        }
+        return sphere_hits_clouds(E, x, y, z, r_pc, active && !hit) || hit;
     }
 
     // ------------------------------------------------------------------------------------------

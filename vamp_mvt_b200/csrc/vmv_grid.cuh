@@ -42,6 +42,11 @@ namespace vmv
         uint32_t q2_rounds;  // fine-item queue capacity in B1 rounds (shared-memory budget of the kernel)
         GridDev grid;
         PairTabDev tab;      // two-joint verdict tables of the robot (n_groups = 0: none)
+        // any-environment instantiation (heightfields / pointclouds next to at most 30 primitives): the packed
+        // environment blob (vmv_device.cuh: EnvHeader + heightfield, CAPT, MVT and clearance-grid records), staged
+        // into shared memory next to the rounded-box records; blob_bytes = 0 otherwise
+        const float *blob;
+        uint32_t blob_bytes;
     };
 
     __device__ __forceinline__ float margin_obj(const float4 *__restrict__ o, float x, float y, float z, float r)

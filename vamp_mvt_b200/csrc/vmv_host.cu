@@ -1504,12 +1504,17 @@ namespace
 
     // The voxel table of `env` for `robot` (built once, synchronously, on first use).  ok = false when
     // the path does not apply (no primitives, more than 64 of them, other content in the environment).
-    int grid_launch_env(int robot, const vmv_env *env, vmv::GridEnv &out, bool &ok, bool &wide)
+    int grid_launch_env(int robot, const vmv_env *env, vmv::GridEnv &out, bool &ok, bool &wide, bool configs = false)
     {
         ok = false;
         wide = false;
         const size_t n_obj = env->uobjs.size() / vmv::kObjRec;
-        if (n_obj == 0 || n_obj > 64 || !env->heightfields.empty() || !env->capts.empty() || !env->mvts.empty() || env->has_attachment)
+        // any environment (configuration batches): heightfields and pointclouds next to at most 30 primitives go through
+        // the grid-culled kernel's any-environment instantiation; attachments and edge batches stay on the per-thread kernel
+        const bool extra = !env->heightfields.empty() || !env->capts.empty() || !env->mvts.empty();
+        const bool ae = extra && configs && n_obj <= 30 && !env->has_attachment && robot_host(robot).n_links <= 64 &&
+                        std::getenv("VMV_NO_AE") == nullptr;
+        if (((n_obj == 0 || extra) && !ae) || n_obj > 64 || env->has_attachment)
         {
             return VMV_OK;
         }
@@ -1548,9 +1553,9 @@ namespace
                 hi[j] = std::min<double>(hi[j], gi.reach);
                 empty = empty || !(hi[j] > lo[j]);
             }
-            if (empty)
+            if (empty || n_obj == 0)
             {
-                // nothing within reach: a 1-voxel table of empty masks far away
+                // nothing within reach (or no primitive at all): a 1-voxel table of empty masks far away
                 lo[0] = lo[1] = lo[2] = 1e6;
                 hi[0] = hi[1] = hi[2] = 1e6 + 1;
             }
@@ -1612,6 +1617,8 @@ namespace
         out.n_objects = static_cast<uint32_t>(n_obj);
         out.max_fine = gi.max_fine;
         out.grid = gc.dev;
+        out.blob = ae ? env->d_blob : nullptr;
+        out.blob_bytes = ae ? static_cast<uint32_t>(env->blob.size() * 4) : 0u;
         wide = gc.wide;
         ok = true;
         return VMV_OK;
@@ -2108,14 +2115,26 @@ extern "C"
         {
             vmv::GridEnv l3{};
             bool ok = false, wide = false;
-            rc = grid_launch_env(robot, env, l3, ok, wide);
+            rc = grid_launch_env(robot, env, l3, ok, wide, true);
             if (rc != VMV_OK)
             {
                 return rc;
             }
             if (ok)
             {
-                rc = ops(robot).configs_v4(robot, wide, rd, l3, d_q, n, d_bits, gather, s);
+                if (l3.blob_bytes > 0)
+                {
+                    // any-environment instantiation: local launch, then the gather (if any) as a push
+                    rc = ops(robot).configs_v4(robot, wide, rd, l3, d_q, n, d_bits, GatherDev{}, s);
+                    if (rc == VMV_OK)
+                    {
+                        return push_gather(gather, d_bits, (n + 31) / 32, s);
+                    }
+                }
+                else
+                {
+                    rc = ops(robot).configs_v4(robot, wide, rd, l3, d_q, n, d_bits, gather, s);
+                }
                 if (rc != VMV_ERR_LIMIT || force == 3)
                 {
                     return rc;

@@ -218,7 +218,7 @@ namespace vmv
         static_assert(M::kPairs < 2048 && M::kTasks < 2048 && M::kLinks <= kGridMaxLinks, "16-bit work-item encoding");
 
         // block-shared part, then one private slice per warp
-        uint32_t off_tasks, off_links, off_pairs, off_pinfo, off_plists, shared_bytes;
+        uint32_t off_tasks, off_links, off_pairs, off_pinfo, off_plists, off_blob, shared_bytes;
         uint32_t w_stash, w_masks, w_q1, w_q2, w_pairq, warp_bytes, q2_cap;
 
         __host__ __device__ static constexpr uint32_t align16(uint32_t v)
@@ -226,7 +226,7 @@ namespace vmv
             return (v + 15u) & ~15u;
         }
 
-        __host__ __device__ SmemLayoutV4(uint32_t n_objects, uint32_t max_fine, uint32_t q2_rounds)
+        __host__ __device__ SmemLayoutV4(uint32_t n_objects, uint32_t max_fine, uint32_t q2_rounds, uint32_t blob_bytes = 0)
         {
             uint32_t o = align16(n_objects * kObjRec * 4);
             off_tasks = o;
@@ -239,6 +239,8 @@ namespace vmv
             o += align16((M::kPairs > 0 ? M::kPairs : 1) * sizeof(PairInfo));
             off_plists = o;
             o += align16(kMaxPairLists * sizeof(SpherePair));
+            off_blob = o;
+            o += align16(blob_bytes);
             shared_bytes = (o + 127u) & ~127u;
 
             uint32_t w = 0;
@@ -278,6 +280,7 @@ namespace vmv
         MaskT *masks;  // this warp's [link][32]
         uint16_t *q1, *q2, *pairq;
         uint32_t q2_cap, round_cap;  // Q2 capacity; most fine items one B1 round can add (32 * max_fine)
+        const float *E;              // any-environment instantiation: the packed environment blob in shared memory
     };
 
     // Block-level staging (once per persistent block) and this warp's slice.
@@ -286,14 +289,14 @@ namespace vmv
     {
         using M = typename R::Model;
         using Lay = SmemLayoutV4<M, MaskT>;
-        const Lay L(env.n_objects, env.max_fine, env.q2_rounds);
+        const Lay L(env.n_objects, env.max_fine, env.q2_rounds, env.blob_bytes);
         const int tid = threadIdx.x, nthr = blockDim.x;
         if (tid == 0)
         {
             mbar_init(barp, 1);
         }
         __syncthreads();
-        if (tid == 0)
+        if (tid == 0 && env.n_objects > 0)
         {
             tma_bulk_g2s(smem, env.objs, env.n_objects * kObjRec * 4, barp);
         }
@@ -328,9 +331,18 @@ namespace vmv
             {
                 dl[i] = __ldg(sl + i);
             }
+            dst = reinterpret_cast<uint32_t *>(smem + L.off_blob);
+            src = reinterpret_cast<const uint32_t *>(env.blob);
+            for (int i = tid; i < static_cast<int>(env.blob_bytes / 4); i += nthr)
+            {
+                dst[i] = __ldg(src + i);
+            }
         }
         __syncthreads();
-        mbar_wait(barp, 0);
+        if (env.n_objects > 0)
+        {
+            mbar_wait(barp, 0);
+        }
 
         unsigned char *mine = smem + L.shared_bytes + (tid >> 5) * L.warp_bytes;
         V4Ctx<R, MaskT> X;
@@ -347,6 +359,7 @@ namespace vmv
         X.pairq = reinterpret_cast<uint16_t *>(mine + L.w_pairq);
         X.q2_cap = L.q2_cap;
         X.round_cap = 32u * env.max_fine;
+        X.E = reinterpret_cast<const float *>(smem + L.off_blob);
         return X;
     }
 
@@ -453,24 +466,41 @@ namespace vmv
         return __reduce_or_sync(kFullWarp, hits);
     }
 
-    // B2: one lane per fine-sphere item, against its link's hit mask.  Returns the colliding states.
-    template <typename R, typename MaskT>
+    // Any-environment instantiation: what a 32-bit candidate mask carries beside its (at most 30) object bits
+    static constexpr uint32_t kAeObjMask = 0x3fffffffu;  // primitive candidates / exact hits
+    static constexpr uint32_t kAeHfBit = 0x40000000u;    // the link's bounding sphere hits a heightfield (exact test, done with the FK)
+    static constexpr uint32_t kAeCloudBit = 0x80000000u; // the clearance grid could not rule the pointclouds out for the bounding sphere
+
+    // B2: one lane per fine-sphere item, against its link's hit mask -- and, in the any-environment instantiation,
+    // against the heightfields and the pointclouds (a link whose bounding sphere hit ANYTHING has its fine spheres
+    // swept against EVERYTHING, reference robots/panda.hh:5633-5645; the pointcloud query is warp-cooperative, so the
+    // whole round calls it together).  Returns the colliding states.
+    template <typename R, typename MaskT, bool AE>
     __device__ __forceinline__ uint32_t v4_fine_items(const V4Ctx<R, MaskT> &X, uint32_t n2, uint32_t invalid)
     {
         const int lane = threadIdx.x & 31;
+        bool has_hf = false, has_cloud = false;
+        if constexpr (AE)
+        {
+            const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(X.E);
+            has_hf = H.n_heightfields > 0, has_cloud = H.n_capts + H.n_mvts > 0;
+        }
         for (uint32_t base = 0; base < n2; base += 32)
         {
             const uint32_t it = base + lane;
             uint32_t hit = 0u;
+            float x = 0.F, y = 0.F, z = 0.F, r = 0.F;
+            bool ask_cloud = false;
+            int c = 0;
             if (it < n2)
             {
                 const uint32_t item = X.q2[it];
-                const int c = item & 31u;
+                c = item & 31u;
                 if (!((invalid >> c) & 1u))
                 {
                     const SphereTask t = X.tasks[item >> 5];
-                    float x, y, z;
                     task_centre<32>(t, X.stash + c, x, y, z);
+                    r = t.r;
                     MaskT m = X.masks[t.link * 32 + c];
                     while (m != 0)
                     {
@@ -481,6 +511,21 @@ namespace vmv
                             break;
                         }
                     }
+                    if constexpr (AE)
+                    {
+                        if (hit == 0u && has_hf && sphere_hits_heightfields(X.E, x, y, z, r))
+                        {
+                            hit = 1u << c;
+                        }
+                        ask_cloud = hit == 0u;
+                    }
+                }
+            }
+            if constexpr (AE)
+            {
+                if (has_cloud && sphere_hits_clouds(X.E, x, y, z, r, ask_cloud))
+                {
+                    hit = 1u << c;
                 }
             }
             invalid |= __reduce_or_sync(kFullWarp, hit);
@@ -490,7 +535,7 @@ namespace vmv
 
     // One pass over 32 states (lane = state in the dense phases).  Returns the warp-uniform mask of
     // invalid states (lanes without a state count as invalid).
-    template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS>
+    template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS, bool AE = false>
     __device__ __forceinline__ uint32_t
     v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const PairTabDev &T, const float (&cfg)[R::Model::kDof], const bool has)
     {
@@ -580,6 +625,38 @@ namespace vmv
                                  : (sink.reach_valid ? grid_lookup_t<MaskT>(G, sink.b[li][0], sink.b[li][1], sink.b[li][2], G.link_class[li])
                                                      : static_cast<MaskT>(G.all_mask));
             });
+        // ---- any environment: the bounding spheres against the heightfields (exact, one gather each) and against the
+        //      clearance grid of the pointclouds (one load each), lane = state, centres still in registers ---------
+        unsigned long long hf_links = 0ull, cloud_links = 0ull;
+        if constexpr (AE)
+        {
+            static_assert(sizeof(MaskT) == 4, "the any-environment instantiation keeps its link flags in 32-bit masks");
+            const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(X.E);
+            const bool has_hf = H.n_heightfields > 0, has_cloud = H.n_capts + H.n_mvts > 0;
+            R::for_each_link(
+                [&](auto l, float br, int, int, float)
+                {
+                    constexpr int li = decltype(l)::value;
+                    if (live)
+                    {
+                        const float x = sink.b[li][0], y = sink.b[li][1], z = sink.b[li][2];
+                        if (has_hf && sphere_hits_heightfields(X.E, x, y, z, br))
+                        {
+                            hf_links |= 1ull << li;
+                        }
+                        if (has_cloud)
+                        {
+                            bool undecided = true;
+                            if (H.off_cloud_grid != 0)
+                            {
+                                const CloudGridRec &g = *reinterpret_cast<const CloudGridRec *>(X.E + H.off_cloud_grid);
+                                undecided = !(cloud_clearance(g, x, y, z) > (br - 1e-6F) + g.r_point_max);
+                            }
+                            cloud_links |= undecided ? (1ull << li) : 0ull;
+                        }
+                    }
+                });
+        }
         __syncwarp();  // stash complete
 
         // ---- C1: allowed link pairs on the bounding spheres -> records; C2 per chunk of pairs -----
@@ -626,9 +703,15 @@ namespace vmv
                 [&](auto l, float, int, int, float)
                 {
                     constexpr int li = decltype(l)::value;
-                    if (cand[li] != 0)
+                    MaskT cm = cand[li];
+                    if constexpr (AE)
                     {
-                        X.masks[li * 32 + lane] = cand[li];
+                        cm = static_cast<MaskT>((static_cast<uint32_t>(cm) & kAeObjMask) | (((hf_links >> li) & 1ull) ? kAeHfBit : 0u) |
+                                                (((cloud_links >> li) & 1ull) ? kAeCloudBit : 0u));
+                    }
+                    if (cm != 0)
+                    {
+                        X.masks[li * 32 + lane] = cm;
                         word |= 1u << (li & 31);
                     }
                     if constexpr ((li & 31) == 31 || li + 1 == M::kLinks)
@@ -651,19 +734,29 @@ namespace vmv
                 {
                     const uint32_t it = base + lane;
                     uint32_t cnt = 0u, first = 0u;
-                    int c = 0;
+                    int c = 0, l = 0;
+                    bool have = false, bound_hit = false, ask_cloud = false;
+                    float x = 0.F, y = 0.F, z = 0.F, rq = 0.F;
+                    MaskT hit = 0;
+                    LinkInfo L{};
                     if (it < n1)
                     {
                         const uint32_t item = X.q1[it];
                         c = item & 31u;
-                        const int l = item >> 5;
+                        l = item >> 5;
                         if (!((invalid >> c) & 1u))
                         {
-                            const LinkInfo L = X.links[l];
+                            have = true;
+                            L = X.links[l];
                             const SphereTask t = X.tasks[L.bound_task];
-                            float x, y, z;
                             task_centre<32>(t, X.stash + c, x, y, z);
-                            MaskT m = X.masks[l * 32 + c], hit = 0;
+                            MaskT m = X.masks[l * 32 + c];
+                            uint32_t flags = 0u;
+                            if constexpr (AE)
+                            {
+                                flags = static_cast<uint32_t>(m) & ~kAeObjMask;
+                                m = static_cast<MaskT>(static_cast<uint32_t>(m) & kAeObjMask);
+                            }
                             while (m != 0)
                             {
                                 const int o = mask_pop_lowest<MaskT>(m);
@@ -672,13 +765,26 @@ namespace vmv
                                     hit |= static_cast<MaskT>(1) << o;
                                 }
                             }
-                            if (hit != 0)
-                            {
-                                X.masks[l * 32 + c] = hit;
-                                cnt = static_cast<uint32_t>(L.n_spheres);
-                                first = static_cast<uint32_t>(L.bound_task + 1);
-                            }
+                            bound_hit = hit != 0 || (flags & kAeHfBit) != 0u;
+                            // the pointclouds are queried with the bounding sphere's own, un-inflated radius
+                            ask_cloud = AE && (flags & kAeCloudBit) != 0u && !bound_hit;
+                            rq = t.r - 1e-6F;
                         }
+                    }
+                    if constexpr (AE)
+                    {
+                        // warp-cooperative: the whole round calls, lanes without a question help scanning
+                        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(X.E);
+                        if (H.n_capts + H.n_mvts > 0 && sphere_hits_clouds(X.E, x, y, z, rq, ask_cloud))
+                        {
+                            bound_hit = true;
+                        }
+                    }
+                    if (have && bound_hit)
+                    {
+                        X.masks[l * 32 + c] = hit;  // what the fine spheres are tested against among the primitives
+                        cnt = static_cast<uint32_t>(L.n_spheres);
+                        first = static_cast<uint32_t>(L.bound_task + 1);
                     }
                     // exclusive prefix sum of cnt over the lanes
                     uint32_t incl = cnt;
@@ -697,7 +803,7 @@ namespace vmv
                     base += 32u;
                 }
                 __syncwarp();
-                invalid = v4_fine_items<R, MaskT>(X, n2, invalid);
+                invalid = v4_fine_items<R, MaskT, AE>(X, n2, invalid);
                 __syncwarp();  // all reads of the queues (and, at the end, of this pass's stash) are done
             } while (base < n1);
         }
@@ -705,7 +811,7 @@ namespace vmv
     }
 
     // Persistent blocks of blockDim.x / 32 autonomous warps; tile t = states [32 t, 32 t + 32).
-    template <typename R, typename MaskT, bool TAB, bool GATHER, int MAXT, int MINB>
+    template <typename R, typename MaskT, bool TAB, bool GATHER, int MAXT, int MINB, bool AE = false>
     __global__ void __launch_bounds__(MAXT, MINB)
         k_validate_configs_v4(
             RobotDev robot,
@@ -750,7 +856,7 @@ namespace vmv
                 ticket = atomicAdd(next_tile, 1u);
             }
 #endif
-            const uint32_t invalid = v4_pass<R, MaskT, TAB, true>(X, env.grid, env.tab, cfg, has);
+            const uint32_t invalid = v4_pass<R, MaskT, TAB, true, AE>(X, env.grid, env.tab, cfg, has);
             publish_verdict<GATHER>(bits, gather, tile, ~invalid, 4);
 #ifndef VMV_V4_STATIC_TILES
             if (!kEarly && lane == 0)

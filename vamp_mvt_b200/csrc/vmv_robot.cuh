@@ -216,12 +216,14 @@ namespace vmvh
         static constexpr int kEdgeThreads = 256, kEdgeBlocks = 1, kEdgeQ2Rounds = 2;
     };
 
-    template <typename R, typename MaskT, bool GATHER>
+    template <typename R, typename MaskT, bool GATHER, bool AE = false>
     int launch_configs_v4(const RobotHost &rh, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits,
                           GatherDev gather, cudaStream_t s)
     {
         using M = typename R::Model;
         using Tune = V4Tune<R::kTune>;
+        // the any-environment instantiation carries the pointcloud scan: a register cap of 128 (512 threads, one block)
+        constexpr int kThreads = AE ? (Tune::kCfgThreads > 512 ? 512 : Tune::kCfgThreads) : Tune::kCfgThreads;
         if (R::PairTab::kUseTables && !rh.inline_covered)
         {
             return fail(VMV_ERR_LIMIT, "robot's inline self-collision pairs are not covered by verdict tables");
@@ -234,12 +236,16 @@ namespace vmvh
             }
         }
         le.q2_rounds = Tune::kCfgQ2Rounds;
-        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds);
-        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, GATHER, Tune::kCfgThreads, Tune::kCfgBlocks>;
+        if (!AE)
+        {
+            le.blob = nullptr, le.blob_bytes = 0;
+        }
+        const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds, le.blob_bytes);
+        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, GATHER, kThreads, Tune::kCfgBlocks, AE>;
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
-        int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, Tune::kCfgThreads, n, warps, grid, smem);
+        int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, kThreads, n, warps, grid, smem);
         if (rc != VMV_OK)
         {
             return rc;
@@ -497,6 +503,18 @@ namespace vmvh
         static int configs_v4(int, bool wide, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits, const GatherDev &g,
                               cudaStream_t s)
         {
+            if (le.blob_bytes > 0)
+            {
+                // heightfields / pointclouds next to at most 30 primitives: the any-environment instantiation (local
+                // launches; a gather is pushed by the caller afterwards)
+                // (Baxter -- tuning class 1, 255 registers -- is faster on the per-thread kernel: measured 1.28e9 vs 0.63e9
+                // configurations/s on a heightfield scene)
+                if (wide || g.world > 0 || R::Model::kLinks > 64 || R::kTune != 0)
+                {
+                    return fail(VMV_ERR_LIMIT, "any-environment grid kernel: not applicable");
+                }
+                return launch_configs_v4<R, uint32_t, false, true>(host(), rd, le, q, n, bits, g, s);
+            }
             if (g.world > 0)
             {
                 return wide ? launch_configs_v4<R, unsigned long long, true>(host(), rd, le, q, n, bits, g, s)
