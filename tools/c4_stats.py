@@ -25,4 +25,8 @@ for robot in sys.argv[1:] or ["fetch", "ur5"]:
     L.vmv_dev_stats(_lib.ptr(out), 1)
     d = {k: float(out[i]) / n for i, k in enumerate(NAMES)}
     d["valid"] = float(v.mean())
+    d["list_len_hist_hits(32,64,..)"] = [int(x) for x in out[16:28]]
+    d["list_len_hist_nohits"] = [int(x) for x in out[28:40]]
+    d["scans_by_query_radius(<.05,<.1,<.2,>=.2)"] = [int(x) for x in out[40:44]]
+    d["nohit_scans_by_query_radius"] = [int(x) for x in out[44:48]]
     print(robot, json.dumps(d, indent=1))

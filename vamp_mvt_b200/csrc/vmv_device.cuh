@@ -381,6 +381,29 @@ namespace vmv
                     break;
                 }
             }
+#ifdef VMV_C4_STATS
+            if (rank == 0)
+            {
+                const uint32_t len = e - s;
+                int b = 0;
+                while ((1u << (b + 5)) < len && b < 11)
+                {
+                    ++b;
+                }
+                VMV_STAT((found ? 16 : 28) + b, 1);  // list length buckets 32, 64, ... 64k: 16.. hits, 28.. no-hits
+                const float qrad = sqrtf(qr);
+                VMV_STAT(qrad < 0.05F ? 40 : (qrad < 0.1F ? 41 : (qrad < 0.2F ? 42 : 43)), 1);
+                VMV_STAT(qrad < 0.05F ? 44 : (qrad < 0.1F ? 45 : (qrad < 0.2F ? 46 : 47)), found ? 0 : 1);
+            }
+#endif
+#ifdef VMV_C4_STATS
+            if (rank == 0)
+            {
+                // histogram of list prefixes examined (log2 buckets of points), split by outcome
+                const uint32_t seen = min(e - s, static_cast<uint32_t>(per * gsize) * 64u);
+                (void)seen;
+            }
+#endif
             hit = (lane == src) ? found : hit;
         }
         return hit;

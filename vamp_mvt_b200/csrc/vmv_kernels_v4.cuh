@@ -523,6 +523,9 @@ namespace vmv
             }
             if constexpr (AE)
             {
+                // (asked in two sub-rounds -- the first open question of every state, then the rest for the states that came
+                // through -- the fine spheres raise a quarter of the pointcloud questions, but every sub-round is a full
+                // descent-and-scan latency: measured Fetch 2.14e8 -> 1.89e8 configurations/s, UR5 4.33e8 -> 4.21e8; not kept)
                 if (has_cloud && sphere_hits_clouds(X.E, x, y, z, r, ask_cloud))
                 {
                     hit = 1u << c;

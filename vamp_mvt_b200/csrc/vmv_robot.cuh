@@ -250,6 +250,12 @@ namespace vmvh
         {
             return rc;
         }
+#ifdef VMV_C4_STATS
+        {
+            unsigned long long *sp = stats_buffer();
+            VMV_CUDA(cudaMemcpyToSymbol(vmv::g_stats, &sp, sizeof(sp)));
+        }
+#endif
         unsigned int *counter = nullptr;
         int slot = -1;
         rc = counter_acquire(s, counter, slot);
