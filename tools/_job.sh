@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_parity.py -x -q -k "capt or mvt or c4 or heightfield" 2>&1 | tail -5 > gpurun_out/r2_t13_tests.log
-python bench.py --no-c5 --no-edges --steps 10 > gpurun_out/r2_t13_bench.json 2> gpurun_out/r2_t13_bench.err
+for c in 15 16 17 18 19 20; do VMV_CHUNK_LOG2=$c python tools/time_e2e.py; done > gpurun_out/r2_e2e.txt 2>&1
+for c in 17 18; do VMV_CHUNK_LOG2=$c python tools/time_e2e.py; done >> gpurun_out/r2_e2e.txt 2>&1

@@ -827,8 +827,11 @@ def emit_cuda(model, tr, frames):
     rconds = []
     for b in pris:
         d = b["dof"]
-        lim = max(abs(model["lower"][d]), abs(model["lower"][d] + model["range"][d])) + BOX_MARGIN
-        rconds.append(f"(fabsf(q[{d}]) <= {lit(lim)})")
+        # the interval the reach bounds were derived for -- not |q| <= max(|lower|, |upper|), which also admits travel
+        # below a positive lower limit
+        lo_d = model["lower"][d] - BOX_MARGIN
+        hi_d = model["lower"][d] + model["range"][d] + BOX_MARGIN
+        rconds.append(f"(q[{d}] >= {lit(lo_d)}) & (q[{d}] <= {lit(hi_d)})")
     out.append("    // the static per-link reach bounds assume prismatic joints inside their limits")
     out.append("    sink.reach_ok(" + (" & ".join(rconds) if rconds else "true") + ");")
     out.append("    // link pairs whose bounding spheres (nearly) always overlap: kinematically feasible fine pairs, ungated")
