@@ -222,7 +222,7 @@ def test_gpu_plan_then_simplify_on_the_sphere_cage():
     scene = scenes.sphere_cage()
     renv = po.add_scene(po.RefEnv(), scenes.packed(scene))
     env = scenes.build_product_env(scene)
-    rm = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000, batch=4096, rng=vmv.panda.halton())
+    rm = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000)
     assert rm.path is not None and len(rm.path) > 2
     planned = np.stack(rm.path)
     assert ref.validate_edges(renv, planned[:-1], planned[1:]).all()
@@ -264,17 +264,14 @@ def test_gpu_halton_sampler_and_fused_validation(robot):
 
 
 @pytest.mark.gpu
-def test_gpu_prm_with_device_sampling_equals_host_sampling():
+def test_gpu_prm_vertices_are_the_valid_samples_of_the_host_halton_stream():
+    """The planner samples on the device; its vertices must be the valid members of the host restatement's stream, in order."""
     env = scenes.build_product_env(scenes.sphere_cage())
-    a = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000, batch=4096, rng=vmv.panda.halton())
-
-    class HostOnly(S.StreamRNG):  # same samples, uploaded instead of generated on the device
-        def __init__(self, h):
-            self.h, self.dist = h, h.dist
-
-        def take(self, n):
-            return self.h.take(n)
-
-    b = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000, batch=4096, rng=HostOnly(vmv.panda.halton()))
-    assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.edges, b.edges)
-    assert a.path is not None and np.array_equal(np.stack(a.path), np.stack(b.path))
+    a = vmv.panda.prm(scenes.CAGE_A, scenes.CAGE_B, env, max_samples=30000)
+    assert a.path is not None and a.samples_drawn > 0
+    q = vmv.panda.halton().at(np.arange(a.samples_drawn))
+    ok = vmv.panda.validate_batch(q, env)
+    want = q[ok]
+    got = a.vertices[2:]
+    assert len(got) <= len(want) and np.array_equal(got, want[: len(got)])
+    assert np.array_equal(a.vertices[0], np.asarray(scenes.CAGE_A, np.float32)) and np.array_equal(a.vertices[1], np.asarray(scenes.CAGE_B, np.float32))
