@@ -12,7 +12,7 @@ from tests import scenes, workloads
 L = _lib.lib()
 L.vmv_dev_stats.argtypes = [C.c_void_p, C.c_int]
 NAMES = ["sphere_queries", "hit_primitives", "grid_lookups", "undecided_after_grid", "capt_active_calls", "need_scan", "lists_scanned",
-         "scan_steps", "points_loaded", "scan_hits", "group_size_sum", "warp_calls", "bounding_queries", "fine_queries", "bounding_hits", "fine_hits"]
+         "scan_steps", "points_loaded", "scan_hits", "group_size_sum", "warp_calls", "table_proven_hits", "table_point_not_listed", "bounding_hits", "fine_hits"]
 for robot in sys.argv[1:] or ["fetch", "ur5"]:
     R = getattr(vmv, robot)
     env, pts, hf, _ = workloads.c4_environment(robot)
@@ -25,8 +25,11 @@ for robot in sys.argv[1:] or ["fetch", "ur5"]:
     L.vmv_dev_stats(_lib.ptr(out), 1)
     d = {k: float(out[i]) / n for i, k in enumerate(NAMES)}
     d["valid"] = float(v.mean())
-    d["list_len_hist_hits(32,64,..)"] = [int(x) for x in out[16:28]]
-    d["list_len_hist_nohits"] = [int(x) for x in out[28:40]]
+    d["points_read_hist_hits(32,64,..)"] = [int(x) for x in out[16:28]]
+    d["points_read_hist_nohits"] = [int(x) for x in out[28:40]]
     d["scans_by_query_radius(<.05,<.1,<.2,>=.2)"] = [int(x) for x in out[40:44]]
     d["nohit_scans_by_query_radius"] = [int(x) for x in out[44:48]]
+    d["tile_cycles_hist(2^13,2^14,..)"] = [int(x) for x in out[48:60]]
+    d["cycles_per_tile: capt call / of which scan loop / probe"] = [float(out[k]) / max(1.0, float(out[61])) for k in (14, 15, 62)]
+    d["tile_cycles_mean"] = float(out[60]) / max(1.0, float(out[61]))
     print(robot, json.dumps(d, indent=1))

@@ -42,13 +42,13 @@ namespace vmv
         float r_point;
         uint32_t nlog2, n_tests, pad0;
         float lo[3];
-        float pad1;
+        float r_max;
         float hi[3];
-        float pad2;
+        float list_reach_sq;      // (r_max + r_point)^2 less a rounding margin: a point this close to a centre is within the lists' reach of its cell
         const float *tests;       // Eytzinger split values, 2^nlog2 - 1
         const float4 *aabbs;      // per leaf: {lo.x lo.y lo.z hi.x}{hi.y hi.z start end}  (2 float4 per leaf)
         const float4 *points;     // affordance points {x y z 0}, padded per leaf to a multiple of 4 with +inf
-        const void *pad3;
+        const uint32_t *flags;    // one bit per Eytzinger node, leaves included (capt_lists_point)
     };
     static_assert(sizeof(CaptRec) == kCaptRec * 4, "CaptRec layout");
 
@@ -74,13 +74,19 @@ namespace vmv
     };
     static_assert(sizeof(MvtRec) == kMvtRec * 4, "MvtRec layout");
 
-    // Clearance grid of the pointclouds (CAPT and MVT together): per voxel a lower bound of the
-    // distance from the voxel CENTRE to the nearest cloud point; the distance function is 1-Lipschitz, so
-    // a position at offset d from the centre is at least (that bound - d) away from every point.  A
-    // pointcloud query can only answer "collision" on an actual point within r + r_point of the centre
-    // (capt.hh:494-509, mvt.hh:383-397), so a sphere whose clearance bound exceeds that radius skips the
-    // tree descent / voxel walk altogether -- the verdict is the one the query would have returned.
+    // Nearest-point table of the pointclouds (CAPT and MVT together): per voxel the cloud point nearest to the voxel
+    // CENTRE, {x, y, z, tag}; tag = cloud << 24 | leaf (the CAPT leaf the point is the representative of; cloud
+    // 0xff = a point of an MVT or of a tree too large for the tag).  Two uses:
+    //  * clearance: the distance function is 1-Lipschitz, so a position at offset d from the centre is at least
+    //    (|nearest - centre| - d) away from every point.  A pointcloud query can only answer "collision" on an actual
+    //    point within r + r_point of the centre (capt.hh:494-509, mvt.hh:383-397), so a sphere whose clearance bound
+    //    exceeds that radius skips the tree descent / voxel walk altogether -- the verdict is the one the query would
+    //    have returned;
+    //  * a proven hit: when the table's point itself lies within r + r_point of the centre AND is on the affordance
+    //    list of the leaf the centre descends to (capt_lists_point evaluates the reference's list construction for
+    //    that one point), the list scan would find it: "collision" without reading the list.
     static constexpr int kCloudGridRec = 12;
+    static constexpr uint32_t kCloudTagNone = 0xffu;
     struct CloudGridRec
     {
         float x0, y0, z0, inv_h;
@@ -88,11 +94,13 @@ namespace vmv
         float outside;      // clearance bound for positions outside the table
         float r_point_max;  // largest r_point of any cloud
         float h;            // voxel edge
-        const float *cells;
+        const float4 *cells;
     };
     static_assert(sizeof(CloudGridRec) == kCloudGridRec * 4, "CloudGridRec layout");
 
-    __device__ __forceinline__ float cloud_clearance(const CloudGridRec &g, float x, float y, float z)
+    // The table entry of the voxel (x, y, z) lies in and the clearance bound it gives; false = outside the table
+    // (near: untouched, clearance: the table's bound for the outside, 0 for a centre that is not finite).
+    __device__ __forceinline__ bool cloud_probe(const CloudGridRec &g, float x, float y, float z, float4 &near, float &clearance)
     {
         const float fx = (x - g.x0) * g.inv_h, fy = (y - g.y0) * g.inv_h, fz = (z - g.z0) * g.inv_h;
         const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
@@ -101,13 +109,26 @@ namespace vmv
         if (!in)
         {
             // a centre that is not finite lands here too: no claim about it
-            return (fabsf(x) < 1e30F && fabsf(y) < 1e30F && fabsf(z) < 1e30F) ? g.outside : 0.F;
+            clearance = (fabsf(x) < 1e30F && fabsf(y) < 1e30F && fabsf(z) < 1e30F) ? g.outside : 0.F;
+            return false;
         }
-        // offset from the voxel centre, in metres, rounded up a little (the table entry already carries
-        // the slack for its own rounding)
-        const float ox = fx - (static_cast<float>(ix) + 0.5F), oy = fy - (static_cast<float>(iy) + 0.5F), oz = fz - (static_cast<float>(iz) + 0.5F);
+        near = __ldg(g.cells + (static_cast<size_t>(iz) * g.ny + iy) * g.nx + ix);
+        // offset of the position from the voxel centre, in metres, rounded up a little; the centre as the build kernel
+        // computes it; the slack (1e-4 m absolute) covers the rounding of all of it
+        const float cx = (static_cast<float>(ix) + 0.5F), cy = (static_cast<float>(iy) + 0.5F), cz = (static_cast<float>(iz) + 0.5F);
+        const float ox = fx - cx, oy = fy - cy, oz = fz - cz;
         const float off = sqrtf(ox * ox + oy * oy + oz * oz) * g.h * 1.0001F;
-        return __ldg(g.cells + (static_cast<size_t>(iz) * g.ny + iy) * g.nx + ix) - off;
+        const float dx = near.x - (g.x0 + cx * g.h), dy = near.y - (g.y0 + cy * g.h), dz = near.z - (g.z0 + cz * g.h);
+        clearance = sqrtf(dx * dx + dy * dy + dz * dz) * 0.99999F - 1e-4F - off;
+        return true;
+    }
+
+    __device__ __forceinline__ float cloud_clearance(const CloudGridRec &g, float x, float y, float z)
+    {
+        float4 near;
+        float c;
+        cloud_probe(g, x, y, z, near, c);
+        return c;
     }
 
     // Table build.  Block = a brick of 8 x 8 x 4 voxels, thread = voxel.  The points arrive sorted along a
@@ -128,7 +149,7 @@ namespace vmv
         int nx,
         int ny,
         int nz,
-        float *__restrict__ out)
+        float4 *__restrict__ out)
     {
         __shared__ float4 tile[kCloudTile];
         const int bxn = (nx + 7) / 8, byn = (ny + 7) / 8;
@@ -139,11 +160,14 @@ namespace vmv
         const float x = x0 + (ix + 0.5F) * h, y = y0 + (iy + 0.5F) * h, z = z0 + (iz + 0.5F) * h;
         const uint32_t n_tiles = (n_points + kCloudTile - 1) / kCloudTile;
         float best = 3.0e38F;
+        uint32_t best_i = 0u;
         for (uint32_t k = 0; k < n_tiles; ++k)
         {
             const float4 p = __ldg(points + static_cast<size_t>(k) * kCloudTile);
             const float dx = p.x - x, dy = p.y - y, dz = p.z - z;
-            best = fminf(best, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            const float d = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            best_i = d < best ? k * kCloudTile : best_i;
+            best = fminf(best, d);
         }
         for (uint32_t k = 0; k < n_tiles; ++k)
         {
@@ -166,14 +190,14 @@ namespace vmv
             {
                 const float4 p = tile[i];
                 const float dx = p.x - x, dy = p.y - y, dz = p.z - z;
-                best = fminf(best, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                const float d = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                best_i = d < best ? base + i : best_i;
+                best = fminf(best, d);
             }
         }
         if (ix < nx && iy < ny && iz < nz)
         {
-            // distance from the voxel centre, less the rounding slack (cloud_clearance subtracts the
-            // query's own offset from the centre)
-            out[(static_cast<size_t>(iz) * ny + iy) * nx + ix] = sqrtf(best) * 0.99999F - 1e-4F;
+            out[(static_cast<size_t>(iz) * ny + iy) * nx + ix] = __ldg(points + best_i);  // {x y z tag}
         }
     }
 
@@ -260,6 +284,9 @@ namespace vmv
         const int lane = threadIdx.x & 31;
         const int rank = __popc(group & ((1u << lane) - 1u));  // position of this lane inside the group
         const int gsize = __popc(group);
+#ifdef VMV_C4_STATS
+        const long long t_call = clock64();
+#endif
         bool need = false, head_hit = false;
         uint32_t start = 0, end = 0;
         float rc_sq = 0.F;
@@ -299,15 +326,22 @@ namespace vmv
                     // afterwards goes to the cooperative scan below.
                     const float qlim0 = rc_sq * 1.00001F;
                     bool h = false, beyond = false;
-#pragma unroll
-                    for (uint32_t u = 0; u < kCaptHead; ++u)
+                    if (start < end)
                     {
-                        if (start + u < end)
+                        // all loads first, every one from a valid address (an entry past the end re-reads the first):
+                        // written with the load inside the bounds test, the compiler chains load -> use -> next load
+                        float4 p[kCaptHead];
+#pragma unroll
+                        for (uint32_t u = 0; u < kCaptHead; ++u)
                         {
-                            const float4 p = __ldg(t.points + start + u);
-                            const float ex = p.x - x, ey = p.y - y, ez = p.z - z;
-                            h = h || (ex * ex + ey * ey + ez * ez <= rc_sq);
-                            beyond = beyond || (p.w > qlim0);
+                            p[u] = __ldg(t.points + (start + u < end ? start + u : start));
+                        }
+#pragma unroll
+                        for (uint32_t u = 0; u < kCaptHead; ++u)
+                        {
+                            const float ex = p[u].x - x, ey = p[u].y - y, ez = p[u].z - z;
+                            h = h | (ex * ex + ey * ey + ez * ez <= rc_sq);
+                            beyond = beyond | (p[u].w > qlim0);
                         }
                     }
                     head_hit = h;
@@ -330,6 +364,9 @@ namespace vmv
             VMV_STAT(10, gsize);
             VMV_STAT(6, __popc(pending));
         }
+#ifdef VMV_C4_STATS
+        const long long t_scan = clock64();
+#endif
         while (pending != 0u)
         {
             const int src = __ffs(pending) - 1;
@@ -347,20 +384,31 @@ namespace vmv
             // dozen a small sphere can reach), while the long no-hit scans of big spheres reach the full width after three
             // steps and are bound by memory latency from there.
             uint32_t per = 1u;
+#ifdef VMV_C4_STATS
+            uint32_t n_read = 0u;
+#endif
             for (uint32_t base = s; base < e; base += per * gsize, per = min(per * 2u, kCaptScanLoads))
             {
+#ifdef VMV_C4_STATS
+                n_read += min(e - base, per * gsize);
+#endif
                 bool h = false, beyond = false;
+                // all loads of the step first, every one from a valid address (a slot past the step's width or the end
+                // of the list re-reads the list's first entry, which has been tested): with the load inside the
+                // bounds test the compiler chains load -> use -> next load and a step costs `per` memory latencies
+                float4 p[kCaptScanLoads];
 #pragma unroll
                 for (uint32_t u = 0; u < kCaptScanLoads; ++u)
                 {
                     const uint32_t i = base + u * gsize + rank;
-                    if (u < per && i < e)
-                    {
-                        const float4 p = __ldg(t.points + i);
-                        const float ex = p.x - qx, ey = p.y - qy, ez = p.z - qz;
-                        h = h || (ex * ex + ey * ey + ez * ez <= qr);
-                        beyond = beyond || (p.w > qlim);
-                    }
+                    p[u] = __ldg(t.points + ((u < per && i < e) ? i : s));
+                }
+#pragma unroll
+                for (uint32_t u = 0; u < kCaptScanLoads; ++u)
+                {
+                    const float ex = p[u].x - qx, ey = p[u].y - qy, ez = p[u].z - qz;
+                    h = h | (ex * ex + ey * ey + ez * ez <= qr);
+                    beyond = beyond | (p[u].w > qlim);
                 }
                 if (rank == 0)
                 {
@@ -384,7 +432,7 @@ namespace vmv
 #ifdef VMV_C4_STATS
             if (rank == 0)
             {
-                const uint32_t len = e - s;
+                const uint32_t len = n_read;  // points read by this scan (not the length of the list)
                 int b = 0;
                 while ((1u << (b + 5)) < len && b < 11)
                 {
@@ -406,7 +454,63 @@ namespace vmv
 #endif
             hit = (lane == src) ? found : hit;
         }
+#ifdef VMV_C4_STATS
+        if (rank == 0)
+        {
+            const long long t_end = clock64();
+            VMV_STAT(14, t_end - t_call);
+            VMV_STAT(15, t_end - t_scan);
+        }
+#endif
         return hit;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // Is the cloud point p -- the representative of leaf `pleaf` -- on the affordance list of the leaf the centre
+    // (x, y, z) descends to?  The reference's list construction (capt.hh:106-119 median split, :150-170 leaf step,
+    // :221-246 what each half inherits) evaluated for ONE point along the centre's root path:
+    //  * above the node where the two root paths part, p belongs to the subtree itself;
+    //  * at that node p sits in the sibling half.  The low half receives the points of the high half within r_max of
+    //    the plane.  The high half receives the low half's points only if the SMALLEST of them is within r_max of the
+    //    plane (the reference scans the sorted half from its first element while the predicate holds) -- one bit per
+    //    node, written by the build;
+    //  * below it p is an inherited candidate: kept on the side the centre takes while within r_max of every plane;
+    //  * at the leaf the candidate must lie within r_max + r_point of the cell -- implied (with the caller's margin) by
+    //    lying that close to the centre, which is inside the cell -- and the leaf must carry a list at all (a cell
+    //    inside the smallest query ball around its representative keeps the representative alone: one bit per leaf).
+    // The additions are the build's own float operations (test +- r_max), so the answer is the build's, bit for bit.
+    // ------------------------------------------------------------------------------------------
+    __device__ __forceinline__ bool capt_node_flag(const CaptRec &t, uint32_t idx)
+    {
+        return ((__ldg(t.flags + (idx >> 5)) >> (idx & 31u)) & 1u) != 0u;
+    }
+
+    __device__ __forceinline__ bool capt_lists_point(const CaptRec &t, float x, float y, float z, float px, float py, float pz, uint32_t pleaf)
+    {
+        uint32_t idx = 0;
+        int k = 0;
+        bool parted = false, ok = true;
+        for (uint32_t i = 0; i < t.nlog2; ++i)
+        {
+            const float split = __ldg(t.tests + idx);
+            const float v = (k == 0) ? x : ((k == 1) ? y : z);
+            const float pv = (k == 0) ? px : ((k == 1) ? py : pz);
+            const bool hi = v >= split;
+            const bool p_hi = ((pleaf >> (t.nlog2 - 1u - i)) & 1u) != 0u;
+            const bool within = hi ? (pv >= __fsub_rn(split, t.r_max)) : (pv <= __fadd_rn(split, t.r_max));
+            if (parted)
+            {
+                ok = ok && within;
+            }
+            else if (hi != p_hi)
+            {
+                parted = true;
+                ok = hi ? capt_node_flag(t, idx) : within;
+            }
+            idx = 2 * idx + 1 + (hi ? 1u : 0u);
+            k = (k == 2) ? 0 : k + 1;
+        }
+        return ok && (!parted || capt_node_flag(t, idx));
     }
 
     // ------------------------------------------------------------------------------------------
@@ -621,14 +725,51 @@ namespace vmv
     {
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
         bool hit = false;
-        // no cloud point within reach: every pointcloud query would answer "no"
+#ifdef VMV_C4_STATS
+        const long long t_probe = clock64();
+#endif
         if (H.off_cloud_grid != 0 && query)
         {
             const CloudGridRec &g = *reinterpret_cast<const CloudGridRec *>(E + H.off_cloud_grid);
-            query = !(cloud_clearance(g, x, y, z) > r_pc + g.r_point_max);
+            float4 near;
+            float clearance;
+            const bool in = cloud_probe(g, x, y, z, near, clearance);
+            // no cloud point within reach: every pointcloud query would answer "no"
+            query = !(clearance > r_pc + g.r_point_max);
             VMV_STAT(2, 1);
             VMV_STAT(3, query ? 1 : 0);
+            const uint32_t tag = __float_as_uint(near.w);
+            if (in && query && (tag >> 24) < H.n_capts)
+            {
+                // the table's point within the query ball and on the list the query would scan: the scan finds it
+                const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * (tag >> 24));
+                const float rr = r_pc + t.r_point;
+                const float ex = near.x - x, ey = near.y - y, ez = near.z - z;
+                const float dsq = ex * ex + ey * ey + ez * ez;
+                // (margins: the comparison the scan makes is reproduced only where rounding cannot flip it)
+                const bool inside = (dsq <= rr * rr * 0.999998F) & (dsq <= t.list_reach_sq);
+                // top-level AABB reject uses r, not r + r_point (capt.hh:431-438)
+                const bool inb = (x + r_pc >= t.lo[0]) & (x - r_pc <= t.hi[0]) & (y + r_pc >= t.lo[1]) & (y - r_pc <= t.hi[1]) &
+                                 (z + r_pc >= t.lo[2]) & (z - r_pc <= t.hi[2]);
+                if (inside && inb && capt_lists_point(t, x, y, z, near.x, near.y, near.z, tag & 0xffffffu))
+                {
+                    hit = true;
+                    query = false;
+                    VMV_STAT(12, 1);
+                }
+                else if (inside && inb)
+                {
+                    VMV_STAT(13, 1);
+                }
+            }
         }
+#ifdef VMV_C4_STATS
+        __syncwarp(__activemask());
+        if ((threadIdx.x & 31) == __ffs(__activemask()) - 1)
+        {
+            VMV_STAT(62, clock64() - t_probe);
+        }
+#endif
         for (uint32_t i = 0; i < H.n_capts; ++i)
         {
             const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * i);

@@ -193,9 +193,14 @@ namespace
         std::vector<float, NoInitAlloc<float>> points;  // per afforded point x, y, z, squared distance from the cell (representative first)
         float top_lo[3], top_hi[3];
         int id;
+        // what vmv::capt_lists_point needs: one bit per Eytzinger node (internal: the high half inherited the low half's
+        // points; leaf: the leaf carries a list beyond its representative), and the leaf every input point represents
+        std::vector<uint32_t> flags;
+        std::vector<uint32_t> leaf_of_point;
         float *d_tests = nullptr;
         float4 *d_aabbs = nullptr;
         float4 *d_points = nullptr;
+        uint32_t *d_flags = nullptr;
     };
 
     // Multi-level Voxel Table, host build (reference collision/mvt.hh:146-170, 437-446, 531-604)
@@ -371,6 +376,7 @@ namespace
         float max_l2, min_l2;
         CaptFragment *out;                              // leaves of this builder go here
         std::vector<CaptTask> *tasks;                   // non-null: collect subtrees at kCaptTaskDepth
+        std::vector<uint8_t> &node_flag;                // per Eytzinger node, leaves included (HCapt::flags, one byte each while building)
         std::vector<std::pair<float, uint32_t>> near;  // scratch of the leaf step
 
         void subdivide(uint32_t begin, uint32_t count, uint32_t i, std::vector<uint32_t> afford, Vol vol, int d, int depth)
@@ -392,6 +398,7 @@ namespace
                         out->top_hi[k] = std::max(out->top_hi[k], rep[k]);
                     }
                     out->points.insert(out->points.end(), {rep[0], rep[1], rep[2], 0.F});
+                    t.leaf_of_point[argsort[begin]] = begin;  // leaves are numbered left to right, as the sorted range is
                     // cell entirely inside the smallest query ball around its representative:
                     // the representative alone decides (capt.hh:39-46,150)
                     const float d0 = std::max(rep[0] - vol.lo[0], vol.hi[0] - rep[0]);
@@ -399,6 +406,7 @@ namespace
                     const float d2 = std::max(rep[2] - vol.lo[2], vol.hi[2] - rep[2]);
                     if (!((d0 * d0 + d1 * d1 + d2 * d2) <= min_l2))
                     {
+                        node_flag[i] = 1;
                         // Same set of afforded points as the reference's list (capt.hh:150-170), but
                         // ordered by their squared distance from the cell, which is kept in .w: a query
                         // centre lies inside the cell it descends to, so a point farther from the cell
@@ -469,6 +477,7 @@ namespace
             {
                 ++new_lo;
             }
+            node_flag[i] = new_hi > begin ? 1 : 0;  // all or nothing: the scan starts at the half's smallest element
             hi_afford.insert(hi_afford.end(), argsort.begin() + begin, argsort.begin() + new_hi);
             lo_afford.insert(lo_afford.end(), argsort.begin() + begin + half, argsort.begin() + new_lo);
             afford.clear();
@@ -499,6 +508,8 @@ namespace
             t.top_hi[k] = -inf;
         }
         t.tests.assign(pow2 - 1, std::numeric_limits<float>::quiet_NaN());
+        std::vector<uint8_t> node_flag(2 * pow2 - 1, 0);
+        t.leaf_of_point.assign(pow2, 0u);
         t.leaf_start.assign(1, 0);
         t.leaf_lo.clear(), t.leaf_hi.clear(), t.points.clear();
         std::vector<uint32_t> argsort(pow2);
@@ -517,7 +528,7 @@ namespace
         fresh(head);
         std::vector<CaptTask> tasks;
         const auto tm0 = std::chrono::steady_clock::now();
-        CaptBuilder top{t, pts, argsort, max_l2, min_l2, &head, &tasks, {}};
+        CaptBuilder top{t, pts, argsort, max_l2, min_l2, &head, &tasks, node_flag, {}};
         top.subdivide(0, static_cast<uint32_t>(pow2), 0, {}, Vol{{-inf, -inf, -inf}, {inf, inf, inf}}, 0, 0);
         const auto tm1 = std::chrono::steady_clock::now();
         std::vector<CaptFragment> frags(tasks.size());
@@ -531,7 +542,7 @@ namespace
                     for (size_t k = next.fetch_add(1); k < tasks.size() && !failed.load(); k = next.fetch_add(1))
                     {
                         fresh(frags[k]);
-                        CaptBuilder b{t, pts, argsort, max_l2, min_l2, &frags[k], nullptr, {}};
+                        CaptBuilder b{t, pts, argsort, max_l2, min_l2, &frags[k], nullptr, node_flag, {}};
                         CaptTask &task = tasks[k];
                         b.subdivide(task.begin, task.count, task.i, std::move(task.afford), task.vol, task.d, kCaptTaskDepth);
                     }
@@ -563,6 +574,12 @@ namespace
         {
             std::fprintf(stderr, "capt_build: top %.2f s, subtrees %.2f s\n", std::chrono::duration<double>(tm1 - tm0).count(),
                          std::chrono::duration<double>(tm2 - tm1).count());
+        }
+        t.leaf_of_point.resize(n);
+        t.flags.assign((node_flag.size() + 31) / 32, 0u);
+        for (size_t k = 0; k < node_flag.size(); ++k)
+        {
+            t.flags[k >> 5] |= node_flag[k] ? (1u << (k & 31)) : 0u;
         }
         // stitch: either everything is in `head` (no tasks) or every leaf is in a task fragment
         std::vector<CaptFragment *> order{&head};
@@ -636,7 +653,8 @@ struct vmv_env
     std::vector<HHeight> heightfields;
     std::vector<HCapt> capts;
     std::vector<HMvt> mvts;
-    std::vector<float> cloud_xyz;  // every point of every pointcloud (clearance grid, vmv_device.cuh)
+    std::vector<float> cloud_xyz;  // every point of every pointcloud (nearest-point table, vmv_device.cuh)
+    std::vector<uint32_t> cloud_tag;  // per point: cloud << 24 | CAPT leaf (cloud 0xff: no list shortcut for this point)
     float cloud_r_point_max = 0.F;
     float cloud_grid_ms = 0.F;
     bool has_attachment = false;
@@ -864,7 +882,9 @@ namespace
                 lo[k] = std::min(lo[k], p[k]);
                 hi[k] = std::max(hi[k], p[k]);
             }
-            pts[i] = make_float4(p[0], p[1], p[2], 0.F);
+            float tag;
+            std::memcpy(&tag, &env->cloud_tag[i], 4);
+            pts[i] = make_float4(p[0], p[1], p[2], tag);
         }
 #ifndef VMV_CLOUD_VOXEL
 #define VMV_CLOUD_VOXEL 0.0125
@@ -935,7 +955,7 @@ namespace
             boxes[2 * k + 1] = make_float4(bhi[1], bhi[2], 0.F, 0.F);
         }
         float4 *d_pts = nullptr, *d_boxes = nullptr;
-        float *d_cells = nullptr;
+        float4 *d_cells = nullptr;
         int rc = upload(env, pts, d_pts);
         if (rc == VMV_OK)
         {
@@ -947,9 +967,9 @@ namespace
         }
         {
             void *p = nullptr;
-            VMV_CUDA(cudaMalloc(&p, n_vox * sizeof(float)));
+            VMV_CUDA(cudaMalloc(&p, n_vox * sizeof(float4)));
             env->owned.push_back(p);
-            d_cells = static_cast<float *>(p);
+            d_cells = static_cast<float4 *>(p);
         }
         cudaEvent_t e0, e1;
         VMV_CUDA(cudaEventCreate(&e0));
@@ -1022,6 +1042,10 @@ namespace
         for (auto &t : env->capts)
         {
             int rc = upload(env, t.tests, t.d_tests);
+            if (rc == VMV_OK)
+            {
+                rc = upload(env, t.flags, t.d_flags);
+            }
             if (rc != VMV_OK)
             {
                 return rc;
@@ -1145,9 +1169,15 @@ namespace
                 r.lo[k] = t.top_lo[k];
                 r.hi[k] = t.top_hi[k];
             }
+            r.r_max = t.r_max;
+            {
+                const float reach = t.r_max + t.r_point;
+                r.list_reach_sq = reach * reach * 0.99999F;
+            }
             r.tests = t.d_tests;
             r.aabbs = t.d_aabbs;
             r.points = t.d_points;
+            r.flags = t.d_flags;
             const uint32_t *w = reinterpret_cast<const uint32_t *>(&r);
             B.insert(B.end(), w, w + vmv::kCaptRec);
         }
@@ -1861,6 +1891,15 @@ extern "C"
             HCapt t;
             capt_build(t, pts, n, r_min, r_max, r_point);
             t.id = env->next_id++;
+            {
+                const size_t cloud = env->capts.size();
+                const bool taggable = cloud < vmv::kCloudTagNone && t.nlog2 <= 24;
+                for (size_t k = 0; k < n; ++k)
+                {
+                    env->cloud_tag.push_back(taggable ? (static_cast<uint32_t>(cloud) << 24 | t.leaf_of_point[k]) : (vmv::kCloudTagNone << 24));
+                }
+                std::vector<uint32_t>().swap(t.leaf_of_point);
+            }
             env->capts.push_back(std::move(t));
             env->cloud_xyz.insert(env->cloud_xyz.end(), pts, pts + 3 * n);
             env->cloud_r_point_max = std::max(env->cloud_r_point_max, r_point);
@@ -1890,6 +1929,7 @@ extern "C"
             }
             t.id = env->next_id++;
             env->mvts.push_back(std::move(t));
+            env->cloud_tag.insert(env->cloud_tag.end(), n, vmv::kCloudTagNone << 24);
             env->cloud_xyz.insert(env->cloud_xyz.end(), pts, pts + 3 * n);
             env->cloud_r_point_max = std::max(env->cloud_r_point_max, r_point);
             env->shapes_dirty = true;
@@ -3804,7 +3844,7 @@ extern "C"
                 for (const auto &t : env->capts)
                 {
                     w.pod(t.r_min), w.pod(t.r_max), w.pod(t.r_point), w.pod(t.nlog2), w.pod(t.top_lo), w.pod(t.top_hi), w.pod(t.id);
-                    w.vec(t.tests), w.vec(t.leaf_lo), w.vec(t.leaf_hi), w.vec(t.leaf_start), w.vec(t.points);
+                    w.vec(t.tests), w.vec(t.leaf_lo), w.vec(t.leaf_hi), w.vec(t.leaf_start), w.vec(t.points), w.vec(t.flags);
                 }
                 w.pod<uint64_t>(env->mvts.size());
                 for (const auto &t : env->mvts)
@@ -3813,7 +3853,7 @@ extern "C"
                     w.pod(t.inv_scale), w.pod(t.grid_width), w.pod(t.id);
                     w.vec(t.cells), w.vec(t.voxels), w.vec(t.points);
                 }
-                w.vec(env->cloud_xyz), w.pod(env->cloud_r_point_max);
+                w.vec(env->cloud_xyz), w.vec(env->cloud_tag), w.pod(env->cloud_r_point_max);
                 w.pod<int>(env->has_attachment ? 1 : 0), w.pod(env->attach_tf), w.vec(env->attach_spheres), w.pod(env->next_id);
             }
             unsigned long long size = w.b.size();
@@ -3866,7 +3906,7 @@ extern "C"
                 for (auto &t : env->capts)
                 {
                     r.pod(t.r_min), r.pod(t.r_max), r.pod(t.r_point), r.pod(t.nlog2), r.pod(t.top_lo), r.pod(t.top_hi), r.pod(t.id);
-                    r.vec(t.tests), r.vec(t.leaf_lo), r.vec(t.leaf_hi), r.vec(t.leaf_start), r.vec(t.points);
+                    r.vec(t.tests), r.vec(t.leaf_lo), r.vec(t.leaf_hi), r.vec(t.leaf_start), r.vec(t.points), r.vec(t.flags);
                 }
                 r.pod(k);
                 env->mvts.clear();
@@ -3878,7 +3918,7 @@ extern "C"
                     r.vec(t.cells), r.vec(t.voxels), r.vec(t.points);
                 }
                 int att = 0;
-                r.vec(env->cloud_xyz), r.pod(env->cloud_r_point_max);
+                r.vec(env->cloud_xyz), r.vec(env->cloud_tag), r.pod(env->cloud_r_point_max);
                 r.pod(att), r.pod(env->attach_tf), r.vec(env->attach_spheres), r.pod(env->next_id);
                 env->has_attachment = att != 0;
                 if (!r.ok)

@@ -859,7 +859,25 @@ namespace vmv
                 ticket = atomicAdd(next_tile, 1u);
             }
 #endif
+#ifdef VMV_C4_STATS
+            const long long t_tile = clock64();
+#endif
             const uint32_t invalid = v4_pass<R, MaskT, TAB, true, AE>(X, env.grid, env.tab, cfg, has);
+#ifdef VMV_C4_STATS
+            if (lane == 0)
+            {
+                // tile durations: log2 buckets 2^13 .. 2^24 cycles at 48..59; total cycles at 60; tiles at 61
+                const long long dt = clock64() - t_tile;
+                int bkt = 0;
+                while ((1ll << (bkt + 13)) < dt && bkt < 11)
+                {
+                    ++bkt;
+                }
+                VMV_STAT(48 + bkt, 1);
+                VMV_STAT(60, dt);
+                VMV_STAT(61, 1);
+            }
+#endif
             publish_verdict<GATHER>(bits, gather, tile, ~invalid, 4);
 #ifndef VMV_V4_STATIC_TILES
             if (!kEarly && lane == 0)
