@@ -34,21 +34,25 @@ namespace vmv
     static constexpr int kCuboidRec = 16;    // {x y z r1}{a1x a1y a1z r2}{a2x a2y a2z r3}{a3x a3y a3z min_d}
     static constexpr int kZCuboidRec = 12;   // {x y z min_d}{a1x a1y a2x a2y}{r1 r2 r3 0}
     static constexpr int kHeightRec = 12;    // {x y z xs}{ys zs xd yd}{xd2 yd2 ptr_lo ptr_hi}
-    static constexpr int kCaptRec = 20;      // see CaptRec
+    static constexpr int kCaptRec = 28;      // see CaptRec
     static constexpr int kAttachHdr = 4;     // {n 0 0 0} then n x {x y z r} (attachment-local)
 
     struct CaptRec
     {
         float r_point;
-        uint32_t nlog2, n_tests, pad0;
-        float lo[3];
+        uint32_t nlog2, n_tests, n_points;
+        float lo[3];              // box of the finite points (top-level reject)
         float r_max;
         float hi[3];
-        float list_reach_sq;      // (r_max + r_point)^2 less a rounding margin: a point this close to a centre is within the lists' reach of its cell
-        const float *tests;       // Eytzinger split values, 2^nlog2 - 1
-        const float4 *aabbs;      // per leaf: {lo.x lo.y lo.z hi.x}{hi.y hi.z start end}  (2 float4 per leaf)
-        const float4 *points;     // affordance points {x y z 0}, padded per leaf to a multiple of 4 with +inf
-        const uint32_t *flags;    // one bit per Eytzinger node, leaves included (capt_lists_point)
+        float list_reach_sq;      // (r_max + r_point)^2 as the build computes it
+        float g_origin[3];        // enumeration grid: origin, cells per metre and cell edge at the finest level
+        float g_inv0;
+        float g_cell0;
+        uint32_t pad[3];
+        const float2 *nodes;      // Eytzinger, 2^nlog2 - 1: {split value, 1 = the high half inherited the low half's points}
+        const uint32_t *leafbits; // two bits per leaf: 1 = carries a list beyond its representative, 2 = representative is finite
+        const float4 *gpts;       // the finite points in Morton order of their finest cell: {x y z leaf}
+        const uint32_t *gstart;   // per level: first point of every cell in Morton order (+ one end entry), capt_grid_offset()
     };
     static_assert(sizeof(CaptRec) == kCaptRec * 4, "CaptRec layout");
 
@@ -261,256 +265,281 @@ namespace vmv
     }
 
     // ------------------------------------------------------------------------------------------
-    // CAPT query (reference collision/capt.hh:428-512), warp-cooperative.
-    // Called by whichever lanes of the warp currently have a query (the converged group,
-    // __activemask()).  Each lane does its own top-AABB reject, Eytzinger descent and leaf-AABB test;
-    // the affordance lists of the lanes that survive are then scanned ONE LIST AT A TIME BY THE WHOLE
-    // GROUP: up to 32 lanes x four 128-bit loads per step, and a ballot ends the scan at the first chunk
-    // with a hit -- or with a point farther from the cell than the query radius (lists are ordered by
-    // that distance; a query of a small sphere reads a short prefix of a list built for r_max).
+    // CAPT query (reference collision/capt.hh:428-512) WITHOUT the affordance lists.
+    //
+    // The reference answers "is any point of the list of the centre's leaf within r + r_point of the centre"; the
+    // list of a leaf is a function of the k-d tree alone (capt.hh:106-119 median split, :150-170 leaf step, :221-246
+    // what each half inherits), and for ONE point p and the leaf L of a centre c that function is cheap:
+    //  * p is L's own representative, or L carries a list at all (a cell inside the smallest query ball around its
+    //    representative keeps the representative alone -- one bit per leaf) and
+    //  * at the node where the root paths of p and c part, p's half was handed to c's half: the low half always
+    //    receives the high half's points within r_max of the plane, but the high half receives the low half's points
+    //    only if the SMALLEST of them is within r_max of the plane (the reference scans the sorted half from its
+    //    first element while the predicate holds) -- one bit per node, collected along c's descent into a mask that
+    //    is indexed by the highest differing bit of the two leaf numbers;
+    //  * below that node p is an inherited candidate, kept on c's side while within r_max of every plane: planes nest,
+    //    so that is "within r_max of c's cell, axis by axis" (for the planes above the parting node it holds trivially);
+    //  * at the leaf, p lies within r_max + r_point of the cell (the build's own float operations, bit for bit).
+    // So the lists -- 7 GB and a 4 s host build for 10^5 points at r_max = 0.24 m -- are not stored.  Candidates come
+    // from (a) the nearest-point table (cloud_probe): a sphere in contact usually contains the table's point, and
+    // (b) a Morton-ordered uniform grid over the raw points, five levels of cell size, enumerated by the whole group
+    // for one query at a time over the box (query ball) x (cell grown by r_max).
     // ------------------------------------------------------------------------------------------
-#ifndef VMV_CAPT_SCAN_LOADS
-#define VMV_CAPT_SCAN_LOADS 8
-#endif
-    static constexpr uint32_t kCaptScanLoads = VMV_CAPT_SCAN_LOADS;
-#ifndef VMV_CAPT_HEAD
-#define VMV_CAPT_HEAD 4
-#endif
-    static constexpr uint32_t kCaptHead = VMV_CAPT_HEAD;  // list entries a lane tests by itself before the cooperative scan
+    static constexpr int kCaptGridBits = 7;    // finest level: 128 cells per axis
+    static constexpr int kCaptGridLevels = 5;  // cell edge g0 * 2^l
+    static constexpr uint32_t kCaptEnumLoads = 4;
 
-    __device__ __forceinline__ bool capt_collides_warp(const CaptRec &t, float x, float y, float z, float r, bool active)
+    __host__ __device__ __forceinline__ uint32_t capt_grid_offset(int level)
+    {
+        // levels are stored one after the other, 8^(bits - l) + 1 entries each
+        uint32_t off = 0;
+        for (int l = 0; l < level; ++l)
+        {
+            off += (1u << (3 * (kCaptGridBits - l))) + 1u;
+        }
+        return off;
+    }
+
+    __host__ __device__ __forceinline__ uint32_t morton_spread(uint32_t v)
+    {
+        v &= 0x3ffu;
+        v = (v | (v << 16)) & 0x030000ffu;
+        v = (v | (v << 8)) & 0x0300f00fu;
+        v = (v | (v << 4)) & 0x030c30c3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
+    }
+
+    struct CaptCell
+    {
+        uint32_t leaf, hmask;  // hmask bit b: c took the high side at the level whose leaf-number bit is b, and that node's high half did NOT inherit
+        float lo[3], hi[3];    // the leaf's cell
+        bool full, finite;
+    };
+
+    __device__ __forceinline__ void capt_descend(const CaptRec &t, float x, float y, float z, CaptCell &c)
+    {
+        const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            c.lo[k] = -inf;
+            c.hi[k] = inf;
+        }
+        c.hmask = 0u;
+        uint32_t idx = 0u, bit = t.nlog2;
+        for (uint32_t i = 0; i < t.nlog2; i += 3)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                if (i + k < t.nlog2)
+                {
+                    const float2 node = __ldg(t.nodes + idx);  // {split, inherited}
+                    const float v = (k == 0) ? x : ((k == 1) ? y : z);
+                    const bool up = v >= node.x;
+                    --bit;
+                    if (up)
+                    {
+                        c.lo[k] = node.x;
+                        c.hmask |= (__float_as_uint(node.y) ^ 1u) << bit;
+                    }
+                    else
+                    {
+                        c.hi[k] = node.x;
+                    }
+                    idx = 2u * idx + 1u + (up ? 1u : 0u);
+                }
+            }
+        }
+        c.leaf = idx - t.n_tests;
+        const uint32_t w = __ldg(t.leafbits + (c.leaf >> 4)) >> (2u * (c.leaf & 15u));
+        c.full = (w & 1u) != 0u;
+        c.finite = (w & 2u) != 0u;
+    }
+
+    // Is the cloud point p = {x y z leaf} on the list of the leaf described by c?
+    __device__ __forceinline__ bool capt_member(const CaptRec &t, const CaptCell &c, const float4 &p)
+    {
+        const uint32_t parted = c.leaf ^ (__float_as_uint(p.w) & 0xffffffu);
+        if (parted == 0u)
+        {
+            return true;  // the leaf's representative
+        }
+        const bool handed = ((c.hmask >> (31 - __clz(parted))) & 1u) == 0u;
+        const float pc[3] = {p.x, p.y, p.z};
+        bool near = true;
+        float dsq = 0.F;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            near = near && (pc[k] >= __fsub_rn(c.lo[k], t.r_max)) && (pc[k] <= __fadd_rn(c.hi[k], t.r_max));
+            const float d = __fsub_rn(pc[k], fminf(fmaxf(pc[k], c.lo[k]), c.hi[k]));
+            dsq = __fadd_rn(dsq, __fmul_rn(d, d));
+        }
+        return c.full && handed && near && (dsq <= t.list_reach_sq);
+    }
+
+    // Called by whichever lanes of the warp currently have a query (the converged group, __activemask()); `active`
+    // false = the lane has nothing to ask but helps.  `near` / `has_near`: this cloud's point from the nearest-point
+    // table for the lane's position.
+    __device__ __forceinline__ bool
+    capt_collides_warp(const CaptRec &t, float x, float y, float z, float r, bool active, const float4 &near, bool has_near)
     {
         const uint32_t group = __activemask();
         const int lane = threadIdx.x & 31;
         const int rank = __popc(group & ((1u << lane) - 1u));  // position of this lane inside the group
         const int gsize = __popc(group);
-#ifdef VMV_C4_STATS
-        const long long t_call = clock64();
-#endif
-        bool need = false, head_hit = false;
-        uint32_t start = 0, end = 0;
-        float rc_sq = 0.F;
-        if (active)
-        {
-            // top-level AABB reject uses r, not r + r_point (capt.hh:431-438)
-            const bool inb = (x + r >= t.lo[0]) & (x - r <= t.hi[0]) & (y + r >= t.lo[1]) & (y - r <= t.hi[1]) &
-                             (z + r >= t.lo[2]) & (z - r <= t.hi[2]);
-            if (inb)
-            {
-                uint32_t idx = 0;
-                int k = 0;
-                for (uint32_t i = 0; i < t.nlog2; ++i)
-                {
-                    const float split = __ldg(t.tests + idx);
-                    const float v = (k == 0) ? x : ((k == 1) ? y : z);
-                    idx = 2 * idx + 1 + (v >= split ? 1u : 0u);
-                    k = (k == 2) ? 0 : k + 1;
-                }
-                const uint32_t leaf = idx - t.n_tests;
-                const float rr = r + t.r_point;
-                rc_sq = rr * rr;
-                const float4 b0 = __ldg(t.aabbs + 2 * leaf);
-                const float4 b1 = __ldg(t.aabbs + 2 * leaf + 1);
-                const float d0 = x - fminf(fmaxf(x, b0.x), b0.w);
-                const float d1 = y - fminf(fmaxf(y, b0.y), b1.x);
-                const float d2 = z - fminf(fmaxf(z, b0.z), b1.y);
-                need = d0 * d0 + d1 * d1 + d2 * d2 <= rc_sq;
-                start = __float_as_uint(b1.z);
-                end = __float_as_uint(b1.w);
-                if (need)
-                {
-                    // The head of the list by the lane itself: the representative of the cell comes first and the rest
-                    // in order of distance from the cell, so a query that hits at all usually hits within the first
-                    // few entries (measured on BASELINE config 4: 80 % of the scans end with a hit).  Four independent
-                    // loads, one latency period for all lanes of the warp together; only what is still undecided
-                    // afterwards goes to the cooperative scan below.
-                    const float qlim0 = rc_sq * 1.00001F;
-                    bool h = false, beyond = false;
-                    if (start < end)
-                    {
-                        // all loads first, every one from a valid address (an entry past the end re-reads the first):
-                        // written with the load inside the bounds test, the compiler chains load -> use -> next load
-                        float4 p[kCaptHead];
-#pragma unroll
-                        for (uint32_t u = 0; u < kCaptHead; ++u)
-                        {
-                            p[u] = __ldg(t.points + (start + u < end ? start + u : start));
-                        }
-#pragma unroll
-                        for (uint32_t u = 0; u < kCaptHead; ++u)
-                        {
-                            const float ex = p[u].x - x, ey = p[u].y - y, ez = p[u].z - z;
-                            h = h | (ex * ex + ey * ey + ez * ez <= rc_sq);
-                            beyond = beyond | (p[u].w > qlim0);
-                        }
-                    }
-                    head_hit = h;
-                    start = min(start + kCaptHead, end);
-                    need = !h && !beyond && start < end;
-                }
-            }
-        }
-
-        bool hit = head_hit;
-        uint32_t pending = __ballot_sync(group, need);
+        CaptCell c;
+        bool need = false, hit = false;
+        const float rr = r + t.r_point;
+        const float rc_sq = rr * rr;
         if (active)
         {
             VMV_STAT(4, 1);
+            // top-level AABB reject uses r, not r + r_point (capt.hh:431-438)
+            const bool inb = (x + r >= t.lo[0]) & (x - r <= t.hi[0]) & (y + r >= t.lo[1]) & (y - r <= t.hi[1]) & (z + r >= t.lo[2]) &
+                             (z - r <= t.hi[2]);
+            if (inb)
+            {
+                capt_descend(t, x, y, z, c);
+                if (c.finite)
+                {
+                    need = true;
+                    if (has_near)
+                    {
+                        const float ex = near.x - x, ey = near.y - y, ez = near.z - z;
+                        if ((ex * ex + ey * ey + ez * ez <= rc_sq) && capt_member(t, c, near))
+                        {
+                            hit = true;
+                            need = false;
+                            VMV_STAT(12, 1);
+                        }
+                    }
+                }
+            }
             VMV_STAT(5, need ? 1 : 0);
         }
-        if (rank == 0)
-        {
-            VMV_STAT(11, 1);
-            VMV_STAT(10, gsize);
-            VMV_STAT(6, __popc(pending));
-        }
-#ifdef VMV_C4_STATS
-        const long long t_scan = clock64();
-#endif
+
+        uint32_t pending = __ballot_sync(group, need);
         while (pending != 0u)
         {
             const int src = __ffs(pending) - 1;
             pending &= pending - 1u;
-            const uint32_t s = __shfl_sync(group, start, src), e = __shfl_sync(group, end, src);
-            const float qx = __shfl_sync(group, x, src), qy = __shfl_sync(group, y, src);
-            const float qz = __shfl_sync(group, z, src), qr = __shfl_sync(group, rc_sq, src);
-            // The list is ordered by squared distance from the cell (.w, written by the host build): the
-            // centre is inside the cell, so once .w exceeds the query radius nothing further can be
-            // within it.  The slack covers the rounding of both squared distances (relative 1e-6).
-            const float qlim = qr * 1.00001F;
+            // the query, for everybody
+            CaptCell q;
+            q.leaf = __shfl_sync(group, c.leaf, src);
+            q.hmask = __shfl_sync(group, c.hmask, src);
+            q.full = __shfl_sync(group, c.full ? 1 : 0, src) != 0;
+            const float qc[3] = {__shfl_sync(group, x, src), __shfl_sync(group, y, src), __shfl_sync(group, z, src)};
+            const float qrr = __shfl_sync(group, rr, src);
+            const float qr = qrr * qrr;
+            float blo[3], bhi[3];
+            bool empty = false;
+            float ext = 0.F;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                q.lo[k] = __shfl_sync(group, c.lo[k], src);
+                q.hi[k] = __shfl_sync(group, c.hi[k], src);
+                // where a listed point within the ball can be (a cull: the exact tests follow per point)
+                blo[k] = fmaxf(qc[k] - qrr, q.lo[k] - t.r_max) - 1e-4F;
+                bhi[k] = fminf(qc[k] + qrr, q.hi[k] + t.r_max) + 1e-4F;
+                empty = empty || (blo[k] > bhi[k]);
+                ext = fmaxf(ext, bhi[k] - blo[k]);
+            }
+            // the level at which the box is at most four cells wide
+            int level = 0;
+            float inv = t.g_inv0;
+            while (level < kCaptGridLevels - 1 && ext * inv > 3.F)
+            {
+                ++level;
+                inv *= 0.5F;
+            }
+            const int dim = (1 << kCaptGridBits) >> level;
+            int i0[3], n[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                const float a = (blo[k] - t.g_origin[k]) * inv, b = (bhi[k] - t.g_origin[k]) * inv;
+                empty = empty || (b < 0.F) || (a >= static_cast<float>(dim));
+                const int ia = max(0, min(dim - 1, __float2int_rd(a))), ib = max(0, min(dim - 1, __float2int_rd(b)));
+                i0[k] = ia;
+                n[k] = ib - ia + 1;
+            }
+            const int n_cells = empty ? 0 : n[0] * n[1] * n[2];
+            const uint32_t *starts = t.gstart + capt_grid_offset(level);
+            const float g = t.g_cell0 * static_cast<float>(1 << level);
             bool found = false;
-            // The step widens as the scan goes on -- 1, 2, 4, then kCaptScanLoads independent 128-bit loads per lane: most
-            // scans need a short prefix of a list built for r_max (a step of 8 x 32 lanes fetched 256 points for the few
-            // dozen a small sphere can reach), while the long no-hit scans of big spheres reach the full width after three
-            // steps and are bound by memory latency from there.
-            uint32_t per = 1u;
-#ifdef VMV_C4_STATS
-            uint32_t n_read = 0u;
-#endif
-            for (uint32_t base = s; base < e; base += per * gsize, per = min(per * 2u, kCaptScanLoads))
+            VMV_STAT(6, rank == 0 ? 1 : 0);
+            for (int cb = 0; cb < n_cells && !found; cb += gsize)
             {
-#ifdef VMV_C4_STATS
-                n_read += min(e - base, per * gsize);
-#endif
-                bool h = false, beyond = false;
-                // all loads of the step first, every one from a valid address (a slot past the step's width or the end
-                // of the list re-reads the list's first entry, which has been tested): with the load inside the
-                // bounds test the compiler chains load -> use -> next load and a step costs `per` memory latencies
-                float4 p[kCaptScanLoads];
+                const int ci = cb + rank;
+                uint32_t s = 0u, e = 0u;
+                if (ci < n_cells)
+                {
+                    const int cx = i0[0] + ci % n[0], cy = i0[1] + (ci / n[0]) % n[1], cz = i0[2] + ci / (n[0] * n[1]);
+                    // the cell against the ball (cell bounds grown by what their float arithmetic can be off)
+                    const int cc[3] = {cx, cy, cz};
+                    float dsq = 0.F;
 #pragma unroll
-                for (uint32_t u = 0; u < kCaptScanLoads; ++u)
-                {
-                    const uint32_t i = base + u * gsize + rank;
-                    p[u] = __ldg(t.points + ((u < per && i < e) ? i : s));
-                }
-#pragma unroll
-                for (uint32_t u = 0; u < kCaptScanLoads; ++u)
-                {
-                    const float ex = p[u].x - qx, ey = p[u].y - qy, ez = p[u].z - qz;
-                    h = h | (ex * ex + ey * ey + ez * ez <= qr);
-                    beyond = beyond | (p[u].w > qlim);
-                }
-                if (rank == 0)
-                {
-                    VMV_STAT(7, 1);
-                    VMV_STAT(8, min(e - base, per * gsize));
-                }
-                if (__any_sync(group, h))
-                {
-                    found = true;
-                    if (rank == 0)
+                    for (int k = 0; k < 3; ++k)
                     {
-                        VMV_STAT(9, 1);
+                        const float lo_k = t.g_origin[k] + static_cast<float>(cc[k]) * g - 1e-4F;
+                        const float hi_k = lo_k + g + 2e-4F;
+                        const float d = qc[k] - fminf(fmaxf(qc[k], lo_k), hi_k);
+                        dsq += d * d;
                     }
-                    break;
+                    if (dsq <= qr * 1.0001F)
+                    {
+                        const uint32_t m = (morton_spread(cx) | (morton_spread(cy) << 1) | (morton_spread(cz) << 2));
+                        s = __ldg(starts + m);
+                        e = __ldg(starts + m + 1);
+                    }
                 }
-                if (__any_sync(group, beyond))
+                uint32_t have = __ballot_sync(group, e > s);
+                while (have != 0u && !found)
                 {
-                    break;
+                    const int cl = __ffs(have) - 1;
+                    have &= have - 1u;
+                    const uint32_t cs = __shfl_sync(group, s, cl), ce = __shfl_sync(group, e, cl);
+                    for (uint32_t base = cs; base < ce; base += kCaptEnumLoads * gsize)
+                    {
+                        // all loads first, every one from a valid address (a slot past the end re-reads the cell's first point)
+                        float4 p[kCaptEnumLoads];
+#pragma unroll
+                        for (uint32_t u = 0; u < kCaptEnumLoads; ++u)
+                        {
+                            const uint32_t i = base + u * gsize + rank;
+                            p[u] = __ldg(t.gpts + (i < ce ? i : cs));
+                        }
+                        bool h = false;
+#pragma unroll
+                        for (uint32_t u = 0; u < kCaptEnumLoads; ++u)
+                        {
+                            const float ex = p[u].x - qc[0], ey = p[u].y - qc[1], ez = p[u].z - qc[2];
+                            h = h || ((ex * ex + ey * ey + ez * ez <= qr) && capt_member(t, q, p[u]));
+                        }
+                        if (rank == 0)
+                        {
+                            VMV_STAT(7, 1);
+                            VMV_STAT(8, min(ce - base, kCaptEnumLoads * gsize));
+                        }
+                        if (__any_sync(group, h))
+                        {
+                            found = true;
+                            break;
+                        }
+                    }
                 }
             }
-#ifdef VMV_C4_STATS
             if (rank == 0)
             {
-                const uint32_t len = n_read;  // points read by this scan (not the length of the list)
-                int b = 0;
-                while ((1u << (b + 5)) < len && b < 11)
-                {
-                    ++b;
-                }
-                VMV_STAT((found ? 16 : 28) + b, 1);  // list length buckets 32, 64, ... 64k: 16.. hits, 28.. no-hits
-                const float qrad = sqrtf(qr);
-                VMV_STAT(qrad < 0.05F ? 40 : (qrad < 0.1F ? 41 : (qrad < 0.2F ? 42 : 43)), 1);
-                VMV_STAT(qrad < 0.05F ? 44 : (qrad < 0.1F ? 45 : (qrad < 0.2F ? 46 : 47)), found ? 0 : 1);
+                VMV_STAT(9, found ? 1 : 0);
             }
-#endif
-#ifdef VMV_C4_STATS
-            if (rank == 0)
-            {
-                // histogram of list prefixes examined (log2 buckets of points), split by outcome
-                const uint32_t seen = min(e - s, static_cast<uint32_t>(per * gsize) * 64u);
-                (void)seen;
-            }
-#endif
             hit = (lane == src) ? found : hit;
         }
-#ifdef VMV_C4_STATS
-        if (rank == 0)
-        {
-            const long long t_end = clock64();
-            VMV_STAT(14, t_end - t_call);
-            VMV_STAT(15, t_end - t_scan);
-        }
-#endif
         return hit;
-    }
-
-    // ------------------------------------------------------------------------------------------
-    // Is the cloud point p -- the representative of leaf `pleaf` -- on the affordance list of the leaf the centre
-    // (x, y, z) descends to?  The reference's list construction (capt.hh:106-119 median split, :150-170 leaf step,
-    // :221-246 what each half inherits) evaluated for ONE point along the centre's root path:
-    //  * above the node where the two root paths part, p belongs to the subtree itself;
-    //  * at that node p sits in the sibling half.  The low half receives the points of the high half within r_max of
-    //    the plane.  The high half receives the low half's points only if the SMALLEST of them is within r_max of the
-    //    plane (the reference scans the sorted half from its first element while the predicate holds) -- one bit per
-    //    node, written by the build;
-    //  * below it p is an inherited candidate: kept on the side the centre takes while within r_max of every plane;
-    //  * at the leaf the candidate must lie within r_max + r_point of the cell -- implied (with the caller's margin) by
-    //    lying that close to the centre, which is inside the cell -- and the leaf must carry a list at all (a cell
-    //    inside the smallest query ball around its representative keeps the representative alone: one bit per leaf).
-    // The additions are the build's own float operations (test +- r_max), so the answer is the build's, bit for bit.
-    // ------------------------------------------------------------------------------------------
-    __device__ __forceinline__ bool capt_node_flag(const CaptRec &t, uint32_t idx)
-    {
-        return ((__ldg(t.flags + (idx >> 5)) >> (idx & 31u)) & 1u) != 0u;
-    }
-
-    __device__ __forceinline__ bool capt_lists_point(const CaptRec &t, float x, float y, float z, float px, float py, float pz, uint32_t pleaf)
-    {
-        uint32_t idx = 0;
-        int k = 0;
-        bool parted = false, ok = true;
-        for (uint32_t i = 0; i < t.nlog2; ++i)
-        {
-            const float split = __ldg(t.tests + idx);
-            const float v = (k == 0) ? x : ((k == 1) ? y : z);
-            const float pv = (k == 0) ? px : ((k == 1) ? py : pz);
-            const bool hi = v >= split;
-            const bool p_hi = ((pleaf >> (t.nlog2 - 1u - i)) & 1u) != 0u;
-            const bool within = hi ? (pv >= __fsub_rn(split, t.r_max)) : (pv <= __fadd_rn(split, t.r_max));
-            if (parted)
-            {
-                ok = ok && within;
-            }
-            else if (hi != p_hi)
-            {
-                parted = true;
-                ok = hi ? capt_node_flag(t, idx) : within;
-            }
-            idx = 2 * idx + 1 + (hi ? 1u : 0u);
-            k = (k == 2) ? 0 : k + 1;
-        }
-        return ok && (!parted || capt_node_flag(t, idx));
     }
 
     // ------------------------------------------------------------------------------------------
@@ -725,43 +754,21 @@ namespace vmv
     {
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
         bool hit = false;
+        float4 near = make_float4(0.F, 0.F, 0.F, 0.F);
+        uint32_t near_cloud = kCloudTagNone;  // the cloud the nearest-point table's entry belongs to
 #ifdef VMV_C4_STATS
         const long long t_probe = clock64();
 #endif
         if (H.off_cloud_grid != 0 && query)
         {
             const CloudGridRec &g = *reinterpret_cast<const CloudGridRec *>(E + H.off_cloud_grid);
-            float4 near;
             float clearance;
             const bool in = cloud_probe(g, x, y, z, near, clearance);
             // no cloud point within reach: every pointcloud query would answer "no"
             query = !(clearance > r_pc + g.r_point_max);
             VMV_STAT(2, 1);
             VMV_STAT(3, query ? 1 : 0);
-            const uint32_t tag = __float_as_uint(near.w);
-            if (in && query && (tag >> 24) < H.n_capts)
-            {
-                // the table's point within the query ball and on the list the query would scan: the scan finds it
-                const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * (tag >> 24));
-                const float rr = r_pc + t.r_point;
-                const float ex = near.x - x, ey = near.y - y, ez = near.z - z;
-                const float dsq = ex * ex + ey * ey + ez * ez;
-                // (margins: the comparison the scan makes is reproduced only where rounding cannot flip it)
-                const bool inside = (dsq <= rr * rr * 0.999998F) & (dsq <= t.list_reach_sq);
-                // top-level AABB reject uses r, not r + r_point (capt.hh:431-438)
-                const bool inb = (x + r_pc >= t.lo[0]) & (x - r_pc <= t.hi[0]) & (y + r_pc >= t.lo[1]) & (y - r_pc <= t.hi[1]) &
-                                 (z + r_pc >= t.lo[2]) & (z - r_pc <= t.hi[2]);
-                if (inside && inb && capt_lists_point(t, x, y, z, near.x, near.y, near.z, tag & 0xffffffu))
-                {
-                    hit = true;
-                    query = false;
-                    VMV_STAT(12, 1);
-                }
-                else if (inside && inb)
-                {
-                    VMV_STAT(13, 1);
-                }
-            }
+            near_cloud = (in && query) ? (__float_as_uint(near.w) >> 24) : kCloudTagNone;
         }
 #ifdef VMV_C4_STATS
         __syncwarp(__activemask());
@@ -774,7 +781,7 @@ namespace vmv
         {
             const CaptRec &t = *reinterpret_cast<const CaptRec *>(E + H.off_capts + kCaptRec * i);
             // lanes without a query keep the warp's loop structure (they help scanning)
-            if (capt_collides_warp(t, x, y, z, r_pc, query && !hit))
+            if (capt_collides_warp(t, x, y, z, r_pc, query && !hit, near, near_cloud == i))
             {
                 hit = true;
             }

@@ -186,21 +186,22 @@ namespace
     struct HCapt
     {
         float r_min, r_max, r_point;
+        float list_reach_sq = 0.F;            // (r_max + r_point)^2, the build's own float value
         int nlog2 = 0;
-        std::vector<float> tests;
-        std::vector<float> leaf_lo, leaf_hi;  // 3 floats per leaf
-        std::vector<uint32_t> leaf_start;     // per leaf + 1, in points
-        std::vector<float, NoInitAlloc<float>> points;  // per afforded point x, y, z, squared distance from the cell (representative first)
+        uint32_t n_points = 0;
+        std::vector<float> nodes;             // per internal node (Eytzinger) {split, bit pattern 1 = the high half inherited the low half}
+        std::vector<uint32_t> leafbits;       // two bits per leaf: 1 = list beyond the representative, 2 = representative finite
+        std::vector<uint32_t> leaf_of_point;  // per input point, until the environment has taken it over
         float top_lo[3], top_hi[3];
+        // enumeration grid over the finite points (vmv_device.cuh: capt_collides_warp)
+        std::vector<float> gpts;              // {x y z leaf} in Morton order of the finest cell
+        std::vector<uint32_t> gstart;         // kCaptGridLevels start tables
+        float g_origin[3] = {0.F, 0.F, 0.F}, g_inv0 = 1.F, g_cell0 = 1.F;
         int id;
-        // what vmv::capt_lists_point needs: one bit per Eytzinger node (internal: the high half inherited the low half's
-        // points; leaf: the leaf carries a list beyond its representative), and the leaf every input point represents
-        std::vector<uint32_t> flags;
-        std::vector<uint32_t> leaf_of_point;
-        float *d_tests = nullptr;
-        float4 *d_aabbs = nullptr;
-        float4 *d_points = nullptr;
-        uint32_t *d_flags = nullptr;
+        float2 *d_nodes = nullptr;
+        uint32_t *d_leafbits = nullptr;
+        float4 *d_gpts = nullptr;
+        uint32_t *d_gstart = nullptr;
     };
 
     // Multi-level Voxel Table, host build (reference collision/mvt.hh:146-170, 437-446, 531-604)
@@ -325,43 +326,19 @@ namespace
     }
 
     // -- CAPT build -------------------------------------------------------------------------
+    // The k-d tree of the reference (capt.hh:106-119: median splits on x, y, z in turn over 2^nlog2 points, the input
+    // padded with +inf) and, per node, the ONE fact about the reference's affordance lists that is not a function of
+    // the split planes: whether the high half was handed the low half's points (capt.hh:232-246 scans the sorted half
+    // from its first element while the predicate holds, so it is all or nothing).  The lists themselves are never
+    // built: vmv::capt_member evaluates membership per point at query time.
     struct Vol
     {
         float lo[3], hi[3];
-        float distsq(const float *p) const
-        {
-            float s = 0.F;
-            for (int k = 0; k < 3; ++k)
-            {
-                const float d = p[k] - std::min(std::max(p[k], lo[k]), hi[k]);
-                s += d * d;
-            }
-            return s;
-        }
-        void extend(const float *p)
-        {
-            for (int k = 0; k < 3; ++k)
-            {
-                lo[k] = std::min(lo[k], p[k]);
-                hi[k] = std::max(hi[k], p[k]);
-            }
-        }
-    };
-
-    // Output of one subtree: leaves in left-to-right order.  The top levels of the tree are split on the
-    // calling thread, the subtrees below kCaptTaskDepth are independent tasks for the host's threads
-    // (disjoint ranges of `argsort` and `tests`), and their fragments are stitched in task order.
-    struct CaptFragment
-    {
-        std::vector<float> leaf_lo, leaf_hi, points;
-        std::vector<uint32_t> leaf_end;  // per leaf, in points, relative to this fragment
-        float top_lo[3], top_hi[3];
     };
 
     struct CaptTask
     {
         uint32_t begin, count, i;
-        std::vector<uint32_t> afford;
         Vol vol;
         int d;
     };
@@ -373,66 +350,32 @@ namespace
         HCapt &t;
         const std::vector<float> &pts;  // padded to 2^nlog2 points with +inf
         std::vector<uint32_t> &argsort;
-        float max_l2, min_l2;
-        CaptFragment *out;                              // leaves of this builder go here
-        std::vector<CaptTask> *tasks;                   // non-null: collect subtrees at kCaptTaskDepth
-        std::vector<uint8_t> &node_flag;                // per Eytzinger node, leaves included (HCapt::flags, one byte each while building)
-        std::vector<std::pair<float, uint32_t>> near;  // scratch of the leaf step
+        float min_l2;
+        std::vector<CaptTask> *tasks;        // non-null: collect subtrees at kCaptTaskDepth
+        std::vector<uint8_t> &leaf_flag;     // per leaf, bit 0: full list, bit 1: finite
 
-        void subdivide(uint32_t begin, uint32_t count, uint32_t i, std::vector<uint32_t> afford, Vol vol, int d, int depth)
+        void subdivide(uint32_t begin, uint32_t count, uint32_t i, Vol vol, int d, int depth)
         {
             if (tasks != nullptr && depth == kCaptTaskDepth && count > 1)
             {
-                tasks->push_back(CaptTask{begin, count, i, std::move(afford), vol, d});
+                tasks->push_back(CaptTask{begin, count, i, vol, d});
                 return;
             }
             if (count == 1)
             {
                 const float *rep = &pts[3 * argsort[begin]];
-                Vol aabb{{rep[0], rep[1], rep[2]}, {rep[0], rep[1], rep[2]}};
                 if (std::isfinite(rep[0]))
                 {
-                    for (int k = 0; k < 3; ++k)
-                    {
-                        out->top_lo[k] = std::min(out->top_lo[k], rep[k]);
-                        out->top_hi[k] = std::max(out->top_hi[k], rep[k]);
-                    }
-                    out->points.insert(out->points.end(), {rep[0], rep[1], rep[2], 0.F});
-                    t.leaf_of_point[argsort[begin]] = begin;  // leaves are numbered left to right, as the sorted range is
+                    // leaves are numbered left to right, as the sorted range is
+                    t.leaf_of_point[argsort[begin]] = begin;
                     // cell entirely inside the smallest query ball around its representative:
                     // the representative alone decides (capt.hh:39-46,150)
                     const float d0 = std::max(rep[0] - vol.lo[0], vol.hi[0] - rep[0]);
                     const float d1 = std::max(rep[1] - vol.lo[1], vol.hi[1] - rep[1]);
                     const float d2 = std::max(rep[2] - vol.lo[2], vol.hi[2] - rep[2]);
-                    if (!((d0 * d0 + d1 * d1 + d2 * d2) <= min_l2))
-                    {
-                        node_flag[i] = 1;
-                        // Same set of afforded points as the reference's list (capt.hh:150-170), but
-                        // ordered by their squared distance from the cell, which is kept in .w: a query
-                        // centre lies inside the cell it descends to, so a point farther from the cell
-                        // than the query radius cannot be within it and the device scan stops there.
-                        near.clear();
-                        for (const uint32_t id : afford)
-                        {
-                            const float *p = &pts[3 * id];
-                            const float dsq = vol.distsq(p);
-                            if (dsq <= max_l2)
-                            {
-                                aabb.extend(p);
-                                near.emplace_back(dsq, id);
-                            }
-                        }
-                        std::stable_sort(near.begin(), near.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
-                        for (const auto &[dsq, id] : near)
-                        {
-                            const float *p = &pts[3 * id];
-                            out->points.insert(out->points.end(), {p[0], p[1], p[2], dsq});
-                        }
-                    }
+                    const bool rep_only = (d0 * d0 + d1 * d1 + d2 * d2) <= min_l2;
+                    leaf_flag[begin] = static_cast<uint8_t>(2 | (rep_only ? 0 : 1));
                 }
-                out->leaf_lo.insert(out->leaf_lo.end(), aabb.lo, aabb.lo + 3);
-                out->leaf_hi.insert(out->leaf_hi.end(), aabb.hi, aabb.hi + 3);
-                out->leaf_end.push_back(static_cast<uint32_t>(out->points.size() / 4));
                 return;
             }
 
@@ -441,51 +384,22 @@ namespace
                 argsort.begin() + begin,
                 argsort.begin() + begin + count,
                 [&](uint32_t a, uint32_t b) { return pts[3 * a + d] < pts[3 * b + d]; });
-            const uint32_t middle = begin + count / 2;
+            const uint32_t half = count / 2, middle = begin + half;
             const float test = static_cast<float>((pts[3 * argsort[middle - 1] + d] + pts[3 * argsort[middle] + d]) / 2.0);
-            t.tests[i] = test;
+            // the high half inherits the low half iff the low half's smallest element is within r_max of the plane
+            const float first = pts[3 * argsort[begin] + d];
+            const uint32_t inherited = (first >= test - t.r_max && std::isfinite(first)) ? 1u : 0u;
+            float inherited_f;
+            std::memcpy(&inherited_f, &inherited, 4);
+            t.nodes[2 * i] = test;
+            t.nodes[2 * i + 1] = inherited_f;
 
-            const uint32_t half = count / 2;
             Vol lo_vol = vol, hi_vol = vol;
             lo_vol.hi[d] = test;
             hi_vol.lo[d] = test;
-
-            std::vector<uint32_t> lo_afford, hi_afford;
-            lo_afford.reserve(afford.size() + half);
-            hi_afford.reserve(afford.size() + half);
-            for (const uint32_t idx : afford)
-            {
-                if (pts[3 * idx + d] <= test + t.r_max)
-                {
-                    lo_afford.push_back(idx);
-                }
-                if (pts[3 * idx + d] >= test - t.r_max)
-                {
-                    hi_afford.push_back(idx);
-                }
-            }
-            // points of the sibling half that may reach into this half: the reference scans each
-            // half from its FIRST (smallest) element while the predicate holds (capt.hh:232-246)
-            uint32_t new_hi = begin, new_lo = begin + half;
-            while (new_hi < begin + half && pts[3 * argsort[new_hi] + d] >= test - t.r_max &&
-                   std::isfinite(pts[3 * argsort[new_hi] + d]))
-            {
-                ++new_hi;
-            }
-            while (new_lo < begin + count && pts[3 * argsort[new_lo] + d] <= test + t.r_max &&
-                   std::isfinite(pts[3 * argsort[new_lo] + d]))
-            {
-                ++new_lo;
-            }
-            node_flag[i] = new_hi > begin ? 1 : 0;  // all or nothing: the scan starts at the half's smallest element
-            hi_afford.insert(hi_afford.end(), argsort.begin() + begin, argsort.begin() + new_hi);
-            lo_afford.insert(lo_afford.end(), argsort.begin() + begin + half, argsort.begin() + new_lo);
-            afford.clear();
-            afford.shrink_to_fit();
-
             const int nd = (d + 1) % 3;
-            subdivide(begin, half, 2 * i + 1, std::move(lo_afford), lo_vol, nd, depth + 1);
-            subdivide(begin + half, half, 2 * i + 2, std::move(hi_afford), hi_vol, nd, depth + 1);
+            subdivide(begin, half, 2 * i + 1, lo_vol, nd, depth + 1);
+            subdivide(begin + half, half, 2 * i + 2, hi_vol, nd, depth + 1);
         }
     };
 
@@ -493,6 +407,8 @@ namespace
     {
         t.r_min = r_min, t.r_max = r_max, t.r_point = r_point;
         const float max_l1 = r_max + r_point;
+        t.list_reach_sq = max_l1 * max_l1;
+        t.n_points = static_cast<uint32_t>(n);
         t.nlog2 = 0;
         while ((size_t(1) << t.nlog2) < n)
         {
@@ -502,37 +418,19 @@ namespace
         const float inf = std::numeric_limits<float>::infinity();
         std::vector<float> pts(points, points + 3 * n);
         pts.resize(3 * pow2, inf);
-        for (int k = 0; k < 3; ++k)
-        {
-            t.top_lo[k] = inf;
-            t.top_hi[k] = -inf;
-        }
-        t.tests.assign(pow2 - 1, std::numeric_limits<float>::quiet_NaN());
-        std::vector<uint8_t> node_flag(2 * pow2 - 1, 0);
+        t.nodes.assign(2 * (pow2 - 1), 0.F);
         t.leaf_of_point.assign(pow2, 0u);
-        t.leaf_start.assign(1, 0);
-        t.leaf_lo.clear(), t.leaf_hi.clear(), t.points.clear();
+        std::vector<uint8_t> leaf_flag(pow2, 0);
         std::vector<uint32_t> argsort(pow2);
         std::iota(argsort.begin(), argsort.end(), 0u);
-        const float max_l2 = max_l1 * max_l1, min_l2 = (r_min + r_point) * (r_min + r_point);
-        auto fresh = [&](CaptFragment &f)
-        {
-            for (int k = 0; k < 3; ++k)
-            {
-                f.top_lo[k] = inf;
-                f.top_hi[k] = -inf;
-            }
-        };
-        // top levels here (a tree shallower than kCaptTaskDepth ends up entirely in `head`)
-        CaptFragment head;
-        fresh(head);
+        const float min_l2 = (r_min + r_point) * (r_min + r_point);
+        // top levels here (a tree shallower than kCaptTaskDepth is done entirely by this call)
         std::vector<CaptTask> tasks;
         const auto tm0 = std::chrono::steady_clock::now();
-        CaptBuilder top{t, pts, argsort, max_l2, min_l2, &head, &tasks, node_flag, {}};
-        top.subdivide(0, static_cast<uint32_t>(pow2), 0, {}, Vol{{-inf, -inf, -inf}, {inf, inf, inf}}, 0, 0);
-        const auto tm1 = std::chrono::steady_clock::now();
-        std::vector<CaptFragment> frags(tasks.size());
+        CaptBuilder top{t, pts, argsort, min_l2, &tasks, leaf_flag};
+        top.subdivide(0, static_cast<uint32_t>(pow2), 0, Vol{{-inf, -inf, -inf}, {inf, inf, inf}}, 0, 0);
         {
+            // the subtrees: disjoint ranges of `argsort`, `nodes`, `leaf_flag`
             std::atomic<size_t> next{0};
             std::atomic<bool> failed{false};  // an exception must not leave a worker thread (std::terminate)
             auto work = [&]()
@@ -541,10 +439,9 @@ namespace
                 {
                     for (size_t k = next.fetch_add(1); k < tasks.size() && !failed.load(); k = next.fetch_add(1))
                     {
-                        fresh(frags[k]);
-                        CaptBuilder b{t, pts, argsort, max_l2, min_l2, &frags[k], nullptr, node_flag, {}};
-                        CaptTask &task = tasks[k];
-                        b.subdivide(task.begin, task.count, task.i, std::move(task.afford), task.vol, task.d, kCaptTaskDepth);
+                        CaptBuilder b{t, pts, argsort, min_l2, nullptr, leaf_flag};
+                        const CaptTask &task = tasks[k];
+                        b.subdivide(task.begin, task.count, task.i, task.vol, task.d, kCaptTaskDepth);
                     }
                 }
                 catch (...)
@@ -569,78 +466,102 @@ namespace
                 throw std::bad_alloc();  // becomes an error code at the ABI (guarded)
             }
         }
-        const auto tm2 = std::chrono::steady_clock::now();
-        if (std::getenv("VMV_CAPT_TIMING"))
-        {
-            std::fprintf(stderr, "capt_build: top %.2f s, subtrees %.2f s\n", std::chrono::duration<double>(tm1 - tm0).count(),
-                         std::chrono::duration<double>(tm2 - tm1).count());
-        }
         t.leaf_of_point.resize(n);
-        t.flags.assign((node_flag.size() + 31) / 32, 0u);
-        for (size_t k = 0; k < node_flag.size(); ++k)
+        t.leafbits.assign((pow2 + 15) / 16, 0u);
+        for (size_t k = 0; k < pow2; ++k)
         {
-            t.flags[k >> 5] |= node_flag[k] ? (1u << (k & 31)) : 0u;
+            t.leafbits[k >> 4] |= static_cast<uint32_t>(leaf_flag[k]) << (2 * (k & 15));
         }
-        // stitch: either everything is in `head` (no tasks) or every leaf is in a task fragment
-        std::vector<CaptFragment *> order{&head};
-        for (CaptFragment &f : frags)
+
+        // the finite points: their box, and the enumeration grid
+        for (int k = 0; k < 3; ++k)
         {
-            order.push_back(&f);
+            t.top_lo[k] = inf;
+            t.top_hi[k] = -inf;
         }
-        std::vector<size_t> at(order.size() + 1, 0);
-        for (size_t k = 0; k < order.size(); ++k)
+        std::vector<uint32_t> finite;
+        for (uint32_t k = 0; k < n; ++k)
         {
-            at[k + 1] = at[k] + order[k]->points.size();
-        }
-        t.points.resize(at.back());  // uninitialised (NoInitAlloc)
-        for (size_t k = 0; k < order.size(); ++k)
-        {
-            const CaptFragment &f = *order[k];
-            const uint32_t base = static_cast<uint32_t>(at[k] / 4);
-            t.leaf_lo.insert(t.leaf_lo.end(), f.leaf_lo.begin(), f.leaf_lo.end());
-            t.leaf_hi.insert(t.leaf_hi.end(), f.leaf_hi.begin(), f.leaf_hi.end());
-            for (const uint32_t e : f.leaf_end)
+            const float *p = points + 3 * size_t(k);
+            // (the tree's leaf step looks at x alone, capt.hh:150; a point with a non-finite y or z can never be within a
+            // finite distance of anything, so it is left out of the grid as well)
+            if (std::isfinite(p[0]))
             {
-                t.leaf_start.push_back(base + e);
+                for (int c = 0; c < 3; ++c)
+                {
+                    t.top_lo[c] = std::min(t.top_lo[c], p[c]);
+                    t.top_hi[c] = std::max(t.top_hi[c], p[c]);
+                }
+                if (std::isfinite(p[1]) && std::isfinite(p[2]))
+                {
+                    finite.push_back(k);
+                }
             }
+        }
+        constexpr int kDim = 1 << vmv::kCaptGridBits;
+        float ext = 0.F;
+        float glo[3] = {0.F, 0.F, 0.F};
+        for (const uint32_t k : finite)
+        {
             for (int c = 0; c < 3; ++c)
             {
-                t.top_lo[c] = std::min(t.top_lo[c], f.top_lo[c]);
-                t.top_hi[c] = std::max(t.top_hi[c], f.top_hi[c]);
+                glo[c] = (k == finite[0]) ? points[3 * size_t(k) + c] : std::min(glo[c], points[3 * size_t(k) + c]);
             }
         }
+        for (const uint32_t k : finite)
         {
-            // the point lists (GBs for a wide r_max) are copied by all threads, fragments released as they go
-            std::atomic<size_t> next{0};
-            auto copy = [&]()
+            for (int c = 0; c < 3; ++c)
             {
-                for (size_t k = next.fetch_add(1); k < order.size(); k = next.fetch_add(1))
-                {
-                    std::vector<float> &src = order[k]->points;
-                    if (!src.empty())
-                    {
-                        std::memcpy(t.points.data() + at[k], src.data(), src.size() * sizeof(float));
-                    }
-                    std::vector<float>().swap(src);
-                }
-            };
-            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-            const size_t n_threads = std::min<size_t>({order.size(), hw, 16});
-            std::vector<std::thread> pool;
-            for (size_t k = 1; k < n_threads; ++k)
-            {
-                pool.emplace_back(copy);
+                ext = std::max(ext, points[3 * size_t(k) + c] - glo[c]);
             }
-            copy();
-            for (auto &th : pool)
+        }
+        t.g_cell0 = std::max(0.04F, ext / (kDim - 0.5F));
+        t.g_inv0 = 1.F / t.g_cell0;
+        for (int c = 0; c < 3; ++c)
+        {
+            t.g_origin[c] = glo[c];
+        }
+        std::vector<std::pair<uint32_t, uint32_t>> keys(finite.size());
+        for (size_t k = 0; k < finite.size(); ++k)
+        {
+            uint32_t cell[3];
+            for (int c = 0; c < 3; ++c)
             {
-                th.join();
+                // the device derives cell ranges from the same expression (vmv_device.cuh)
+                const float a = (points[3 * size_t(finite[k]) + c] - t.g_origin[c]) * t.g_inv0;
+                cell[c] = static_cast<uint32_t>(std::max(0, std::min(kDim - 1, static_cast<int>(std::floor(a)))));
+            }
+            keys[k] = {vmv::morton_spread(cell[0]) | (vmv::morton_spread(cell[1]) << 1) | (vmv::morton_spread(cell[2]) << 2), finite[k]};
+        }
+        std::sort(keys.begin(), keys.end());
+        t.gpts.resize(4 * keys.size());
+        for (size_t k = 0; k < keys.size(); ++k)
+        {
+            const uint32_t id = keys[k].second;
+            float leaf;
+            std::memcpy(&leaf, &t.leaf_of_point[id], 4);
+            t.gpts[4 * k] = points[3 * size_t(id)], t.gpts[4 * k + 1] = points[3 * size_t(id) + 1], t.gpts[4 * k + 2] = points[3 * size_t(id) + 2];
+            t.gpts[4 * k + 3] = leaf;
+        }
+        t.gstart.assign(vmv::capt_grid_offset(vmv::kCaptGridLevels), 0u);
+        for (int l = 0; l < vmv::kCaptGridLevels; ++l)
+        {
+            uint32_t *st = t.gstart.data() + vmv::capt_grid_offset(l);
+            const uint32_t cells = 1u << (3 * (vmv::kCaptGridBits - l));
+            size_t at = 0;
+            for (uint32_t m = 0; m <= cells; ++m)
+            {
+                while (at < keys.size() && (keys[at].first >> (3 * l)) < m)
+                {
+                    ++at;
+                }
+                st[m] = static_cast<uint32_t>(at);
             }
         }
         if (std::getenv("VMV_CAPT_TIMING"))
         {
-            std::fprintf(stderr, "capt_build: %zu points, %zu tasks, %zu afforded entries (%.1f MB)\n", n, tasks.size(), t.points.size() / 4,
-                         t.points.size() * 4 / 1e6);
+            std::fprintf(stderr, "capt_build: %zu points (%zu finite), %zu subtrees, %.3f s\n", n, finite.size(), tasks.size(),
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - tm0).count());
         }
     }
 }  // namespace
@@ -1041,43 +962,27 @@ namespace
         }
         for (auto &t : env->capts)
         {
-            int rc = upload(env, t.tests, t.d_tests);
+            float *dn = nullptr, *dp = nullptr;
+            int rc = upload(env, t.nodes, dn);
             if (rc == VMV_OK)
             {
-                rc = upload(env, t.flags, t.d_flags);
+                rc = upload(env, t.leafbits, t.d_leafbits);
+            }
+            if (rc == VMV_OK)
+            {
+                rc = upload(env, t.gpts, dp);
+            }
+            if (rc == VMV_OK)
+            {
+                rc = upload(env, t.gstart, t.d_gstart);
             }
             if (rc != VMV_OK)
             {
                 return rc;
             }
-            const size_t leaves = t.leaf_start.size() - 1;
-            std::vector<float4> aabbs(2 * leaves);
-            for (size_t z = 0; z < leaves; ++z)
-            {
-                float s, e;
-                const uint32_t us = t.leaf_start[z], ue = t.leaf_start[z + 1];
-                std::memcpy(&s, &us, 4);
-                std::memcpy(&e, &ue, 4);
-                aabbs[2 * z] = make_float4(t.leaf_lo[3 * z], t.leaf_lo[3 * z + 1], t.leaf_lo[3 * z + 2], t.leaf_hi[3 * z]);
-                aabbs[2 * z + 1] = make_float4(t.leaf_hi[3 * z + 1], t.leaf_hi[3 * z + 2], s, e);
-            }
-            rc = upload(env, aabbs, t.d_aabbs);
-            if (rc != VMV_OK)
-            {
-                return rc;
-            }
-            {
-                // straight from the build's array (GBs for a wide r_max: no staging copy)
-                float *dp = nullptr;
-                rc = upload(env, t.points, dp);
-                t.d_points = reinterpret_cast<float4 *>(dp);
-            }
-            if (rc != VMV_OK)
-            {
-                return rc;
-            }
+            t.d_nodes = reinterpret_cast<float2 *>(dn);
+            t.d_gpts = reinterpret_cast<float4 *>(dp);
         }
-
         for (auto &t : env->mvts)
         {
             int rc = upload(env, t.cells, t.d_cells);
@@ -1163,21 +1068,22 @@ namespace
             vmv::CaptRec r{};
             r.r_point = t.r_point;
             r.nlog2 = static_cast<uint32_t>(t.nlog2);
-            r.n_tests = static_cast<uint32_t>(t.tests.size());
+            r.n_tests = static_cast<uint32_t>(t.nodes.size() / 2);
+            r.n_points = t.n_points;
             for (int k = 0; k < 3; ++k)
             {
                 r.lo[k] = t.top_lo[k];
                 r.hi[k] = t.top_hi[k];
+                r.g_origin[k] = t.g_origin[k];
             }
             r.r_max = t.r_max;
-            {
-                const float reach = t.r_max + t.r_point;
-                r.list_reach_sq = reach * reach * 0.99999F;
-            }
-            r.tests = t.d_tests;
-            r.aabbs = t.d_aabbs;
-            r.points = t.d_points;
-            r.flags = t.d_flags;
+            r.list_reach_sq = t.list_reach_sq;
+            r.g_inv0 = t.g_inv0;
+            r.g_cell0 = t.g_cell0;
+            r.nodes = t.d_nodes;
+            r.leafbits = t.d_leafbits;
+            r.gpts = t.d_gpts;
+            r.gstart = t.d_gstart;
             const uint32_t *w = reinterpret_cast<const uint32_t *>(&r);
             B.insert(B.end(), w, w + vmv::kCaptRec);
         }
@@ -1888,12 +1794,16 @@ extern "C"
             {
                 return fail(VMV_ERR_ARG, "vmv_env_add_capt: null argument");
             }
+            if (n > (size_t(1) << 24))
+            {
+                return fail(VMV_ERR_LIMIT, "vmv_env_add_capt: more than 2^24 points in one pointcloud");
+            }
             HCapt t;
             capt_build(t, pts, n, r_min, r_max, r_point);
             t.id = env->next_id++;
             {
                 const size_t cloud = env->capts.size();
-                const bool taggable = cloud < vmv::kCloudTagNone && t.nlog2 <= 24;
+                const bool taggable = cloud < vmv::kCloudTagNone;
                 for (size_t k = 0; k < n; ++k)
                 {
                     env->cloud_tag.push_back(taggable ? (static_cast<uint32_t>(cloud) << 24 | t.leaf_of_point[k]) : (vmv::kCloudTagNone << 24));
@@ -3843,8 +3753,9 @@ extern "C"
                 w.pod<uint64_t>(env->capts.size());
                 for (const auto &t : env->capts)
                 {
-                    w.pod(t.r_min), w.pod(t.r_max), w.pod(t.r_point), w.pod(t.nlog2), w.pod(t.top_lo), w.pod(t.top_hi), w.pod(t.id);
-                    w.vec(t.tests), w.vec(t.leaf_lo), w.vec(t.leaf_hi), w.vec(t.leaf_start), w.vec(t.points), w.vec(t.flags);
+                    w.pod(t.r_min), w.pod(t.r_max), w.pod(t.r_point), w.pod(t.list_reach_sq), w.pod(t.nlog2), w.pod(t.n_points), w.pod(t.top_lo), w.pod(t.top_hi);
+                    w.pod(t.g_origin), w.pod(t.g_inv0), w.pod(t.g_cell0), w.pod(t.id);
+                    w.vec(t.nodes), w.vec(t.leafbits), w.vec(t.gpts), w.vec(t.gstart);
                 }
                 w.pod<uint64_t>(env->mvts.size());
                 for (const auto &t : env->mvts)
@@ -3905,8 +3816,9 @@ extern "C"
                 env->capts.resize(r.ok ? k : 0);
                 for (auto &t : env->capts)
                 {
-                    r.pod(t.r_min), r.pod(t.r_max), r.pod(t.r_point), r.pod(t.nlog2), r.pod(t.top_lo), r.pod(t.top_hi), r.pod(t.id);
-                    r.vec(t.tests), r.vec(t.leaf_lo), r.vec(t.leaf_hi), r.vec(t.leaf_start), r.vec(t.points), r.vec(t.flags);
+                    r.pod(t.r_min), r.pod(t.r_max), r.pod(t.r_point), r.pod(t.list_reach_sq), r.pod(t.nlog2), r.pod(t.n_points), r.pod(t.top_lo), r.pod(t.top_hi);
+                    r.pod(t.g_origin), r.pod(t.g_inv0), r.pod(t.g_cell0), r.pod(t.id);
+                    r.vec(t.nodes), r.vec(t.leafbits), r.vec(t.gpts), r.vec(t.gstart);
                 }
                 r.pod(k);
                 env->mvts.clear();
