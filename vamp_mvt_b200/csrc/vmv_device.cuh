@@ -104,7 +104,9 @@ namespace vmv
 
     // The table entry of the voxel (x, y, z) lies in and the clearance bound it gives; false = outside the table
     // (near: untouched, clearance: the table's bound for the outside, 0 for a centre that is not finite).
-    __device__ __forceinline__ bool cloud_probe(const CloudGridRec &g, float x, float y, float z, float4 &near, float &clearance)
+    // (not inlined, like the other per-link environment tests below: the any-environment kernels call them once per link
+    // from straight-line code and are bound by instruction fetch)
+    static __device__ __noinline__ bool cloud_probe(const CloudGridRec &g, float x, float y, float z, float4 &near, float &clearance)
     {
         const float fx = (x - g.x0) * g.inv_h, fy = (y - g.y0) * g.inv_h, fz = (z - g.z0) * g.inv_h;
         const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
@@ -383,15 +385,19 @@ namespace vmv
     // Called by whichever lanes of the warp currently have a query (the converged group, __activemask()); `active`
     // false = the lane has nothing to ask but helps.  `near` / `has_near`: this cloud's point from the nearest-point
     // table for the lane's position.
-    __device__ __forceinline__ bool
+    // (not inlined: the any-environment kernels call it from two places and are bound by instruction fetch as it is)
+    static __device__ __noinline__ bool
     capt_collides_warp(const CaptRec &t, float x, float y, float z, float r, bool active, const float4 &near, bool has_near)
     {
         const uint32_t group = __activemask();
         const int lane = threadIdx.x & 31;
         const int rank = __popc(group & ((1u << lane) - 1u));  // position of this lane inside the group
         const int gsize = __popc(group);
-        CaptCell c;
+        CaptCell c = {};
         bool need = false, hit = false;
+#ifdef VMV_C4_STATS
+        const long long t_call = clock64();
+#endif
         const float rr = r + t.r_point;
         const float rc_sq = rr * rr;
         if (active)
@@ -422,6 +428,14 @@ namespace vmv
         }
 
         uint32_t pending = __ballot_sync(group, need);
+#ifdef VMV_C4_STATS
+        const long long t_enum = clock64();
+        if (rank == 0)
+        {
+            VMV_STAT(11, 1);
+            VMV_STAT(10, gsize);
+        }
+#endif
         while (pending != 0u)
         {
             const int src = __ffs(pending) - 1;
@@ -498,6 +512,12 @@ namespace vmv
                     }
                 }
                 uint32_t have = __ballot_sync(group, e > s);
+                if (rank == 0)
+                {
+                    VMV_STAT(16, 1);              // cell-lookup rounds
+                    VMV_STAT(17, __popc(have));   // cells with points, inside the ball's reach
+                    VMV_STAT(18, n_cells);
+                }
                 while (have != 0u && !found)
                 {
                     const int cl = __ffs(have) - 1;
@@ -539,6 +559,14 @@ namespace vmv
             }
             hit = (lane == src) ? found : hit;
         }
+#ifdef VMV_C4_STATS
+        if (rank == 0)
+        {
+            const long long t_end = clock64();
+            VMV_STAT(14, t_end - t_call);
+            VMV_STAT(15, t_end - t_enum);
+        }
+#endif
         return hit;
     }
 
@@ -614,7 +642,7 @@ namespace vmv
     // r_pc is the radius used for pointcloud queries (see check_state: a link's bounding sphere is
     // queried with its exact, un-inflated radius there).
     // heightfields for one sphere (reference collision/sphere_heightfield.hh:9-30); no warp-level operations
-    __device__ __forceinline__ bool sphere_hits_heightfields(const float *__restrict__ E, float x, float y, float z, float r)
+    static __device__ __noinline__ bool sphere_hits_heightfields(const float *__restrict__ E, float x, float y, float z, float r)
     {
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
         for (uint32_t i = 0; i < H.n_heightfields; ++i)

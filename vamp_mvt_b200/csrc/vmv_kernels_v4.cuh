@@ -985,6 +985,7 @@ namespace vmv
                 // hand out up to 4 rake blocks: round r takes the r-th pending block of every live edge
                 const int rem = dead ? 0 : steps - next;
                 int n_slots = 0, got = 0, owner = 0, round = 0;
+#pragma unroll 1
                 for (int r = 0; n_slots < 4; ++r)
                 {
                     uint32_t m = __ballot_sync(kFullWarp, rem > r);
@@ -992,6 +993,7 @@ namespace vmv
                     {
                         break;
                     }
+#pragma unroll 1
                     while (m != 0u && n_slots < 4)
                     {
                         const int o = __ffs(static_cast<int>(m)) - 1;
@@ -1014,18 +1016,30 @@ namespace vmv
                 next += got;
                 float cfg[M::kDof];
                 {
+                    float bk[M::kDof];
 #pragma unroll
                     for (int j = 0; j < M::kDof; ++j)
                     {
                         const float v = __shfl_sync(kFullWarp, vec[j], owner);
                         const float st = __shfl_sync(kFullWarp, start[j], owner);
-                        const float bk = __shfl_sync(kFullWarp, back[j], owner);
-                        float c = fmaf(v, pct, st);
-                        for (int k = 0; k < step; ++k)
+                        bk[j] = __shfl_sync(kFullWarp, back[j], owner);
+                        cfg[j] = fmaf(v, pct, st);
+                    }
+                    // (one rolled loop over the steps: unrolled per joint this was 8 KB of a kernel that is bound by
+                    // instruction fetch -- the body is past the 32 KB instruction cache, profiles/r2_edges_v1)
+#pragma unroll 1
+                    for (int k = 0; k < step; ++k)
+                    {
+#pragma unroll
+                        for (int j = 0; j < M::kDof; ++j)
                         {
-                            c = __fsub_rn(c, bk);
+                            cfg[j] = __fsub_rn(cfg[j], bk[j]);
                         }
-                        cfg[j] = has ? c : 0.F;
+                    }
+#pragma unroll
+                    for (int j = 0; j < M::kDof; ++j)
+                    {
+                        cfg[j] = has ? cfg[j] : 0.F;
                     }
                 }
                 const uint32_t invalid = v4_pass<R, MaskT, TAB, false>(X, env.grid, env.tab, cfg, has);
