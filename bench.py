@@ -656,7 +656,7 @@ def main() -> int:
                     cd = cnt4.as_dict()
                     by = (algorithmic_cloud_bytes(cd, nlog2) / nsc + R.dimension() * 4 + 1 / 8)
                     cap = captured_all.get(f"c4_{rb}", {})
-                    # The kernel is bound by the latency of dependent loads (tree descents, affordance-list scans), not by
+                    # The kernel is bound by the latency of dependent loads (tree descents, point enumeration) and by instruction fetch, not by
                     # bandwidth: `achieved` is the HBM traffic ncu measured for this kernel on this workload per launch
                     # (profiles/) over the live kernel time, i.e. the honest position against the HBM roof; the bytes the
                     # REFERENCE's control flow would read from its tree for the same queries are given next to it.
@@ -674,8 +674,8 @@ def main() -> int:
                                        "sm_cycles_active_min_avg_max": cap.get("sm_cycles_active_min_avg_max"),
                                        "kernel": cap.get("kernel"),
                                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "B200_PROFILING.md fallback",
-                                       "note": "latency-bound: issue slots ~20 % busy, DRAM ~1.5 % of peak (ncu); achieved = measured DRAM bytes per "
-                                               "launch / kernel time; the minimum algorithmic traffic is 4*dof B in + 1 bit out per configuration"}
+                                       "note": "latency- and instruction-fetch-bound: issue slots 25-34 % busy, DRAM ~1 % of peak (ncu); achieved = measured "
+                                               "DRAM bytes per launch / kernel time; the minimum algorithmic traffic is 4*dof B in + 1 bit out per configuration"}
                 c4[rb] = blk
             except Exception as ex:
                 c4[rb] = {"error": repr(ex)}

@@ -289,7 +289,9 @@ namespace vmv
     // ------------------------------------------------------------------------------------------
     static constexpr int kCaptGridBits = 7;    // finest level: 128 cells per axis
     static constexpr int kCaptGridLevels = 5;  // cell edge g0 * 2^l
-    static constexpr uint32_t kCaptEnumLoads = 4;
+    // independent 128-bit loads per lane and step of the enumeration (measured on BASELINE config 4: 2 -> Fetch 0.578 /
+    // UR5 0.452 ms, 4 -> 0.621 / 0.473, 8 -> 0.759 / 0.602: cells hold a few dozen points, wider steps load padding)
+    static constexpr uint32_t kCaptEnumLoads = 2;
 
     __host__ __device__ __forceinline__ uint32_t capt_grid_offset(int level)
     {
@@ -462,10 +464,13 @@ namespace vmv
                 empty = empty || (blo[k] > bhi[k]);
                 ext = fmaxf(ext, bhi[k] - blo[k]);
             }
-            // the level at which the box is at most four cells wide
+            // the level at which the box is at most four (six) cells wide
             int level = 0;
             float inv = t.g_inv0;
-            while (level < kCaptGridLevels - 1 && ext * inv > 3.F)
+                        // (wide boxes -- a link's bounding sphere in a big free-space cell -- take finer cells, six across: fewer
+            // points outside the ball are read; measured against a fixed span of 3 and of 5 on BASELINE config 4)
+            const float span = ext > 0.25F ? 5.F : 3.F;
+            while (level < kCaptGridLevels - 1 && ext * inv > span)
             {
                 ++level;
                 inv *= 0.5F;
@@ -582,7 +587,7 @@ namespace vmv
         return v <= 0.F ? 0 : (v >= 65535.F ? 65535 : static_cast<int>(v));
     }
 
-    __device__ __forceinline__ bool mvt_collides(const MvtRec &t, float x, float y, float z, float r)
+    static __device__ __noinline__ bool mvt_collides(const MvtRec &t, float x, float y, float z, float r)
     {
         const float q = r + t.r_point, q2 = q * q;
         if (x + q < t.g_min[0] || x - q > t.g_max[0] || y + q < t.g_min[1] || y - q > t.g_max[1] || z + q < t.g_min[2] ||
@@ -778,7 +783,7 @@ namespace vmv
 
     // The pointclouds (CAPT and MVT) for one sphere, warp-cooperative: every lane of the converged group calls,
     // `query` false = the lane has nothing to ask but helps scanning.  The clearance grid answers first.
-    __device__ __forceinline__ bool sphere_hits_clouds(const float *__restrict__ E, float x, float y, float z, float r_pc, bool query)
+    static __device__ __noinline__ bool sphere_hits_clouds(const float *__restrict__ E, float x, float y, float z, float r_pc, bool query)
     {
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
         bool hit = false;
