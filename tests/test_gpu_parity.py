@@ -264,6 +264,78 @@ def test_capt_pointcloud_and_heightfield(robot):
     assert_edge_verdicts(O, oenv, a, b, R.validate_motion_batch(a, b, env), O.validate_edges(oenv, a, b), "capt+heightfield edges", has_cloud=True)
 
 
+def _capt_cases():
+    """Clouds and build parameters that stress what the list-free CAPT query derives from the tree: tiny and
+    non-power-of-two clouds, coordinate ties (lattice points, duplicates), leaves that keep their representative
+    alone (large r_min), queries wider than the lists reach (r_max below the robot's radii), fat points."""
+    rng = np.random.default_rng(11)
+    surf = np.concatenate([rng.uniform([0.25, -0.5, 0.0], [0.8, 0.5, 0.03], size=(3000, 3)),
+                           rng.normal([0.45, 0.25, 0.55], 0.06, size=(1500, 3)),
+                           rng.uniform([-0.7, -0.7, 0.0], [0.7, 0.7, 1.1], size=(300, 3))]).astype(np.float32)
+    surf = surf[np.hypot(surf[:, 0], surf[:, 1]) > 0.3]
+    lattice = (np.stack(np.meshgrid(np.arange(0.3, 0.75, 0.05), np.arange(-0.4, 0.45, 0.05), np.arange(0.0, 1.0, 0.25), indexing="ij"), -1)
+               .reshape(-1, 3).astype(np.float32))
+    dup = np.concatenate([surf[:700], surf[:700], surf[:300]])
+    yield "two points", np.array([[0.45, 0.1, 0.5], [0.3, -0.3, 0.3]], np.float32), (0.03, 0.1, 0.0025)
+    yield "three points", surf[[5, 1900, 3300]], (0.03, 0.1, 0.0025)
+    for n in (7, 64, 65, 1000):
+        yield f"{n} points", surf[rng.choice(len(surf), n, replace=False)], (0.03, 0.1, 0.0025)
+    # (exact coordinate ties are left out: which half a tied point lands in is the sort's choice, std::sort in the
+    # reference, and the C oracle's own sort disagrees with it on 8 of 6000 configurations of the plain lattice)
+    yield "lattice, jittered by 1e-5", lattice + rng.uniform(-1e-5, 1e-5, size=lattice.shape).astype(np.float32), (0.03, 0.1, 0.0025)
+    yield "duplicates", dup, (0.03, 0.1, 0.0025)
+    yield "lists shorter than the queries (r_max 0.04)", surf, (0.01, 0.04, 0.0025)
+    yield "representative-only leaves (r_min 0.09)", surf, (0.09, 0.1, 0.0025)
+    yield "wide lists (r_max 0.3)", surf[::2], (0.01, 0.3, 0.0025)
+    yield "fat points (r_point 0.03)", surf, (0.03, 0.1, 0.03)
+    yield "zero-radius points", surf, (0.03, 0.1, 0.0)
+
+
+def test_capt_without_lists_on_adversarial_clouds():
+    """The CAPT query evaluates list membership per point instead of storing lists (vmv_device.cuh: capt_member): it must
+    reproduce the reference's lists -- including what they MISS -- on clouds and parameters chosen to hit every rule."""
+    R, O = vmv.panda, po.Oracle("panda")
+    ref = po.Ref("panda") if po.ref_available() else None
+    q = scenes.random_configs("panda", 6000, seed=77)
+    seen_invalid = 0
+    for name, pts, (r_min, r_max, r_point) in _capt_cases():
+        env, oenv = vmv.Environment(), po.OracleEnv()
+        env.add_capt_pointcloud(pts, r_min, r_max, r_point)
+        oenv.add_capt(pts, r_min, r_max, r_point)
+        got = R.validate_batch(q, env)
+        if ref is not None:
+            renv = po.RefEnv()
+            renv.add_capt(pts, r_min, r_max, r_point)
+            want = ref.validate_configs(renv, q, threads=8)
+        else:
+            want = O.validate_configs(oenv, q)
+        seen_invalid += int((~want).sum())
+        # classified on the oracle's restatement of the SAME tree (lists and all): a mismatch must sit on a decision
+        # boundary of that structure, not merely near the raw surface
+        assert_verdicts("panda", O, oenv, q, got, want, f"list-free CAPT, {name}", has_cloud=True)
+        a, b = q[:600], q[600:1200]
+        assert_edge_verdicts(O, oenv, a, b, R.validate_motion_batch(a, b, env), O.validate_edges(oenv, a, b), f"list-free CAPT edges, {name}", has_cloud=True)
+    assert seen_invalid > 2000
+    # a single point (the reference's own query crashes on a tree without a split; the oracle's does not)
+    env, oenv = vmv.Environment(), po.OracleEnv()
+    one = np.array([[0.45, 0.1, 0.5]], np.float32)
+    env.add_capt_pointcloud(one, 0.03, 0.1, 0.0025)
+    oenv.add_capt(one, 0.03, 0.1, 0.0025)
+    assert_verdicts("panda", O, oenv, q, R.validate_batch(q, env), O.validate_configs(oenv, q), "list-free CAPT, one point", has_cloud=True)
+    # two trees and a voxel table in one environment: the nearest-point table spans all of them
+    pts = next(c for c in _capt_cases() if c[0] == "1000 points")[1]
+    env, oenv = vmv.Environment(), po.OracleEnv()
+    for e in (env, oenv):
+        add = e.add_capt_pointcloud if e is env else e.add_capt
+        add(pts[:500], 0.03, 0.1, 0.0025)
+        add(pts[500:] + np.float32(0.01), 0.01, 0.05, 0.01)
+    lo, hi = [-1.0, -1.0, -0.2], [1.0, 1.0, 1.4]
+    extra = (pts[::3] + np.float32([0.0, 0.02, 0.1])).astype(np.float32)
+    env.add_mvt_pointcloud(extra, 0.03, 0.1, lo, hi, 0.0025)
+    oenv.add_mvt(extra, 0.03, 0.1, lo, hi, 0.0025)
+    assert_verdicts("panda", O, oenv, q, R.validate_batch(q, env), O.validate_configs(oenv, q), "two CAPTs + MVT", has_cloud=True)
+
+
 @pytest.mark.parametrize("robot", ["fetch", "ur5"])
 def test_c4_baseline_size(robot):
     """BASELINE config 4 at its full size: a CAPT over 100 k synthetic surface points plus a 256 x 256 heightfield
