@@ -1,1 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "adversarial" 2>&1 | tail -30 > gpurun_out/r2_t30_tests.log
+python tools/time_kernels.py > gpurun_out/r2_t31_k.txt 2>&1
+python tools/time_c4.py >> gpurun_out/r2_t31_k.txt 2>&1
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -4 >> gpurun_out/r2_t31_k.txt

@@ -536,6 +536,16 @@ namespace vmv
         return invalid;
     }
 
+    template <int N, typename F>
+    __device__ __forceinline__ void static_for(F &&f)
+    {
+        if constexpr (N > 0)
+        {
+            static_for<N - 1>(f);
+            f(std::integral_constant<int, N - 1>{});
+        }
+    }
+
     // One pass over 32 states (lane = state in the dense phases).  Returns the warp-uniform mask of
     // invalid states (lanes without a state count as invalid).
     template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS, bool AE = false>
@@ -549,28 +559,21 @@ namespace vmv
         static_assert(kWords <= kPairTabWords, "pair masks of the verdict tables");
 
         // ---- two-joint verdict tables: one byte per group, loaded ahead of the FK ------------------
+        // (the groups and their joints are compile-time facts of the robot: gen/<robot>_pairtab.h)
+        constexpr int kGroups = TAB ? (R::PairTab::kGroups < kPairTabMaxGroups ? R::PairTab::kGroups : kPairTabMaxGroups) : 0;
         unsigned char cell[kPairTabMaxGroups] = {2, 2, 2, 2};
-        if (TAB)
-        {
-#pragma unroll
-            for (int g = 0; g < kPairTabMaxGroups; ++g)
+        static_for<kGroups>(
+            [&](auto gc)
             {
-                if (g < T.n_groups)
-                {
-                    float qa = 0.F, qb = 0.F;
-#pragma unroll
-                    for (int j = 0; j < M::kDof; ++j)
-                    {
-                        qa = (j == T.dof_a[g]) ? cfg[j] : qa;
-                        qb = (j == T.dof_b[g]) ? cfg[j] : qb;
-                    }
-                    // clamped: the byte is only used for states inside the joint box
-                    const int ia = min(max(__float2int_rd((qa - T.lo_a[g]) * T.inv_a[g]), 0), T.na[g] - 1);
-                    const int ib = min(max(__float2int_rd((qb - T.lo_b[g]) * T.inv_b[g]), 0), T.nb[g] - 1);
-                    cell[g] = __ldg(T.cells[g] + static_cast<size_t>(ia) * T.nb[g] + ib);
-                }
-            }
-        }
+                constexpr int g = decltype(gc)::value;
+                constexpr int da = R::PairTab::dof_a(g), db = R::PairTab::dof_b(g);
+                const float qa = cfg[da >= 0 ? da : 0];
+                const float qb = db >= 0 ? cfg[db >= 0 ? db : 0] : 0.F;
+                // clamped: the byte is only used for states inside the joint box
+                const int ia = min(max(__float2int_rd((qa - T.lo_a[g]) * T.inv_a[g]), 0), T.na[g] - 1);
+                const int ib = min(max(__float2int_rd((qb - T.lo_b[g]) * T.inv_b[g]), 0), T.nb[g] - 1);
+                cell[g] = __ldg(T.cells[g] + static_cast<size_t>(ia) * T.nb[g] + ib);
+            });
 
         // ---- A: FK ------------------------------------------------------------------------------
         StashBoundSink<32, M::kLinks, !TAB> sink;
@@ -597,7 +600,7 @@ namespace vmv
 #pragma unroll
             for (int g = 0; g < kPairTabMaxGroups; ++g)
             {
-                if (g < T.n_groups)
+                if (g < kGroups)
                 {
                     sink.self_hit = sink.self_hit || cell[g] == 1;
                     if (cell[g] != 2)
