@@ -1,3 +1,2 @@
-python tools/time_kernels.py > gpurun_out/r2_t31_k.txt 2>&1
-python tools/time_c4.py >> gpurun_out/r2_t31_k.txt 2>&1
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -4 >> gpurun_out/r2_t31_k.txt
+for v in e320 e640 c768 c576; do VMV_LIB=variants/lib_$v.so timeout 200 python tools/time_kernels.py >> gpurun_out/r2_t32_k.txt 2>&1; done
+python tools/time_kernels.py >> gpurun_out/r2_t32_k.txt 2>&1
