@@ -1,2 +1,4 @@
-for v in e320 e640 c768 c576; do VMV_LIB=variants/lib_$v.so timeout 200 python tools/time_kernels.py >> gpurun_out/r2_t32_k.txt 2>&1; done
-python tools/time_kernels.py >> gpurun_out/r2_t32_k.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_t33_smoke.log 2>&1
+python bench.py > gpurun_out/r2_t33_bench.json 2> gpurun_out/r2_t33_bench.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_t33_ref.json 2>> gpurun_out/r2_t33_bench.err
+python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/b.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu.log 2>&1
