@@ -1,4 +1,3 @@
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_t33_smoke.log 2>&1
-python bench.py > gpurun_out/r2_t33_bench.json 2> gpurun_out/r2_t33_bench.err
-python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_t33_ref.json 2>> gpurun_out/r2_t33_bench.err
-python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/b.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu.log 2>&1
+python tools/time_c4.py > gpurun_out/r2_t35_c4.txt 2>&1
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "capt or c4 or mvt or pointcloud or attach or fuzz or adversarial" 2>&1 | tail -5 >> gpurun_out/r2_t35_c4.txt
+python tools/time_generic.py >> gpurun_out/r2_t35_c4.txt 2>&1

@@ -631,40 +631,7 @@ namespace vmv
                                  : (sink.reach_valid ? grid_lookup_t<MaskT>(G, sink.b[li][0], sink.b[li][1], sink.b[li][2], G.link_class[li])
                                                      : static_cast<MaskT>(G.all_mask));
             });
-        // ---- any environment: the bounding spheres against the heightfields (exact, one gather each) and against the
-        //      clearance grid of the pointclouds (one load each), lane = state, centres still in registers ---------
-        unsigned long long hf_links = 0ull, cloud_links = 0ull;
-        if constexpr (AE)
-        {
-            static_assert(sizeof(MaskT) == 4, "the any-environment instantiation keeps its link flags in 32-bit masks");
-            const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(X.E);
-            const bool has_hf = H.n_heightfields > 0, has_cloud = H.n_capts + H.n_mvts > 0;
-            R::for_each_link(
-                [&](auto l, float br, int, int, float)
-                {
-                    constexpr int li = decltype(l)::value;
-                    if (live)
-                    {
-                        const float x = sink.b[li][0], y = sink.b[li][1], z = sink.b[li][2];
-                        if (has_hf && sphere_hits_heightfields(X.E, x, y, z, br))
-                        {
-                            hf_links |= 1ull << li;
-                        }
-                        if (has_cloud)
-                        {
-                            bool undecided = true;
-                            if (H.off_cloud_grid != 0)
-                            {
-                                const CloudGridRec &g = *reinterpret_cast<const CloudGridRec *>(X.E + H.off_cloud_grid);
-                                undecided = !(cloud_clearance(g, x, y, z) > (br - 1e-6F) + g.r_point_max);
-                            }
-                            cloud_links |= undecided ? (1ull << li) : 0ull;
-                        }
-                    }
-                });
-        }
         __syncwarp();  // stash complete
-
         // ---- C1: allowed link pairs on the bounding spheres -> records; C2 per chunk of pairs -----
         if (M::kPairs > 0)
         {
@@ -700,6 +667,45 @@ namespace vmv
             __syncwarp();  // the record queue's memory is reused below
         }
 
+        // ---- any environment: the bounding spheres against the heightfields (exact, one gather each) and against the
+        //      nearest-point table of the pointclouds (one load each), lane = state.  A ROLLED loop over the links, each
+        //      centre re-derived from the frame stash the way B1 does it (the kernel is bound by instruction fetch: unrolled
+        //      over the centres in registers this phase was 7 KB for Fetch); the two flags wait in the link's mask slot
+        //      (which shares its memory with the record queue of C1/C2: this phase runs after them, and only for the states
+        //      the self-collision check has left).
+        if constexpr (AE)
+        {
+            static_assert(sizeof(MaskT) == 4, "the any-environment instantiation keeps its link flags in 32-bit masks");
+            const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(X.E);
+            const bool has_hf = H.n_heightfields > 0, has_cloud = H.n_capts + H.n_mvts > 0;
+#pragma unroll 1
+            for (int li = 0; li < M::kLinks; ++li)
+            {
+                uint32_t flags = 0u;
+                if (live && !((invalid >> lane) & 1u))
+                {
+                    const SphereTask t = X.tasks[X.links[li].bound_task];
+                    float x, y, z;
+                    task_centre<32>(t, X.stash + lane, x, y, z);
+                    if (has_hf && sphere_hits_heightfields(X.E, x, y, z, t.r))
+                    {
+                        flags |= kAeHfBit;
+                    }
+                    if (has_cloud)
+                    {
+                        bool undecided = true;
+                        if (H.off_cloud_grid != 0)
+                        {
+                            const CloudGridRec &g = *reinterpret_cast<const CloudGridRec *>(X.E + H.off_cloud_grid);
+                            undecided = !(cloud_clearance(g, x, y, z) > (t.r - 1e-6F) + g.r_point_max);
+                        }
+                        flags |= undecided ? kAeCloudBit : 0u;
+                    }
+                }
+                X.masks[li * 32 + lane] = static_cast<MaskT>(flags);
+            }
+        }
+
         // ---- B0: candidate masks -> (state, link) items -------------------------------------------
         uint32_t n1 = 0u;
         {
@@ -712,8 +718,7 @@ namespace vmv
                     MaskT cm = cand[li];
                     if constexpr (AE)
                     {
-                        cm = static_cast<MaskT>((static_cast<uint32_t>(cm) & kAeObjMask) | (((hf_links >> li) & 1ull) ? kAeHfBit : 0u) |
-                                                (((cloud_links >> li) & 1ull) ? kAeCloudBit : 0u));
+                        cm = static_cast<MaskT>((static_cast<uint32_t>(cm) & kAeObjMask) | static_cast<uint32_t>(X.masks[li * 32 + lane]));
                     }
                     if (cm != 0)
                     {
