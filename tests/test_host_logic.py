@@ -204,3 +204,28 @@ def test_shard_bounds_cover_and_align():
             assert spans[0][0] == 0 and spans[-1][1] == n
             for (lo, hi), (lo2, _) in zip(spans, spans[1:]):
                 assert hi == lo2 and lo % 32 == 0 and lo2 % 32 == 0 or hi == n
+
+
+@pytest.mark.gpu
+def test_capt_host_build_takes_any_cloud():
+    """`add_capt_pointcloud` is host work (the k-d tree of capt.hh:106-119, no affordance lists): it must accept the clouds the
+    reference accepts -- empty, tiny, non-power-of-two, duplicated, with coordinate ties -- in milliseconds, and refuse what
+    its 24-bit leaf tags cannot address.  (Marked gpu because an environment belongs to a device from its first shape on.)"""
+    import time
+
+    rng = np.random.default_rng(0)
+    clouds = [np.zeros((0, 3), np.float32), rng.random((1, 3)), rng.random((2, 3)), rng.random((3, 3)), rng.random((1000, 3)),
+              np.repeat(rng.random((10, 3)), 7, axis=0), np.round(rng.random((500, 3)), 1)]
+    for pts in clouds:
+        env = vmv.Environment()
+        env.add_capt_pointcloud(pts.astype(np.float32), 0.01, 0.08, 0.0025)
+        assert vmv.panda.validate_batch(np.zeros((64, 7), np.float32), env).shape == (64,)  # commits and queries the tree
+    big = (rng.random((100_000, 3)) * [2.0, 2.0, 1.0]).astype(np.float32)
+    env = vmv.Environment()
+    t0 = time.perf_counter()
+    env.add_capt_pointcloud(big, 0.03, 0.24, 0.0025)
+    assert time.perf_counter() - t0 < 5.0  # 0.05 s on 16 threads; the lists of the reference take 9 s at this r_max
+    L = _lib.lib()
+    few = np.zeros((4, 3), np.float32)
+    rc = L.vmv_env_add_capt(env.handle, _lib.ptr(few), (1 << 24) + 1, 0.01, 0.08, 0.0025)  # refused before the points are read
+    assert rc < 0 and b"2^24" in L.vmv_last_error()
