@@ -1,3 +1,2 @@
-python tools/time_kernels.py > gpurun_out/r2_t36_k.txt 2>&1
-python tools/time_c4.py >> gpurun_out/r2_t36_k.txt 2>&1
-python -m pytest tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -x 2>&1 | tail -4 >> gpurun_out/r2_t36_k.txt
+python bench.py --no-cpu --no-c5 --no-c4 --no-edges > gpurun_out/r2_t37_bench.json 2> gpurun_out/r2_t37_bench.err
+python bench.py --no-cpu --no-c5 --no-c4 --no-edges >> gpurun_out/r2_t37_bench.json 2>> gpurun_out/r2_t37_bench.err
