@@ -260,6 +260,9 @@ extern "C"
     uint64_t vmv_launch_count(void);
     /* development aid: 64 counters filled by builds compiled with -DVMV_C4_STATS (zeros otherwise) */
     int vmv_dev_stats(uint64_t *out64, int reset);
+    /* development / tests: FNV-1a digests of the k-th CAPT's tables {nodes, leaf flags, grid points, grid starts}: the device
+     * build (default) and the host build (environment variable VMV_CAPT_HOST_BUILD) must agree bit for bit */
+    int vmv_env_capt_digest(const vmv_env *env, int k, uint64_t *out4);
     /* testing aid: 0 = automatic choice (default), 1 = force the generic per-thread kernel,
      * 2 = force the block-cooperative kernel, 3 = force the grid-culled kernel (2 and 3 fail with
      * VMV_ERR_LIMIT when they do not apply to the environment) */

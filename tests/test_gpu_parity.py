@@ -687,3 +687,36 @@ def test_batched_prm_solves_the_sphere_cage():
     lo, hi = e.min(axis=1), e.max(axis=1)  # the reference validated every edge as (earlier vertex -> later vertex)
     ea, eb = rm.vertices[lo], rm.vertices[hi]
     assert_edge_verdicts(O, oenv, ea, eb, np.ones(len(e), bool), O.validate_edges(oenv, ea, eb), "roadmap edges")
+
+
+def test_capt_device_build_equals_host_build():
+    """The CAPT tables built on the device (segmented bitonic sorts, vmv_capt_build.cuh) against the host build (the reference's
+    recursion restated, `VMV_CAPT_HOST_BUILD`): nodes, leaf flags, grid points and grid start tables bit for bit, on clouds
+    without coordinate ties (which half a tied point lands in is the sort's choice in both)."""
+    import ctypes as C
+    import os
+
+    from vamp_mvt_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    clouds = [rng.random((n, 3)).astype(np.float32) * np.float32([1.5, 1.5, 1.0]) for n in (1, 2, 3, 5, 64, 65, 1000, 2048, 2049, 5000)]
+    # 10^5 points with pairwise distinct coordinates on every axis (a uniform float32 sample of this size has hundreds of ties)
+    n = 100_000
+    clouds.append(np.stack([rng.permutation(n), rng.permutation(n), rng.permutation(n)], -1).astype(np.float32) * np.float32([2e-5, 2e-5, 1e-5]))
+    for pts in clouds:
+        digests = []
+        for host in (False, True):
+            if host:
+                os.environ["VMV_CAPT_HOST_BUILD"] = "1"
+            else:
+                os.environ.pop("VMV_CAPT_HOST_BUILD", None)
+            try:
+                env = vmv.Environment()
+                env.add_capt_pointcloud(pts, 0.03, 0.24, vmv.POINT_RADIUS)
+                out = (C.c_uint64 * 4)()
+                _lib.check(L.vmv_env_capt_digest(env.handle, 0, out))
+                digests.append(tuple(out))
+            finally:
+                os.environ.pop("VMV_CAPT_HOST_BUILD", None)
+        assert digests[0] == digests[1], f"{len(pts)} points: device {digests[0]} vs host {digests[1]}"

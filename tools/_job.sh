@@ -1,2 +1,1 @@
-python bench.py --no-cpu --no-c5 --no-c4 --no-edges > gpurun_out/r2_t37_bench.json 2> gpurun_out/r2_t37_bench.err
-python bench.py --no-cpu --no-c5 --no-c4 --no-edges >> gpurun_out/r2_t37_bench.json 2>> gpurun_out/r2_t37_bench.err
+python -m pytest tests/test_gpu_parity.py tests/test_host_logic.py tests/test_gpu_comm.py -m gpu -q 2>&1 | tail -8 > gpurun_out/r2_t38.txt

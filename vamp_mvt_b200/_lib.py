@@ -110,6 +110,7 @@ def lib():
         L.vmv_comm_local_row.argtypes = [vp, i32]
         L.vmv_comm_publish.argtypes = [vp, i32, sz, vp]
         L.vmv_comm_acquire.argtypes = [vp, i32, vp]
+        L.vmv_env_capt_digest.argtypes = [vp, i32, vp]
         _lib = L
     return _lib
 
