@@ -3,7 +3,8 @@
 // lists per point at query time), so the build is 17 rounds of "sort every node's range along one axis, read the split
 // off the middle": one segmented bitonic sort per level over (coordinate, point index) pairs -- segments are aligned
 // powers of two, so the network of a plain bitonic sort serves, with the last merge of every segment ascending.
-// Ties are ordered by the point index (the reference's std::sort leaves them unspecified).
+// Ties are ordered by the point index: which half a point lands in when it ties with the median is the choice of the
+// reference's sort (pdqsort_branchless, unstable) and unspecified there; the host build (std::sort) makes a third choice.
 // Then: per node {split, inherited bit}, per leaf its two flags (walking its root path for the cell) and the leaf of every
 // input point; the Morton grid of the raw points (one more sort, by cell code) and its per-level start tables.
 #pragma once
@@ -106,6 +107,15 @@ namespace vmv
             ++launches;
         }
         return cudaGetLastError();
+    }
+
+    static __global__ void k_fill_u32(uint32_t *__restrict__ dst, uint32_t pattern, size_t count)
+    {
+        const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (i < count)
+        {
+            dst[i] = pattern;
+        }
     }
 
     static __global__ void k_capt_gather_axis(const float *__restrict__ pts, const uint32_t *__restrict__ idx, uint32_t n, int d, float *__restrict__ key)

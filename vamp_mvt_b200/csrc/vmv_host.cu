@@ -203,6 +203,11 @@ namespace
         uint32_t *d_leafbits = nullptr;
         float4 *d_gpts = nullptr;
         uint32_t *d_gstart = nullptr;
+        // device build: the four tables live in one allocation that belongs to this cloud (not to a commit), and the host
+        // vectors above stay empty until somebody needs them (vmv_env_broadcast, vmv_env_capt_digest)
+        void *d_block = nullptr;
+        uint32_t n_grid_points = 0;
+        bool host_valid = true;
     };
 
     // Multi-level Voxel Table, host build (reference collision/mvt.hh:146-170, 437-446, 531-604)
@@ -600,12 +605,50 @@ namespace
         }
     };
 
+    cudaError_t cuMemsetD32Async_or_kernel(float *dst, uint32_t pattern, size_t count, cudaStream_t st)
+    {
+        if (count == 0)
+        {
+            return cudaSuccess;
+        }
+        vmv::k_fill_u32<<<static_cast<unsigned>((count + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint32_t *>(dst), pattern, count);
+        return cudaGetLastError();
+    }
+
+    // the host-side copy of a device-built cloud's tables, on demand
+    int capt_ensure_host(const HCapt &ct)
+    {
+        HCapt &t = const_cast<HCapt &>(ct);
+        if (t.host_valid || t.d_block == nullptr)
+        {
+            return VMV_OK;
+        }
+        const size_t pow2 = size_t(1) << t.nlog2;
+        t.nodes.assign(2 * (pow2 - 1), 0.F);
+        t.leafbits.assign((pow2 + 15) / 16, 0u);
+        t.gpts.assign(4 * size_t(t.n_grid_points), 0.F);
+        t.gstart.assign(vmv::capt_grid_offset(vmv::kCaptGridLevels), 0u);
+        if (!t.nodes.empty())
+        {
+            VMV_CUDA(cudaMemcpy(t.nodes.data(), t.d_nodes, t.nodes.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+        VMV_CUDA(cudaMemcpy(t.leafbits.data(), t.d_leafbits, t.leafbits.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (!t.gpts.empty())
+        {
+            VMV_CUDA(cudaMemcpy(t.gpts.data(), t.d_gpts, t.gpts.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+        VMV_CUDA(cudaMemcpy(t.gstart.data(), t.d_gstart, t.gstart.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        t.host_valid = true;
+        return VMV_OK;
+    }
+
     // The same tables built on the device (vmv_capt_build.cuh): one segmented bitonic sort per level of the tree, one more for
     // the Morton grid.  The results are copied back into the host-side description (the environment is re-packed from
     // it at every commit and serialised from it by vmv_env_broadcast); 10^5 points: ~3 ms instead of ~55 ms.
     // Points that are NaN are left to the host build (the sort's comparison needs a total order).
     int capt_build_device(HCapt &t, const float *points, size_t n, float r_min, float r_max, float r_point)
     {
+        const auto tm0 = std::chrono::steady_clock::now();
         t.r_min = r_min, t.r_max = r_max, t.r_point = r_point;
         const float max_l1 = r_max + r_point;
         t.list_reach_sq = max_l1 * max_l1;
@@ -623,29 +666,37 @@ namespace
         capt_frame(t, points, n, finite);
         const uint32_t m = static_cast<uint32_t>(finite.size());
 
-        DevScratch scratch;
-        float *d_pts = nullptr, *d_key = nullptr;
-        uint32_t *d_idx = nullptr, *d_leafbits = nullptr, *d_leaf_of = nullptr, *d_code = nullptr, *d_order = nullptr, *d_gstart = nullptr;
-        float2 *d_nodes = nullptr;
-        float4 *d_gpts = nullptr;
+        // two allocations: the tables (they stay with the cloud) and the scratch of this build
         const uint32_t n_starts = vmv::capt_grid_offset(vmv::kCaptGridLevels);
-        VMV_CUDA(scratch.get(d_pts, 3 * size_t(n_pad)));
-        VMV_CUDA(scratch.get(d_key, n_pad));
-        VMV_CUDA(scratch.get(d_idx, n_pad));
-        VMV_CUDA(scratch.get(d_nodes, pow2));
-        VMV_CUDA(scratch.get(d_leafbits, (pow2 + 15) / 16));
-        VMV_CUDA(scratch.get(d_leaf_of, n_pad));
-        VMV_CUDA(scratch.get(d_code, n_pad));
-        VMV_CUDA(scratch.get(d_order, n_pad));
-        VMV_CUDA(scratch.get(d_gpts, m));
-        VMV_CUDA(scratch.get(d_gstart, n_starts));
-        {
-            std::vector<float> padded(points, points + 3 * n);
-            padded.resize(3 * size_t(n_pad), inf);
-            VMV_CUDA(cudaMemcpy(d_pts, padded.data(), padded.size() * sizeof(float), cudaMemcpyHostToDevice));
-        }
-        uint64_t launches = 0;
+        auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+        const size_t b_nodes = up(size_t(pow2) * sizeof(float2)), b_bits = up(size_t((pow2 + 15) / 16) * 4), b_gpts = up(size_t(std::max(m, 1u)) * sizeof(float4)),
+                     b_starts = up(size_t(n_starts) * 4);
+        unsigned char *block = nullptr;
+        VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&block), b_nodes + b_bits + b_gpts + b_starts));
+        t.d_block = block;
+        float2 *d_nodes = reinterpret_cast<float2 *>(block);
+        uint32_t *d_leafbits = reinterpret_cast<uint32_t *>(block + b_nodes);
+        float4 *d_gpts = reinterpret_cast<float4 *>(block + b_nodes + b_bits);
+        uint32_t *d_gstart = reinterpret_cast<uint32_t *>(block + b_nodes + b_bits + b_gpts);
+        DevScratch scratch;
+        unsigned char *tmp = nullptr;
+        const size_t b_pts = up(3 * size_t(n_pad) * 4), b_arr = up(size_t(n_pad) * 4);
+        VMV_CUDA(scratch.get(tmp, b_pts + 5 * b_arr));
+        float *d_pts = reinterpret_cast<float *>(tmp), *d_key = reinterpret_cast<float *>(tmp + b_pts);
+        uint32_t *d_idx = reinterpret_cast<uint32_t *>(tmp + b_pts + b_arr), *d_leaf_of = reinterpret_cast<uint32_t *>(tmp + b_pts + 2 * b_arr),
+                 *d_code = reinterpret_cast<uint32_t *>(tmp + b_pts + 3 * b_arr), *d_order = reinterpret_cast<uint32_t *>(tmp + b_pts + 4 * b_arr);
         cudaStream_t st = nullptr;
+        if (n > 0)
+        {
+            VMV_CUDA(cudaMemcpyAsync(d_pts, points, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+        if (n_pad > n)
+        {
+            // +inf is 0x7f800000: the padding of the reference's tree (capt.hh:318-322)
+            VMV_CUDA(cuMemsetD32Async_or_kernel(d_pts + 3 * n, 0x7f800000u, 3 * (size_t(n_pad) - n), st));
+        }
+        const auto tm1 = std::chrono::steady_clock::now();
+        uint64_t launches = 0;
         const unsigned gb = (n_pad + 255) / 256;
         // (the codes kernel also writes the identity permutation: used here for the tree's order, below for the grid's)
         vmv::k_capt_codes<<<gb, 256, 0, st>>>(d_pts, static_cast<uint32_t>(n), n_pad, t.g_origin[0], t.g_origin[1], t.g_origin[2], t.g_inv0, d_code, d_idx);
@@ -675,26 +726,28 @@ namespace
         VMV_CUDA(cudaGetLastError());
         g_launches += launches;
 
-        t.nodes.assign(2 * size_t(pow2 - 1), 0.F);
-        t.leafbits.assign((pow2 + 15) / 16, 0u);
-        t.leaf_of_point.assign(n, 0u);
-        t.gpts.assign(4 * size_t(m), 0.F);
-        t.gstart.assign(n_starts, 0u);
-        if (pow2 > 1)
+        if (std::getenv("VMV_CAPT_TIMING"))
         {
-            VMV_CUDA(cudaMemcpyAsync(t.nodes.data(), d_nodes, t.nodes.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+            cudaStreamSynchronize(st);
         }
-        VMV_CUDA(cudaMemcpyAsync(t.leafbits.data(), d_leafbits, t.leafbits.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        const auto tm2 = std::chrono::steady_clock::now();
+        t.d_nodes = d_nodes, t.d_leafbits = d_leafbits, t.d_gpts = d_gpts, t.d_gstart = d_gstart;
+        t.n_grid_points = m;
+        t.host_valid = false;
+        t.nodes.clear(), t.leafbits.clear(), t.gpts.clear(), t.gstart.clear();
+        t.leaf_of_point.resize(n);
         if (n > 0)
         {
             VMV_CUDA(cudaMemcpyAsync(t.leaf_of_point.data(), d_leaf_of, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
-        if (m > 0)
-        {
-            VMV_CUDA(cudaMemcpyAsync(t.gpts.data(), d_gpts, t.gpts.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
-        }
-        VMV_CUDA(cudaMemcpyAsync(t.gstart.data(), d_gstart, t.gstart.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         VMV_CUDA(cudaStreamSynchronize(st));
+        if (std::getenv("VMV_CAPT_TIMING"))
+        {
+            const auto tm3 = std::chrono::steady_clock::now();
+            auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            std::fprintf(stderr, "capt_build_device: %zu points: frame + alloc + upload %.2f ms, %llu launches %.2f ms, download %.2f ms\n", n, ms(tm0, tm1),
+                         static_cast<unsigned long long>(launches), ms(tm1, tm2), ms(tm2, tm3));
+        }
         return VMV_OK;
     }
 }  // namespace
@@ -749,6 +802,19 @@ struct vmv_env
     // verdict of the robot's world-fixed links against this environment (any-environment kernels): 0 not checked yet,
     // 1 clear, 2 in collision (then every configuration is invalid)
     mutable int static_state[VMV_N_ROBOTS] = {0, 0, 0, 0};
+
+    // the device-built tables of the pointclouds (they belong to the clouds, not to a commit)
+    void release_clouds()
+    {
+        for (auto &t : capts)
+        {
+            if (t.d_block)
+            {
+                cudaFree(t.d_block);
+                t.d_block = nullptr;
+            }
+        }
+    }
 
     void release_device()
     {
@@ -1095,6 +1161,10 @@ namespace
         }
         for (auto &t : env->capts)
         {
+            if (t.d_block != nullptr)
+            {
+                continue;  // built on the device: the tables are where the build left them
+            }
             float *dn = nullptr, *dp = nullptr;
             int rc = upload(env, t.nodes, dn);
             if (rc == VMV_OK)
@@ -1201,7 +1271,7 @@ namespace
             vmv::CaptRec r{};
             r.r_point = t.r_point;
             r.nlog2 = static_cast<uint32_t>(t.nlog2);
-            r.n_tests = static_cast<uint32_t>(t.nodes.size() / 2);
+            r.n_tests = (1u << t.nlog2) - 1u;
             r.n_points = t.n_points;
             for (int k = 0; k < 3; ++k)
             {
@@ -1812,6 +1882,7 @@ extern "C"
         if (env != nullptr)
         {
             env->release_device();
+            env->release_clouds();
             delete env;
         }
     }
@@ -3277,6 +3348,13 @@ extern "C"
             return fail(VMV_ERR_ARG, "vmv_env_capt_digest: bad argument");
         }
         const HCapt &t = env->capts[static_cast<size_t>(k)];
+        {
+            const int rc = capt_ensure_host(t);
+            if (rc != VMV_OK)
+            {
+                return rc;
+            }
+        }
         auto fnv = [](const void *p, size_t bytes)
         {
             uint64_t h = 1469598103934665603ull;
@@ -3926,6 +4004,11 @@ extern "C"
                 w.pod<uint64_t>(env->capts.size());
                 for (const auto &t : env->capts)
                 {
+                    const int rch = capt_ensure_host(t);
+                    if (rch != VMV_OK)
+                    {
+                        return rch;
+                    }
                     w.pod(t.r_min), w.pod(t.r_max), w.pod(t.r_point), w.pod(t.list_reach_sq), w.pod(t.nlog2), w.pod(t.n_points), w.pod(t.top_lo), w.pod(t.top_hi);
                     w.pod(t.g_origin), w.pod(t.g_inv0), w.pod(t.g_cell0), w.pod(t.id);
                     w.vec(t.nodes), w.vec(t.leafbits), w.vec(t.gpts), w.vec(t.gstart);
@@ -3985,6 +4068,7 @@ extern "C"
                     h.xd = xd, h.yd = yd;
                 }
                 r.pod(k);
+                env->release_clouds();
                 env->capts.clear();
                 env->capts.resize(r.ok ? k : 0);
                 for (auto &t : env->capts)
