@@ -79,7 +79,8 @@ extern "C"
     /* CAPT(points, r_min, r_max, r_point): capt.hh:299-369 (add_capt_pointcloud, environment.cc:150-160).
      * Builds the reference's k-d tree (median splits, capt.hh:106-119) and NOT its affordance lists: the queries
      * evaluate list membership per point from the tree (same verdicts, including the points the reference's lists
-     * miss), so the call costs ~50 ms per 10^5 points instead of seconds.  At most 2^24 points (VMV_ERR_LIMIT). */
+     * miss), and the tree is built on the GPU (segmented bitonic sorts): ~3.5 ms per 10^5 points instead of seconds.
+     * At most 2^24 points (VMV_ERR_LIMIT). */
     int vmv_env_add_capt(vmv_env *env, const float *points_xyz, size_t n, float r_min, float r_max, float r_point);
     /* MVT(points, r_min, r_max, workspace_aabb_min, workspace_aabb_max, r_point): mvt.hh:146-170
      * (add_mvt_pointcloud, environment.cc:163-176).  The grid is cubic, floor(workspace x-width /
