@@ -632,6 +632,11 @@ def main() -> int:
     c4 = None
     if not args.no_c4 and world == 1:
         c4 = {}
+        # the first CAPT build of a process also loads the build kernels' module (~0.5 s, once): taken on a 256-point cloud
+        # and reported on its own, so that `capt_build_ms` is what every further pointcloud costs
+        t0 = time.perf_counter()
+        vmv.Environment().add_capt_pointcloud(np.random.default_rng(0).random((256, 3)).astype(np.float32), 0.01, 0.1, 0.0025)
+        first_build_ms = (time.perf_counter() - t0) * 1e3
         for rb in ("fetch", "ur5"):
             try:
                 R = getattr(vmv, rb)
@@ -662,7 +667,7 @@ def main() -> int:
                 e2e4 = (time.perf_counter() - t0) / 5
                 got4 = _lib.unpack_bits(db.cpu().numpy().view(np.uint32), N_C4)
                 blk = {"workload": f"C4 {rb}: 2^18 configs vs CAPT({len(pts)} points, r_point 0.0025) + 256x256 heightfield",
-                       "value": N_C4 / (ms4 * 1e-3), "unit": "configs/s", "ms_per_step": ms4, "capt_build_ms": build_ns / 1e6,
+                       "value": N_C4 / (ms4 * 1e-3), "unit": "configs/s", "ms_per_step": ms4, "capt_build_ms": build_ns / 1e6, "capt_first_build_in_process_ms": first_build_ms,
                        "e2e": {"value": N_C4 / e2e4, "unit": "configs/s", "h2d_bytes_per_step": int(q4.nbytes), "d2h_bytes_per_step": (N_C4 + 31) // 32 * 4},
                        "valid_fraction": float(got4.mean())}
                 if not args.no_cpu:
