@@ -580,31 +580,6 @@ namespace
         }
     }
 
-    // device allocations that live as long as one build
-    struct DevScratch
-    {
-        std::vector<void *> p;
-        ~DevScratch()
-        {
-            for (void *q : p)
-            {
-                cudaFree(q);
-            }
-        }
-        template <typename T>
-        cudaError_t get(T *&out, size_t count)
-        {
-            void *q = nullptr;
-            const cudaError_t e = cudaMalloc(&q, std::max<size_t>(16, count * sizeof(T)));
-            if (e == cudaSuccess)
-            {
-                p.push_back(q);
-            }
-            out = static_cast<T *>(q);
-            return e;
-        }
-    };
-
     cudaError_t cuMemsetD32Async_or_kernel(float *dst, uint32_t pattern, size_t count, cudaStream_t st)
     {
         if (count == 0)
@@ -678,10 +653,28 @@ namespace
         uint32_t *d_leafbits = reinterpret_cast<uint32_t *>(block + b_nodes);
         float4 *d_gpts = reinterpret_cast<float4 *>(block + b_nodes + b_bits);
         uint32_t *d_gstart = reinterpret_cast<uint32_t *>(block + b_nodes + b_bits + b_gpts);
-        DevScratch scratch;
-        unsigned char *tmp = nullptr;
+        // the scratch of a build is kept per device between builds (grow-only): clouds arrive per frame, and a cudaMalloc /
+        // cudaFree pair costs more than the 161 launches of the build
+        static std::mutex scratch_mutex;
+        static unsigned char *scratch_mem[kMaxDevices] = {};
+        static size_t scratch_cap[kMaxDevices] = {};
+        std::lock_guard<std::mutex> scratch_lock(scratch_mutex);
+        int device = 0;
+        VMV_CUDA(cudaGetDevice(&device));
+        device %= kMaxDevices;
         const size_t b_pts = up(3 * size_t(n_pad) * 4), b_arr = up(size_t(n_pad) * 4);
-        VMV_CUDA(scratch.get(tmp, b_pts + 5 * b_arr));
+        if (scratch_cap[device] < b_pts + 5 * b_arr)
+        {
+            if (scratch_mem[device] != nullptr)
+            {
+                cudaFree(scratch_mem[device]);
+                scratch_mem[device] = nullptr;
+                scratch_cap[device] = 0;
+            }
+            VMV_CUDA(cudaMalloc(reinterpret_cast<void **>(&scratch_mem[device]), b_pts + 5 * b_arr));
+            scratch_cap[device] = b_pts + 5 * b_arr;
+        }
+        unsigned char *tmp = scratch_mem[device];
         float *d_pts = reinterpret_cast<float *>(tmp), *d_key = reinterpret_cast<float *>(tmp + b_pts);
         uint32_t *d_idx = reinterpret_cast<uint32_t *>(tmp + b_pts + b_arr), *d_leaf_of = reinterpret_cast<uint32_t *>(tmp + b_pts + 2 * b_arr),
                  *d_code = reinterpret_cast<uint32_t *>(tmp + b_pts + 3 * b_arr), *d_order = reinterpret_cast<uint32_t *>(tmp + b_pts + 4 * b_arr);
@@ -2017,6 +2010,10 @@ extern "C"
                 const int rc = capt_build_device(t, pts, n, r_min, r_max, r_point);
                 if (rc != VMV_OK)
                 {
+                    if (t.d_block != nullptr)
+                    {
+                        cudaFree(t.d_block);
+                    }
                     return rc;
                 }
             }
