@@ -980,6 +980,7 @@ namespace
 
     int build_cloud_grid(vmv_env *env, vmv::CloudGridRec &g)
     {
+        const auto tm_grid0 = std::chrono::steady_clock::now();
         const size_t n = env->cloud_xyz.size() / 3;
         float lo[3] = {3e38F, 3e38F, 3e38F}, hi[3] = {-3e38F, -3e38F, -3e38F};
         std::vector<float4> pts(n);
@@ -1101,6 +1102,11 @@ namespace
         VMV_CUDA(cudaEventElapsedTime(&env->cloud_grid_ms, e0, e1));
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
+        if (std::getenv("VMV_CAPT_TIMING"))
+        {
+            std::fprintf(stderr, "build_cloud_grid: %zu points, %zu voxels (h = %.4f m): kernel %.2f ms, host side %.2f ms\n", n, n_vox, h, env->cloud_grid_ms,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm_grid0).count() - env->cloud_grid_ms);
+        }
         g.x0 = lo[0] - kCloudReach, g.y0 = lo[1] - kCloudReach, g.z0 = lo[2] - kCloudReach;
         g.inv_h = static_cast<float>(1.0 / h);
         g.nx = dim[0], g.ny = dim[1], g.nz = dim[2];
