@@ -34,3 +34,16 @@ for r in ("ur5", "fetch", "baxter"):
     sc = scenes.random_scene(1, keep_out=0.5)
     print(r, R.validate_batch(scenes.random_configs(r, 4200, seed=1), scenes.build_product_env(sc)).mean())
 print("ok")
+# the list-free CAPT on the warp-autonomous any-environment kernel (>= 1024 configurations), device-built trees of several sizes
+for n in (1, 2, 5, 700, 3000):
+    envc = vmv.Environment()
+    envc.add_capt_pointcloud(pts[:n], 0.012, 0.08, vmv.POINT_RADIUS)
+    print("capt", n, vmv.panda.validate_batch(q[:2048], envc).mean())
+hf = vmv.make_heightfield([0, 0, -0.3], [0.05, 0.05, 1.0], [32, 32], (0.1 * rng.random((32, 32))).astype(np.float32))
+envh = vmv.Environment()
+envh.add_capt_pointcloud(pts, 0.03, 0.24, vmv.POINT_RADIUS)
+envh.add_heightfield(hf)
+for r in ("panda", "ur5", "fetch"):
+    R = getattr(vmv, r)
+    print("capt + heightfield", r, R.validate_batch(scenes.random_configs(r, 2048, seed=2), envh).mean())
+print("ok 2")
