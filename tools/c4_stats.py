@@ -32,5 +32,6 @@ for robot in sys.argv[1:] or ["fetch", "ur5"]:
     d["tile_cycles_hist(2^13,2^14,..)"] = [int(x) for x in out[48:60]]
     d["cycles_per_tile: capt call / of which scan loop / probe"] = [float(out[k]) / max(1.0, float(out[61])) for k in (14, 15, 62)]
     d["enum: lookup rounds / cells with points / cells in box (per config)"] = [float(out[k]) / n for k in (16, 17, 18)]
+    d["index_violations (must be 0)"] = int(out[63])
     d["tile_cycles_mean"] = float(out[60]) / max(1.0, float(out[61]))
     print(robot, json.dumps(d, indent=1))

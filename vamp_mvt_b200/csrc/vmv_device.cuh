@@ -48,7 +48,8 @@ namespace vmv
         float g_origin[3];        // enumeration grid: origin, cells per metre and cell edge at the finest level
         float g_inv0;
         float g_cell0;
-        uint32_t pad[3];
+        uint32_t n_grid_points;   // entries of gpts
+        uint32_t pad[2];
         const float2 *nodes;      // Eytzinger, 2^nlog2 - 1: {split value, 1 = the high half inherited the low half's points}
         const uint32_t *leafbits; // two bits per leaf: 1 = carries a list beyond its representative, 2 = representative is finite
         const float4 *gpts;       // the finite points in Morton order of their finest cell: {x y z leaf}
@@ -517,6 +518,14 @@ namespace vmv
                         const uint32_t m = (morton_spread(cx) | (morton_spread(cy) << 1) | (morton_spread(cz) << 2));
                         s = __ldg(starts + m);
                         e = __ldg(starts + m + 1);
+#ifdef VMV_C4_STATS
+                        // development build: every index this query derives must be inside its table
+                        if (m + 1u >= capt_grid_offset(level + 1) - capt_grid_offset(level) || s > e || e > t.n_grid_points ||
+                            cx >= dim || cy >= dim || cz >= dim)
+                        {
+                            VMV_STAT(63, 1);
+                        }
+#endif
                     }
                 }
                 uint32_t have = __ballot_sync(group, e > s);

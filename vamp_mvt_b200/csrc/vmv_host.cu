@@ -1282,6 +1282,7 @@ namespace
             r.list_reach_sq = t.list_reach_sq;
             r.g_inv0 = t.g_inv0;
             r.g_cell0 = t.g_cell0;
+            r.n_grid_points = t.d_block != nullptr ? t.n_grid_points : static_cast<uint32_t>(t.gpts.size() / 4);
             r.nodes = t.d_nodes;
             r.leafbits = t.d_leafbits;
             r.gpts = t.d_gpts;
