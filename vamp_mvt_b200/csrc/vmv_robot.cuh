@@ -222,8 +222,14 @@ namespace vmvh
     {
         using M = typename R::Model;
         using Tune = V4Tune<R::kTune>;
-        // the any-environment instantiation carries the pointcloud scan: a register cap of 128 (512 threads, one block)
-        constexpr int kThreads = AE ? (Tune::kCfgThreads > 512 ? 512 : Tune::kCfgThreads) : Tune::kCfgThreads;
+        // the any-environment instantiation carries the pointcloud queries: blocks of 256 threads
+        // (measured on BASELINE config 4, Fetch / UR5: 256 threads 0.522 / 0.348 ms, 320 0.522 / 0.352, 384 0.523 / 0.351,
+        // 448 0.523 / 0.376, 512 0.560 / 0.401, 640 0.532 / 0.362 -- the kernel does not need more than 14 resident warps, and
+        // under the 128-register cap of a 512-thread block the compiler spills; two blocks of 256 fit per SM)
+#ifndef VMV_AE_THREADS
+#define VMV_AE_THREADS 256
+#endif
+        constexpr int kThreads = AE ? (Tune::kCfgThreads > VMV_AE_THREADS ? VMV_AE_THREADS : Tune::kCfgThreads) : Tune::kCfgThreads;
         if (R::PairTab::kUseTables && !rh.inline_covered)
         {
             return fail(VMV_ERR_LIMIT, "robot's inline self-collision pairs are not covered by verdict tables");
