@@ -34,6 +34,14 @@ namespace vmv
         unsigned char link_class[kGridMaxLinks];
     };
 
+    // Attachment (reference fkcc_attach): spheres in the attachment's frame, the frame relative to the end-effector body
+    struct AttachDev
+    {
+        const float4 *spheres;  // n x {x y z r}
+        uint32_t n;
+        float tf[12];           // ee_tf(robot) * attachment offset, row-major 3x4
+    };
+
     struct GridEnv
     {
         const float4 *objs;  // n_objects rounded-box records
@@ -47,6 +55,7 @@ namespace vmv
         // into shared memory next to the rounded-box records; blob_bytes = 0 otherwise
         const float *blob;
         uint32_t blob_bytes;
+        AttachDev att;       // n = 0: nothing attached
     };
 
     __device__ __forceinline__ float margin_obj(const float4 *__restrict__ o, float x, float y, float z, float r)

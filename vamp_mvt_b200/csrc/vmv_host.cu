@@ -1653,7 +1653,8 @@ namespace
         const bool extra = !env->heightfields.empty() || !env->capts.empty() || !env->mvts.empty();
         const bool ae = extra && configs && n_obj <= 30 && !env->has_attachment && robot_host(robot).n_links <= 64 &&
                         std::getenv("VMV_NO_AE") == nullptr;
-        if (((n_obj == 0 || extra) && !ae) || n_obj > 64 || env->has_attachment)
+        // an attachment rides along on primitive environments (phase D of the grid-culled kernels)
+        if (((n_obj == 0 || extra) && !ae) || n_obj > 64 || (env->has_attachment && (extra || std::getenv("VMV_NO_V4_ATTACH") != nullptr)))
         {
             return VMV_OK;
         }
@@ -1758,6 +1759,22 @@ namespace
         out.grid = gc.dev;
         out.blob = ae ? env->d_blob : nullptr;
         out.blob_bytes = ae ? static_cast<uint32_t>(env->blob.size() * 4) : 0u;
+        out.att = vmv::AttachDev{};
+        if (env->has_attachment)
+        {
+            // the spheres sit at the tail of the device blob ({n 0 0 0} then n x {x y z r}); tf = ee_tf(robot) * attachment offset
+            out.att.spheres = reinterpret_cast<const float4 *>(env->d_blob) + (env->attach_off + vmv::kAttachHdr) / 4;
+            out.att.n = static_cast<uint32_t>(env->attach_spheres.size() / 4);
+            const float *E = robot_host(robot).ee_tf;
+            for (int i = 0; i < 3; ++i)
+            {
+                for (int j = 0; j < 4; ++j)
+                {
+                    const float s = E[4 * i] * env->attach_tf[j] + E[4 * i + 1] * env->attach_tf[4 + j] + E[4 * i + 2] * env->attach_tf[8 + j];
+                    out.att.tf[4 * i + j] = (j == 3) ? s + E[4 * i + 3] : s;
+                }
+            }
+        }
         wide = gc.wide;
         ok = true;
         return VMV_OK;

@@ -281,6 +281,8 @@ namespace vmv
         uint16_t *q1, *q2, *pairq;
         uint32_t q2_cap, round_cap;  // Q2 capacity; most fine items one B1 round can add (32 * max_fine)
         const float *E;              // any-environment instantiation: the packed environment blob in shared memory
+        const int *attach_links;     // the links an attachment is checked against (global memory, kAttachLinks entries)
+        uint32_t n_objects;
     };
 
     // Block-level staging (once per persistent block) and this warp's slice.
@@ -360,6 +362,8 @@ namespace vmv
         X.q2_cap = L.q2_cap;
         X.round_cap = 32u * env.max_fine;
         X.E = reinterpret_cast<const float *>(smem + L.off_blob);
+        X.attach_links = robot.attach_links;
+        X.n_objects = env.n_objects;
         return X;
     }
 
@@ -536,6 +540,128 @@ namespace vmv
         return invalid;
     }
 
+    // D: the attachment (reference fkcc_attach, robots/panda.hh:15308-15440; validity.hh:259-301), lane = state: its spheres,
+    // posed by the end-effector frame, against every primitive of the environment and against the links of attach_links
+    // (bounding sphere first).  Primitive environments only (the any-environment batches with an attachment stay on the
+    // per-thread kernel).  Returns true for a state in collision.
+    // (Not inlined, and handed plain pointers: batches without an attachment must not carry this code through their passes --
+    // inlined it cost the edge kernel 5 %, which is bound by instruction fetch)
+    template <typename M>
+    static __device__ __noinline__ bool v4_attachment(const float *stash, const float4 *objs, uint32_t n_objects, const SphereTask *tasks,
+                                                      const LinkInfo *links, const int *attach_links, const AttachDev *Ap, bool alive)
+    {
+        const AttachDev &A = *Ap;
+        struct
+        {
+            const float *stash;
+            const float4 *objs;
+            uint32_t n_objects;
+            const SphereTask *tasks;
+            const LinkInfo *links;
+            const int *attach_links;
+        } X{stash, objs, n_objects, tasks, links, attach_links};
+        const int lane = 0;  // `stash` is already offset by the lane
+        if (!alive)
+        {
+            return false;
+        }
+        // T = F[ee_body] * tf   (Attachment::pose, collision/attachments.hh:43-55)
+        float T[12];
+        {
+            float F[12];
+            if (M::kEeBody == 0)
+            {
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                {
+                    F[k] = (k % 5 == 0) ? 1.F : 0.F;
+                }
+            }
+            else
+            {
+                const float *stash = X.stash + lane;
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                {
+                    F[k] = (k % 4 == 2) ? 0.F : stash[((M::kEeBody - 1) * kFrameFloats + frame_slot(k)) * 32];
+                }
+                F[2] = fmaf(F[4], F[9], -(F[8] * F[5]));
+                F[6] = fmaf(F[8], F[1], -(F[0] * F[9]));
+                F[10] = fmaf(F[0], F[5], -(F[4] * F[1]));
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const float s = F[4 * i] * A.tf[j] + F[4 * i + 1] * A.tf[4 + j] + F[4 * i + 2] * A.tf[8 + j];
+                    T[4 * i + j] = (j == 3) ? s + F[4 * i + 3] : s;
+                }
+            }
+        }
+        auto posed = [&](uint32_t i, float &x, float &y, float &z) -> float
+        {
+            const float4 s = __ldg(A.spheres + i);
+            x = fmaf(T[0], s.x, fmaf(T[1], s.y, fmaf(T[2], s.z, T[3])));
+            y = fmaf(T[4], s.x, fmaf(T[5], s.y, fmaf(T[6], s.z, T[7])));
+            z = fmaf(T[8], s.x, fmaf(T[9], s.y, fmaf(T[10], s.z, T[11])));
+            return s.w;
+        };
+        // attachment vs environment (validity.hh:259-276)
+        for (uint32_t i = 0; i < A.n; ++i)
+        {
+            float x, y, z;
+            const float r = posed(i, x, y, z);
+            for (uint32_t o = 0; o < X.n_objects; ++o)
+            {
+                if (sign_set(margin_obj(X.objs + 4 * o, x, y, z, r)))
+                {
+                    return true;
+                }
+            }
+        }
+        // attachment vs links, bounding sphere first (validity.hh:278-301)
+        for (int k = 0; k < M::kAttachLinks; ++k)
+        {
+            const LinkInfo li = X.links[__ldg(X.attach_links + k)];
+            const SphereTask tb = X.tasks[li.bound_task];
+            float bx, by, bz;
+            task_centre<32>(tb, X.stash + lane, bx, by, bz);
+            bool near = false;
+            for (uint32_t i = 0; i < A.n && !near; ++i)
+            {
+                float x, y, z;
+                const float r = posed(i, x, y, z);
+                const float dx = bx - x, dy = by - y, dz = bz - z;
+                const float rs = tb.r + r;
+                near = sign_set((dx * dx + dy * dy + dz * dz) - rs * rs);
+            }
+            if (!near)
+            {
+                continue;
+            }
+            for (int f = 0; f < li.n_spheres; ++f)
+            {
+                const SphereTask tf = X.tasks[li.bound_task + 1 + f];
+                float fx, fy, fz;
+                task_centre<32>(tf, X.stash + lane, fx, fy, fz);
+                for (uint32_t i = 0; i < A.n; ++i)
+                {
+                    float x, y, z;
+                    const float r = posed(i, x, y, z);
+                    const float dx = fx - x, dy = fy - y, dz = fz - z;
+                    const float rs = tf.r + r;
+                    if (sign_set((dx * dx + dy * dy + dz * dz) - rs * rs))
+                    {
+                        return true;
+                    }
+                }
+            }
+        }
+        return false;
+    }
+
     template <int N, typename F>
     __device__ __forceinline__ void static_for(F &&f)
     {
@@ -550,7 +676,7 @@ namespace vmv
     // invalid states (lanes without a state count as invalid).
     template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS, bool AE = false>
     __device__ __forceinline__ uint32_t
-    v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const PairTabDev &T, const float (&cfg)[R::Model::kDof], const bool has)
+    v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const PairTabDev &T, const AttachDev &A, const float (&cfg)[R::Model::kDof], const bool has)
     {
         using M = typename R::Model;
         using Lay = SmemLayoutV4<M, MaskT>;
@@ -818,6 +944,14 @@ namespace vmv
                 __syncwarp();  // all reads of the queues (and, at the end, of this pass's stash) are done
             } while (base < n1);
         }
+        // ---- D: attachment (only for the states everything else has left) --------------------------
+        // (the untaken branch and its call cost the edge kernel 1.2 %, measured A/B; the configuration kernel nothing)
+        if (!AE && A.n > 0u)
+        {
+            const bool bad = v4_attachment<M>(X.stash + lane, X.objs, X.n_objects, X.tasks, X.links, X.attach_links, &A, has && !((invalid >> lane) & 1u));
+            invalid |= __ballot_sync(kFullWarp, bad);
+            __syncwarp();  // this pass's stash has been read
+        }
         return invalid;
     }
 
@@ -870,7 +1004,7 @@ namespace vmv
 #ifdef VMV_C4_STATS
             const long long t_tile = clock64();
 #endif
-            const uint32_t invalid = v4_pass<R, MaskT, TAB, true, AE>(X, env.grid, env.tab, cfg, has);
+            const uint32_t invalid = v4_pass<R, MaskT, TAB, true, AE>(X, env.grid, env.tab, env.att, cfg, has);
 #ifdef VMV_C4_STATS
             if (lane == 0)
             {
@@ -1050,7 +1184,7 @@ namespace vmv
                         cfg[j] = has ? cfg[j] : 0.F;
                     }
                 }
-                const uint32_t invalid = v4_pass<R, MaskT, TAB, false>(X, env.grid, env.tab, cfg, has);
+                const uint32_t invalid = v4_pass<R, MaskT, TAB, false>(X, env.grid, env.tab, env.att, cfg, has);
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
                 {
