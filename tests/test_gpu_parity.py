@@ -720,3 +720,48 @@ def test_capt_device_build_equals_host_build():
             finally:
                 os.environ.pop("VMV_CAPT_HOST_BUILD", None)
         assert digests[0] == digests[1], f"{len(pts)} points: device {digests[0]} vs host {digests[1]}"
+
+
+@pytest.mark.parametrize("robot", ["panda", "fetch"])
+def test_attachment_next_to_a_pointcloud(robot):
+    """A grasped object in a CAPT + heightfield + primitives environment: configuration batches run the any-environment kernel
+    with the attachment as its last phase, edge batches the per-thread kernel; both against the oracle and the reference."""
+    rng = np.random.default_rng(9)
+    R, O = getattr(vmv, robot), po.Oracle(robot)
+    m = O.model
+    pts = np.concatenate([rng.uniform([0.3, -0.6, 0.0], [0.9, 0.6, 0.02], size=(4000, 3)),
+                          rng.normal([0.55, 0.25, 0.55], 0.06, size=(2000, 3))]).astype(np.float32)
+    pts = pts[np.hypot(pts[:, 0], pts[:, 1]) > (0.5 if robot == "fetch" else 0.3)]
+    xd, yd = 48, 48
+    data = (0.3 * rng.random((yd, xd)) ** 3).astype(np.float32)
+    yy, xx = np.mgrid[0:yd, 0:xd]
+    data[np.hypot(xx - xd / 2, yy - yd / 2) < 12] = 0.0
+    sc = scenes.random_scene(2, keep_out=KEEP_OUT[robot])
+    env = scenes.build_product_env(sc)
+    oenv = po.add_scene(po.OracleEnv(), scenes.packed(sc))
+    renv = po.add_scene(po.RefEnv(), scenes.packed(sc)) if po.ref_available() else None
+    hf = vmv.make_heightfield([0, 0, -0.25], [0.05, 0.05, 1.0], [xd, yd], data)
+    env.add_capt_pointcloud(pts, m["min_radius"], m["max_radius"], vmv.POINT_RADIUS)
+    env.add_heightfield(hf)
+    for e in (oenv, renv):
+        if e is not None:
+            e.add_capt(pts, m["min_radius"], m["max_radius"], vmv.POINT_RADIUS)
+            e.add_heightfield(hf.packed(), xd, yd, data.reshape(-1))
+    tf = np.eye(4, dtype=np.float32)
+    tf[:3, 3] = [0.0, 0.0, 0.08]
+    att = vmv.Attachment(tf)
+    att.add_spheres([vmv.Sphere([0, 0, 0], 0.04), vmv.Sphere([0, 0, 0.06], 0.03), vmv.Sphere([0.03, 0, 0.1], 0.025)])
+    q = scenes.random_configs(robot, 8000, seed=51)
+    before = R.validate_batch(q, env)
+    assert 0.05 < before.mean() < 0.95
+    env.attach(att)
+    oenv.attach(att.packed_tf12(), att.packed_spheres())
+    got = R.validate_batch(q, env)
+    assert (got != before).any() and not np.any(got & ~before)  # the attachment can only remove valid configurations
+    assert_verdicts(robot, O, oenv, q, got, O.validate_configs(oenv, q), "attachment + pointcloud vs oracle", has_cloud=True)
+    if renv is not None:
+        renv.attach(att.packed_tf12(), att.packed_spheres())
+        assert_verdicts(robot, O, oenv, q, got, po.Ref(robot).validate_configs(renv, q, threads=8), "attachment + pointcloud vs reference", has_cloud=True)
+    assert np.array_equal(got[:512], R.validate_batch(q[:512], env))  # small batches take the per-thread kernel: same verdicts
+    a, b = scenes.random_edges(robot, 800, seed=52)
+    assert_edge_verdicts(O, oenv, a, b, R.validate_motion_batch(a, b, env), O.validate_edges(oenv, a, b), "attachment + pointcloud edges", has_cloud=True)

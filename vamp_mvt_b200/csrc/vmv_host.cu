@@ -1651,10 +1651,9 @@ namespace
         // any environment (configuration batches): heightfields and pointclouds next to at most 30 primitives go through
         // the grid-culled kernel's any-environment instantiation; attachments and edge batches stay on the per-thread kernel
         const bool extra = !env->heightfields.empty() || !env->capts.empty() || !env->mvts.empty();
-        const bool ae = extra && configs && n_obj <= 30 && !env->has_attachment && robot_host(robot).n_links <= 64 &&
-                        std::getenv("VMV_NO_AE") == nullptr;
-        // an attachment rides along on primitive environments (phase D of the grid-culled kernels)
-        if (((n_obj == 0 || extra) && !ae) || n_obj > 64 || (env->has_attachment && (extra || std::getenv("VMV_NO_V4_ATTACH") != nullptr)))
+        const bool ae = extra && configs && n_obj <= 30 && robot_host(robot).n_links <= 64 && std::getenv("VMV_NO_AE") == nullptr;
+        // an attachment rides along (phase D of the grid-culled kernels; next to pointclouds for configuration batches only)
+        if (((n_obj == 0 || extra) && !ae) || n_obj > 64 || (env->has_attachment && std::getenv("VMV_NO_V4_ATTACH") != nullptr))
         {
             return VMV_OK;
         }

@@ -540,6 +540,42 @@ namespace vmv
         return invalid;
     }
 
+    // T = F[ee_body] * tf   (Attachment::pose, collision/attachments.hh:43-55); `stash` already offset by the lane
+    template <typename M>
+    __device__ __forceinline__ void attachment_frame(const float *stash, const AttachDev &A, float (&T)[12])
+    {
+        float F[12];
+        if (M::kEeBody == 0)
+        {
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+            {
+                F[k] = (k % 5 == 0) ? 1.F : 0.F;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+            {
+                F[k] = (k % 4 == 2) ? 0.F : stash[((M::kEeBody - 1) * kFrameFloats + frame_slot(k)) * 32];
+            }
+            F[2] = fmaf(F[4], F[9], -(F[8] * F[5]));
+            F[6] = fmaf(F[8], F[1], -(F[0] * F[9]));
+            F[10] = fmaf(F[0], F[5], -(F[4] * F[1]));
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const float s = F[4 * i] * A.tf[j] + F[4 * i + 1] * A.tf[4 + j] + F[4 * i + 2] * A.tf[8 + j];
+                T[4 * i + j] = (j == 3) ? s + F[4 * i + 3] : s;
+            }
+        }
+    }
+
     // D: the attachment (reference fkcc_attach, robots/panda.hh:15308-15440; validity.hh:259-301), lane = state: its spheres,
     // posed by the end-effector frame, against every primitive of the environment and against the links of attach_links
     // (bounding sphere first).  Primitive environments only (the any-environment batches with an attachment stay on the
@@ -565,41 +601,8 @@ namespace vmv
         {
             return false;
         }
-        // T = F[ee_body] * tf   (Attachment::pose, collision/attachments.hh:43-55)
         float T[12];
-        {
-            float F[12];
-            if (M::kEeBody == 0)
-            {
-#pragma unroll
-                for (int k = 0; k < 12; ++k)
-                {
-                    F[k] = (k % 5 == 0) ? 1.F : 0.F;
-                }
-            }
-            else
-            {
-                const float *stash = X.stash + lane;
-#pragma unroll
-                for (int k = 0; k < 12; ++k)
-                {
-                    F[k] = (k % 4 == 2) ? 0.F : stash[((M::kEeBody - 1) * kFrameFloats + frame_slot(k)) * 32];
-                }
-                F[2] = fmaf(F[4], F[9], -(F[8] * F[5]));
-                F[6] = fmaf(F[8], F[1], -(F[0] * F[9]));
-                F[10] = fmaf(F[0], F[5], -(F[4] * F[1]));
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-            {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                {
-                    const float s = F[4 * i] * A.tf[j] + F[4 * i + 1] * A.tf[4 + j] + F[4 * i + 2] * A.tf[8 + j];
-                    T[4 * i + j] = (j == 3) ? s + F[4 * i + 3] : s;
-                }
-            }
-        }
+        attachment_frame<M>(X.stash + lane, A, T);
         auto posed = [&](uint32_t i, float &x, float &y, float &z) -> float
         {
             const float4 s = __ldg(A.spheres + i);
@@ -662,6 +665,42 @@ namespace vmv
         return false;
     }
 
+    // Any environment: the attachment's spheres against everything (validity.hh:259-276) -- primitives and heightfields per lane,
+    // the pointcloud query warp-cooperative like everywhere else (EVERY lane of the warp calls; `alive` false = the lane only
+    // helps) -- then the links (the routine above, told there are no primitives).  Out of line for the same reason.
+    template <typename M>
+    static __device__ __noinline__ bool v4_attachment_any(const float *stash, const float4 *objs, uint32_t n_objects, const float *E, const SphereTask *tasks,
+                                                          const LinkInfo *links, const int *attach_links, const AttachDev *Ap, bool alive)
+    {
+        const AttachDev &A = *Ap;
+        const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);
+        float T[12];
+        attachment_frame<M>(stash, A, T);
+        bool bad = false;
+        for (uint32_t i = 0; i < A.n; ++i)
+        {
+            const float4 sp = __ldg(A.spheres + i);
+            const float x = fmaf(T[0], sp.x, fmaf(T[1], sp.y, fmaf(T[2], sp.z, T[3])));
+            const float y = fmaf(T[4], sp.x, fmaf(T[5], sp.y, fmaf(T[6], sp.z, T[7])));
+            const float z = fmaf(T[8], sp.x, fmaf(T[9], sp.y, fmaf(T[10], sp.z, T[11])));
+            bool h = false;
+            if (alive && !bad)
+            {
+                for (uint32_t o = 0; o < n_objects && !h; ++o)
+                {
+                    h = sign_set(margin_obj(objs + 4 * o, x, y, z, sp.w));
+                }
+                h = h || (H.n_heightfields > 0 && sphere_hits_heightfields(E, x, y, z, sp.w));
+            }
+            if (H.n_capts + H.n_mvts > 0)
+            {
+                h = sphere_hits_clouds(E, x, y, z, sp.w, alive && !bad && !h) || h;
+            }
+            bad = bad || h;
+        }
+        return bad || v4_attachment<M>(stash, objs, 0u, tasks, links, attach_links, Ap, alive && !bad);
+    }
+
     template <int N, typename F>
     __device__ __forceinline__ void static_for(F &&f)
     {
@@ -674,7 +713,7 @@ namespace vmv
 
     // One pass over 32 states (lane = state in the dense phases).  Returns the warp-uniform mask of
     // invalid states (lanes without a state count as invalid).
-    template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS, bool AE = false>
+    template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS, bool AE = false, bool AE_ATT = false>
     __device__ __forceinline__ uint32_t
     v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const PairTabDev &T, const AttachDev &A, const float (&cfg)[R::Model::kDof], const bool has)
     {
@@ -945,6 +984,18 @@ namespace vmv
             } while (base < n1);
         }
         // ---- D: attachment (only for the states everything else has left) --------------------------
+        // (an instantiation of its own, launched only when something is attached: with this call in, the plain any-environment
+        // kernel needed 158 registers instead of 121 and lost 12 % on BASELINE config 4)
+        if constexpr (AE && AE_ATT)
+        {
+            if (A.n > 0u)
+            {
+                const bool bad = v4_attachment_any<M>(X.stash + lane, X.objs, X.n_objects, X.E, X.tasks, X.links, X.attach_links, &A,
+                                                      has && !((invalid >> lane) & 1u));
+                invalid |= __ballot_sync(kFullWarp, bad);
+                __syncwarp();  // this pass's stash has been read
+            }
+        }
         // (the untaken branch and its call cost the edge kernel 1.2 %, measured A/B; the configuration kernel nothing)
         if (!AE && A.n > 0u)
         {
@@ -956,7 +1007,7 @@ namespace vmv
     }
 
     // Persistent blocks of blockDim.x / 32 autonomous warps; tile t = states [32 t, 32 t + 32).
-    template <typename R, typename MaskT, bool TAB, bool GATHER, int MAXT, int MINB, bool AE = false>
+    template <typename R, typename MaskT, bool TAB, bool GATHER, int MAXT, int MINB, bool AE = false, bool AE_ATT = false>
     __global__ void __launch_bounds__(MAXT, MINB)
         k_validate_configs_v4(
             RobotDev robot,
@@ -1004,7 +1055,7 @@ namespace vmv
 #ifdef VMV_C4_STATS
             const long long t_tile = clock64();
 #endif
-            const uint32_t invalid = v4_pass<R, MaskT, TAB, true, AE>(X, env.grid, env.tab, env.att, cfg, has);
+            const uint32_t invalid = v4_pass<R, MaskT, TAB, true, AE, AE_ATT>(X, env.grid, env.tab, env.att, cfg, has);
 #ifdef VMV_C4_STATS
             if (lane == 0)
             {

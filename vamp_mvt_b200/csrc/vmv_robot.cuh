@@ -216,7 +216,7 @@ namespace vmvh
         static constexpr int kEdgeThreads = 256, kEdgeBlocks = 1, kEdgeQ2Rounds = 2;
     };
 
-    template <typename R, typename MaskT, bool GATHER, bool AE = false>
+    template <typename R, typename MaskT, bool GATHER, bool AE = false, bool AE_ATT = false>
     int launch_configs_v4(const RobotHost &rh, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits,
                           GatherDev gather, cudaStream_t s)
     {
@@ -247,7 +247,10 @@ namespace vmvh
             le.blob = nullptr, le.blob_bytes = 0;
         }
         const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds, le.blob_bytes);
-        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, GATHER, kThreads, Tune::kCfgBlocks, AE>;
+        // (any environment with an attachment: two blocks of 256 per SM, so at most 128 registers -- left alone the compiler
+        // takes 158 and only one block fits)
+        constexpr int kBlocks = (AE_ATT && kThreads <= 256) ? 2 : Tune::kCfgBlocks;
+        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, GATHER, kThreads, kBlocks, AE, AE_ATT>;
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
@@ -525,7 +528,8 @@ namespace vmvh
                 {
                     return fail(VMV_ERR_LIMIT, "any-environment grid kernel: not applicable");
                 }
-                return launch_configs_v4<R, uint32_t, false, true>(host(), rd, le, q, n, bits, g, s);
+                return le.att.n > 0 ? launch_configs_v4<R, uint32_t, false, true, true>(host(), rd, le, q, n, bits, g, s)
+                                    : launch_configs_v4<R, uint32_t, false, true>(host(), rd, le, q, n, bits, g, s);
             }
             if (g.world > 0)
             {
