@@ -2312,9 +2312,9 @@ extern "C"
             }
             if (ok)
             {
-                if (l3.blob_bytes > 0)
+                if (l3.blob_bytes > 0 || l3.att.n > 0)
                 {
-                    // any-environment instantiation: local launch, then the gather (if any) as a push
+                    // any-environment / attachment instantiations: local launch, then the gather (if any) as a push
                     rc = ops(robot).configs_v4(robot, wide, rd, l3, d_q, n, d_bits, GatherDev{}, s);
                     if (rc == VMV_OK)
                     {
@@ -2405,7 +2405,19 @@ extern "C"
             }
             if (ok)
             {
-                rc = ops(robot).edges_v4(robot, wide, rd, l3, d_a, d_b, d_pairs, n, res, d_bits, gather, s);
+                if (l3.att.n > 0 && gather.world > 0)
+                {
+                    // attachment instantiation: local launch, then the gather as a push
+                    rc = ops(robot).edges_v4(robot, wide, rd, l3, d_a, d_b, d_pairs, n, res, d_bits, GatherDev{}, s);
+                    if (rc == VMV_OK)
+                    {
+                        return push_gather(gather, d_bits, (n + 31) / 32, s);
+                    }
+                }
+                else
+                {
+                    rc = ops(robot).edges_v4(robot, wide, rd, l3, d_a, d_b, d_pairs, n, res, d_bits, gather, s);
+                }
                 if (rc != VMV_ERR_LIMIT || force == 3)
                 {
                     return rc;

@@ -713,7 +713,7 @@ namespace vmv
 
     // One pass over 32 states (lane = state in the dense phases).  Returns the warp-uniform mask of
     // invalid states (lanes without a state count as invalid).
-    template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS, bool AE = false, bool AE_ATT = false>
+    template <typename R, typename MaskT, bool TAB, bool SPLIT_ALWAYS, bool AE = false, bool ATT = false>
     __device__ __forceinline__ uint32_t
     v4_pass(const V4Ctx<R, MaskT> &X, const GridDev &G, const PairTabDev &T, const AttachDev &A, const float (&cfg)[R::Model::kDof], const bool has)
     {
@@ -986,7 +986,7 @@ namespace vmv
         // ---- D: attachment (only for the states everything else has left) --------------------------
         // (an instantiation of its own, launched only when something is attached: with this call in, the plain any-environment
         // kernel needed 158 registers instead of 121 and lost 12 % on BASELINE config 4)
-        if constexpr (AE && AE_ATT)
+        if constexpr (AE && ATT)
         {
             if (A.n > 0u)
             {
@@ -996,8 +996,8 @@ namespace vmv
                 __syncwarp();  // this pass's stash has been read
             }
         }
-        // (the untaken branch and its call cost the edge kernel 1.2 %, measured A/B; the configuration kernel nothing)
-        if (!AE && A.n > 0u)
+        // (instantiations of their own here too: the untaken branch and its call cost the edge kernel 1.2 %, measured A/B)
+        if constexpr (!AE && ATT)
         {
             const bool bad = v4_attachment<M>(X.stash + lane, X.objs, X.n_objects, X.tasks, X.links, X.attach_links, &A, has && !((invalid >> lane) & 1u));
             invalid |= __ballot_sync(kFullWarp, bad);
@@ -1007,7 +1007,7 @@ namespace vmv
     }
 
     // Persistent blocks of blockDim.x / 32 autonomous warps; tile t = states [32 t, 32 t + 32).
-    template <typename R, typename MaskT, bool TAB, bool GATHER, int MAXT, int MINB, bool AE = false, bool AE_ATT = false>
+    template <typename R, typename MaskT, bool TAB, bool GATHER, int MAXT, int MINB, bool AE = false, bool ATT = false>
     __global__ void __launch_bounds__(MAXT, MINB)
         k_validate_configs_v4(
             RobotDev robot,
@@ -1055,7 +1055,7 @@ namespace vmv
 #ifdef VMV_C4_STATS
             const long long t_tile = clock64();
 #endif
-            const uint32_t invalid = v4_pass<R, MaskT, TAB, true, AE, AE_ATT>(X, env.grid, env.tab, env.att, cfg, has);
+            const uint32_t invalid = v4_pass<R, MaskT, TAB, true, AE, ATT>(X, env.grid, env.tab, env.att, cfg, has);
 #ifdef VMV_C4_STATS
             if (lane == 0)
             {
@@ -1089,7 +1089,7 @@ namespace vmv
     // and rake-step count in registers.  Every pass checks 4 rake blocks (8 tines each) of the
     // reference's schedule (planning/validate.hh:31-64), handed out round-robin over the edges still
     // alive, so an edge found invalid drops its remaining blocks -- the reference's early return.
-    template <typename R, typename MaskT, bool TAB, bool INDEXED, bool GATHER, int MAXT, int MINB>
+    template <typename R, typename MaskT, bool TAB, bool INDEXED, bool GATHER, int MAXT, int MINB, bool ATT = false>
     __global__ void __launch_bounds__(MAXT, MINB) k_validate_edges_v4(
         RobotDev robot,
         const __grid_constant__ GridEnv env,
@@ -1235,7 +1235,7 @@ namespace vmv
                         cfg[j] = has ? cfg[j] : 0.F;
                     }
                 }
-                const uint32_t invalid = v4_pass<R, MaskT, TAB, false>(X, env.grid, env.tab, env.att, cfg, has);
+                const uint32_t invalid = v4_pass<R, MaskT, TAB, false, false, ATT>(X, env.grid, env.tab, env.att, cfg, has);
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
                 {

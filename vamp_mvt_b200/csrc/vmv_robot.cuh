@@ -216,7 +216,7 @@ namespace vmvh
         static constexpr int kEdgeThreads = 256, kEdgeBlocks = 1, kEdgeQ2Rounds = 2;
     };
 
-    template <typename R, typename MaskT, bool GATHER, bool AE = false, bool AE_ATT = false>
+    template <typename R, typename MaskT, bool GATHER, bool AE = false, bool ATT = false>
     int launch_configs_v4(const RobotHost &rh, const vmv::RobotDev &rd, vmv::GridEnv le, const float *q, size_t n, uint32_t *bits,
                           GatherDev gather, cudaStream_t s)
     {
@@ -249,8 +249,8 @@ namespace vmvh
         const vmv::SmemLayoutV4<M, MaskT> L(le.n_objects, le.max_fine, le.q2_rounds, le.blob_bytes);
         // (any environment with an attachment: two blocks of 256 per SM, so at most 128 registers -- left alone the compiler
         // takes 158 and only one block fits)
-        constexpr int kBlocks = (AE_ATT && kThreads <= 256) ? 2 : Tune::kCfgBlocks;
-        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, GATHER, kThreads, kBlocks, AE, AE_ATT>;
+        constexpr int kBlocks = (AE && ATT && kThreads <= 256) ? 2 : Tune::kCfgBlocks;
+        auto kernel = vmv::k_validate_configs_v4<R, MaskT, R::PairTab::kUseTables, GATHER, kThreads, kBlocks, AE, ATT>;
         int warps = 0;
         unsigned grid = 0;
         uint32_t smem = 0;
@@ -284,7 +284,7 @@ namespace vmvh
         return rc;
     }
 
-    template <typename R, typename MaskT, bool GATHER>
+    template <typename R, typename MaskT, bool GATHER, bool ATT = false>
     int launch_edges_v4(const RobotHost &rh, const vmv::RobotDev &rd, vmv::GridEnv le, const float *a, const float *b, const uint32_t *pairs, size_t n,
                         float resolution, uint32_t *bits, GatherDev gather, cudaStream_t s)
     {
@@ -321,7 +321,7 @@ namespace vmvh
         cudaError_t e = cudaSuccess;
         if (pairs != nullptr)
         {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, GATHER, Tune::kEdgeThreads, Tune::kEdgeBlocks>;
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, true, GATHER, Tune::kEdgeThreads, Tune::kEdgeBlocks, ATT>;
             int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, Tune::kEdgeThreads, units, warps, grid, smem);
             rc = rc == VMV_OK ? counter_acquire(s, counter, slot) : rc;
             if (rc != VMV_OK)
@@ -334,7 +334,7 @@ namespace vmvh
         }
         else
         {
-            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, GATHER, Tune::kEdgeThreads, Tune::kEdgeBlocks>;
+            auto kernel = vmv::k_validate_edges_v4<R, MaskT, R::PairTab::kUseTables, false, GATHER, Tune::kEdgeThreads, Tune::kEdgeBlocks, ATT>;
             int rc = v4_geometry(kernel, L.shared_bytes, L.warp_bytes, Tune::kEdgeThreads, units, warps, grid, smem);
             rc = rc == VMV_OK ? counter_acquire(s, counter, slot) : rc;
             if (rc != VMV_OK)
@@ -531,10 +531,20 @@ namespace vmvh
                 return le.att.n > 0 ? launch_configs_v4<R, uint32_t, false, true, true>(host(), rd, le, q, n, bits, g, s)
                                     : launch_configs_v4<R, uint32_t, false, true>(host(), rd, le, q, n, bits, g, s);
             }
+            if (g.world > 0 && le.att.n > 0)
+            {
+                return fail(VMV_ERR_LIMIT, "grid kernel with fused gather: not applicable with an attachment");
+            }
             if (g.world > 0)
             {
                 return wide ? launch_configs_v4<R, unsigned long long, true>(host(), rd, le, q, n, bits, g, s)
                             : launch_configs_v4<R, uint32_t, true>(host(), rd, le, q, n, bits, g, s);
+            }
+            if (le.att.n > 0)
+            {
+                // something is attached: the instantiations that carry phase D (local launches; a gather is pushed afterwards)
+                return wide ? launch_configs_v4<R, unsigned long long, false, false, true>(host(), rd, le, q, n, bits, g, s)
+                            : launch_configs_v4<R, uint32_t, false, false, true>(host(), rd, le, q, n, bits, g, s);
             }
             return wide ? launch_configs_v4<R, unsigned long long, false>(host(), rd, le, q, n, bits, g, s)
                         : launch_configs_v4<R, uint32_t, false>(host(), rd, le, q, n, bits, g, s);
@@ -543,10 +553,19 @@ namespace vmvh
         static int edges_v4(int, bool wide, const vmv::RobotDev &rd, vmv::GridEnv le, const float *a, const float *b, const uint32_t *pairs, size_t n,
                             float resolution, uint32_t *bits, const GatherDev &g, cudaStream_t s)
         {
+            if (g.world > 0 && le.att.n > 0)
+            {
+                return fail(VMV_ERR_LIMIT, "grid kernel with fused gather: not applicable with an attachment");
+            }
             if (g.world > 0)
             {
                 return wide ? launch_edges_v4<R, unsigned long long, true>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s)
                             : launch_edges_v4<R, uint32_t, true>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s);
+            }
+            if (le.att.n > 0)
+            {
+                return wide ? launch_edges_v4<R, unsigned long long, false, true>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s)
+                            : launch_edges_v4<R, uint32_t, false, true>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s);
             }
             return wide ? launch_edges_v4<R, unsigned long long, false>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s)
                         : launch_edges_v4<R, uint32_t, false>(host(), rd, le, a, b, pairs, n, resolution, bits, g, s);
