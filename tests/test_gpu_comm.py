@@ -99,6 +99,19 @@ def _rank_main(rank: int, world: int, uid_path: str, out_dir: str):
             _lib.check(L.vmv_stream_sync(None))
             results["edges_nccl"] = np.concatenate([_lib.unpack_bits(words[r * per : (r + 1) * per], esizes[r]) for r in range(world)])
             results["edges_local"] = vmv.panda.validate_motion_batch(V[pairs[:, 0]], V[pairs[:, 1]], env)
+            # something attached (every rank attaches to its replica): the grid-culled kernels carry the attachment in
+            # instantiations without fused stores, the gather is pushed behind the launch
+            att = vmv.Attachment(np.eye(4, dtype=np.float32))
+            att.add_spheres([vmv.Sphere([0, 0, 0.05], 0.03), vmv.Sphere([0.02, 0, 0.12], 0.04)])
+            env.attach(att)
+            C.validate_configs_gather(vmv.panda.id, env.handle, 0, shard_ptr, hi - lo)
+            C.wait(0)
+            results["configs_att"] = C.read_window(0, sizes)
+            results["configs_att_local"] = vmv.panda.validate_batch(q, env)
+            C.validate_edges_indexed_gather(vmv.panda.id, env.handle, 1, dV, len(V), dP + elo * 8, ehi - elo)
+            C.wait(1)
+            results["edges_att"] = C.read_window(1, esizes)
+            results["edges_att_local"] = vmv.panda.validate_motion_batch(V[pairs[:, 0]], V[pairs[:, 1]], env)
     np.savez(Path(out_dir) / f"rank{rank}.npz", **results)
     C.close()
 
@@ -116,6 +129,8 @@ def _check(out_dir, world):
         assert np.array_equal(d["edges_fused"], d["edges_local"])
         assert np.array_equal(d["edges_nccl"], d["edges_local"])
         assert np.array_equal(d["edges_ce"], d["edges_local"])
+        assert np.array_equal(d["configs_att"], d["configs_att_local"]) and (d["configs_att_local"] != d["configs_cloud0_local"]).any()
+        assert np.array_equal(d["edges_att"], d["edges_att_local"])
 
 
 def test_single_rank_communicator(tmp_path):
