@@ -11,8 +11,8 @@ from tests import scenes, workloads
 
 L = _lib.lib()
 L.vmv_dev_stats.argtypes = [C.c_void_p, C.c_int]
-NAMES = ["sphere_queries", "hit_primitives", "grid_lookups", "undecided_after_grid", "capt_active_calls", "need_scan", "lists_scanned",
-         "scan_steps", "points_loaded", "scan_hits", "group_size_sum", "warp_calls", "table_proven_hits", "table_point_not_listed", "bounding_hits", "fine_hits"]
+NAMES = ["sphere_queries", "hit_primitives", "grid_lookups", "undecided_after_grid", "capt_active_calls", "need_enumeration", "enumerations",
+         "enumeration_steps", "points_loaded", "enumeration_hits", "group_size_sum", "warp_calls", "table_proven_hits", "table_point_not_listed", "bounding_hits", "fine_hits"]
 for robot in sys.argv[1:] or ["fetch", "ur5"]:
     R = getattr(vmv, robot)
     env, pts, hf, _ = workloads.c4_environment(robot)

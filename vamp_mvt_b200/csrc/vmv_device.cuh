@@ -25,7 +25,7 @@ namespace vmv
         uint32_t n_zcuboids, n_heightfields, n_capts, n_attach;
         uint32_t off_spheres, off_capsules, off_zcapsules, off_cuboids;
         uint32_t off_zcuboids, off_heightfields, off_capts, off_attach;
-        uint32_t n_mvts, off_mvts, off_cloud_grid, pad1;  // off_cloud_grid = 0: no clearance grid
+        uint32_t n_mvts, off_mvts, off_cloud_grid, pad1;  // off_cloud_grid = 0: no nearest-point table
     };
 
     static constexpr int kSphereRec = 8;     // {x y z r}{min_d 0 0 0}
@@ -89,7 +89,7 @@ namespace vmv
     //    have returned;
     //  * a proven hit: when the table's point itself lies within r + r_point of the centre AND is on the affordance
     //    list of the leaf the centre descends to (capt_lists_point evaluates the reference's list construction for
-    //    that one point), the list scan would find it: "collision" without reading the list.
+    //    that one point), the reference's list scan would find it: "collision" without any list.
     static constexpr int kCloudGridRec = 12;
     static constexpr uint32_t kCloudTagNone = 0xffu;
     struct CloudGridRec
@@ -794,7 +794,7 @@ namespace vmv
     }
 
     // The pointclouds (CAPT and MVT) for one sphere, warp-cooperative: every lane of the converged group calls,
-    // `query` false = the lane has nothing to ask but helps scanning.  The clearance grid answers first.
+    // `query` false = the lane has nothing to ask but helps.  The nearest-point table answers first.
     static __device__ __noinline__ bool sphere_hits_clouds(const float *__restrict__ E, float x, float y, float z, float r_pc, bool query)
     {
         const EnvHeader &H = *reinterpret_cast<const EnvHeader *>(E);

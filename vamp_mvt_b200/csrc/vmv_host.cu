@@ -1,5 +1,5 @@
 // Host side of the C ABI (include/vamp_b200.h): environment construction, packing and upload, the
-// robot-independent kernels (voxel tables, clearance grid, Halton, CenterVox, gather), the multi-GPU
+// robot-independent kernels (voxel tables, nearest-point table, CAPT build, Halton, CenterVox, gather), the multi-GPU
 // communicator, and the entry points, which dispatch to the per-robot launchers (vmv_robot_<name>.cu)
 // through vmvh::RobotOps.  No torch, no CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
@@ -765,7 +765,7 @@ struct vmv_env
     bool committed = false;
     // shapes_dirty: a primitive, heightfield or pointcloud changed since the last commit (full re-pack); an
     // attach / detach alone only rewrites the attachment tail of the blob (a few hundred bytes) and keeps every
-    // device array, voxel table and the clearance grid -- attach / detach are O(1) in the reference too
+    // device array, voxel table and the nearest-point table -- attach / detach are O(1) in the reference too
     // (std::optional<Attachment>, collision/environment.hh:28)
     bool shapes_dirty = true;
     int device = -1;

@@ -272,7 +272,7 @@ namespace vmv
     // Configurations, one per lane: every lane is its own unit (no early stop on a neighbour's collision), but the
     // lanes of a warp stay in the loops TOGETHER until the last one is done, and a lane without work keeps calling
     // sphere_hits_env as a helper.  The pointcloud scans inside are cooperative over the lanes that arrive together:
-    // with per-lane loops the late lanes -- the ones that went on to fine spheres -- scanned their affordance lists
+    // with per-lane loops the late lanes -- the ones that went on to fine spheres -- worked through their pointcloud queries
     // in ever smaller groups, a lone lane reading 8 points per step from a list of thousands (measured on BASELINE
     // config 4: the stragglers were 2.3x the average SM time).
     struct LaneVote

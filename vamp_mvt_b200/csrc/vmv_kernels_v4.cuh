@@ -473,7 +473,7 @@ namespace vmv
     // Any-environment instantiation: what a 32-bit candidate mask carries beside its (at most 30) object bits
     static constexpr uint32_t kAeObjMask = 0x3fffffffu;  // primitive candidates / exact hits
     static constexpr uint32_t kAeHfBit = 0x40000000u;    // the link's bounding sphere hits a heightfield (exact test, done with the FK)
-    static constexpr uint32_t kAeCloudBit = 0x80000000u; // the clearance grid could not rule the pointclouds out for the bounding sphere
+    static constexpr uint32_t kAeCloudBit = 0x80000000u; // the nearest-point table could not rule the pointclouds out for the bounding sphere
 
     // B2: one lane per fine-sphere item, against its link's hit mask -- and, in the any-environment instantiation,
     // against the heightfields and the pointclouds (a link whose bounding sphere hit ANYTHING has its fine spheres
