@@ -123,6 +123,9 @@ def oracle_lib():
         L.or_min_clearance.restype = C.c_double
         L.or_validate_edge.restype = C.c_int
         L.or_capt_query.restype = C.c_int
+        L.or_capt_nlog2.restype = C.c_int
+        L.or_capt_tests.restype = C.POINTER(C.c_float)
+        L.or_capt_leaf_list.restype = C.c_size_t
         _oracle_lib = L
     return _oracle_lib
 
@@ -226,6 +229,20 @@ class OracleEnv(_EnvBase):
 
     def __init__(self):
         super().__init__(oracle_lib())
+
+    def capt_tree(self, which: int = 0):
+        """(nlog2, split values in Eytzinger order) of the which-th CAPT."""
+        n = self.lib.or_capt_nlog2(self.h, C.c_size_t(which))
+        t = self.lib.or_capt_tests(self.h, C.c_size_t(which))
+        return n, np.ctypeslib.as_array(t, shape=((1 << n) - 1,)).copy() if n > 0 else np.zeros(0, np.float32)
+
+    def capt_leaf_list(self, leaf: int, which: int = 0) -> np.ndarray:
+        """The affordance list of one leaf, representative first, as [k][3]."""
+        k = self.lib.or_capt_leaf_list(self.h, C.c_size_t(which), C.c_size_t(leaf), None, C.c_size_t(0))
+        out = np.zeros((k, 3), np.float32)
+        if k:
+            self.lib.or_capt_leaf_list(self.h, C.c_size_t(which), C.c_size_t(leaf), _fp(out), C.c_size_t(k))
+        return out
 
 
 class RefEnv(_EnvBase):

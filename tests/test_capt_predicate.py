@@ -1,0 +1,128 @@
+"""The claim the list-free CAPT rests on, proved on the CPU against the oracle's lists (which are pinned against the reference's):
+
+    the affordance list of a leaf (reference collision/capt.hh:121-287) is a function of the k-d tree alone, and for ONE point p
+    and ONE leaf L membership is: p is L's representative, or -- L carries a list at all, and at the node where the two root paths
+    part p's half was handed to L's half (low half: always what is within r_max of the plane; high half: all or nothing,
+    decided by the low half's SMALLEST element), and p lies within r_max of L's cell axis by axis, and within r_max + r_point
+    of the cell.
+
+This file restates that predicate in numpy exactly as `vmv_device.cuh: capt_descend / capt_member` evaluate it (same float32
+operations) and compares the set it yields, leaf by leaf, with the list the oracle built the reference's way.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+f32 = np.float32
+
+
+def _cells_and_flags(pts, leaf_reps, nlog2, tests, r_max):
+    """Per leaf: cell bounds and the mask of levels where the path turns high at a node whose high half did NOT inherit."""
+    n_leaves = 1 << nlog2
+    lo = np.full((n_leaves, 3), -np.inf, f32)
+    hi = np.full((n_leaves, 3), np.inf, f32)
+    hmask = np.zeros(n_leaves, np.uint32)
+    # inherited bit per node: the smallest finite coordinate (on the node's axis) among the low half's representatives
+    inherited = np.zeros(max(len(tests), 1), bool)
+    for level in range(nlog2):
+        seg = n_leaves >> level
+        d = level % 3
+        for m in range(1 << level):
+            node = (1 << level) - 1 + m
+            low = leaf_reps[m * seg : m * seg + seg // 2, d]
+            low = low[np.isfinite(low)]
+            inherited[node] = len(low) > 0 and low.min() >= f32(tests[node]) - f32(r_max)
+    for leaf in range(n_leaves):
+        node = 0
+        for level in range(nlog2):
+            d = level % 3
+            up = (leaf >> (nlog2 - 1 - level)) & 1
+            if up:
+                lo[leaf, d] = tests[node]
+                if not inherited[node]:
+                    hmask[leaf] |= np.uint32(1) << np.uint32(nlog2 - 1 - level)
+            else:
+                hi[leaf, d] = tests[node]
+            node = 2 * node + 1 + up
+    return lo, hi, hmask
+
+
+def _predicted_list(leaf, pts, leaf_of, lo, hi, hmask, full, r_max, reach_sq):
+    """Indices of the points the predicate puts on the list of `leaf` (the device's capt_member, vectorised over the points)."""
+    parted = np.uint32(leaf) ^ leaf_of.astype(np.uint32)
+    rep = parted == 0
+    msb = np.zeros(len(pts), np.int64)
+    nz = parted != 0
+    msb[nz] = np.floor(np.log2(parted[nz].astype(np.float64))).astype(np.int64)
+    handed = ((hmask[leaf] >> msb.astype(np.uint32)) & 1) == 0
+    near = np.ones(len(pts), bool)
+    dsq = np.zeros(len(pts), f32)
+    for k in range(3):
+        near &= (pts[:, k] >= f32(lo[leaf, k]) - f32(r_max)) & (pts[:, k] <= f32(hi[leaf, k]) + f32(r_max))
+        d = (pts[:, k] - np.minimum(np.maximum(pts[:, k], lo[leaf, k]), hi[leaf, k])).astype(f32)
+        dsq = (dsq + (d * d).astype(f32)).astype(f32)
+    member = rep | (full[leaf] & handed & near & (dsq <= reach_sq))
+    return np.nonzero(member)[0]
+
+
+CASES = [
+    ("uniform", 300, (0.02, 0.12, 0.0025)),
+    ("surface", 500, (0.03, 0.2, 0.0025)),
+    ("representative-only leaves", 300, (0.15, 0.2, 0.0025)),
+    ("lists shorter than anything", 300, (0.005, 0.02, 0.0)),
+    ("non power of two", 137, (0.02, 0.15, 0.01)),
+    ("wide lists", 200, (0.02, 0.6, 0.0025)),
+]
+
+
+@pytest.mark.parametrize("name,n,radii", CASES, ids=[c[0] for c in CASES])
+def test_list_membership_is_a_function_of_the_tree(name, n, radii):
+    rng = np.random.default_rng(len(name) * 7 + n)
+    if name == "surface":
+        pts = np.concatenate([rng.uniform([0, 0, 0], [1, 1, 0.02], size=(n // 2, 3)), rng.normal([0.5, 0.5, 0.4], 0.08, size=(n - n // 2, 3))])
+    else:
+        pts = rng.uniform([0, 0, 0], [1.0, 0.8, 0.6], size=(n, 3))
+    pts = pts.astype(f32)
+    assert len(np.unique(pts[:, 0])) == n and len(np.unique(pts[:, 1])) == n and len(np.unique(pts[:, 2])) == n  # no ties
+    r_min, r_max, r_point = (f32(v) for v in radii)
+    env = po.OracleEnv()
+    env.add_capt(pts, r_min, r_max, r_point)
+    nlog2, tests = env.capt_tree()
+    n_leaves = 1 << nlog2
+    lists = [env.capt_leaf_list(z) for z in range(n_leaves)]
+    # the representative of a leaf is the first entry of its list; padding leaves (+inf) have none
+    leaf_reps = np.full((n_leaves, 3), np.inf, f32)
+    leaf_of = np.zeros(n, np.int64)
+    key = {tuple(p): i for i, p in enumerate(pts)}
+    for z, L in enumerate(lists):
+        if len(L):
+            leaf_reps[z] = L[0]
+            leaf_of[key[tuple(L[0])]] = z
+    assert sorted(leaf_of.tolist()) == sorted(set(leaf_of.tolist())) and np.isfinite(leaf_reps[:, 0]).sum() == n
+    lo, hi, hmask = _cells_and_flags(pts, leaf_reps, nlog2, tests, r_max)
+    # a leaf carries a list unless its cell lies inside the smallest query ball around its representative (capt.hh:39-46)
+    min_l2 = f32((r_min + r_point) * (r_min + r_point))
+    full = np.zeros(n_leaves, bool)
+    for z in range(n_leaves):
+        if np.isfinite(leaf_reps[z, 0]):
+            d = np.maximum(leaf_reps[z] - lo[z], hi[z] - leaf_reps[z]).astype(f32)
+            full[z] = not (f32(f32(d[0] * d[0]) + f32(d[1] * d[1])) + f32(d[2] * d[2]) <= min_l2)
+    reach = f32(r_max + r_point)
+    reach_sq = f32(reach * reach)
+    holes = 0
+    for z in range(n_leaves):
+        if not np.isfinite(leaf_reps[z, 0]):
+            assert len(lists[z]) == 0
+            continue
+        want = sorted(key[tuple(p)] for p in lists[z])
+        got = sorted(_predicted_list(z, pts, leaf_of, lo, hi, hmask, full, r_max, reach_sq).tolist())
+        assert got == want, f"{name}: leaf {z}: predicate {len(got)} points, oracle list {len(want)}"
+        # how much the reference's lists MISS of what lies within reach of the cell (the all-or-nothing hand-over)
+        dsq = np.zeros(n, f32)
+        for k in range(3):
+            d = (pts[:, k] - np.minimum(np.maximum(pts[:, k], lo[z, k]), hi[z, k])).astype(f32)
+            dsq = (dsq + (d * d).astype(f32)).astype(f32)
+        holes += int(full[z]) * (int((dsq <= reach_sq).sum()) - len(want))
+    if name in ("surface", "wide lists"):
+        assert holes > 0  # the quirk is exercised: complete lists would hold more
