@@ -140,6 +140,10 @@ def ref_lib():
         L = C.CDLL(str(REF_SO))
         L.ref_env_create.restype = C.c_void_p
         L.ref_env_dump.restype = C.c_size_t
+        if hasattr(L, "ref_capt_nlog2"):
+            L.ref_capt_nlog2.restype = C.c_int
+            L.ref_capt_tests.restype = C.POINTER(C.c_float)
+            L.ref_capt_leaf_list.restype = C.c_size_t
         L.ref_time_configs.restype = C.c_double
         L.ref_time_edges.restype = C.c_double
         if hasattr(L, "ref_simplify"):
@@ -210,6 +214,21 @@ class _EnvBase:
         p = _f32(points).reshape(-1, 3)
         getattr(self.lib, self.prefix + "env_add_raw_cloud")(self.h, _fp(p), C.c_size_t(len(p)), C.c_float(r_point))
 
+    def capt_tree(self, which: int = 0):
+        """(nlog2, split values in Eytzinger order) of the which-th CAPT."""
+        n = getattr(self.lib, self.prefix + "capt_nlog2")(self.h, C.c_size_t(which))
+        t = getattr(self.lib, self.prefix + "capt_tests")(self.h, C.c_size_t(which))
+        return n, np.ctypeslib.as_array(t, shape=((1 << n) - 1,)).copy() if n > 0 else np.zeros(0, np.float32)
+
+    def capt_leaf_list(self, leaf: int, which: int = 0) -> np.ndarray:
+        """The affordance list of one leaf, representative first, as [k][3]."""
+        k = getattr(self.lib, self.prefix + "capt_leaf_list")(self.h, C.c_size_t(which), C.c_size_t(leaf), None, C.c_size_t(0))
+        out = np.zeros((k, 3), np.float32)
+        if k:
+            getattr(self.lib, self.prefix + "capt_leaf_list")(self.h, C.c_size_t(which), C.c_size_t(leaf), _fp(out), C.c_size_t(k))
+        return out
+
+
     def attach(self, tf12, spheres):
         s = _f32(spheres).reshape(-1, 4)
         getattr(self.lib, self.prefix + "env_attach")(self.h, _fp(_f32(tf12)), _fp(s), C.c_size_t(len(s)))
@@ -229,21 +248,6 @@ class OracleEnv(_EnvBase):
 
     def __init__(self):
         super().__init__(oracle_lib())
-
-    def capt_tree(self, which: int = 0):
-        """(nlog2, split values in Eytzinger order) of the which-th CAPT."""
-        n = self.lib.or_capt_nlog2(self.h, C.c_size_t(which))
-        t = self.lib.or_capt_tests(self.h, C.c_size_t(which))
-        return n, np.ctypeslib.as_array(t, shape=((1 << n) - 1,)).copy() if n > 0 else np.zeros(0, np.float32)
-
-    def capt_leaf_list(self, leaf: int, which: int = 0) -> np.ndarray:
-        """The affordance list of one leaf, representative first, as [k][3]."""
-        k = self.lib.or_capt_leaf_list(self.h, C.c_size_t(which), C.c_size_t(leaf), None, C.c_size_t(0))
-        out = np.zeros((k, 3), np.float32)
-        if k:
-            self.lib.or_capt_leaf_list(self.h, C.c_size_t(which), C.c_size_t(leaf), _fp(out), C.c_size_t(k))
-        return out
-
 
 class RefEnv(_EnvBase):
     prefix = "ref_"

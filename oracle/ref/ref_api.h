@@ -24,6 +24,9 @@ extern "C"
     void ref_env_add_capsule(void *env, const float *f8);
     void ref_env_add_heightfield(void *env, const float *f6, size_t xd, size_t yd, const float *data);
     void ref_env_add_capt(void *env, const float *pts, size_t n, float r_min, float r_max, float r_point);
+    int ref_capt_nlog2(void *env, size_t which);
+    const float *ref_capt_tests(void *env, size_t which);
+    size_t ref_capt_leaf_list(void *env, size_t which, size_t leaf, float *out_xyz, size_t cap);
     void ref_env_add_mvt(
         void *env,
         const float *pts,

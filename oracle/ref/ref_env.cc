@@ -7,6 +7,7 @@
 #include <vamp/collision/filter_centervox.hh>
 #include "ref_api.h"
 
+#include <cmath>
 #include <cstring>
 #include <memory>
 
@@ -118,6 +119,40 @@ extern "C"
         vc::HeightField<float> h(f[0], f[1], f[2], f[3], f[4], f[5], xd, yd, d);
         h.name = E(env).name();
         E(env).env.heightfields.emplace_back(h);
+    }
+
+    // the reference's own CAPT, opened up for tests/test_capt_predicate.py: depth, split values, the list of one leaf
+    int ref_capt_nlog2(void *env, size_t which)
+    {
+        return E(env).env.capt_pointclouds[which].nlog2;
+    }
+
+    const float *ref_capt_tests(void *env, size_t which)
+    {
+        return E(env).env.capt_pointclouds[which].tests.data();
+    }
+
+    size_t ref_capt_leaf_list(void *env, size_t which, size_t leaf, float *out_xyz, size_t cap)
+    {
+        const auto &t = E(env).env.capt_pointclouds[which];
+        size_t n = 0;
+        for (uint32_t i = t.aff_starts[leaf]; i < t.aff_starts[leaf + 1]; ++i)
+        {
+            const auto xs = t.affordances[0][i].to_array(), ys = t.affordances[1][i].to_array(), zs = t.affordances[2][i].to_array();
+            for (size_t l = 0; l < xs.size(); ++l)
+            {
+                if (!std::isfinite(xs[l]))
+                {
+                    continue;
+                }
+                if (n < cap)
+                {
+                    out_xyz[3 * n] = xs[l], out_xyz[3 * n + 1] = ys[l], out_xyz[3 * n + 2] = zs[l];
+                }
+                ++n;
+            }
+        }
+        return n;
     }
 
     void ref_env_add_capt(void *env, const float *pts, size_t n, float r_min, float r_max, float r_point)

@@ -7,7 +7,8 @@
     of the cell.
 
 This file restates that predicate in numpy exactly as `vmv_device.cuh: capt_descend / capt_member` evaluate it (same float32
-operations) and compares the set it yields, leaf by leaf, with the list the oracle built the reference's way.
+operations) and compares the set it yields, leaf by leaf, with the list the oracle built the reference's way -- and with the list
+the REFERENCE ITSELF built (its own collision/capt.hh compiled in place, oracle/_ref), read out of its CAPT object.
 """
 import numpy as np
 import pytest
@@ -76,8 +77,11 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("builder", ["oracle", "reference"])
 @pytest.mark.parametrize("name,n,radii", CASES, ids=[c[0] for c in CASES])
-def test_list_membership_is_a_function_of_the_tree(name, n, radii):
+def test_list_membership_is_a_function_of_the_tree(name, n, radii, builder):
+    if builder == "reference" and not (po.ref_available() and hasattr(po.ref_lib(), "ref_capt_nlog2")):
+        pytest.skip("the compiled reference (oracle/_ref) is not here")
     rng = np.random.default_rng(len(name) * 7 + n)
     if name == "surface":
         pts = np.concatenate([rng.uniform([0, 0, 0], [1, 1, 0.02], size=(n // 2, 3)), rng.normal([0.5, 0.5, 0.4], 0.08, size=(n - n // 2, 3))])
@@ -86,7 +90,7 @@ def test_list_membership_is_a_function_of_the_tree(name, n, radii):
     pts = pts.astype(f32)
     assert len(np.unique(pts[:, 0])) == n and len(np.unique(pts[:, 1])) == n and len(np.unique(pts[:, 2])) == n  # no ties
     r_min, r_max, r_point = (f32(v) for v in radii)
-    env = po.OracleEnv()
+    env = po.OracleEnv() if builder == "oracle" else po.RefEnv()  # the reference: ITS tree, ITS lists (collision/capt.hh)
     env.add_capt(pts, r_min, r_max, r_point)
     nlog2, tests = env.capt_tree()
     n_leaves = 1 << nlog2
