@@ -264,6 +264,9 @@ extern "C"
     /* development / tests: FNV-1a digests of the k-th CAPT's tables {nodes, leaf flags, grid points, grid starts}: the device
      * build (default) and the host build (environment variable VMV_CAPT_HOST_BUILD) must agree bit for bit */
     int vmv_env_capt_digest(const vmv_env *env, int k, uint64_t *out4);
+    /* development / tests: the k-th CAPT's nodes in Eytzinger order, {split value, inherited bit} per node (the split values are
+     * the reference's CAPT::tests); returns the number of floats (2 per node), copies at most cap_floats */
+    long vmv_env_capt_nodes(const vmv_env *env, int k, float *out, size_t cap_floats);
     /* testing aid: 0 = automatic choice (default), 1 = force the generic per-thread kernel,
      * 2 = force the block-cooperative kernel, 3 = force the grid-culled kernel (2 and 3 fail with
      * VMV_ERR_LIMIT when they do not apply to the environment) */

@@ -765,3 +765,28 @@ def test_attachment_next_to_a_pointcloud(robot):
     assert np.array_equal(got[:512], R.validate_batch(q[:512], env))  # small batches take the per-thread kernel: same verdicts
     a, b = scenes.random_edges(robot, 800, seed=52)
     assert_edge_verdicts(O, oenv, a, b, R.validate_motion_batch(a, b, env), O.validate_edges(oenv, a, b), "attachment + pointcloud edges", has_cloud=True)
+
+
+def test_capt_tree_equals_the_references():
+    """The device-built tree against the REFERENCE's own (its CAPT object read out through oracle/_ref): split values bit for
+    bit, on clouds without coordinate ties."""
+    import ctypes as C
+
+    from vamp_mvt_b200 import _lib
+
+    if not (po.ref_available() and hasattr(po.ref_lib(), "ref_capt_nlog2")):
+        pytest.skip("the compiled reference (oracle/_ref) is not here")
+    L = _lib.lib()
+    rng = np.random.default_rng(8)
+    for n in (2, 3, 17, 300, 1000, 4097, 30000):
+        pts = (np.stack([rng.permutation(n), rng.permutation(n), rng.permutation(n)], -1).astype(np.float32) + np.float32(0.25)) * np.float32([3e-5, 2e-5, 1e-5])
+        env, renv = vmv.Environment(), po.RefEnv()
+        env.add_capt_pointcloud(pts, 0.02, 0.15, vmv.POINT_RADIUS)
+        renv.add_capt(pts, 0.02, 0.15, vmv.POINT_RADIUS)
+        nlog2, tests = renv.capt_tree()
+        k = L.vmv_env_capt_nodes(env.handle, 0, None, 0)
+        assert k == 2 * len(tests)
+        nodes = np.zeros(k, np.float32)
+        L.vmv_env_capt_nodes(env.handle, 0, _lib.ptr(nodes), k)
+        ours = nodes[0::2]
+        assert np.array_equal(ours.view(np.uint32), tests.view(np.uint32)), f"{n} points: {int((ours.view(np.uint32) != tests.view(np.uint32)).sum())} split values differ"

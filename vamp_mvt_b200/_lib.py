@@ -111,6 +111,8 @@ def lib():
         L.vmv_comm_publish.argtypes = [vp, i32, sz, vp]
         L.vmv_comm_acquire.argtypes = [vp, i32, vp]
         L.vmv_env_capt_digest.argtypes = [vp, i32, vp]
+        L.vmv_env_capt_nodes.argtypes = [vp, i32, vp, C.c_size_t]
+        L.vmv_env_capt_nodes.restype = C.c_long
         _lib = L
     return _lib
 

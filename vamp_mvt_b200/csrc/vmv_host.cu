@@ -3404,6 +3404,25 @@ extern "C"
         return VMV_OK;
     }
 
+    long vmv_env_capt_nodes(const vmv_env *env, int k, float *out, size_t cap_floats)
+    {
+        if (env == nullptr || k < 0 || static_cast<size_t>(k) >= env->capts.size())
+        {
+            return fail(VMV_ERR_ARG, "vmv_env_capt_nodes: bad argument");
+        }
+        const HCapt &t = env->capts[static_cast<size_t>(k)];
+        const int rc = capt_ensure_host(t);
+        if (rc != VMV_OK)
+        {
+            return rc;
+        }
+        if (out != nullptr)
+        {
+            std::memcpy(out, t.nodes.data(), std::min(cap_floats, t.nodes.size()) * sizeof(float));
+        }
+        return static_cast<long>(t.nodes.size());
+    }
+
     uint64_t vmv_launch_count(void)
     {
         return g_launches.load();
