@@ -402,6 +402,20 @@ def main() -> int:
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e_value = world * N_CONFIGS / e2e_s
 
+    # the same public call path WITHOUT the upload: the planners draw every sample from the Halton sequence, which the library
+    # evaluates on the device (vmv_validate_halton: fill + validate + D2H of one bit per sample) -- what a batched sampling
+    # front-end pays end to end.  Reported next to `e2e`, never instead of it.
+    n_h = int(min(1_000_000, L.vmv_halton_exact_limit(robot.id)))
+    h_bits = torch.zeros((n_h + 31) // 32, dtype=torch.int32).pin_memory()
+    for _ in range(3):
+        _lib.check(L.vmv_validate_halton(robot.id, h_env, 0, n_h, h_bits.data_ptr(), None))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        _lib.check(L.vmv_validate_halton(robot.id, h_env, 0, n_h, h_bits.data_ptr(), None))
+    barrier()
+    halton_s = max_over_ranks((time.perf_counter() - t0) / 10)
+
     # ---- C3 edges -------------------------------------------------------------------------------------
     edges = None
     if not args.no_edges:
@@ -742,6 +756,9 @@ def main() -> int:
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": N_CONFIGS * dof * 4, "d2h_bytes_per_step": n_words * 4,
                 "ms_per_step": e2e_s * 1e3, "api": "vmv_validate_configs (host pointers, pinned)"},
+        "e2e_device_sampled": {"value": world * n_h / halton_s, "unit": "configs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": (n_h + 31) // 32 * 4,
+                               "ms_per_step": halton_s * 1e3, "samples_per_gpu": n_h,
+                               "api": "vmv_validate_halton (the reference's Halton sampler evaluated on the device; every rank the same samples)"},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
